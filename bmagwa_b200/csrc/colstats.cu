@@ -1,0 +1,290 @@
+// colstats.cu -- per-proposal column statistics (src/model.hpp:453-470) and the probit latent
+// update.
+//
+// For each candidate SNP c of a move, in ONE launch:  x_c'y, x_c'E_j, x_c'x_l for the model's
+// SNPs l, and x_c'x_d among the candidates.  The reference unpacks the column to n doubles and
+// runs ddot + dgemv over the n x k double matrix it keeps per model (and copies on every
+// accept/reject, model.hpp:115-162); here the model's columns stay packed (the store IS the
+// gamma-column cache) and genotype-by-genotype products are exact integer popcount arithmetic.
+#include "common.cuh"
+#include "store.cuh"
+#include "philox.cuh"
+
+namespace bmg {
+
+constexpr int kSegWords = 2048;  // words of a column handled by one CTA (32768 individuals)
+
+struct ColStatArgs {
+  const uint32_t* const* cand_cols;   // m_c packed columns
+  const uint32_t* const* model_cols;  // k packed columns
+  int m_c, k, m_e;
+  int64_t n, W;
+  int n_seg;
+  const double* y;   // n
+  const double* e;   // n x m_e col-major
+  double* out;       // [m_c][n_seg][n_tasks], n_tasks = m_e + 1 + k + m_c  (task 0 = y, 1.. = E_j, then loci, then cands)
+};
+
+__device__ __forceinline__ int packed_dot(uint32_t a, uint32_t b)
+{
+  // fields hold values 0,1,2 as 00,01,10:  a*b = 4 a1 b1 + 2 a1 b0 + 2 a0 b1 + a0 b0
+  const uint32_t M = 0x55555555u;
+  const uint32_t a0 = a & M, a1 = (a >> 1) & M, b0 = b & M, b1 = (b >> 1) & M;
+  return 4 * __popc(a1 & b1) + 2 * (__popc(a1 & b0) + __popc(a0 & b1)) + __popc(a0 & b0);
+}
+
+__global__ void __launch_bounds__(256) k_column_stats(const ColStatArgs a)
+{
+  __shared__ uint32_t cw[kSegWords];
+  const int c = blockIdx.x, seg = blockIdx.y;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nw = blockDim.x >> 5;
+  const int64_t w0 = (int64_t)seg * kSegWords;
+  const int nwords = (int)min((int64_t)kSegWords, a.W - w0);
+  const uint32_t* col = a.cand_cols[c];
+  for (int w = t; w < nwords; w += blockDim.x) cw[w] = col[w0 + w];
+  __syncthreads();
+  const int n_tasks = a.m_e + 1 + a.k + a.m_c;
+  double* out = a.out + ((int64_t)c * a.n_seg + seg) * n_tasks;
+  for (int task = warp; task < n_tasks; task += nw) {
+    double res;
+    if (task <= a.m_e) {
+      // x_c . y (task 0) or x_c . E_j (task 1 + j)
+      const double* vec = task == 0 ? a.y : a.e + (int64_t)(task - 1) * a.n;
+      double acc = 0.0;
+      for (int w = lane; w < nwords; w += 32) {
+        const uint32_t word = cw[w];
+        if (word == 0) continue;
+        const int64_t i0 = 16 * (w0 + w);
+#pragma unroll
+        for (int p = 0; p < 16; ++p) {
+          const int64_t i = i0 + p;
+          const double g = (double)((word >> (2 * p)) & 3u);
+          if (i < a.n) acc = fma(g, vec[i], acc);
+        }
+      }
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      res = acc;
+    } else {
+      const int q = task - a.m_e - 1;
+      const uint32_t* other = q < a.k ? a.model_cols[q] : a.cand_cols[q - a.k];
+      int acc = 0;
+      for (int w = lane; w < nwords; w += 32) acc += packed_dot(cw[w], other[w0 + w]);
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      res = (double)acc;
+    }
+    if (lane == 0) out[task] = res;
+  }
+}
+
+// ---- sparse corrections for imputed cells (the dense columns hold 0 there) -------------------
+struct ColMissArgs {
+  const int64_t* snp_local;      // m_c + k entries: local index of each involved SNP, -1 if not local
+  const uint32_t* const* cols;   // m_c + k packed columns (candidates first)
+  const int64_t* off; const int32_t* idx; const int8_t* val;
+  int m_c, k, m_e;
+  int64_t n;
+  const double* y; const double* e;
+  double* out;                   // [m_c][n_tasks] final (segment-summed) results, corrected in place
+};
+
+__device__ __forceinline__ double value_with_overlay(const ColMissArgs& a, int which, int64_t i)
+{
+  // genotype of involved SNP `which` at individual i including the chain's imputed value
+  const int64_t j = a.snp_local[which];
+  if (j >= 0) {
+    int64_t lo = a.off[j], hi = a.off[j + 1];
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      const int32_t v = a.idx[mid];
+      if (v == (int32_t)i) return (double)a.val[mid];
+      if (v < (int32_t)i) lo = mid + 1; else hi = mid;
+    }
+  }
+  return (double)((a.cols[which][i >> 4] >> (2 * (i & 15))) & 3u);
+}
+
+// one thread per (candidate c, task); serial over the few imputed cells involved
+__global__ void k_column_stats_missfix(const ColMissArgs a)
+{
+  const int n_tasks = a.m_e + 1 + a.k + a.m_c;
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= a.m_c * n_tasks) return;
+  const int c = gid / n_tasks, task = gid % n_tasks;
+  const int64_t jc = a.snp_local[c];
+  double corr = 0.0;
+  if (task <= a.m_e) {
+    if (jc >= 0) {
+      const double* vec = task == 0 ? a.y : a.e + (int64_t)(task - 1) * a.n;
+      for (int64_t q = a.off[jc]; q < a.off[jc + 1]; ++q) corr += (double)a.val[q] * vec[a.idx[q]];
+    }
+  } else {
+    const int q2 = task - a.m_e - 1;
+    const int other = q2 < a.k ? a.m_c + q2 : q2 - a.k;   // index into the involved-SNP list
+    const int64_t jo = a.snp_local[other];
+    // cells imputed in c: val_c * x_other(i) (x_other with ITS overlay)
+    if (jc >= 0)
+      for (int64_t q = a.off[jc]; q < a.off[jc + 1]; ++q)
+        if (a.val[q]) corr += (double)a.val[q] * value_with_overlay(a, other, a.idx[q]);
+    // cells imputed in other but observed in c: x_c(i) * val_other
+    if (jo >= 0 && other != c)
+      for (int64_t q = a.off[jo]; q < a.off[jo + 1]; ++q) {
+        if (!a.val[q]) continue;
+        const int64_t i = a.idx[q];
+        bool c_missing = false;
+        if (jc >= 0) {
+          int64_t lo = a.off[jc], hi = a.off[jc + 1];
+          while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            const int32_t v = a.idx[mid];
+            if (v == (int32_t)i) { c_missing = true; break; }
+            if (v < (int32_t)i) lo = mid + 1; else hi = mid;
+          }
+        }
+        if (!c_missing) corr += (double)((a.cols[c][i >> 4] >> (2 * (i & 15))) & 3u) * (double)a.val[q];
+      }
+  }
+  if (corr != 0.0) a.out[(int64_t)c * n_tasks + task] += corr;
+}
+
+__global__ void k_sum_segments(const double* __restrict__ seg_out, int m_c, int n_seg, int n_tasks, double* __restrict__ out)
+{
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= m_c * n_tasks) return;
+  const int c = gid / n_tasks, task = gid % n_tasks;
+  double s = 0.0;
+  for (int g = 0; g < n_seg; ++g) s += seg_out[((int64_t)c * n_seg + g) * n_tasks + task];
+  out[gid] = s;
+}
+
+void chain_column_stats(Chain* c, const int64_t* cand, int m_c, const int64_t* loci, int k, double* xy, double* xe,
+                        double* xx_model, double* xx_cand)
+{
+  Store* s = c->store;
+  BMG_REQUIRE(m_c >= 1 && m_c <= 256, "bmg_chain_column_stats: 1..256 candidates per call");
+  BMG_REQUIRE(k >= 0 && k <= 2048, "bmg_chain_column_stats: model size must be <= 2048");
+  BMG_CUDA(cudaSetDevice(s->device));
+  cudaStream_t st = c->stream;
+  const int n_tasks = s->m_e + 1 + k + m_c;
+  const int n_seg = (int)((s->W + kSegWords - 1) / kSegWords);
+  const size_t need = (size_t)m_c * n_tasks * (n_seg + 1);
+  if (c->cs_out.n < need) { c->cs_out.alloc(need * 2); c->h_cs.alloc(need * 2); }
+  const size_t n_ptr = (size_t)(m_c + k) * 2;
+  if (c->cs_idx.n < n_ptr + 16) c->cs_idx.alloc(n_ptr * 2 + 4096);
+  if (c->h_stage_i.n < n_ptr + 16) c->h_stage_i.alloc(n_ptr * 2 + 4096);
+  BMG_CUDA(cudaStreamSynchronize(st));
+  int64_t* hp = c->h_stage_i.p;
+  bool any_missing = false;
+  for (int i = 0; i < m_c + k; ++i) {
+    const int64_t snp = i < m_c ? cand[i] : loci[i - m_c];
+    hp[i] = (int64_t)(uintptr_t)s->column_ptr(snp);
+    const int64_t j = s->is_local(snp) ? snp - s->lo : -1;
+    hp[m_c + k + i] = j;
+    if (j >= 0 && s->h_miss_off[j + 1] > s->h_miss_off[j]) any_missing = true;
+  }
+  BMG_CUDA(cudaMemcpyAsync(c->cs_idx.p, hp, n_ptr * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  ColStatArgs a;
+  a.cand_cols = reinterpret_cast<const uint32_t* const*>(c->cs_idx.p);
+  a.model_cols = reinterpret_cast<const uint32_t* const*>(c->cs_idx.p + m_c);
+  a.m_c = m_c; a.k = k; a.m_e = s->m_e; a.n = s->n; a.W = s->W; a.n_seg = n_seg; a.y = c->y.p; a.e = s->e.p;
+  double* seg_out = c->cs_out.p + (size_t)m_c * n_tasks;
+  double* fin = c->cs_out.p;
+  a.out = n_seg == 1 ? fin : seg_out;
+  k_column_stats<<<dim3(m_c, n_seg), 256, 0, st>>>(a);
+  count_launch();
+  if (n_seg > 1) {
+    k_sum_segments<<<(m_c * n_tasks + 127) / 128, 128, 0, st>>>(seg_out, m_c, n_seg, n_tasks, fin);
+    count_launch();
+  }
+  if (any_missing) {
+    ColMissArgs ma;
+    ma.snp_local = c->cs_idx.p + (m_c + k);
+    ma.cols = reinterpret_cast<const uint32_t* const*>(c->cs_idx.p);
+    ma.off = s->miss_off.p; ma.idx = s->miss_idx.p; ma.val = c->miss_val.p;
+    ma.m_c = m_c; ma.k = k; ma.m_e = s->m_e; ma.n = s->n; ma.y = c->y.p; ma.e = s->e.p; ma.out = fin;
+    k_column_stats_missfix<<<(m_c * n_tasks + 63) / 64, 64, 0, st>>>(ma);
+    count_launch();
+  }
+  BMG_CUDA(cudaGetLastError());
+  BMG_CUDA(cudaMemcpyAsync(c->h_cs.p, fin, (size_t)m_c * n_tasks * sizeof(double), cudaMemcpyDeviceToHost, st));
+  BMG_CUDA(cudaStreamSynchronize(st));
+  for (int ci = 0; ci < m_c; ++ci) {
+    const double* row = c->h_cs.p + (size_t)ci * n_tasks;
+    if (xy) xy[ci] = row[0];
+    if (xe) for (int j = 0; j < s->m_e; ++j) xe[(size_t)ci * s->m_e + j] = row[1 + j];
+    if (xx_model) for (int l = 0; l < k; ++l) xx_model[(size_t)ci * k + l] = row[1 + s->m_e + l];
+    if (xx_cand) for (int d = 0; d < m_c; ++d) xx_cand[(size_t)ci * m_c + d] = row[1 + s->m_e + k + d];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// probit latent update (no reference counterpart)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_probit(const double* __restrict__ ye, const double* __restrict__ yg,
+                                                const uint8_t* __restrict__ is_case, const double* __restrict__ u_in,
+                                                uint64_t seed, uint64_t counter, int64_t n, double* __restrict__ y,
+                                                double* __restrict__ partial)
+{
+  __shared__ double sm[2][8];
+  double s1 = 0.0, s2 = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double mu = yg[i] + ye[i];
+    double u;
+    if (u_in) u = u_in[i];
+    else { Philox g(seed, counter, (uint64_t)i); u = g.u01(); }
+    // inverse-CDF draw from N(mu,1) truncated to (0,inf) [case] or (-inf,0] [control], always through the lower tail
+    const double z = is_case[i] ? mu - normcdfinv(u * normcdf(mu)) : mu + normcdfinv(u * normcdf(-mu));
+    y[i] = z;
+    s1 += z;
+    s2 += z * z;
+  }
+  for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { sm[0][warp] = s1; sm[1][warp] = s2; }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    double s = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += sm[threadIdx.x][w];
+    partial[(int64_t)blockIdx.x * 2 + threadIdx.x] = s;
+  }
+}
+
+__global__ void k_reduce_final2(const double* __restrict__ partial, int blocks, int nq, double* __restrict__ out)
+{
+  const int q = threadIdx.x;
+  if (q >= nq) return;
+  double s = 0.0;
+  for (int b = 0; b < blocks; ++b) s += partial[(int64_t)b * nq + q];
+  out[q] = s;
+}
+
+void chain_probit_update(Chain* c, const uint8_t* is_case, const double* u01, uint64_t seed, uint64_t counter,
+                         double* stats2)
+{
+  Store* s = c->store;
+  BMG_REQUIRE(c->residual_valid, "bmg_chain_probit_update: call bmg_chain_residual first (it leaves the fitted values)");
+  BMG_CUDA(cudaSetDevice(s->device));
+  cudaStream_t st = c->stream;
+  if (is_case) {
+    if (c->is_case.n == 0) c->is_case.alloc(s->n);
+    BMG_CUDA(cudaMemcpyAsync(c->is_case.p, is_case, s->n, cudaMemcpyHostToDevice, st));
+    c->have_case = true;
+  }
+  BMG_REQUIRE(c->have_case, "bmg_chain_probit_update: case/control labels were never set");
+  DevBuf<double> u_dev;
+  if (u01) {
+    u_dev.alloc(s->n);
+    BMG_CUDA(cudaMemcpyAsync(u_dev.p, u01, s->n * sizeof(double), cudaMemcpyHostToDevice, st));
+  }
+  const int blocks = (int)std::min<int64_t>(1024, (s->n + 255) / 256);
+  k_probit<<<blocks, 256, 0, st>>>(c->yhat_e.p, c->yhat_g.p, c->is_case.p, u01 ? u_dev.p : nullptr, seed, counter, s->n, c->y.p,
+                                   c->red_partial.p);
+  k_reduce_final2<<<1, 32, 0, st>>>(c->red_partial.p, blocks, 2, c->red_out.p);
+  count_launch(2);
+  BMG_CUDA(cudaGetLastError());
+  BMG_CUDA(cudaMemcpyAsync(c->h_red.p, c->red_out.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  BMG_CUDA(cudaStreamSynchronize(st));
+  c->residual_valid = false;  // the phenotype changed: the residual must be rebuilt
+  if (stats2) { stats2[0] = c->h_red.p[0]; stats2[1] = c->h_red.p[1]; }
+}
+
+}  // namespace bmg

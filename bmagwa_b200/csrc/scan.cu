@@ -1,0 +1,742 @@
+// scan.cu -- fitted values / residual, the all-SNP Rao-Blackwell genotype scan, its epilogue.
+//
+// Replaces RaoBlackwellizer::p_raoblackwell (src/sampler.cpp:32-261): for every SNP j of the
+// shard  dot_j = sum_i x_ij r_i  over the packed 2-bit column, then the O(1) per-SNP algebra
+// (centring with the cached moments, tau, sigma2, model-prior change -> p_r[j]).
+//
+// Roofline: HBM-bound packed GEMV co-limited by the FP64 pipe (one DFMA per genotype).
+// The kernel keeps the non-DFMA instruction count per genotype at ~1:
+//   * the residual lives in REGISTERS (each thread owns 32 fixed individuals for the whole
+//     kernel), so no load instruction is needed per genotype;
+//   * a genotype is turned into an fp64 operand with ONE integer instruction and no shift:
+//     the 2-bit value field at bits [2p+1:2p] of the packed word, masked in place, IS the low
+//     word of a denormal double  c * 2^(2p) * 2^-1074 ; the residual of the individual at
+//     position p is pre-scaled by the exact power of two 2^(960-2p), so every product equals
+//     c * r * 2^-114 exactly inside the FMA and all 32 genotypes of a thread accumulate into one
+//     register;  the final sum is multiplied by 2^114 (exact).
+//   * packed tiles are staged global -> shared with bulk-async copies (cp.async.bulk + mbarrier,
+//     the TMA engine; SASS UBLKCP) in a 3-stage ring, so no registers are spent on prefetch.
+#include <cuda_runtime.h>
+#include <math.h>
+#include "common.cuh"
+#include "store.cuh"
+#include "philox.cuh"
+
+namespace bmg {
+
+// exponent of the residual pre-scaling; products carry 2^(RSCALE-1074)
+#define BMG_RSCALE 960
+#define BMG_UNSCALE 114  // 1074 - 960
+
+constexpr int kTileSnps = 16;   // SNPs per pipeline stage
+constexpr int kStages = 3;
+constexpr int kBatch = 8;       // SNPs accumulated per warp-transpose
+constexpr int kMaxWarps = 8;
+
+// ---------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + bulk async copy (Blackwell/Hopper TMA engine, non-tensor form)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ uint2 ldg_stream_u2(const uint32_t* p)
+{
+  uint2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+  return v;
+}
+
+// genotype field -> fp64 operand: (w & (3 << 2p)) read as the low word of a double with a zero
+// high word is the denormal  c * 2^(2p) * 2^-1074  (c = 0, 1, 2)
+__device__ __forceinline__ double field_as_double(uint32_t w, int p)
+{
+  return __hiloint2double(0, (int)(w & (3u << (2 * p))));
+}
+
+// 32 genotypes (two packed words) times 32 register-resident pre-scaled residuals
+__device__ __forceinline__ void fma_words(double (&acc)[kBatch], const uint2 (&w)[kBatch], const double (&rp)[32])
+{
+#pragma unroll
+  for (int p = 0; p < 16; ++p) {
+#pragma unroll
+    for (int i = 0; i < kBatch; ++i) acc[i] = fma(field_as_double(w[i].x, p), rp[p], acc[i]);
+  }
+#pragma unroll
+  for (int p = 0; p < 16; ++p) {
+#pragma unroll
+    for (int i = 0; i < kBatch; ++i) acc[i] = fma(field_as_double(w[i].y, p), rp[16 + p], acc[i]);
+  }
+}
+
+// butterfly transpose-reduce of 8 per-lane sums over the 32 lanes.  Slot i of a lane holds SNP
+// (i ^ x) of the batch with x = lane bits 4..2, so partners always exchange the SAME SNP and no
+// select instructions are needed.  On return acc[0] of every lane holds the warp total of SNP x.
+__device__ __forceinline__ void warp_transpose_reduce(double (&acc)[kBatch])
+{
+#pragma unroll
+  for (int i = 0; i < 4; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i + 4], 16);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i + 2], 8);
+  acc[0] += __shfl_xor_sync(0xffffffffu, acc[1], 4);
+  acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], 2);
+  acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], 1);
+}
+
+struct ScanArgs {
+  const uint32_t* codes;   // local shard, stride Wp words
+  int64_t Wp;              // column stride in words
+  int64_t m;               // local SNPs
+  const double* r_scaled;  // 16 * n_chunks * chunk_words doubles, zero beyond n
+  int chunk_words;         // words of a column one CTA covers (64 * warps)
+  int n_chunks;
+  int64_t tiles;           // ceil(m / kTileSnps)
+  int slices;              // CTAs per chunk
+  double* out;             // [n_chunks][m]
+};
+
+// ---------------------------------------------------------------------------------------
+// variant 1: bulk-async staged.   dynamic smem: kStages * kTileSnps * row_words words, then
+// partial sums [2][kMaxWarps][kTileSnps] doubles, then kStages mbarriers.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32 * kMaxWarps, 2) k_scan_dots_tma(const ScanArgs a)
+{
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nwarps = blockDim.x >> 5;
+  const int chunk = blockIdx.x % a.n_chunks, slice = blockIdx.x / a.n_chunks;
+  const bool whole = (a.n_chunks == 1);
+  const int row_words = whole ? (int)a.Wp : a.chunk_words;
+  const int64_t c0 = (int64_t)chunk * a.chunk_words;  // first word of this chunk in a column
+  const int row_copy_words = whole ? (int)a.Wp : (int)min((int64_t)a.chunk_words, a.Wp - c0);
+  const int stage_words = kTileSnps * row_words;
+
+  uint32_t* stage0 = reinterpret_cast<uint32_t*>(smem_raw);
+  double* part = reinterpret_cast<double*>(smem_raw + (size_t)kStages * stage_words * 4);
+  uint64_t* full = reinterpret_cast<uint64_t*>(part + 2 * kMaxWarps * kTileSnps);
+
+  const int64_t tile_lo = a.tiles * slice / a.slices, tile_hi = a.tiles * (slice + 1) / a.slices;
+  const int64_t my_tiles = tile_hi - tile_lo;
+
+  if (t == 0) {
+    for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // producer: one thread issues the copies of a tile
+  auto issue = [&](int64_t it) {
+    const int s = (int)(it % kStages);
+    const int64_t snp0 = (tile_lo + it) * kTileSnps;
+    const int rows = (int)min((int64_t)kTileSnps, a.m - snp0);
+    uint32_t* dst = stage0 + (size_t)s * stage_words;
+    if (whole) {
+      const uint32_t bytes = (uint32_t)rows * (uint32_t)row_words * 4u;
+      mbar_expect_tx(&full[s], bytes);
+      bulk_g2s(dst, a.codes + snp0 * a.Wp, bytes, &full[s]);
+    } else {
+      const uint32_t rb = (uint32_t)row_copy_words * 4u;
+      mbar_expect_tx(&full[s], rb * (uint32_t)rows);
+      for (int rr = 0; rr < rows; ++rr) bulk_g2s(dst + (size_t)rr * row_words, a.codes + (snp0 + rr) * a.Wp + c0, rb, &full[s]);
+    }
+  };
+  if (t == 0)
+    for (int64_t it = 0; it < min((int64_t)kStages, my_tiles); ++it) issue(it);
+
+  // the 32 individuals this thread owns for the whole kernel
+  double rp[32];
+  {
+    const double* src = a.r_scaled + 16 * (c0 + 2 * t);
+#pragma unroll
+    for (int p = 0; p < 32; ++p) rp[p] = src[p];
+  }
+  const int x = (lane >> 2) & 7;  // slot permutation of warp_transpose_reduce
+
+  for (int64_t it = 0; it < my_tiles; ++it) {
+    const int s = (int)(it % kStages);
+    mbar_wait(&full[s], (uint32_t)((it / kStages) & 1));
+    const uint32_t* sm = stage0 + (size_t)s * stage_words + 2 * t;
+    double* mypart = part + (size_t)(it & 1) * kMaxWarps * kTileSnps + warp * kTileSnps;
+#pragma unroll
+    for (int b = 0; b < kTileSnps / kBatch; ++b) {
+      uint2 w[kBatch];
+      double acc[kBatch];
+#pragma unroll
+      for (int i = 0; i < kBatch; ++i) {
+        w[i] = *reinterpret_cast<const uint2*>(sm + (size_t)(b * kBatch + (i ^ x)) * row_words);
+        acc[i] = 0.0;
+      }
+      fma_words(acc, w, rp);
+      warp_transpose_reduce(acc);
+      if ((lane & 3) == 0) mypart[b * kBatch + x] = acc[0];
+    }
+    __syncthreads();  // partials visible; every thread is done reading stage s
+    if (t == 0 && it + kStages < my_tiles) issue(it + kStages);
+    if (t < kTileSnps) {
+      const int64_t snp = (tile_lo + it) * kTileSnps + t;
+      if (snp < a.m) {
+        const double* pp = part + (size_t)(it & 1) * kMaxWarps * kTileSnps + t;
+        double sum = 0.0;
+        for (int wv = 0; wv < nwarps; ++wv) sum += pp[wv * kTileSnps];
+        a.out[(int64_t)chunk * a.m + snp] = scalbn(sum, BMG_UNSCALE);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// variant 0: direct vectorised global loads with a register double buffer (no smem staging)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32 * kMaxWarps, 2) k_scan_dots_ldg(const ScanArgs a)
+{
+  __shared__ double part[2 * kMaxWarps * kTileSnps];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nwarps = blockDim.x >> 5;
+  const int chunk = blockIdx.x % a.n_chunks, slice = blockIdx.x / a.n_chunks;
+  const int64_t c0 = (int64_t)chunk * a.chunk_words;
+  const int64_t tile_lo = a.tiles * slice / a.slices, tile_hi = a.tiles * (slice + 1) / a.slices;
+  const int64_t batches = (tile_hi - tile_lo) * (kTileSnps / kBatch);
+  const int64_t snp_base = tile_lo * kTileSnps;
+  const int64_t my_w = c0 + 2 * t;
+  // threads whose words lie beyond the padded column read word 0 instead (their residuals are 0)
+  const int64_t w_off = (my_w + 1 < a.Wp) ? my_w : 0;
+
+  double rp[32];
+  {
+    const double* src = a.r_scaled + 16 * my_w;
+#pragma unroll
+    for (int p = 0; p < 32; ++p) rp[p] = src[p];
+  }
+  const int x = (lane >> 2) & 7;
+
+  auto load_batch = [&](int64_t bi, uint2 (&w)[kBatch]) {
+#pragma unroll
+    for (int i = 0; i < kBatch; ++i) {
+      int64_t snp = snp_base + bi * kBatch + (i ^ x);
+      snp = snp < a.m ? snp : a.m - 1;
+      w[i] = ldg_stream_u2(a.codes + snp * a.Wp + w_off);
+    }
+  };
+
+  uint2 wn[kBatch];
+  if (batches > 0) load_batch(0, wn);
+  for (int64_t bi = 0; bi < batches; ++bi) {
+    uint2 w[kBatch];
+    double acc[kBatch];
+#pragma unroll
+    for (int i = 0; i < kBatch; ++i) {
+      w[i] = wn[i];
+      acc[i] = 0.0;
+    }
+    if (bi + 1 < batches) load_batch(bi + 1, wn);
+    fma_words(acc, w, rp);
+    warp_transpose_reduce(acc);
+    double* mypart = part + (size_t)(bi & 1) * kMaxWarps * kTileSnps + warp * kTileSnps;
+    if ((lane & 3) == 0) mypart[x] = acc[0];
+    __syncthreads();
+    if (t < kBatch) {
+      const int64_t snp = snp_base + bi * kBatch + t;
+      if (snp < a.m) {
+        const double* pp = part + (size_t)(bi & 1) * kMaxWarps * kTileSnps + t;
+        double sum = 0.0;
+        for (int wv = 0; wv < nwarps; ++wv) sum += pp[wv * kTileSnps];
+        a.out[(int64_t)chunk * a.m + snp] = scalbn(sum, BMG_UNSCALE);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// fitted values and residual
+// ---------------------------------------------------------------------------------------
+struct YhatArgs {
+  const uint32_t* const* cols;  // k device pointers to packed columns (local or peer)
+  const double* beta_g;         // k
+  const double* beta_e;         // m_e
+  const double* e;              // n x m_e col-major
+  int k, m_e;
+  int64_t n, W;
+  double* yhat_e;
+  double* yhat_g;
+};
+
+// one thread per packed word (16 individuals)
+__global__ void k_yhat(const YhatArgs a)
+{
+  const int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (w >= a.W) return;
+  double g[16];
+#pragma unroll
+  for (int p = 0; p < 16; ++p) g[p] = 0.0;
+  for (int l = 0; l < a.k; ++l) {
+    const uint32_t word = a.cols[l][w];
+    const double b = a.beta_g[l];
+#pragma unroll
+    for (int p = 0; p < 16; ++p) g[p] = fma(b, (double)((word >> (2 * p)) & 3u), g[p]);
+  }
+  const int64_t i0 = 16 * w;
+#pragma unroll
+  for (int p = 0; p < 16; ++p) {
+    const int64_t i = i0 + p;
+    if (i < a.n) {
+      double ev = 0.0;
+      for (int c = 0; c < a.m_e; ++c) ev = fma(a.beta_e[c], a.e[(int64_t)c * a.n + i], ev);
+      a.yhat_e[i] = ev;
+      a.yhat_g[i] = g[p];
+    }
+  }
+}
+
+// imputed cells of in-model SNPs (the dense column holds 0 there): yhat_g[idx] += beta * val
+__global__ void k_yhat_missfix(const int32_t* __restrict__ idx, const int8_t* __restrict__ val, int64_t cnt, double beta,
+                               double* __restrict__ yhat_g)
+{
+  const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (q >= cnt) return;
+  if (val[q]) atomicAdd(&yhat_g[idx[q]], beta * (double)val[q]);
+}
+
+constexpr int kRed = 9;
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// r = y - (yhat_g + yhat_e); r_scaled; 9 block-partial reductions (fixed order => deterministic)
+__global__ void __launch_bounds__(256) k_residual(const double* __restrict__ y, const double* __restrict__ ye,
+                                                  const double* __restrict__ yg, int64_t n, int64_t n_pad,
+                                                  double* __restrict__ r, double* __restrict__ r_scaled,
+                                                  double* __restrict__ partial)
+{
+  __shared__ double sm[kRed][8];
+  double acc[kRed];
+#pragma unroll
+  for (int q = 0; q < kRed; ++q) acc[q] = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_pad; i += (int64_t)gridDim.x * blockDim.x) {
+    if (i < n) {
+      const double e = ye[i], g = yg[i], yh = g + e, rv = y[i] - yh;
+      r[i] = rv;
+      r_scaled[i] = scalbn(rv, BMG_RSCALE - 2 * (int)(i & 15));
+      acc[0] += rv;
+      acc[1] += e;  acc[2] += e * e;
+      acc[3] += g;  acc[4] += g * g;
+      acc[5] += yh; acc[6] += yh * yh;
+      acc[7] += g * g;
+      acc[8] += (e - y[i]) * g;
+    } else {
+      r_scaled[i] = 0.0;
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < kRed; ++q) {
+    const double v = warp_sum(acc[q]);
+    if (lane == 0) sm[q][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < kRed) {
+    double s = 0.0;
+    for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) s += sm[threadIdx.x][wv];
+    partial[(int64_t)blockIdx.x * kRed + threadIdx.x] = s;
+  }
+}
+
+__global__ void k_reduce_final(const double* __restrict__ partial, int blocks, int nq, double* __restrict__ out)
+{
+  const int q = threadIdx.x;
+  if (q >= nq) return;
+  double s = 0.0;
+  for (int b = 0; b < blocks; ++b) s += partial[(int64_t)b * nq + q];
+  out[q] = s;
+}
+
+// ---------------------------------------------------------------------------------------
+// missing-cell corrections of the scan: one warp per SNP that has missing cells
+// out[3j..] = { sum val * r[idx], sum val, sum val^2 }
+// ---------------------------------------------------------------------------------------
+__global__ void k_miss_corr(const int64_t* __restrict__ off, const int32_t* __restrict__ idx,
+                            const int8_t* __restrict__ val, const double* __restrict__ r, int64_t m,
+                            double* __restrict__ out)
+{
+  const int64_t j = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (j >= m) return;
+  const int64_t lo = off[j], hi = off[j + 1];
+  if (hi == lo) return;
+  double d = 0.0, s1 = 0.0, s2 = 0.0;
+  for (int64_t q = lo + lane; q < hi; q += 32) {
+    const double v = (double)val[q];
+    d += v * r[idx[q]];
+    s1 += v;
+    s2 += v * v;
+  }
+  d = warp_sum(d); s1 = warp_sum(s1); s2 = warp_sum(s2);
+  if (lane == 0) { out[3 * j] = d; out[3 * j + 1] = s1; out[3 * j + 2] = s2; }
+}
+
+// ---------------------------------------------------------------------------------------
+// per-SNP algebra of the scan (src/sampler.cpp:90-206, n_types == 1)
+// ---------------------------------------------------------------------------------------
+struct FinalizeArgs {
+  const double* dot_partial; int n_chunks; int64_t m, lo, n;
+  const int32_t* n1; const int32_t* n2;
+  const double* miss_corr;  // may be null
+  const int64_t* loci; const double* beta_g; const double* tau_g; int k;
+  double sum_r, sigma2, lmp_add, lmp_rem;
+  int tau_mode; double tau_shared; const double* tau_snp;
+  uint64_t seed, counter; double nu_tau2, s2_tau2, alpha2;
+  double* dot; double* p_r;
+};
+
+__global__ void __launch_bounds__(256) k_scan_finalize(const FinalizeArgs a)
+{
+  const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (j >= a.m) return;
+  double dot = 0.0;
+  for (int c = 0; c < a.n_chunks; ++c) dot += a.dot_partial[(int64_t)c * a.m + j];
+  double s = (double)(a.n1[j] + 2 * a.n2[j]);
+  double xx = (double)(a.n1[j] + 4 * a.n2[j]);
+  const double dn = (double)a.n;
+  double v = xx - s * s / dn;                       // precomputed_snp_covariances.hpp:116-117
+  if (a.miss_corr) {                                 // data_model.cpp:105-167, type A
+    const double dc = a.miss_corr[3 * j], sv = a.miss_corr[3 * j + 1], sv2 = a.miss_corr[3 * j + 2];
+    dot += dc;
+    v += sv2 - sv * (s * 2.0 + sv) / dn;
+    s += sv;
+    xx += sv2;
+  }
+  a.dot[j] = dot;
+
+  double tau;
+  if (a.tau_mode == 0) tau = a.tau_shared;
+  else if (a.tau_mode == 1) tau = a.tau_snp[j];
+  else {                                             // prior.hpp:192-199 with a counter-based generator
+    Philox g(a.seed, a.counter, (uint64_t)(a.lo + j));
+    double val = -1.0;
+    while (!(val > 0.0) || !isfinite(val)) val = a.nu_tau2 * a.s2_tau2 / (2.0 * g.gamma(0.5 * a.nu_tau2));
+    tau = 1.0 / (a.alpha2 * val);
+  }
+  int pos = -1;
+  const int64_t gj = a.lo + j;
+  for (int l = 0; l < a.k; ++l)
+    if (a.loci[l] == gj) pos = l;
+  double mr, lmp;
+  if (pos < 0) {                                     // sampler.cpp:109-115
+    mr = a.sum_r / dn;
+    lmp = a.lmp_add;
+  } else {                                           // sampler.cpp:116-149: residual without SNP j
+    const double b = a.beta_g[pos];
+    if (a.tau_mode != 0) tau = a.tau_g[pos];
+    dot += b * xx;                                   // x.(r + b x) = x.r + b x.x
+    mr = (a.sum_r + b * s) / dn;
+    lmp = a.lmp_rem;
+  }
+  const double rx = dot - s * mr;                    // sampler.cpp:188
+  const double det = v + tau;
+  const double exp_term = (rx * rx) / det;
+  double p = exp_term / (2.0 * a.sigma2) - 0.5 * (log(det) - log(tau)) + lmp;
+  p = exp(p);
+  a.p_r[j] = isfinite(p) ? p / (1.0 + p) : 1.0;      // sampler.cpp:200-206
+}
+
+// ---------------------------------------------------------------------------------------
+// epilogue of Sampler::sample's rao block (src/sampler.cpp:739-803) + flat initialisation
+// ---------------------------------------------------------------------------------------
+__global__ void k_adapt(const double* __restrict__ p_r, int64_t m, int upd_rao, double rz1, double rz2, int upd_prop,
+                        double pz1, double pz2, double q_add_min, double q_rem_min, double* __restrict__ p_rao,
+                        double* __restrict__ p_prop, double* __restrict__ q_add, double* __restrict__ q_rem)
+{
+  const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  const double pr = p_r[j];
+  if (upd_rao) p_rao[j] = __dadd_rn(__dmul_rn(rz2, p_rao[j]), __ddiv_rn(pr, rz1));
+  if (upd_prop) {
+    const double pp = __dadd_rn(__dmul_rn(pz2, p_prop[j]), __ddiv_rn(pr, pz1));
+    p_prop[j] = pp;
+    q_add[j] = fmax(pp, q_add_min);
+    q_rem[j] = fmax(1.0 - pp, q_rem_min);
+  }
+}
+
+__global__ void k_fill_flat(int64_t m, double value, double q_add_min, double q_rem_min, double* __restrict__ p_prop,
+                            double* __restrict__ q_add, double* __restrict__ q_rem, double* __restrict__ p_rao)
+{
+  const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  p_prop[j] = value;
+  q_add[j] = fmax(value, q_add_min);
+  q_rem[j] = fmax(1.0 - value, q_rem_min);
+  p_rao[j] = 0.0;
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+static void choose_scan_geometry(Chain* c)
+{
+  const Store* s = c->store;
+  const int64_t W = s->W;
+  double best = -1.0;
+  int best_nw = 1;
+  for (int nw = 1; nw <= kMaxWarps; ++nw) {
+    const int64_t chunks = (W + 64 * nw - 1) / (64 * nw);
+    const int ctas = 16 / nw;  // 128 registers/thread => 512 threads per SM
+    const double eff = (double)W / (double)(chunks * 64 * nw) * (double)(ctas * nw) / 16.0;
+    if (eff > best + 1e-9 || (eff > best - 1e-9 && nw > best_nw)) { best = eff; best_nw = nw; }
+  }
+  c->scan_warps = best_nw;
+  c->scan_chunk_words = 64 * best_nw;
+  c->scan_chunks = (int)((W + c->scan_chunk_words - 1) / c->scan_chunk_words);
+}
+
+static size_t scan_smem_bytes(const Chain* c)
+{
+  const Store* s = c->store;
+  const int64_t row_words = c->scan_chunks == 1 ? s->Wp : c->scan_chunk_words;
+  return (size_t)kStages * kTileSnps * row_words * 4 + 2 * kMaxWarps * kTileSnps * sizeof(double) + kStages * sizeof(uint64_t);
+}
+
+Chain* chain_create(Store* s)
+{
+  BMG_REQUIRE(s->m_e >= 1, "bmg_chain_create: call bmg_store_set_phenotype first");
+  BMG_CUDA(cudaSetDevice(s->device));
+  std::unique_ptr<Chain> c(new Chain());
+  c->store = s;
+  BMG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  choose_scan_geometry(c.get());
+  const int64_t n = s->n, m = s->m;
+  const int64_t n_pad = 16 * (int64_t)c->scan_chunks * c->scan_chunk_words;
+  c->y.alloc(n);
+  BMG_CUDA(cudaMemcpy(c->y.p, s->y.p, n * sizeof(double), cudaMemcpyDeviceToDevice));
+  c->yhat_e.alloc(n); c->yhat_g.alloc(n); c->r.alloc(n); c->r_scaled.alloc(n_pad);
+  c->red_partial.alloc(1024 * 16); c->red_out.alloc(16); c->h_red.alloc(16);
+  if (s->n_missing > 0) {
+    c->miss_val.alloc((size_t)s->n_missing);
+    BMG_CUDA(cudaMemset(c->miss_val.p, 0, (size_t)s->n_missing));   // data_model.hpp:80-84
+    c->miss_corr.alloc(3 * m);
+    BMG_CUDA(cudaMemset(c->miss_corr.p, 0, 3 * m * sizeof(double)));
+  }
+  c->dot_partial.alloc((size_t)c->scan_chunks * m);
+  c->dot.alloc(m); c->p_r.alloc(m); c->p_rao.alloc(m); c->p_proposal.alloc(m); c->q_add.alloc(m); c->q_rem.alloc(m);
+  BMG_CUDA(cudaMemset(c->p_r.p, 0, m * sizeof(double)));
+  BMG_CUDA(cudaMemset(c->p_rao.p, 0, m * sizeof(double)));
+  BMG_CUDA(cudaMemset(c->p_proposal.p, 0, m * sizeof(double)));
+  BMG_CUDA(cudaMemset(c->q_add.p, 0, m * sizeof(double)));
+  BMG_CUDA(cudaMemset(c->q_rem.p, 0, m * sizeof(double)));
+  c->loci_dev.alloc(2048); c->beta_dev.alloc(2048 + 64); c->taug_dev.alloc(2048);
+  c->h_stage.alloc(8192); c->h_stage_i.alloc(4096);
+  c->cdf_blocks = (m + c->cdf_block - 1) / c->cdf_block;
+  c->cdf_add.alloc(c->cdf_blocks); c->cdf_rem.alloc(c->cdf_blocks);
+  c->zero_add.alloc(m); c->zero_rem.alloc(m);
+  BMG_CUDA(cudaMemset(c->zero_add.p, 0, m));
+  BMG_CUDA(cudaMemset(c->zero_rem.p, 0, m));
+  c->sample_out.alloc(4); c->h_sample.alloc(4);
+  const size_t smem = scan_smem_bytes(c.get());
+  BMG_REQUIRE(smem <= 227 * 1024, "scan tile does not fit in shared memory");
+  BMG_CUDA(cudaFuncSetAttribute(k_scan_dots_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // CTAs per chunk: fill every SM with as many resident CTAs as registers/smem allow
+  int per_sm = 1;
+  BMG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan_dots_tma, 32 * c->scan_warps, smem));
+  if (per_sm < 1) per_sm = 1;
+  const int64_t tiles = (m + kTileSnps - 1) / kTileSnps;
+  int64_t slices = ((int64_t)per_sm * s->sm_count) / c->scan_chunks;
+  if (slices < 1) slices = 1;
+  if (slices > tiles) slices = tiles;
+  c->scan_ctas_per_chunk = (int)slices;
+  BMG_CUDA(cudaDeviceSynchronize());
+  return c.release();
+}
+
+void chain_destroy(Chain* c)
+{
+  if (!c) return;
+  cudaSetDevice(c->store->device);
+  if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+  delete c;
+}
+
+void chain_set_missing(Chain* c, int64_t snp, const int8_t* vals, int64_t count)
+{
+  Store* s = c->store;
+  BMG_REQUIRE(s->is_local(snp), "bmg_chain_set_missing: SNP not in the local shard");
+  const int64_t j = snp - s->lo, lo = s->h_miss_off[j], cnt = s->h_miss_off[j + 1] - lo;
+  BMG_REQUIRE(cnt == count, "bmg_chain_set_missing: count does not match the number of missing cells of the SNP");
+  if (cnt == 0) return;
+  for (int64_t q = 0; q < cnt; ++q) BMG_REQUIRE(vals[q] >= 0 && vals[q] <= 2, "bmg_chain_set_missing: values must be 0, 1 or 2");
+  BMG_CUDA(cudaSetDevice(s->device));
+  BMG_CUDA(cudaMemcpyAsync(c->miss_val.p + lo, vals, (size_t)cnt, cudaMemcpyHostToDevice, c->stream));
+  BMG_CUDA(cudaStreamSynchronize(c->stream));
+}
+
+// uploads loci / beta / tau of the current model into the chain's device scratch
+static void upload_model(Chain* c, const int64_t* loci, const double* beta_g, const double* tau_g, int k)
+{
+  BMG_REQUIRE(k >= 0 && k <= 2048, "model size must be <= 2048");
+  if (k == 0) return;
+  // staged through pinned memory so the copies are truly asynchronous
+  BMG_CUDA(cudaStreamSynchronize(c->stream));
+  for (int l = 0; l < k; ++l) {
+    c->h_stage_i.p[l] = loci[l];
+    c->h_stage.p[l] = beta_g ? beta_g[l] : 0.0;
+    c->h_stage.p[2048 + l] = tau_g ? tau_g[l] : 0.0;
+  }
+  BMG_CUDA(cudaMemcpyAsync(c->loci_dev.p, c->h_stage_i.p, k * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+  BMG_CUDA(cudaMemcpyAsync(c->beta_dev.p, c->h_stage.p, k * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  BMG_CUDA(cudaMemcpyAsync(c->taug_dev.p, c->h_stage.p + 2048, k * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+}
+
+void chain_residual(Chain* c, const int64_t* loci, const double* beta_e, const double* beta_g, int k, double* stats9)
+{
+  Store* s = c->store;
+  BMG_CUDA(cudaSetDevice(s->device));
+  BMG_REQUIRE(k >= 0 && k <= 2048, "bmg_chain_residual: model size must be <= 2048");
+  cudaStream_t st = c->stream;
+  upload_model(c, loci, beta_g, nullptr, k);
+  // beta_e and column pointers
+  BMG_CUDA(cudaStreamSynchronize(st));
+  for (int j = 0; j < s->m_e; ++j) c->h_stage.p[4096 + j] = beta_e[j];
+  BMG_CUDA(cudaMemcpyAsync(c->beta_dev.p + 2048, c->h_stage.p + 4096, s->m_e * sizeof(double), cudaMemcpyHostToDevice, st));
+  static_assert(sizeof(const uint32_t*) == sizeof(int64_t), "pointer size");
+  for (int l = 0; l < k; ++l) c->h_stage_i.p[2048 + l] = (int64_t)(uintptr_t)s->column_ptr(loci[l]);
+  if (c->cs_idx.n < 4096) c->cs_idx.alloc(4096);
+  if (k) BMG_CUDA(cudaMemcpyAsync(c->cs_idx.p, c->h_stage_i.p + 2048, k * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  YhatArgs ya;
+  ya.cols = reinterpret_cast<const uint32_t* const*>(c->cs_idx.p);
+  ya.beta_g = c->beta_dev.p; ya.beta_e = c->beta_dev.p + 2048; ya.e = s->e.p;
+  ya.k = k; ya.m_e = s->m_e; ya.n = s->n; ya.W = s->W; ya.yhat_e = c->yhat_e.p; ya.yhat_g = c->yhat_g.p;
+  k_yhat<<<(unsigned)((s->W + 127) / 128), 128, 0, st>>>(ya);
+  count_launch();
+  if (s->n_missing > 0) {
+    for (int l = 0; l < k; ++l) {
+      if (!s->is_local(loci[l])) continue;  // peers' imputed cells are not visible here (out of scope)
+      const int64_t j = loci[l] - s->lo, lo = s->h_miss_off[j], cnt = s->h_miss_off[j + 1] - lo;
+      if (cnt == 0) continue;
+      k_yhat_missfix<<<(unsigned)((cnt + 127) / 128), 128, 0, st>>>(s->miss_idx.p + lo, c->miss_val.p + lo, cnt, beta_g[l],
+                                                                    c->yhat_g.p);
+      count_launch();
+    }
+  }
+  const int64_t n_pad = (int64_t)c->r_scaled.n;
+  int blocks = (int)std::min<int64_t>(1024, (n_pad + 255) / 256);
+  k_residual<<<blocks, 256, 0, st>>>(c->y.p, c->yhat_e.p, c->yhat_g.p, s->n, n_pad, c->r.p, c->r_scaled.p, c->red_partial.p);
+  count_launch();
+  k_reduce_final<<<1, 32, 0, st>>>(c->red_partial.p, blocks, kRed, c->red_out.p);
+  count_launch();
+  BMG_CUDA(cudaGetLastError());
+  BMG_CUDA(cudaMemcpyAsync(c->h_red.p, c->red_out.p, kRed * sizeof(double), cudaMemcpyDeviceToHost, st));
+  BMG_CUDA(cudaStreamSynchronize(st));
+  c->sum_r = c->h_red.p[0];
+  c->residual_valid = true;
+  if (stats9) for (int q = 0; q < kRed; ++q) stats9[q] = c->h_red.p[q];
+}
+
+void chain_scan_dots(Chain* c)
+{
+  Store* s = c->store;
+  BMG_REQUIRE(c->residual_valid, "scan: call bmg_chain_residual first");
+  BMG_CUDA(cudaSetDevice(s->device));
+  ScanArgs a;
+  a.codes = s->codes.p; a.Wp = s->Wp; a.m = s->m; a.r_scaled = c->r_scaled.p;
+  a.chunk_words = (int)c->scan_chunk_words; a.n_chunks = c->scan_chunks;
+  a.tiles = (s->m + kTileSnps - 1) / kTileSnps; a.slices = c->scan_ctas_per_chunk; a.out = c->dot_partial.p;
+  const unsigned grid = (unsigned)(c->scan_chunks * c->scan_ctas_per_chunk);
+  if (c->scan_variant == 1)
+    k_scan_dots_tma<<<grid, 32 * c->scan_warps, scan_smem_bytes(c), c->stream>>>(a);
+  else
+    k_scan_dots_ldg<<<grid, 32 * c->scan_warps, 0, c->stream>>>(a);
+  count_launch();
+  BMG_CUDA(cudaGetLastError());
+}
+
+void chain_scan(Chain* c, const int64_t* loci, const double* beta_g, const double* tau_g, int k,
+                const bmg_scan_params* prm, double* p_r_host)
+{
+  Store* s = c->store;
+  BMG_REQUIRE(prm != nullptr, "bmg_chain_scan: params required");
+  BMG_REQUIRE(prm->tau_mode >= 0 && prm->tau_mode <= 2, "bmg_chain_scan: tau_mode must be 0, 1 or 2");
+  BMG_REQUIRE(prm->sigma2 > 0, "bmg_chain_scan: sigma2 must be positive");
+  BMG_CUDA(cudaSetDevice(s->device));
+  cudaStream_t st = c->stream;
+  upload_model(c, loci, beta_g, tau_g, k);
+  if (prm->tau_mode == 1) {
+    BMG_REQUIRE(prm->tau_host != nullptr, "bmg_chain_scan: tau_host required for tau_mode 1");
+    if (c->tau_dev.n < (size_t)s->m) c->tau_dev.alloc(s->m);
+    BMG_CUDA(cudaMemcpyAsync(c->tau_dev.p, prm->tau_host, s->m * sizeof(double), cudaMemcpyHostToDevice, st));
+  }
+  chain_scan_dots(c);
+  if (s->n_missing > 0) {
+    k_miss_corr<<<(unsigned)((s->m * 32 + 127) / 128), 128, 0, st>>>(s->miss_off.p, s->miss_idx.p, c->miss_val.p, c->r.p, s->m,
+                                                                     c->miss_corr.p);
+    count_launch();
+  }
+  FinalizeArgs f;
+  f.dot_partial = c->dot_partial.p; f.n_chunks = c->scan_chunks; f.m = s->m; f.lo = s->lo; f.n = s->n;
+  f.n1 = s->n1.p; f.n2 = s->n2.p; f.miss_corr = s->n_missing > 0 ? c->miss_corr.p : nullptr;
+  f.loci = c->loci_dev.p; f.beta_g = c->beta_dev.p; f.tau_g = c->taug_dev.p; f.k = k;
+  f.sum_r = c->sum_r; f.sigma2 = prm->sigma2; f.lmp_add = prm->lmp_add; f.lmp_rem = prm->lmp_rem;
+  f.tau_mode = prm->tau_mode; f.tau_shared = prm->tau_shared; f.tau_snp = c->tau_dev.p;
+  f.seed = prm->tau_seed; f.counter = prm->tau_counter; f.nu_tau2 = prm->nu_tau2; f.s2_tau2 = prm->s2_tau2; f.alpha2 = prm->alpha2;
+  f.dot = c->dot.p; f.p_r = c->p_r.p;
+  k_scan_finalize<<<(unsigned)((s->m + 255) / 256), 256, 0, st>>>(f);
+  count_launch();
+  BMG_CUDA(cudaGetLastError());
+  if (p_r_host) {
+    BMG_CUDA(cudaMemcpyAsync(p_r_host, c->p_r.p, s->m * sizeof(double), cudaMemcpyDeviceToHost, st));
+    BMG_CUDA(cudaStreamSynchronize(st));
+  }
+}
+
+void chain_adapt(Chain* c, int update_rao, int64_t n_rao_mean, int update_prop, int64_t n_prop_mean, double q_add_min,
+                 double q_rem_min)
+{
+  Store* s = c->store;
+  BMG_CUDA(cudaSetDevice(s->device));
+  const double rz1 = (double)(n_rao_mean + 1), rz2 = (double)n_rao_mean / rz1;      // sampler.cpp:740-741
+  const double pz1 = (double)(n_prop_mean + 1), pz2 = (double)n_prop_mean / pz1;    // sampler.cpp:762-763
+  k_adapt<<<(unsigned)((s->m + 255) / 256), 256, 0, c->stream>>>(c->p_r.p, s->m, update_rao, rz1, rz2, update_prop, pz1, pz2,
+                                                                 q_add_min, q_rem_min, c->p_rao.p, c->p_proposal.p,
+                                                                 c->q_add.p, c->q_rem.p);
+  count_launch();
+  BMG_CUDA(cudaGetLastError());
+  if (update_prop) chain_partial_cdf(c);
+}
+
+void chain_init_flat(Chain* c, double value, double q_add_min, double q_rem_min)
+{
+  Store* s = c->store;
+  BMG_CUDA(cudaSetDevice(s->device));
+  k_fill_flat<<<(unsigned)((s->m + 255) / 256), 256, 0, c->stream>>>(s->m, value, q_add_min, q_rem_min, c->p_proposal.p,
+                                                                     c->q_add.p, c->q_rem.p, c->p_rao.p);
+  count_launch();
+  BMG_CUDA(cudaGetLastError());
+  chain_partial_cdf(c);
+}
+
+}  // namespace bmg

@@ -1,0 +1,83 @@
+// store.cuh -- internal C++ interface between the modules of libbmagwa_b200.so
+#pragma once
+#include <memory>
+#include "common.cuh"
+#include "../../include/bmagwa_b200.h"
+
+namespace bmg {
+
+// ---- store.cu
+Store* store_create(const uint8_t* bed, bool on_device, int64_t n, int64_t m_g, int64_t lo, int64_t hi, bool recode,
+                    int device);
+void store_set_phenotype(Store* s, const double* y, const double* e, int m_e);
+void store_get_column(const Store* s, int64_t snp, int type, const int8_t* miss_vals_dev, bool overlay,
+                      double* out_host, cudaStream_t st);
+
+// ---- chain state (scan.cu, colstats.cu, weights.cu, probit.cu)
+struct Chain {
+  Store* store = nullptr;
+  cudaStream_t stream = nullptr;
+  int scan_variant = 1;
+  // scan geometry (chosen once per chain from n and the SM count)
+  int scan_warps = 0;        // warps per CTA
+  int64_t scan_chunk_words = 0;  // words of each column one CTA covers
+  int scan_chunks = 0;       // CTAs along the individual axis
+  int scan_ctas_per_chunk = 0;
+  // phenotype the chain works on (a copy of the store's y; the probit update overwrites it)
+  DevBuf<double> y;
+  DevBuf<uint8_t> is_case;
+  bool have_case = false;
+  // fitted values / residual
+  DevBuf<double> yhat_e, yhat_g, r, r_scaled;   // n, n, n, 16*W (zero padded)
+  DevBuf<double> red_partial;                   // block partials of the residual reductions
+  DevBuf<double> red_out;                       // 16 doubles
+  PinnedBuf<double> h_red;                      // pinned mirror
+  double sum_r = 0.0;
+  bool residual_valid = false;
+  // per-chain imputed values of the missing cells (same CSR as the store)
+  DevBuf<int8_t> miss_val;
+  DevBuf<double> miss_corr;                     // 3 per local SNP: (dot corr, sum val, sum val^2)
+  // scan outputs and the per-SNP arrays Sampler keeps (sampler.hpp:201-258)
+  DevBuf<double> dot_partial;                   // scan_chunks * m
+  DevBuf<double> dot;                           // m
+  DevBuf<double> p_r, p_rao, p_proposal, q_add, q_rem;
+  DevBuf<double> tau_dev;                       // per-SNP tau upload (tau_mode 1)
+  DevBuf<int64_t> loci_dev;
+  DevBuf<double> beta_dev, taug_dev;
+  PinnedBuf<double> h_stage;                    // pinned staging for small H2D/D2H
+  PinnedBuf<int64_t> h_stage_i;
+  // proposal weights: partial CDFs + zero flags
+  int64_t cdf_block = 256;
+  int64_t cdf_blocks = 0;
+  DevBuf<double> cdf_add, cdf_rem;              // block sums over in-order positions (all items)
+  DevBuf<double> cdf_eff_add, cdf_eff_rem;      // same, zeroed items excluded
+  DevBuf<uint8_t> zero_add, zero_rem;           // per local SNP
+  DevBuf<double> sample_out;                    // {snp, total}
+  PinnedBuf<double> h_sample;
+  // column statistics scratch
+  DevBuf<double> cs_out;
+  PinnedBuf<double> h_cs;
+  DevBuf<int64_t> cs_idx;
+  size_t cs_cap = 0;
+};
+
+Chain* chain_create(Store* s);
+void chain_destroy(Chain* c);
+void chain_set_missing(Chain* c, int64_t snp, const int8_t* vals, int64_t count);
+void chain_residual(Chain* c, const int64_t* loci, const double* beta_e, const double* beta_g, int k, double* stats9);
+void chain_scan_dots(Chain* c);
+void chain_scan(Chain* c, const int64_t* loci, const double* beta_g, const double* tau_g, int k,
+                const bmg_scan_params* prm, double* p_r_host);
+void chain_adapt(Chain* c, int update_rao, int64_t n_rao_mean, int update_prop, int64_t n_prop_mean, double q_add_min,
+                 double q_rem_min);
+void chain_init_flat(Chain* c, double value, double q_add_min, double q_rem_min);
+void chain_partial_cdf(Chain* c);
+void chain_sample(Chain* c, int which, double u01, int64_t* snp, double* total);
+void chain_set_zeroed(Chain* c, int which, int64_t snp, int flag);
+void chain_fill_zeroed(Chain* c, int which, int flag);
+void chain_column_stats(Chain* c, const int64_t* cand, int m_c, const int64_t* loci, int k, double* xy, double* xe,
+                        double* xx_model, double* xx_cand);
+void chain_probit_update(Chain* c, const uint8_t* is_case, const double* u01, uint64_t seed, uint64_t counter,
+                         double* stats2);
+
+}  // namespace bmg

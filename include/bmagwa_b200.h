@@ -1,0 +1,206 @@
+/* bmagwa_b200.h -- C ABI of the B200-native BMAGWA hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, int status
+ * (0 = ok, non-zero = error, text via bmg_last_error()), no C++/torch types.  The reference has
+ * no FFI of its own; each entry point below replaces the C++ member calls cited next to it
+ * (paths relative to the reference tree).  A reference maintainer would bind these from
+ * data.cpp / data_model.cpp / sampler.cpp / model.hpp as shown in INTEGRATION.md.
+ *
+ * Ownership and threading follow the reference (data.hpp:33-38, main.cpp:70-95):
+ *   - a bmg_store is created once, is immutable afterwards and may be shared, read-only, by
+ *     any number of chains/threads;
+ *   - a bmg_chain owns all per-chain mutable device state (imputed genotypes, residual,
+ *     p_r / p_rao / p_proposal, proposal weights) and one CUDA stream; calls on one chain must
+ *     come from one host thread at a time;
+ *   - every host pointer argument is ordinary (pageable or pinned) host memory unless the
+ *     name says *_dev.
+ * All SNP indices are GLOBAL (0 .. m_g-1); a store may hold only the shard [snp_lo, snp_hi).
+ * Effect "type": 0 = A (additive), 1 = H, 2 = D, 3 = R   (data_model.hpp:41).
+ */
+#ifndef BMAGWA_B200_H
+#define BMAGWA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BMG_ABI_VERSION 1
+
+typedef struct bmg_store bmg_store;
+typedef struct bmg_chain bmg_chain;
+typedef struct bmg_sampler bmg_sampler;
+
+/* ---- library ------------------------------------------------------------------------- */
+int bmg_abi_version(void);
+/* Thread-local text of the last error raised on the calling thread ("" if none). */
+const char* bmg_last_error(void);
+/* Number of CUDA devices visible; < 0 on error.  The library has NO CPU fallback: every compute
+ * entry point fails with an error when no sm_100 device is present. */
+int bmg_device_count(void);
+/* Counter of kernels launched by this library in this process (for bench.py's gpu_launches). */
+uint64_t bmg_launch_count(void);
+
+/* ---- genotype store: Data::Data + read_g + recode + handle_missing_g + var/mean --------
+ * (data.hpp:45-72, data.cpp:245-273,324-376,403-434) and PrecomputedSNPCovariances
+ * (precomputed_snp_covariances.hpp:58-131).
+ *
+ * bed_payload: the PLINK .bed bytes AFTER the 3-byte header, starting at SNP snp_lo, i.e.
+ * (snp_hi - snp_lo) * ceil(n/4) bytes, SNP-major, 4 individuals per byte (data.cpp:40-54).
+ * The payload is uploaded, re-coded on the device into the store's own packed 2-bit layout
+ * (value-coded: 00=0, 01=1, 10=2; missing cells held in a sparse index), optionally swapped to
+ * minor-allele counts, and per-SNP integer counts / moments are computed there.
+ * payload_on_device != 0: bed_payload is a device pointer (data generated or staged on the GPU). */
+int bmg_store_create(const uint8_t* bed_payload, int payload_on_device, int64_t n, int64_t m_g,
+                     int64_t snp_lo, int64_t snp_hi, int recode_to_minor, int device, bmg_store** out);
+int bmg_store_destroy(bmg_store* s);
+
+/* Phenotype and covariates (Data::_y, Data::_e; data.hpp:75-76).  e is n x m_e column-major and
+ * INCLUDES the leading column of ones the reference adds (data.hpp:50,56), so m_e >= 1. */
+int bmg_store_set_phenotype(bmg_store* s, const double* y, const double* e, int m_e);
+
+int bmg_store_dims(const bmg_store* s, int64_t* n, int64_t* m_g, int64_t* snp_lo, int64_t* snp_hi,
+                   int* m_e, int64_t* n_missing_cells);
+/* Per local SNP: counts of genotype 1 and 2 among observed cells, number of missing cells, and
+ * whether recode swapped it (any pointer may be NULL). */
+int bmg_store_counts(const bmg_store* s, int32_t* n1, int32_t* n2, int32_t* n_miss, uint8_t* swapped);
+/* Data::var_x / mean_x (data.cpp:403-434) and var_y / yy (data.hpp:67-70) over the LOCAL shard:
+ * out = {sum over SNPs of per-SNP mean, number of SNPs in that sum, sum of per-SNP variance,
+ * number in that sum, var_y, yy}; a multi-shard caller adds the first four across shards. */
+int bmg_store_summaries(const bmg_store* s, double* out6);
+/* Moment cache for types={A}: xx[2*j] = sum x, xx[2*j+1] = sum x^2 - (sum x)^2/n, missing = 0
+ * (precomputed_snp_covariances.hpp:113-117).  j is local. */
+int bmg_store_moments(const bmg_store* s, double* xx);
+/* Missing index (Data::miss_loc / miss_prior, data.cpp:341-376): offsets[local m + 1], idx
+ * (row indices, may be NULL to size), prior3 (3 cumulative counts per local SNP, may be NULL). */
+int bmg_store_missing(const bmg_store* s, int64_t* offsets, int64_t* idx, double* prior3);
+/* Data::get_genotypes_<type>(snp, v) (data.cpp:56-138): n doubles, missing = -1. */
+int bmg_store_get_column(const bmg_store* s, int64_t snp, int type, double* out);
+/* Device pointer / stride of the packed shard (for peers reading columns over NVLink);
+ * ipc_handle receives the 64-byte cudaIpcMemHandle_t of the allocation. */
+int bmg_store_export(const bmg_store* s, void* ipc_handle64, int64_t* words_per_snp);
+/* Attach a peer shard [snp_lo, snp_hi) living on another GPU/process (opened from its IPC
+ * handle, or a raw device pointer when same_process != 0). */
+int bmg_store_attach_peer(bmg_store* s, const void* ipc_handle64_or_ptr, int same_process,
+                          int64_t snp_lo, int64_t snp_hi);
+
+/* ---- chain: DataModel + RaoBlackwellizer + the arrays Sampler keeps per chain ---------- */
+int bmg_chain_create(bmg_store* s, bmg_chain** out);
+int bmg_chain_destroy(bmg_chain* c);
+/* Blocks until all work queued on the chain's stream is complete. */
+int bmg_chain_sync(bmg_chain* c);
+/* The chain's CUDA stream as a cudaStream_t value (for event timing by the caller). */
+void* bmg_chain_stream(bmg_chain* c);
+
+/* DataModel::miss_val (data_model.hpp:127-131): imputed values (0,1,2) of ALL missing cells of
+ * local SNP `snp`, in miss_loc order. */
+int bmg_chain_set_missing(bmg_chain* c, int64_t snp, const int8_t* vals, int64_t count);
+/* DataModel::get_genotypes_<type>(snp, v) (data_model.cpp:30-72): overlay applied. */
+int bmg_chain_get_column(bmg_chain* c, int64_t snp, int type, double* out);
+
+/* Fitted values and residual for the current model (what Model::compute_pve leaves in y_hat,
+ * model.hpp:345-392, and RaoBlackwellizer takes r = y - y_hat from, sampler.cpp:48-49):
+ * y_hat = E beta_e + sum_l beta_g[l] x_{loci[l]}, built on the device from packed columns.
+ * stats9 (may be NULL) = {sum r, sum yhat_e, sum yhat_e^2, sum yhat_g, sum yhat_g^2, sum yhat,
+ * sum yhat^2, xb'xb, (E beta_e - y)'xb}: the reductions behind compute_pve and
+ * Prior::sample_alpha (prior.cpp:47-58). */
+int bmg_chain_residual(bmg_chain* c, const int64_t* loci, const double* beta_e, const double* beta_g,
+                       int k, double* stats9);
+/* Copy the residual (n doubles) back, for tests. */
+int bmg_chain_get_residual(bmg_chain* c, double* r);
+
+typedef struct bmg_scan_params {
+  double sigma2;        /* cmodel->sigma2                                   sampler.cpp:39   */
+  double lmp_add;       /* log prior change of adding type A                sampler.cpp:56-59 */
+  double lmp_rem;       /* same with one in-model SNP removed               sampler.cpp:61-73 */
+  int32_t tau_mode;     /* 0 shared value, 1 per-SNP values drawn by the host in reference
+                           order (parity mode), 2 per-SNP values drawn on the device with a
+                           counter-based generator (throughput mode)           */
+  double tau_shared;    /* inv_tau2_alpha2 when tau_mode == 0               sampler.cpp:78-86 */
+  const double* tau_host; /* m_g(local) values when tau_mode == 1          sampler.cpp:99-106 */
+  uint64_t tau_seed;    /* tau_mode == 2: key (seed, scan counter)                            */
+  uint64_t tau_counter;
+  double nu_tau2, s2_tau2, alpha2; /* prior of the per-SNP draw             prior.hpp:192-199 */
+} bmg_scan_params;
+
+/* RaoBlackwellizer::p_raoblackwell (sampler.hpp:73-74, sampler.cpp:32-261), single type A, over
+ * the LOCAL shard, using the residual left by bmg_chain_residual.  In-model SNPs (loci, with
+ * their beta and inv_tau2_alpha2) get the "residual without this SNP" treatment of
+ * sampler.cpp:116-149.  p_r stays on the device; pass p_r_host != NULL to also copy it back. */
+int bmg_chain_scan(bmg_chain* c, const int64_t* loci, const double* beta_g, const double* tau_g, int k,
+                   const bmg_scan_params* prm, double* p_r_host);
+/* Only the x_j . r reductions of the scan (dot[local m]); the roofline kernel in isolation. */
+int bmg_chain_scan_dots(bmg_chain* c, double* dot_host);
+/* Kernel variant used by bmg_chain_scan/_dots: 0 = direct vectorised global loads,
+ * 1 = bulk-async (TMA) staging through shared memory.  Default chosen by the library. */
+int bmg_chain_set_scan_variant(bmg_chain* c, int variant);
+
+/* The scan epilogue of Sampler::sample (sampler.cpp:739-803): running means and weights.
+ *   update_rao:      p_rao      = running mean of p_r (n_rao_mean samples so far)
+ *   update_proposal: p_proposal = running mean of p_r (n_prop_mean samples so far), then
+ *                    q_add = max(p_proposal, q_add_min), q_rem = max(1 - p_proposal, q_rem_min)
+ * and the partial CDFs (block sums of q_add, q_rem over the in-order permutation, D5). */
+int bmg_chain_adapt(bmg_chain* c, int update_rao, int64_t n_rao_mean, int update_proposal,
+                    int64_t n_prop_mean, double q_add_min, double q_rem_min);
+/* Sampler::initialize_p_proposal_flat (sampler.hpp:351-362) + the weight set-up of
+ * sampler.cpp:594-598. */
+int bmg_chain_init_proposal_flat(bmg_chain* c, double value, double q_add_min, double q_rem_min);
+/* which: 0 p_r, 1 p_rao, 2 p_proposal, 3 q_add, 4 q_rem (local m doubles each). */
+int bmg_chain_get_array(bmg_chain* c, int which, double* out);
+/* Partial CDFs: number of blocks, block size (in in-order positions) and the per-block sums of
+ * q_add / q_rem (either may be NULL); the last entry of a running sum of these is total_w(). */
+int bmg_chain_partial_cdf(bmg_chain* c, int64_t* n_blocks, int64_t* block_size, double* add_sums,
+                          double* rem_sums);
+/* DiscreteDistribution::sample() (discrete_distribution.hpp:125-153) evaluated on the device:
+ * which 0 = dd_add, 1 = dd_rem; u01 in [0,1); zeroed items are excluded.  Returns the sampled
+ * global SNP and the total weight used. */
+int bmg_chain_sample(bmg_chain* c, int which, double u01, int64_t* snp, double* total_w);
+/* adddate / remdate (discrete_distribution.hpp:156-201): zero / un-zero an item. */
+int bmg_chain_set_zeroed(bmg_chain* c, int which, int64_t snp, int zeroed);
+/* Zero every item of dd_rem (sampler.cpp:601-605) / clear all flags. */
+int bmg_chain_fill_zeroed(bmg_chain* c, int which, int zeroed);
+
+/* Model::update_likelihood_on_add's data reductions (model.hpp:453-470) for m_c candidate SNPs
+ * in one launch: xy[c] = x_c'y; xe[c*m_e + j] = x_c'E_j; xx_model[c*k + l] = x_c'x_{loci[l]};
+ * xx_cand[c*m_c + d] = x_c'x_d (d = c gives x_c'x_c).  Genotype-by-genotype products are exact
+ * integers (popcount arithmetic on the packed columns). */
+int bmg_chain_column_stats(bmg_chain* c, const int64_t* cand, int m_c, const int64_t* loci, int k,
+                           double* xy, double* xe, double* xx_model, double* xx_cand);
+
+/* Probit latent-variable update (NEW; no reference counterpart):
+ * z_i ~ N(yhat_i, 1) truncated to (0, inf) for cases and (-inf, 0] for controls, using the
+ * fitted values left by bmg_chain_residual; the working phenotype of the chain becomes z.
+ * is_case == NULL keeps the labels of the previous call.  u01 == NULL draws the uniforms on the
+ * device (seed, counter); otherwise n host uniforms are used (parity with the oracle).
+ * stats2 (may be NULL) = {sum z, sum z^2}. */
+int bmg_chain_probit_update(bmg_chain* c, const uint8_t* is_case, const double* u01, uint64_t seed,
+                            uint64_t counter, double* stats2);
+int bmg_chain_get_phenotype(bmg_chain* c, double* y_out);
+
+/* ---- host sampler: Options + Sampler::sample (options.hpp, sampler.cpp:551-880) --------
+ * The C++ MH driver of the reference re-implemented over the entry points above; reads the
+ * reference's INI file and writes the reference's output files (Appendix C of SURVEY.md). */
+int bmg_sampler_create(const char* ini_path, int chain_index, int device, bmg_sampler** out);
+/* Same, over a store that already exists (chains share it, main.cpp:54-76). */
+int bmg_sampler_create_on_store(const char* ini_path, int chain_index, bmg_store* s, bmg_sampler** out);
+/* key=value overrides applied after the INI file (e.g. "tau_rng=device", "do_n_iter=1000"). */
+int bmg_sampler_set_option(bmg_sampler* sp, const char* key, const char* value);
+/* Opens output files, initialises the chain (sampler.cpp:592-620). */
+int bmg_sampler_begin(bmg_sampler* sp);
+/* Runs n_iter MCMC iterations (the loop body of sampler.cpp:626-834). */
+int bmg_sampler_run(bmg_sampler* sp, int64_t n_iter);
+/* Writes _rao.dat, _samplerstats.txt, closes files (sampler.cpp:836-879). */
+int bmg_sampler_end(bmg_sampler* sp);
+/* stats: {iterations done, accepted, model size, log likelihood, seconds in moves,
+ * seconds in scans, scans done, kernels launched}. */
+int bmg_sampler_stats(bmg_sampler* sp, double* out8);
+bmg_store* bmg_sampler_store(bmg_sampler* sp);
+bmg_chain* bmg_sampler_chain(bmg_sampler* sp);
+int bmg_sampler_destroy(bmg_sampler* sp);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BMAGWA_B200_H */

@@ -1,0 +1,388 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every check calls the CUDA path through
+the C ABI (bmagwa_b200.api over libbmagwa_b200.so) and compares with the CPU oracle
+(oracle/oracle.c) on the same seeded inputs, or with the committed reference goldens.
+
+Bars: bit-exact for genotype decode, counts, missing index, recode flags and the moment cache;
+x_j'r to 1e-12 relative to ||x_j||*||r|| and p_r to 1e-9 absolute (north star: 1e-9; H7 explains
+why the dot product is compared against the norm product, not its own magnitude)."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+from bmagwa_b200 import synth
+from oracle import cpu
+from tests.helpers import load_plink, load_small
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def api():
+    from bmagwa_b200 import api as _api
+    return _api
+
+
+def make_data(n, m, seed, miss_rate=0.0, m_e=2):
+    payload, f = synth.make_genotypes(n, m, seed=seed, miss_rate=miss_rate)
+    y, causal, beta = synth.make_phenotype(payload, f, n, m, seed=seed, n_causal=min(20, m))
+    rs = np.random.default_rng(seed + 2)
+    E = rs.uniform(size=(n, m_e))
+    return payload, y, E
+
+
+def oracle_store(payload, n, m, recode):
+    bed = payload.copy()
+    sw = cpu.recode_minor(bed, n, m) if recode else np.zeros(m, dtype=np.uint8)
+    return bed, sw
+
+
+# ------------------------------------------------------------------------------- store (a1-a4)
+@pytest.mark.parametrize("n,m,miss,recode", [(30, 7, 0.0, True), (203, 300, 0.01, True), (1000, 257, 0.0, False),
+                                             (5000, 64, 0.002, True), (16, 5, 0.2, True), (1, 3, 0.0, False),
+                                             (33, 40, 0.5, True)])
+def test_store_decode_counts_moments_missing_bit_exact(api, n, m, miss, recode):
+    payload, y, E = make_data(n, m, seed=n + m, miss_rate=miss)
+    bed, sw = oracle_store(payload, n, m, recode)
+    st = api.GenotypeStore(payload, n, m, recode_to_minor=recode)
+    st.set_phenotype(y, E)
+    n1, n2, nm, swapped = st.counts()
+    assert np.array_equal(swapped, sw)
+    G = cpu.decode_matrix(bed, n, m, 0)
+    assert np.array_equal(n1, (G == 1).sum(axis=0)) and np.array_equal(n2, (G == 2).sum(axis=0))
+    assert np.array_equal(nm, (G == -1).sum(axis=0))
+    for j in range(0, m, max(1, m // 23)):
+        for t in range(4):
+            assert np.array_equal(st.get_column(j, t), cpu.decode_column(bed, n, j, t)), (j, t)
+    assert np.array_equal(st.moments(), cpu.moments(bed, n, m))
+    off, idx, prior = st.missing()
+    off2, idx2, prior2 = cpu.missing_index(bed, n, m)
+    assert np.array_equal(off, off2) and np.array_equal(idx, idx2)
+    has = (off[1:] - off[:-1]) > 0
+    assert np.array_equal(prior[has], prior2[has])
+    if n > 1:
+        mean, var = cpu.g_var_and_mean(bed, n, m)
+        s = st.summaries()
+        assert s["mean_x"] == mean and (s["var_x"] == var or (math.isnan(var) and math.isnan(s["var_x"])))
+        assert s["var_y"] == pytest.approx(cpu.var(y), rel=1e-14)
+    st.close()
+
+
+def test_store_reference_fixtures_bit_exact(api, ref_tests, golden, golden_data_dir):
+    """The reference's own decode goldens (src/tests/data_tests.hpp:40-47,130-140,171-190)."""
+    raw = cpu.read_bed(os.path.join(golden_data_dir, "plinktest.bed"), 5, 10)
+    st = api.GenotypeStore(raw, 5, 10, recode_to_minor=False)
+    G = np.array(ref_tests["plinktest"]["genotypes_snp_major"], dtype=np.float64)
+    for j in range(10):
+        assert np.array_equal(st.get_column(j, 0), G[j])
+        for t in range(1, 4):
+            assert np.array_equal(st.get_column(j, t), golden["plink_cols_raw"][t][:, j])
+    off, idx, prior = st.missing()
+    assert list(idx[off[0]:off[1]]) == [3] and list(prior[0]) == [1, 2, 4]
+    assert list(idx[off[3]:off[4]]) == [1] and list(prior[3]) == [2, 3, 4]
+    assert np.array_equal(st.moments(), golden["plink_moments"])
+    # overlay (data_model.cpp:30-72): SNP0/ind3 := 2, SNP3/ind1 := 1
+    _, y = load_plink(golden_data_dir)
+    st.set_phenotype(y)
+    ch = api.Chain(st)
+    ch.set_missing(0, [2])
+    ch.set_missing(3, [1])
+    for t in range(4):
+        for j in range(10):
+            assert np.array_equal(ch.get_column(j, t), golden["plink_cols_overlay"][t][:, j])
+    ch.close()
+    st.close()
+    raw = cpu.read_bed(os.path.join(golden_data_dir, "small_modelspace.bed"), 30, 7)
+    st = api.GenotypeStore(raw, 30, 7, recode_to_minor=True)
+    for j in range(7):
+        assert np.array_equal(st.get_column(j, 0), golden["small_cols_A"][:, j])
+    assert np.array_equal(st.moments(), golden["small_moments"])
+    st.close()
+
+
+# ------------------------------------------------------------------- residual + scan (a5, a9)
+def random_state(n, m, m_e, k, seed):
+    rs = np.random.default_rng(seed)
+    loci = np.sort(rs.choice(m, size=k, replace=False)) if k else np.zeros(0, dtype=np.int64)
+    rs.shuffle(loci)
+    beta_e = rs.normal(size=m_e + 1) * 0.2
+    beta_g = rs.normal(size=k) * 0.3
+    tau_g = rs.uniform(1.0, 8.0, size=k)
+    return loci.astype(np.int64), beta_e, beta_g, tau_g
+
+
+def oracle_yhat(bed, n, loci, beta_e, beta_g, E, miss=None):
+    Ef = np.concatenate([np.ones((n, 1)), E], axis=1)
+    ye = Ef @ beta_e
+    yg = np.zeros(n)
+    for l, b in zip(loci, beta_g):
+        if miss is None:
+            x = cpu.decode_column(bed, n, int(l), 0)
+            x[x < 0] = 0
+        else:
+            off, idx, val = miss
+            x = cpu.decode_column_overlay(bed, n, int(l), 0, idx[off[l]:off[l + 1]], val[off[l]:off[l + 1]])
+        yg += b * x
+    return ye, yg
+
+
+@pytest.mark.parametrize("variant", [1, 0])
+@pytest.mark.parametrize("n,m,k,miss,tau_mode", [
+    (30, 7, 2, 0.0, 0), (203, 300, 3, 0.01, 1), (1000, 500, 0, 0.0, 0), (1000, 500, 5, 0.0, 1),
+    (5000, 1000, 4, 0.0, 0), (5000, 333, 3, 0.003, 1), (10007, 120, 2, 0.0, 0), (50000, 64, 3, 0.0, 1),
+    (17, 3, 1, 0.0, 0)])
+def test_scan_matches_oracle(api, variant, n, m, k, miss, tau_mode):
+    payload, y, E = make_data(n, m, seed=3 * n + m, miss_rate=miss)
+    bed, _ = oracle_store(payload, n, m, True)
+    st = api.GenotypeStore(payload, n, m, recode_to_minor=True)
+    st.set_phenotype(y, E)
+    ch = api.Chain(st)
+    ch.set_scan_variant(variant)
+    loci, beta_e, beta_g, tau_g = random_state(n, m, 2, min(k, m), seed=n)
+    k = loci.size
+    off, idx, _ = cpu.missing_index(bed, n, m)
+    rs = np.random.default_rng(5)
+    val = rs.integers(0, 3, size=idx.size).astype(np.int8)
+    for j in range(m):
+        if off[j + 1] > off[j]:
+            ch.set_missing(j, val[off[j]:off[j + 1]])
+    miss_t = (off, idx, val)
+    ye, yg = oracle_yhat(bed, n, loci, beta_e, beta_g, E, miss_t)
+    stats = ch.residual(loci, beta_e, beta_g)
+    r = ch.get_residual()
+    r_or = y - (yg + ye)
+    assert np.allclose(r, r_or, rtol=0, atol=1e-13 * max(1.0, np.abs(r_or).max()))
+    assert stats["sum_r"] == pytest.approx(r_or.sum(), abs=1e-9)
+    assert stats["xbxb"] == pytest.approx(yg @ yg, rel=1e-12, abs=1e-12)
+    assert stats["ebxb"] == pytest.approx((ye - y) @ yg, rel=1e-11, abs=1e-10)
+    assert stats["sum_yhat2"] == pytest.approx(((ye + yg) ** 2).sum(), rel=1e-12)
+    # scan
+    lmp_add, lmp_rem = -3.1, -2.7   # the two tabulated model-prior changes (sampler.cpp:52-76); any values do
+    tau = 3.7 if tau_mode == 0 else rs.uniform(0.5, 9.0, size=m)
+    model_ind = -np.ones(m, dtype=np.int32)
+    for i, l in enumerate(loci):
+        model_ind[l] = i
+    sigma2 = 0.8
+    xx = cpu.moments(bed, n, m)
+    p_or, dot_or, _ = cpu.scan_A(bed, n, m, xx, y, ye + yg, model_ind, beta_g, tau_g, tau, tau_mode, sigma2, lmp_add, lmp_rem,
+                                 miss=miss_t, want_dot=True)
+    p = ch.scan(loci, beta_g, tau_g, sigma2, lmp_add, lmp_rem, tau=tau)
+    assert np.abs(p - p_or).max() < 1e-9, np.abs(p - p_or).max()
+    # the raw reduction x_j'r (dense part; the oracle's dot for in-model SNPs includes beta x'x, so compare off-model)
+    dots = ch.scan_dots()
+    G = cpu.decode_matrix(bed, n, m, 0)
+    G[G < 0] = 0
+    ref_dense = G.T @ r_or
+    scale = np.sqrt((G * G).sum(axis=0)) * np.linalg.norm(r_or) + 1e-300
+    assert (np.abs(dots - ref_dense) / scale).max() < 1e-12
+    ch.close()
+    st.close()
+
+
+def test_scan_reference_goldens(api, golden, golden_data_dir):
+    """p_r of the unmodified reference for small_modelspace (tests/golden/ref_outputs.npz)."""
+    raw = cpu.read_bed(os.path.join(golden_data_dir, "small_modelspace.bed"), 30, 7)
+    _, y = load_small(golden_data_dir)
+    st = api.GenotypeStore(raw, 30, 7, recode_to_minor=True)
+    st.set_phenotype(y)
+    ch = api.Chain(st)
+    pp = golden["small_prior"]
+    P = cpu.Prior.make(7, 2, 2)
+    # empty model, residual = y  (src/tests/raoblackwellizer_tests.hpp:31-93): beta_e = 0 gives y_hat = 0
+    ch.residual([], [0.0], [])
+    p = ch.scan([], [], [], 0.7, P.log_add([0] * 5, 0, 0), 0.0, tau=pp[8])
+    assert np.abs(p - golden["small0_scan_empty_resid_y"]).max() < 1e-12
+    # two SNPs in the model
+    ch.residual([2, 5], [0.05], [0.4, -0.3])
+    assert np.allclose(y - ch.get_residual(), golden["small0_two_snps_yhat"], rtol=0, atol=1e-14)
+    p = ch.scan([2, 5], [0.4, -0.3], [11.0, 7.5], 0.9, P.log_add([2, 0, 0, 0, 0], 2, 0), P.log_add([1, 0, 0, 0, 0], 1, 0),
+                tau=pp[8])
+    assert np.abs(p - golden["small0_scan_two_snps"]).max() < 1e-12
+    ch.close()
+    st.close()
+
+
+def test_scan_device_tau_draws_have_the_prior_distribution(api):
+    """tau_mode 2 (throughput mode): 1/(alpha2 * Inv-chi2(nu, s2)) per SNP, drawn on the device.
+    With y = 1 and an empty model the centred statistic rx is exactly 0, so p_r can be inverted for tau in
+    closed form:  logit p = -0.5 log((v + tau)/tau)  =>  tau = v / (exp(-2 logit p) - 1)."""
+    n, m = 64, 200000
+    payload, _, _ = make_data(n, m, seed=12)
+    y = np.ones(n)
+    st = api.GenotypeStore(payload, n, m, recode_to_minor=False)
+    st.set_phenotype(y)
+    ch = api.Chain(st)
+    ch.residual([], [0.0], [])
+    nu, s2, alpha2, sigma2 = 5.0, 0.05, 1.3, 1.0
+    kw = dict(tau_mode=2, seed=99, nu_tau2=nu, s2_tau2=s2, alpha2=alpha2)
+    p = ch.scan([], [], [], sigma2, 0.0, 0.0, counter=1, **kw)
+    p2 = ch.scan([], [], [], sigma2, 0.0, 0.0, counter=1, **kw)
+    assert np.array_equal(p, p2)            # counter-based: reproducible
+    p3 = ch.scan([], [], [], sigma2, 0.0, 0.0, counter=2, **kw)
+    assert not np.array_equal(p, p3)        # a new scan counter gives new draws
+    v = st.moments()[:, 1]
+    ok = v > 0.5
+    logit = np.log(p[ok]) - np.log1p(-p[ok])
+    tau = v[ok] / np.expm1(-2.0 * logit)
+    g = nu * s2 * alpha2 * tau / 2.0        # the underlying Gamma(nu/2, 1) draw
+    assert g.mean() == pytest.approx(nu / 2, rel=0.02)
+    assert g.var() == pytest.approx(nu / 2, rel=0.05)
+    assert np.mean(g < 1.0) == pytest.approx(0.150855, abs=0.01)   # P[Gamma(2.5) < 1]
+    ch.close()
+    st.close()
+
+
+# --------------------------------------------------------------------------- epilogue + weights
+def test_adapt_and_partial_cdf_and_device_sampler(api):
+    n, m = 100, 1000
+    payload, y, E = make_data(n, m, seed=42)
+    st = api.GenotypeStore(payload, n, m, recode_to_minor=True)
+    st.set_phenotype(y, E)
+    ch = api.Chain(st)
+    q_add_min, q_rem_min = 1.0 / (m - 20), 1.0 / 20
+    ch.init_proposal_flat(20.0 / m, q_add_min, q_rem_min)
+    assert np.array_equal(ch.get_array("p_proposal"), np.full(m, 20.0 / m))
+    ch.residual([], np.zeros(3), [])
+    p = ch.scan([], [], [], 1.0, -3.0, 0.0, tau=4.0)
+    prop0 = ch.get_array("p_proposal")
+    ch.adapt(True, 0, True, 1, q_add_min, q_rem_min)
+    assert np.array_equal(ch.get_array("p_rao"), cpu.running_mean(np.zeros(m), p, 0))
+    prop = cpu.running_mean(prop0, p, 1)
+    assert np.array_equal(ch.get_array("p_proposal"), prop)
+    qa, qr = cpu.proposal_weights(prop, q_add_min, q_rem_min)
+    assert np.array_equal(ch.get_array("q_add"), qa) and np.array_equal(ch.get_array("q_rem"), qr)
+    bs, a_sums, r_sums = ch.partial_cdf()
+    order = cpu.inorder_permutation(m)
+    want = np.add.reduceat(qa[order], np.arange(0, m, bs))
+    assert np.allclose(a_sums, want, rtol=1e-14)
+    assert a_sums.sum() == pytest.approx(qa.sum(), rel=1e-13)
+    # device sampler == in-order CDF search of the oracle, with zeroing
+    zeroed = np.zeros(m, dtype=np.uint8)
+    rs = np.random.default_rng(1)
+    for step in range(60):
+        if step % 3 == 0:
+            j = int(rs.integers(0, m))
+            zeroed[j] ^= 1
+            ch.set_zeroed(0, j, bool(zeroed[j]))
+        u = float(rs.uniform())
+        snp, tot = ch.sample(0, u)
+        assert snp == cpu.dd_sample(qa, zeroed, order, u)
+        assert tot == pytest.approx(cpu.dd_total(qa, zeroed), rel=1e-13)
+    # dd_rem: everything zeroed except the model's SNPs (sampler.cpp:601-605)
+    ch.fill_zeroed(1, True)
+    zr = np.ones(m, dtype=np.uint8)
+    for j in (3, 500, 999):
+        ch.set_zeroed(1, j, False)
+        zr[j] = 0
+    for u in (0.0, 0.3, 0.6, 0.999999):
+        snp, tot = ch.sample(1, u)
+        assert snp == cpu.dd_sample(qr, zr, order, u)
+    ch.close()
+    st.close()
+
+
+# ------------------------------------------------------------------------------ column stats (a7)
+@pytest.mark.parametrize("n,m,miss", [(203, 300, 0.02), (5000, 200, 0.0), (40000, 50, 0.001)])
+def test_column_stats_match_oracle(api, n, m, miss):
+    payload, y, E = make_data(n, m, seed=n + 1, miss_rate=miss)
+    bed, _ = oracle_store(payload, n, m, True)
+    st = api.GenotypeStore(payload, n, m, recode_to_minor=True)
+    st.set_phenotype(y, E)
+    ch = api.Chain(st)
+    off, idx, _ = cpu.missing_index(bed, n, m)
+    rs = np.random.default_rng(8)
+    val = rs.integers(0, 3, size=idx.size).astype(np.int8)
+    for j in range(m):
+        if off[j + 1] > off[j]:
+            ch.set_missing(j, val[off[j]:off[j + 1]])
+    loci = rs.choice(m, size=6, replace=False).astype(np.int64)
+    cand = np.array([c for c in rs.choice(m, size=12, replace=False) if c not in loci][:5], dtype=np.int64)
+
+    def col(j):
+        return cpu.decode_column_overlay(bed, n, int(j), 0, idx[off[j]:off[j + 1]], val[off[j]:off[j + 1]])
+
+    Ef = np.concatenate([np.ones((n, 1)), E], axis=1)
+    X = np.concatenate([Ef, np.stack([col(l) for l in loci], axis=1)], axis=1)
+    xy, xe, xm, xc = ch.column_stats(cand, loci)
+    for ci, c in enumerate(cand):
+        x = col(c)
+        xy_or, xxcol = cpu.column_stats(x, y, X)
+        assert xy[ci] == pytest.approx(xy_or, rel=1e-12, abs=1e-10)
+        assert np.allclose(xe[ci], xxcol[:3], rtol=1e-12, atol=1e-10)
+        assert np.array_equal(xm[ci], xxcol[3:-1])         # genotype x genotype: exact integers
+        assert xc[ci, ci] == xxcol[-1]
+        for di, d in enumerate(cand):
+            assert xc[ci, di] == col(d) @ x
+    ch.close()
+    st.close()
+
+
+# ------------------------------------------------------------------------------------ probit (a11)
+def test_probit_latent_update_matches_oracle(api):
+    n, m = 4000, 50
+    payload, y, E = make_data(n, m, seed=77)
+    bed, _ = oracle_store(payload, n, m, True)
+    st = api.GenotypeStore(payload, n, m, recode_to_minor=True)
+    is_case = (y > 0).astype(np.uint8)
+    st.set_phenotype(is_case.astype(np.float64), E)
+    ch = api.Chain(st)
+    loci, beta_e, beta_g, _ = random_state(n, m, 2, 3, seed=4)
+    ch.residual(loci, beta_e, beta_g)
+    ye, yg = oracle_yhat(bed, n, loci, beta_e, beta_g, E)
+    rs = np.random.default_rng(2)
+    u = rs.uniform(size=n)
+    stats = ch.probit_update(is_case, u)
+    z = ch.get_phenotype()
+    z_or = cpu.probit_latent(ye + yg, is_case, u)
+    assert np.allclose(z, z_or, rtol=1e-9, atol=1e-9)   # tolerance of the north star for fp64 statistics
+    assert (z[is_case == 1] > 0).all() and (z[is_case == 0] <= 0).all()
+    assert stats[0] == pytest.approx(z_or.sum(), rel=1e-9) and stats[1] == pytest.approx((z_or ** 2).sum(), rel=1e-9)
+    # device-drawn uniforms: right support, reproducible per (seed, counter)
+    ch.residual(loci, beta_e, beta_g)
+    ch.probit_update(None, None, seed=5, counter=9)
+    z1 = ch.get_phenotype()
+    assert (z1[is_case == 1] > 0).all() and (z1[is_case == 0] <= 0).all()
+    # the next residual is built from z
+    ch.residual(loci, beta_e, beta_g)
+    assert np.allclose(ch.get_residual(), z1 - (ye + yg), rtol=0, atol=1e-12)
+    ch.close()
+    st.close()
+
+
+# ------------------------------------------------------- full-size property checks (BASELINE C2)
+def test_scan_full_size_linearity_and_checksum(api):
+    """n=5000 x m=100000 (BASELINE config 2): size-independent properties instead of an oracle pass:
+    linearity in the residual and a checksum  sum_j x_j'r = (sum_j x_j)'r  from the integer counts."""
+    import torch
+    n, m = 5000, 100000
+    B = (n + 3) // 4
+    g = torch.Generator(device="cuda").manual_seed(1)
+    raw = torch.randint(0, 256, (m * B,), dtype=torch.uint8, device="cuda", generator=g)
+    raw &= 0b10111011   # clear bit 2 of each nibble-pair => fewer 01 codes; remaining 01 are missing cells
+    rs = np.random.default_rng(3)
+    y = rs.normal(size=n)
+    st = api.GenotypeStore(None, n, m, recode_to_minor=True, payload_device_ptr=raw.data_ptr())
+    st.set_phenotype(y)
+    ch = api.Chain(st)
+    ch.residual([], [0.0], [])
+    d1 = ch.scan_dots()
+    ch.set_scan_variant(0)
+    d0 = ch.scan_dots()
+    assert np.abs(d1 - d0).max() <= 1e-12 * np.abs(d1).max()
+    # linearity: residual scaled by -2.5 (beta_e = 3.5 on an all-ones covariate gives y - 3.5; use y2 = a*y instead)
+    st2 = api.GenotypeStore(None, n, m, recode_to_minor=True, payload_device_ptr=raw.data_ptr())
+    st2.set_phenotype(-2.5 * y)
+    ch2 = api.Chain(st2)
+    ch2.residual([], [0.0], [])
+    assert np.allclose(ch2.scan_dots(), -2.5 * d1, rtol=1e-13, atol=1e-9)
+    # checksum against the per-individual allele totals computed independently with torch
+    codes = torch.stack([(raw.view(m, B) >> s) & 3 for s in (0, 2, 4, 6)], dim=2).reshape(m, 4 * B)[:, :n]
+    lut = torch.tensor([0, 0, 1, 2], dtype=torch.float64, device="cuda")   # 01 (missing) -> 0
+    _, _, _, swapped = st.counts()
+    sw = torch.from_numpy(swapped.astype(np.bool_)).cuda()
+    vals = lut[codes.long()]
+    vals = torch.where(sw[:, None] & (codes != 1), 2.0 - vals, vals)
+    tot = vals.sum(dim=0).cpu().numpy()
+    assert d1.sum() == pytest.approx(tot @ y, rel=1e-11)
+    ch.close(); ch2.close(); st.close(); st2.close()

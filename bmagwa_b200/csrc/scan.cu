@@ -18,6 +18,7 @@
 //     the TMA engine; SASS UBLKCP) in a 3-stage ring, so no registers are spent on prefetch.
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "store.cuh"
 #include "philox.cuh"
@@ -81,18 +82,35 @@ __device__ __forceinline__ double field_as_double(uint32_t w, int p)
   return __hiloint2double(0, (int)(w & (3u << (2 * p))));
 }
 
+// one genotype: mask the 2-bit field in place, view it as the low word of a double whose high word is 0
+// (a denormal), and accumulate.  volatile keeps the interleaved issue order written below, so that
+// consecutive DFMAs belong to different accumulators (the FP64 pipe has a long dependent latency).
+__device__ __forceinline__ void fma_field(double& acc, uint32_t w, uint32_t mask, double r)
+{
+  asm volatile(
+      "{\n"
+      ".reg .b32 t;\n"
+      ".reg .f64 x;\n"
+      "and.b32 t, %1, %2;\n"
+      "mov.b64 x, {t, %3};\n"
+      "fma.rn.f64 %0, x, %4, %0;\n"
+      "}\n"
+      : "+d"(acc)
+      : "r"(w), "r"(mask), "r"(0), "d"(r));
+}
+
 // 32 genotypes (two packed words) times 32 register-resident pre-scaled residuals
 __device__ __forceinline__ void fma_words(double (&acc)[kBatch], const uint2 (&w)[kBatch], const double (&rp)[32])
 {
 #pragma unroll
   for (int p = 0; p < 16; ++p) {
 #pragma unroll
-    for (int i = 0; i < kBatch; ++i) acc[i] = fma(field_as_double(w[i].x, p), rp[p], acc[i]);
+    for (int i = 0; i < kBatch; ++i) fma_field(acc[i], w[i].x, 3u << (2 * p), rp[p]);
   }
 #pragma unroll
   for (int p = 0; p < 16; ++p) {
 #pragma unroll
-    for (int i = 0; i < kBatch; ++i) acc[i] = fma(field_as_double(w[i].y, p), rp[16 + p], acc[i]);
+    for (int i = 0; i < kBatch; ++i) fma_field(acc[i], w[i].y, 3u << (2 * p), rp[16 + p]);
   }
 }
 
@@ -510,6 +528,10 @@ static void choose_scan_geometry(Chain* c)
     const int ctas = 16 / nw;  // 128 registers/thread => 512 threads per SM
     const double eff = (double)W / (double)(chunks * 64 * nw) * (double)(ctas * nw) / 16.0;
     if (eff > best + 1e-9 || (eff > best - 1e-9 && nw > best_nw)) { best = eff; best_nw = nw; }
+  }
+  if (const char* env = getenv("BMG_SCAN_WARPS")) {   // development override
+    const int v = atoi(env);
+    if (v >= 1 && v <= kMaxWarps) best_nw = v;
   }
   c->scan_warps = best_nw;
   c->scan_chunk_words = 64 * best_nw;

@@ -20,7 +20,7 @@ OBJ = os.path.join(PKG, "build")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC,-fvisibility=hidden,-O3,-march=x86-64-v3",
+    "-Xcompiler", "-fPIC,-fvisibility=hidden,-O3,-march=x86-64-v3,-ffp-contract=off",
     "--expt-relaxed-constexpr",
 ]
 

@@ -1,0 +1,130 @@
+// sampler.hpp -- the Metropolis-Hastings driver of one chain.
+//
+// Re-implementation of bmagwa::Sampler for the PMV sampler with effect type A
+// (src/sampler.hpp:87-1780, src/sampler.cpp:264-1049): move 0 multistep additions/removals with
+// delayed rejection, move 1 swap with a nearby SNP, move 2 state change of nearby SNPs, move-size
+// adaptation, the tau2/alpha Gibbs steps, the Rao-Blackwell scan schedule and the reference's
+// output files.  The random-number stream is consumed in the reference's order, so a fixed-seed
+// chain reproduces the reference's accepted-move sequence until the first floating-point tie.
+//
+// Every O(n) or O(n m_g) quantity comes from the device through the chain handle:
+//   bmg::chain_column_stats  ONE launch per move for all SNPs the move adds
+//   bmg::chain_residual / chain_scan / chain_adapt  at every n_rao-th iteration
+// and nothing in this file touches a genotype.
+#pragma once
+#include <cstdint>
+#include <fstream>
+#include <memory>
+#include <string>
+#include <vector>
+#include "../store.cuh"
+#include "dataset.hpp"
+#include "model.hpp"
+#include "options.hpp"
+#include "rng.hpp"
+
+namespace bmg {
+
+class Sampler {
+ public:
+  // Takes ownership of nothing: store and dataset summaries must outlive the sampler.
+  Sampler(const Options& opts, int chain_index, Store* store, const std::vector<double>& y, const std::vector<double>& e,
+          double var_y, double yy, double var_x, double mean_x);
+  ~Sampler();
+
+  void set_option(const std::string& key, const std::string& value);
+  void initialize_p_proposal_flat();   // sampler.hpp:351-362
+  void print_prior();                  // sampler.hpp:384-390
+  void begin();                        // sampler.cpp:551-623 (everything before the loop)
+  void run(int64_t n_iter);            // sampler.cpp:625-834
+  void end();                          // sampler.cpp:836-879
+  void stats(double* out8) const;
+  Chain* chain() { return chain_; }
+  Store* store() { return store_; }
+
+ private:
+  // ---- configuration (sampler.hpp:395-411)
+  Options opt_;
+  std::string basename_;
+  uint32_t seed_;
+  size_t n_, m_g_, m_e_;
+  size_t n_iter_ = 0, n_accepted_ = 0, n_rao_, n_rao_burnin_, n_sample_tau2_and_missing_, thin_, verbosity_;
+  bool flat_proposal_dist_, adaptation_, save_beta_;
+  bool tau_on_device_ = false;
+  // ---- state
+  Store* store_;
+  Chain* chain_ = nullptr;
+  ChainRng rng_;
+  std::unique_ptr<Prior> prior_;
+  Model current_, proposal_;   // the reference's current_model / new_model
+  ExhModel exh_;
+  std::vector<int32_t> pos_in_proposal_;   // model_inds of the proposal model: SNP -> term index or -1
+  std::vector<int32_t> pos_in_current_;
+  std::vector<double> p_rao_;              // fetched at the end only
+  size_t p_proposal_n_ = 1;
+  int p_rao_n_ = 0;
+  double q_add_min_, q_rem_min_;
+  ProposalCdf dd_add_, dd_rem_;
+  PinnedBuf<double> h_w_;                  // pinned staging of the in-order weights
+  std::vector<double> h_cdf_;
+  // ---- moves (sampler.hpp:442-483)
+  double p_moves_[7], p_moves_cumsum_[7];
+  unsigned char max_move_size_;
+  size_t max_nbh_;
+  double p_move_size_, p_move_size_nbs_, p_move_size_nbc_;
+  bool adapt_p_move_size_;
+  std::vector<double> q_p_move_size_, q_p_move_size_nbs_, q_p_move_size_nbc_, r_move_size_sum_, r_move_size_n_, q_p0_move_size_;
+  size_t n_acpt_moves_[7], n_moves_[7];
+  double acpt_move_size_goal_;
+  std::vector<size_t> move_inds_add_, move_inds_rem_, move_inds_;
+  std::vector<int64_t> move_inds_map_;
+  std::vector<char> move_isadd_;
+  unsigned char movesize_ = 0;
+  unsigned char delay_rejection_;
+  std::vector<double> dr_model_probabilities_, dr_q_add_, dr_q_rem_, dr_log_q_add_types_;
+  std::vector<unsigned char> dr_bit_to_normalized_order_;
+  MoveGram gram_;
+  // ---- book-keeping (samplerstats.hpp)
+  unsigned long n_upd_add_ = 0, n_upd_rem_ = 0, n_comp_ = 0;
+  double move_seconds_ = 0.0, scan_seconds_ = 0.0;
+  size_t n_scans_ = 0;
+  double t_start_ = 0.0;
+  double pves_[3] = {0, 0, 0};
+  uint64_t tau_counter_ = 0;
+  // ---- output files
+  struct Files;
+  std::unique_ptr<Files> files_;
+  bool begun_ = false;
+
+  // helpers
+  double q_add(size_t snp) const { return dd_add_.weight((uint32_t)snp); }
+  double q_rem(size_t snp) const { return dd_rem_.weight((uint32_t)snp); }
+  void copy_proposal_to_current();
+  void copy_current_to_proposal();
+  void fetch_gram(const std::vector<uint32_t>& cand);
+  void add_to_proposal(uint32_t snp, double inv_tau2_alpha2);
+  void readd_to_proposal(uint32_t snp);
+  void remove_from_proposal(int model_ind);
+  void refresh_weights_from_device(bool first);
+  void compute_p_moves();
+  void sample_missing() {}   // no missing cells in the supported inputs (checked at construction)
+  void rao_block();
+  // moves
+  unsigned char do_multistep_additions_and_removals();
+  void prepare_addrem(double& log_q_forward, unsigned char& n_removals, unsigned char ms);
+  void backward_prepare_addrem(double& log_q_backward, unsigned char ms);
+  void do_addrem(double& log_q_forward, double& log_q_backward, double& log_mpc, unsigned char ms);
+  unsigned char do_switch_of_nearby_snps();
+  unsigned char do_statechange_of_nearby_snps();
+  void undo_move0_flags();
+  unsigned char delayed_rejection_move0(unsigned char ms_rem, double log_r, double log_q_forward, double log_q_backward);
+  void adapt_p_move_size_acptrate(double t);
+  void adapt_p_move_size_jd_mb();
+};
+
+void compute_exhaustive_modelset(size_t n_inds, ExhModel* exh, double* log_model_probabilities, double& max_log_model);
+void compute_proposal_probs_for_exh_modelset(int n_inds, const unsigned char* bit_to_normalized_order, const double* q_add,
+                                             const double* q_rem, double z_add, double z_rem, size_t const_loci, size_t m_g,
+                                             double* log_prop_probs);
+
+}  // namespace bmg

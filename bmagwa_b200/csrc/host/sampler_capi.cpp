@@ -1,15 +1,143 @@
-// sampler_capi.cpp -- extern "C" entry points of the host sampler (placeholder until sampler.cpp lands)
+// sampler_capi.cpp -- extern "C" entry points of the host sampler (include/bmagwa_b200.h, bmg_sampler_*).
+//
+// bmg_sampler_create does what main() does for one chain (src/main.cpp:47-76): parse the INI file,
+// load .fam/.y/.e/.bed, build the device store (recode, counts, moment cache), construct the sampler.
+#include <memory>
 #include "../common.cuh"
+#include "../store.cuh"
 #include "../../../include/bmagwa_b200.h"
+#include "dataset.hpp"
+#include "options.hpp"
+#include "sampler.hpp"
+
+using namespace bmg;
+
 #define BMG_API extern "C" __attribute__((visibility("default")))
-static int nyi() { bmg::set_last_error("host sampler not built into this library yet"); return 1; }
-BMG_API int bmg_sampler_create(const char*, int, int, bmg_sampler**) { return nyi(); }
-BMG_API int bmg_sampler_create_on_store(const char*, int, bmg_store*, bmg_sampler**) { return nyi(); }
-BMG_API int bmg_sampler_set_option(bmg_sampler*, const char*, const char*) { return nyi(); }
-BMG_API int bmg_sampler_begin(bmg_sampler*) { return nyi(); }
-BMG_API int bmg_sampler_run(bmg_sampler*, int64_t) { return nyi(); }
-BMG_API int bmg_sampler_end(bmg_sampler*) { return nyi(); }
-BMG_API int bmg_sampler_stats(bmg_sampler*, double*) { return nyi(); }
-BMG_API bmg_store* bmg_sampler_store(bmg_sampler*) { return nullptr; }
-BMG_API bmg_chain* bmg_sampler_chain(bmg_sampler*) { return nullptr; }
-BMG_API int bmg_sampler_destroy(bmg_sampler*) { return 0; }
+
+namespace {
+struct SamplerHandle {
+  std::unique_ptr<Options> opt;
+  std::unique_ptr<Dataset> data;
+  Store* store = nullptr;
+  bool owns_store = false;
+  std::unique_ptr<Sampler> sampler;
+  int chain_index = 0;
+  bool flat_done = false;
+  ~SamplerHandle()
+  {
+    sampler.reset();
+    if (owns_store && store) {
+      cudaSetDevice(store->device);
+      delete store;
+    }
+  }
+};
+
+SamplerHandle* H(bmg_sampler* sp)
+{
+  BMG_REQUIRE(sp != nullptr, "null sampler handle");
+  return reinterpret_cast<SamplerHandle*>(sp);
+}
+
+SamplerHandle* make(const char* ini, int chain_index, int device, Store* existing)
+{
+  BMG_REQUIRE(ini != nullptr, "bmg_sampler_create: null ini path");
+  std::unique_ptr<SamplerHandle> h(new SamplerHandle());
+  h->chain_index = chain_index;
+  h->opt.reset(new Options(ini, /*quiet=*/chain_index != 0));
+  const Options& o = *h->opt;
+  BMG_REQUIRE(chain_index >= 0 && (size_t)chain_index < o.n_threads, "bmg_sampler_create: chain_index must be < thread.n_threads");
+  h->data.reset(new Dataset(o.n, o.m_g, o.m_e, o.file_fam, o.file_g, o.file_e, o.file_y, existing == nullptr));
+  if (existing) {
+    BMG_REQUIRE(existing->n == (int64_t)o.n && existing->m_g == (int64_t)o.m_g, "bmg_sampler_create_on_store: store dimensions differ from the INI file");
+    h->store = existing;
+  } else {
+    h->store = store_create(h->data->bed.data(), false, (int64_t)o.n, (int64_t)o.m_g, 0, (int64_t)o.m_g,
+                            o.recode_g_to_minor_allele_count, device >= 0 ? device : o.device);
+    h->owns_store = true;
+    std::vector<uint8_t>().swap(h->data->bed);   // the packed genotypes now live on the device only
+    store_set_phenotype(h->store, h->data->y.data(), h->data->e.data(), (int)h->data->m_e);
+  }
+  const double* sm = h->store->summaries;
+  const double mean_x = sm[0] / sm[1], var_x = sm[2] / sm[3];
+  h->sampler.reset(new Sampler(o, chain_index, h->store, h->data->y, h->data->e, sm[4], sm[5], var_x, mean_x));
+  return h.release();
+}
+}  // namespace
+
+#define BMG_TRY try {
+#define BMG_CATCH                      \
+  return 0;                            \
+  }                                    \
+  catch (const std::exception& e)      \
+  {                                    \
+    set_last_error(e.what());          \
+    return 1;                          \
+  }                                    \
+  catch (...)                          \
+  {                                    \
+    set_last_error("unknown error");   \
+    return 1;                          \
+  }
+
+BMG_API int bmg_sampler_create(const char* ini_path, int chain_index, int device, bmg_sampler** out)
+{
+  BMG_TRY
+  BMG_REQUIRE(out != nullptr, "bmg_sampler_create: null argument");
+  *out = reinterpret_cast<bmg_sampler*>(make(ini_path, chain_index, device, nullptr));
+  BMG_CATCH
+}
+BMG_API int bmg_sampler_create_on_store(const char* ini_path, int chain_index, bmg_store* s, bmg_sampler** out)
+{
+  BMG_TRY
+  BMG_REQUIRE(out != nullptr && s != nullptr, "bmg_sampler_create_on_store: null argument");
+  *out = reinterpret_cast<bmg_sampler*>(make(ini_path, chain_index, -1, reinterpret_cast<Store*>(s)));
+  BMG_CATCH
+}
+BMG_API int bmg_sampler_set_option(bmg_sampler* sp, const char* key, const char* value)
+{
+  BMG_TRY
+  BMG_REQUIRE(key && value, "bmg_sampler_set_option: null argument");
+  H(sp)->sampler->set_option(key, value);
+  BMG_CATCH
+}
+BMG_API int bmg_sampler_begin(bmg_sampler* sp)
+{
+  BMG_TRY
+  SamplerHandle* h = H(sp);
+  if (h->chain_index == 0) h->sampler->print_prior();   // main.cpp:77
+  if (!h->flat_done) { h->sampler->initialize_p_proposal_flat(); h->flat_done = true; }   // main.cpp:114
+  h->sampler->begin();
+  BMG_CATCH
+}
+BMG_API int bmg_sampler_run(bmg_sampler* sp, int64_t n_iter)
+{
+  BMG_TRY
+  BMG_REQUIRE(n_iter >= 0, "bmg_sampler_run: negative iteration count");
+  H(sp)->sampler->run(n_iter);
+  BMG_CATCH
+}
+BMG_API int bmg_sampler_end(bmg_sampler* sp)
+{
+  BMG_TRY
+  H(sp)->sampler->end();
+  BMG_CATCH
+}
+BMG_API int bmg_sampler_stats(bmg_sampler* sp, double* out8)
+{
+  BMG_TRY
+  BMG_REQUIRE(out8, "bmg_sampler_stats: null argument");
+  H(sp)->sampler->stats(out8);
+  BMG_CATCH
+}
+BMG_API bmg_store* bmg_sampler_store(bmg_sampler* sp) { return sp ? reinterpret_cast<bmg_store*>(reinterpret_cast<SamplerHandle*>(sp)->store) : nullptr; }
+BMG_API bmg_chain* bmg_sampler_chain(bmg_sampler* sp)
+{
+  return sp ? reinterpret_cast<bmg_chain*>(reinterpret_cast<SamplerHandle*>(sp)->sampler->chain()) : nullptr;
+}
+BMG_API int bmg_sampler_destroy(bmg_sampler* sp)
+{
+  BMG_TRY
+  delete reinterpret_cast<SamplerHandle*>(sp);
+  BMG_CATCH
+}

@@ -51,6 +51,7 @@ struct Chain {
   int64_t cdf_blocks = 0;
   DevBuf<double> cdf_add, cdf_rem;              // block sums over in-order positions (all items)
   DevBuf<double> cdf_eff_add, cdf_eff_rem;      // same, zeroed items excluded
+  DevBuf<double> q_add_io, q_rem_io;            // weights in in-order layout (what the host mirror copies)
   DevBuf<uint8_t> zero_add, zero_rem;           // per local SNP
   DevBuf<double> sample_out;                    // {snp, total}
   PinnedBuf<double> h_sample;

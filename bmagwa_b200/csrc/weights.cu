@@ -27,7 +27,8 @@ __device__ __forceinline__ double block_reduce_256(double v, double* sm)
 // block b: sums of q over in-order positions [256 b, 256 (b+1)); raw and zero-aware
 __global__ void __launch_bounds__(256) k_block_sums(const double* __restrict__ q, const uint8_t* __restrict__ zeroed,
                                                     const int32_t* __restrict__ inorder, int64_t m,
-                                                    double* __restrict__ raw, double* __restrict__ eff)
+                                                    double* __restrict__ raw, double* __restrict__ eff,
+                                                    double* __restrict__ q_inorder)
 {
   __shared__ double sm[8];
   const int64_t pos = (int64_t)blockIdx.x * 256 + threadIdx.x;
@@ -36,6 +37,7 @@ __global__ void __launch_bounds__(256) k_block_sums(const double* __restrict__ q
     const int32_t j = inorder[pos];
     w = q[j];
     we = zeroed[j] ? 0.0 : w;
+    q_inorder[pos] = w;
   }
   const double s = block_reduce_256(w, sm);
   const double se = block_reduce_256(we, sm);
@@ -129,11 +131,14 @@ void chain_partial_cdf(Chain* c)
 {
   Store* s = c->store;
   BMG_CUDA(cudaSetDevice(s->device));
-  if (c->cdf_eff_add.n == 0) { c->cdf_eff_add.alloc(c->cdf_blocks); c->cdf_eff_rem.alloc(c->cdf_blocks); }
+  if (c->cdf_eff_add.n == 0) {
+    c->cdf_eff_add.alloc(c->cdf_blocks); c->cdf_eff_rem.alloc(c->cdf_blocks);
+    c->q_add_io.alloc(s->m); c->q_rem_io.alloc(s->m);
+  }
   k_block_sums<<<(unsigned)c->cdf_blocks, 256, 0, c->stream>>>(c->q_add.p, c->zero_add.p, s->inorder.p, s->m, c->cdf_add.p,
-                                                              c->cdf_eff_add.p);
+                                                              c->cdf_eff_add.p, c->q_add_io.p);
   k_block_sums<<<(unsigned)c->cdf_blocks, 256, 0, c->stream>>>(c->q_rem.p, c->zero_rem.p, s->inorder.p, s->m, c->cdf_rem.p,
-                                                              c->cdf_eff_rem.p);
+                                                              c->cdf_eff_rem.p, c->q_rem_io.p);
   count_launch(2);
   BMG_CUDA(cudaGetLastError());
 }
@@ -151,10 +156,10 @@ void chain_set_zeroed(Chain* c, int which, int64_t snp, int flag)
   // refresh the zero-aware partial sums (all blocks: m/256 tiny CTAs; keeps the kernel count at two)
   if (which == 0)
     k_block_sums<<<(unsigned)c->cdf_blocks, 256, 0, c->stream>>>(c->q_add.p, c->zero_add.p, s->inorder.p, s->m, c->cdf_add.p,
-                                                                c->cdf_eff_add.p);
+                                                                c->cdf_eff_add.p, c->q_add_io.p);
   else
     k_block_sums<<<(unsigned)c->cdf_blocks, 256, 0, c->stream>>>(c->q_rem.p, c->zero_rem.p, s->inorder.p, s->m, c->cdf_rem.p,
-                                                                c->cdf_eff_rem.p);
+                                                                c->cdf_eff_rem.p, c->q_rem_io.p);
   count_launch();
   BMG_CUDA(cudaGetLastError());
 }

@@ -160,6 +160,8 @@ void Sampler::set_option(const std::string& key, const std::string& value)
     basename_ = value;
   } else if (key == "verbosity") {
     verbosity_ = (size_t)std::stoul(value);
+  } else if (key == "reference_quirks") {
+    reference_quirks_ = value != "0";
   } else if (key == "scan_variant") {
     chain_->scan_variant = std::stoi(value);
   } else {
@@ -384,6 +386,7 @@ void Sampler::run(int64_t do_n_iter)
       f.sigma2.write(reinterpret_cast<const char*>(&current_.sigma2), sizeof(double));
       if (save_beta_) f.beta.write(reinterpret_cast<const char*>(current_.beta.data()), current_.beta.size() * sizeof(double));
       current_.compute_pve(n_, pves_);
+      track_fitted_values();
       f.pve.write(reinterpret_cast<const char*>(pves_), 3 * sizeof(double));
       const double a = prior_->alpha();
       f.alpha.write(reinterpret_cast<const char*>(&a), sizeof(double));
@@ -402,6 +405,21 @@ void Sampler::run(int64_t do_n_iter)
   n_iter_ = end_iter;
 }
 
+// y_hat as Model::compute_pve leaves it (model.hpp:345-392), kept as coefficients (see sampler.hpp)
+void Sampler::track_fitted_values()
+{
+  const bool have_g = current_.size() > 0, have_e = m_e_ > 1;
+  if (have_g || !have_e || !reference_quirks_) {
+    fitted_.loci.assign(current_.loci.begin(), current_.loci.end());
+    fitted_.beta_g.assign(current_.beta.begin() + m_e_, current_.beta.end());
+    fitted_.beta_e.assign(current_.beta.begin(), current_.beta.begin() + m_e_);
+  } else {
+    // no SNP term: the reference adds E beta_e onto whatever y_hat held (zeros before the first call)
+    if (fitted_.beta_e.size() != m_e_) fitted_.beta_e.assign(m_e_, 0.0);
+    for (size_t j = 0; j < m_e_; ++j) fitted_.beta_e[j] += current_.beta[j];
+  }
+}
+
 // the rao block of the loop (sampler.cpp:731-811)
 void Sampler::rao_block()
 {
@@ -413,7 +431,7 @@ void Sampler::rao_block()
     const double t0 = wall_seconds();
     const int k = (int)current_.size();
     std::vector<int64_t> loci(current_.loci.begin(), current_.loci.end());
-    chain_residual(chain_, loci.data(), current_.beta.data(), current_.beta.data() + m_e_, k, nullptr);
+    chain_residual(chain_, fitted_.loci.data(), fitted_.beta_e.data(), fitted_.beta_g.data(), (int)fitted_.loci.size(), nullptr);
     bmg_scan_params prm;
     std::memset(&prm, 0, sizeof(prm));
     prm.sigma2 = current_.sigma2;

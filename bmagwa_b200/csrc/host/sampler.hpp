@@ -91,6 +91,12 @@ class Sampler {
   double t_start_ = 0.0;
   double pves_[3] = {0, 0, 0};
   uint64_t tau_counter_ = 0;
+  // what Model::compute_pve leaves in y_hat (model.hpp:345-392), tracked as coefficients: y_hat = X[loci] beta_g + E beta_e.
+  // Reference quirk kept for drop-in parity: with covariates and NO SNP term in the model compute_pve does not reset
+  // y_hat, it adds E beta_e onto the previous content; option reference_quirks=0 uses the fresh fitted values instead.
+  struct FittedState { std::vector<int64_t> loci; std::vector<double> beta_g, beta_e; } fitted_;
+  bool reference_quirks_ = true;
+  void track_fitted_values();
   // ---- output files
   struct Files;
   std::unique_ptr<Files> files_;

@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""bench.py -- MCMC iterations/sec of the BMAGWA SNP-inclusion sampler on B200 (BASELINE.json metric),
+with the genotype-scan roofline and the reference CPU sampler beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C2] ...
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+A STEP is one Rao-Blackwell period of the sampler: n_rao MCMC iterations (moves 0/1/2 with delayed
+rejection, tau2/alpha Gibbs every 10, thinning every 10) ending with ONE all-SNP genotype scan and
+its epilogue (reference: Sampler::sample loop, src/sampler.cpp:626-834).  value = iterations/sec
+summed over the chains of the job.  Sampler/prior settings are those of the reference's bundled
+testdata/testdata.ini; data are seeded synthetic genotypes (bmagwa_b200/synth.py).
+
+Workload at N=1: BASELINE.json configs[1] ("C2": n=5,000 x p=100,000, linear, single chain).
+N>1: one chain per rank (the reference's own multi-core mode, thread.n_threads = N, src/main.cpp:70-95),
+every rank holding the whole C2 store; no data-path collective, scaling "weak".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: n, m_g, covariates (excluding the constant), description
+    "C1s": dict(n=1000, m_g=10000, m_e=2, desc="synthetic stand-in for testdata/testdata.ini (n=1,000 x p=10,000)"),
+    "C2": dict(n=5000, m_g=100000, m_e=2, desc="synthetic linear GWAS n=5,000 x p=100,000 SNPs, single chain"),
+    "C2x": dict(n=5000, m_g=1000000, m_e=2, desc="synthetic linear GWAS n=5,000 x p=1,000,000 SNPs"),
+}
+GEN_SEED = 20121101
+CHAIN_SEEDS = [1234, 2345, 3456, 4567, 5678, 6789, 7890, 8901]
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def dataset_dir(w, n_threads):
+    base = os.environ.get("BMAGWA_BENCH_DIR", os.path.join(tempfile.gettempdir(), "bmagwa_bench"))
+    return os.path.join(base, "%s_n%d_m%d_t%d" % (w, WORKLOADS[w]["n"], WORKLOADS[w]["m_g"], n_threads))
+
+
+def prepare_dataset(w, n_rao, n_threads, out_dir, do_n_iter):
+    """Writes (or reuses) the synthetic data set and an INI file with testdata.ini's settings."""
+    from bmagwa_b200 import synth
+    spec = WORKLOADS[w]
+    d = dataset_dir(w, n_threads)
+    os.makedirs(out_dir, exist_ok=True)
+    marker = os.path.join(d, "done")
+    ini_kw = dict(do_n_iter=do_n_iter, n_rao=n_rao, n_rao_burnin=1000, thin=10, n_sample_tau2_and_missing=10,
+                  delay_rejection=10, max_move_size=20, use_individual_tau2=1, e_qg=20, var_qg=300, n_threads=n_threads,
+                  seeds=",".join(str(s) for s in CHAIN_SEEDS[:n_threads]), outbase=os.path.join(out_dir, "chain"),
+                  verbosity=0)
+    if not os.path.exists(marker):
+        t0 = time.time()
+        synth.write_dataset(d, "syn", n=spec["n"], m_g=spec["m_g"], m_e=spec["m_e"], seed=GEN_SEED, **ini_kw)
+        open(marker, "w").write("ok")
+        log("[bench] generated %s in %.1f s" % (d, time.time() - t0))
+    base = os.path.join(d, "syn")
+    cfg = dict(base=base, recode=1, n=spec["n"], m_g=spec["m_g"], m_e=spec["m_e"], save_beta=0)
+    cfg.update(ini_kw)
+    ini = os.path.join(out_dir, "bench.ini")
+    with open(ini, "w") as fh:
+        fh.write(synth.INI_TEMPLATE.format(**cfg))
+    return ini, spec
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.idx = device_index
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return None
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+            out, _ = self.p.communicate()
+        sm, smax, reasons = [], [], set()
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def scan_traffic(workload):
+    """dram bytes per scan launch from the committed ncu --set full capture (profiles/), or None."""
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "scan_traffic.json")))
+        return prof.get(workload)
+    except Exception:
+        return None
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the unmodified reference sampler on the host cores (oracle/_ref)
+# ------------------------------------------------------------------------------------------------
+def run_reference_chains(ini, n_chains, n_rao, warmup, steps):
+    """Returns (seconds of the timed K steps, per-chain stats).  One pthread-like host thread per chain over one
+    shared Data, as main.cpp does."""
+    from oracle import ref
+    parent = ref.Ref(ini, 0)
+    chains = [parent] + [ref.Ref(ini, t, parent=parent) for t in range(1, n_chains)]
+
+    def phase(fn_name, iters):
+        res = [None] * n_chains
+
+        def work(i):
+            chains[i].set_do_n_iter(iters)
+            res[i] = getattr(chains[i], fn_name)()
+        th = [threading.Thread(target=work, args=(i,)) for i in range(n_chains)]
+        t0 = time.perf_counter()
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        return time.perf_counter() - t0, res
+
+    if warmup > 0:
+        phase("run_chain", warmup * n_rao)
+        secs, per = phase("continue_chain", steps * n_rao)
+    else:
+        secs, per = phase("run_chain", steps * n_rao)
+    for c in reversed(chains):
+        c.close()
+    return secs, per
+
+
+def reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    from oracle import ref
+    spec = WORKLOADS[args.workload]
+    n_chains = max(1, args.gpus)
+    out = {"metric": "mcmc_iterations_per_sec", "unit": "iterations/s", "impl": "reference", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f64", "data": "synthetic"}
+    if not ref.available():
+        out["unavailable"] = "oracle/_ref (the reference compiled against the shims) is not present on this box"
+        print(json.dumps(out))
+        return
+    with tempfile.TemporaryDirectory() as tmp:
+        ini, _ = prepare_dataset(args.workload, args.n_rao, n_chains, tmp, args.n_rao)
+        t0 = time.time()
+        secs, _ = run_reference_chains(ini, n_chains, args.n_rao, args.warmup, args.steps)
+        log("[bench] reference arm total %.1f s" % (time.time() - t0))
+    iters = n_chains * args.steps * args.n_rao
+    value = iters / secs
+    cores = os.cpu_count()
+    out.update({
+        "value": value, "ms_per_step": 1e3 * secs / args.steps,
+        "config": {"workload": "%s: %s; %d chain(s), one host thread each (the reference's only parallelism, thread.n_threads)"
+                   % (args.workload, spec["desc"], n_chains), "n": spec["n"], "m_g": spec["m_g"], "n_rao": args.n_rao,
+                   "step": "%d MCMC iterations incl. one all-SNP scan" % args.n_rao},
+        "cpu_baseline": {"value": value, "unit": "iterations/s", "cores": n_chains, "kind": "reference",
+                         "sample": "%d timed iterations per chain after %d warm-up, unmodified reference sources built against "
+                                   "oracle/shim (OpenBLAS 1 thread per chain), host has %s cores"
+                                   % (args.steps * args.n_rao, args.warmup * args.n_rao, cores)},
+        "e2e": {"value": value, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    })
+    print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def ours_arm(args, rank, local_rank, world):
+    import torch
+    from bmagwa_b200 import _lib, api
+    import ctypes as C
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = local_rank
+    torch.cuda.set_device(dev)
+    L = _lib.lib()
+    spec = WORKLOADS[args.workload]
+    n, m = spec["n"], spec["m_g"]
+    tmp = tempfile.mkdtemp(prefix="bmagwa_bench_r%d_" % rank)
+    if rank == 0:
+        prepare_dataset(args.workload, args.n_rao, world, tmp, args.n_rao)
+    if dist is not None:
+        dist.barrier()
+    ini, _ = prepare_dataset(args.workload, args.n_rao, world, tmp, args.n_rao)
+
+    def transfers():
+        a, b = C.c_uint64(), C.c_uint64()
+        L.bmg_transfer_bytes(C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    # ---- device-resident measurement: store already in HBM when the timed region starts
+    s = api.Sampler(ini, rank, dev, tau_rng=args.tau_rng)
+    s.set_option("basename", os.path.join(tmp, "chain%d" % rank))
+    s.begin()
+    chain = L.bmg_sampler_chain(s.h)
+    stream = torch.cuda.ExternalStream(L.bmg_chain_stream(chain), device=torch.device("cuda", dev))
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    L.bmg_chain_scan_kernel_time(chain, 1, None, None, 1)
+
+    def step():
+        with torch.cuda.stream(stream):
+            flush.zero_()            # evict the 125 MB store from the 126 MB L2 before every step
+        s.run(args.n_rao)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    L.bmg_chain_scan_kernel_time(chain, 1, None, None, 1)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = ClockSampler(dev)
+    clocks.start()
+    launches0 = L.bmg_launch_count()
+    h2d0, d2h0 = transfers()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    e1.synchronize()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    ev_ms = e0.elapsed_time(e1)
+    clk = clocks.stop()
+    launches = L.bmg_launch_count() - launches0
+    h2d1, d2h1 = transfers()
+    ms_tot, n_l = C.c_double(), C.c_int64()
+    L.bmg_chain_scan_kernel_time(chain, 1, C.byref(ms_tot), C.byref(n_l), 0)
+    st = s.stats()
+    s.end()
+    s.close()
+    elapsed_ms = max(ev_ms, 0.0)
+    if dist is not None:
+        t = torch.tensor([elapsed_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+        dist.barrier()
+
+    # ---- end to end through the public API: INI + data files on the host -> store upload + re-coding ->
+    #      begin -> K steps -> end (Rao-Blackwell means back on the host)
+    torch.cuda.synchronize()
+    h2d_a, d2h_a = transfers()
+    t0 = time.perf_counter()
+    s2 = api.Sampler(ini, rank, dev, tau_rng=args.tau_rng)
+    s2.set_option("basename", os.path.join(tmp, "e2e%d" % rank))
+    s2.begin()
+    for _ in range(args.steps):
+        s2.run(args.n_rao)
+    s2.end()
+    torch.cuda.synchronize()
+    e2e_secs = time.perf_counter() - t0
+    h2d_b, d2h_b = transfers()
+    s2.close()
+    if dist is not None:
+        t = torch.tensor([e2e_secs], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_secs = float(t.item())
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    iters = world * args.steps * args.n_rao
+    value = iters / (elapsed_ms * 1e-3)
+    peak, peak_src = measured_peak()
+    B = (n + 3) // 4
+    bytes_scan = m * B + 8 * m + 8 * n          # packed genotypes once + dot out + residual in
+    scan_ms = ms_tot.value / max(1, n_l.value)
+    achieved = bytes_scan / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
+    out = {
+        "metric": "mcmc_iterations_per_sec", "value": value, "unit": "iterations/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "%s: %s%s" % (args.workload, spec["desc"], "" if world == 1 else "; %d independent chains, one per GPU" % world),
+                   "n": n, "m_g": m, "n_rao": args.n_rao, "step": "%d MCMC iterations incl. one all-SNP scan" % args.n_rao,
+                   "sampler": "testdata/testdata.ini settings (PMV, thin 10, DR 10, individual tau2)",
+                   "tau_rng": args.tau_rng, "l2": "256 MiB write on the chain's stream before every step, inside the timed region",
+                   "timing": "CUDA events on the chain's stream, max over ranks; wall %.3f ms/step" % (1e3 * wall / args.steps)},
+        "e2e": {"value": world * args.steps * args.n_rao / e2e_secs, "unit": "iterations/s",
+                "h2d_bytes_per_step": (h2d_b - h2d_a) / args.steps, "d2h_bytes_per_step": (d2h_b - d2h_a) / args.steps,
+                "what": "bmg_sampler_create (INI + .fam/.y/.e/.bed on the host -> H2D + device re-coding) + begin + %d steps + end, wall clock"
+                        % args.steps},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "k_scan_dots (genotype scan reduction, variant %s)" % os.environ.get("BMG_SCAN_VARIANT", "default"),
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": scan_traffic(args.workload),
+                     "bytes_per_launch": bytes_scan, "avg_launch_ms": scan_ms, "launches_timed": int(n_l.value), "peak_source": peak_src},
+        "clocks": clk,
+        "breakdown": {"move_seconds": st["move_seconds"], "scan_seconds": st["scan_seconds"], "scans": st["scans"],
+                      "h2d_bytes_per_step_resident": (h2d1 - h2d0) / args.steps, "d2h_bytes_per_step_resident": (d2h1 - d2h0) / args.steps},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(args, spec)
+    print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(args, spec):
+    """The reference sampler (oracle/_ref) on this box's host cores, bounded sample of the same workload."""
+    from oracle import ref
+    if not ref.available():
+        return {"value": None, "unit": "iterations/s", "cores": 0, "kind": "port",
+                "sample": "oracle/_ref not present on this box; no sampler-level CPU number (the C oracle restates kernels only)"}
+    with tempfile.TemporaryDirectory() as tmp:
+        ini, _ = prepare_dataset(args.workload, args.n_rao, 1, tmp, args.n_rao)
+        t0 = time.time()
+        secs, _ = run_reference_chains(ini, 1, args.n_rao, 1, 2)
+        log("[bench] cpu_baseline total %.1f s (timed %.2f s)" % (time.time() - t0, secs))
+    return {"value": 2 * args.n_rao / secs, "unit": "iterations/s", "cores": 1, "kind": "reference",
+            "sample": "%d timed iterations (2 steps) after one warm-up step of one chain of the unmodified reference sampler "
+                      "(oracle/_ref, OpenBLAS 1 thread); the reference is single-threaded per chain; host has %s cores"
+                      % (2 * args.n_rao, os.cpu_count())}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--n-rao", type=int, default=500, dest="n_rao")
+    ap.add_argument("--tau-rng", default="device", choices=["device", "host"], dest="tau_rng")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        log("[bench] note: fewer than 3 warm-up steps requested")
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+    else:
+        if world != args.gpus and world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+        ours_arm(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -26,6 +26,7 @@ SIGNATURES = {
     "bmg_last_error": (C.c_char_p, []),
     "bmg_device_count": (C.c_int, []),
     "bmg_launch_count": (u64, []),
+    "bmg_transfer_bytes": (None, [C.POINTER(u64), C.POINTER(u64)]),
     "bmg_store_create": (C.c_int, [vp, C.c_int, i64, i64, i64, i64, C.c_int, C.c_int, C.POINTER(vp)]),
     "bmg_store_destroy": (C.c_int, [vp]),
     "bmg_store_set_phenotype": (C.c_int, [vp, f64p, f64p, C.c_int]),
@@ -48,6 +49,7 @@ SIGNATURES = {
     "bmg_chain_scan": (C.c_int, [vp, i64p, f64p, f64p, C.c_int, C.POINTER(ScanParams), f64p]),
     "bmg_chain_scan_dots": (C.c_int, [vp, f64p]),
     "bmg_chain_set_scan_variant": (C.c_int, [vp, C.c_int]),
+    "bmg_chain_scan_kernel_time": (C.c_int, [vp, C.c_int, f64p, i64p, C.c_int]),
     "bmg_chain_adapt": (C.c_int, [vp, C.c_int, i64, C.c_int, i64, f64, f64]),
     "bmg_chain_init_proposal_flat": (C.c_int, [vp, f64, f64, f64]),
     "bmg_chain_get_array": (C.c_int, [vp, C.c_int, f64p]),

@@ -4,7 +4,7 @@
 #include "store.cuh"
 
 namespace bmg {
-std::atomic<uint64_t> g_launches{0};
+std::atomic<uint64_t> g_launches{0}, g_h2d_bytes{0}, g_d2h_bytes{0};
 static thread_local std::string t_last_error;
 void set_last_error(const std::string& m) { t_last_error = m; }
 }  // namespace bmg
@@ -57,6 +57,11 @@ BMG_API int bmg_device_count(void)
   return n;
 }
 BMG_API uint64_t bmg_launch_count(void) { return g_launches.load(); }
+BMG_API void bmg_transfer_bytes(uint64_t* h2d, uint64_t* d2h)
+{
+  if (h2d) *h2d = g_h2d_bytes.load();
+  if (d2h) *d2h = g_d2h_bytes.load();
+}
 
 // ---- store --------------------------------------------------------------------------------
 BMG_API int bmg_store_create(const uint8_t* bed_payload, int payload_on_device, int64_t n, int64_t m_g, int64_t snp_lo,
@@ -109,10 +114,10 @@ BMG_API int bmg_store_counts(const bmg_store* s, int32_t* n1, int32_t* n2, int32
   BMG_TRY
   const Store* st = S(s);
   BMG_CUDA(cudaSetDevice(st->device));
-  if (n1) BMG_CUDA(cudaMemcpy(n1, st->n1.p, st->m * sizeof(int32_t), cudaMemcpyDeviceToHost));
-  if (n2) BMG_CUDA(cudaMemcpy(n2, st->n2.p, st->m * sizeof(int32_t), cudaMemcpyDeviceToHost));
-  if (n_miss) BMG_CUDA(cudaMemcpy(n_miss, st->nmiss.p, st->m * sizeof(int32_t), cudaMemcpyDeviceToHost));
-  if (swapped) BMG_CUDA(cudaMemcpy(swapped, st->swapped.p, st->m, cudaMemcpyDeviceToHost));
+  if (n1) bmg::copy_d2h_sync(n1, st->n1.p, st->m * sizeof(int32_t));
+  if (n2) bmg::copy_d2h_sync(n2, st->n2.p, st->m * sizeof(int32_t));
+  if (n_miss) bmg::copy_d2h_sync(n_miss, st->nmiss.p, st->m * sizeof(int32_t));
+  if (swapped) bmg::copy_d2h_sync(swapped, st->swapped.p, st->m);
   BMG_CATCH
 }
 
@@ -130,7 +135,7 @@ BMG_API int bmg_store_moments(const bmg_store* s, double* xx)
   const Store* st = S(s);
   BMG_REQUIRE(xx, "bmg_store_moments: null argument");
   BMG_CUDA(cudaSetDevice(st->device));
-  BMG_CUDA(cudaMemcpy(xx, st->mom.p, 2 * st->m * sizeof(double), cudaMemcpyDeviceToHost));
+  bmg::copy_d2h_sync(xx, st->mom.p, 2 * st->m * sizeof(double));
   BMG_CATCH
 }
 
@@ -142,15 +147,15 @@ BMG_API int bmg_store_missing(const bmg_store* s, int64_t* offsets, int64_t* idx
   if (offsets) std::memcpy(offsets, st->h_miss_off.data(), (st->m + 1) * sizeof(int64_t));
   if (idx && st->n_missing > 0) {
     std::vector<int32_t> tmp(st->n_missing);
-    BMG_CUDA(cudaMemcpy(tmp.data(), st->miss_idx.p, st->n_missing * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    bmg::copy_d2h_sync(tmp.data(), st->miss_idx.p, st->n_missing * sizeof(int32_t));
     for (int64_t q = 0; q < st->n_missing; ++q) idx[q] = tmp[q];
   }
   if (prior3) {
     // Data::handle_missing_g (data.cpp:357-372): cumulative counts of 0/1/2 among the observed cells
     std::vector<int32_t> a(st->m), b(st->m), c(st->m);
-    BMG_CUDA(cudaMemcpy(a.data(), st->n1.p, st->m * sizeof(int32_t), cudaMemcpyDeviceToHost));
-    BMG_CUDA(cudaMemcpy(b.data(), st->n2.p, st->m * sizeof(int32_t), cudaMemcpyDeviceToHost));
-    BMG_CUDA(cudaMemcpy(c.data(), st->nmiss.p, st->m * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    bmg::copy_d2h_sync(a.data(), st->n1.p, st->m * sizeof(int32_t));
+    bmg::copy_d2h_sync(b.data(), st->n2.p, st->m * sizeof(int32_t));
+    bmg::copy_d2h_sync(c.data(), st->nmiss.p, st->m * sizeof(int32_t));
     for (int64_t j = 0; j < st->m; ++j) {
       const double n0 = (double)(st->n - c[j] - a[j] - b[j]);
       prior3[3 * j] = n0;
@@ -261,7 +266,7 @@ BMG_API int bmg_chain_get_residual(bmg_chain* c, double* r)
   Chain* ch = Cn(c);
   BMG_REQUIRE(r && ch->residual_valid, "bmg_chain_get_residual: no residual available");
   BMG_CUDA(cudaSetDevice(ch->store->device));
-  BMG_CUDA(cudaMemcpyAsync(r, ch->r.p, ch->store->n * sizeof(double), cudaMemcpyDeviceToHost, ch->stream));
+  bmg::copy_d2h(r, ch->r.p, ch->store->n * sizeof(double), ch->stream);
   BMG_CUDA(cudaStreamSynchronize(ch->stream));
   BMG_CATCH
 }
@@ -282,7 +287,7 @@ BMG_API int bmg_chain_scan_dots(bmg_chain* c, double* dot_host)
     // sum the per-chunk partials on the host side of the copy (tests / roofline probe only)
     const int64_t m = ch->store->m;
     std::vector<double> tmp((size_t)ch->scan_chunks * m);
-    BMG_CUDA(cudaMemcpyAsync(tmp.data(), ch->dot_partial.p, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, ch->stream));
+    bmg::copy_d2h(tmp.data(), ch->dot_partial.p, tmp.size() * sizeof(double), ch->stream);
     BMG_CUDA(cudaStreamSynchronize(ch->stream));
     for (int64_t j = 0; j < m; ++j) {
       double s = 0.0;
@@ -297,6 +302,29 @@ BMG_API int bmg_chain_set_scan_variant(bmg_chain* c, int variant)
   BMG_TRY
   BMG_REQUIRE(variant == 0 || variant == 1, "bmg_chain_set_scan_variant: variant must be 0 or 1");
   Cn(c)->scan_variant = variant;
+  BMG_CATCH
+}
+BMG_API int bmg_chain_scan_kernel_time(bmg_chain* c, int enable, double* ms_total, int64_t* launches, int reset)
+{
+  BMG_TRY
+  Chain* ch = Cn(c);
+  BMG_CUDA(cudaSetDevice(ch->store->device));
+  ch->time_scan = enable != 0;
+  if (ms_total || launches) {
+    BMG_CUDA(cudaStreamSynchronize(ch->stream));
+    double tot = ch->scan_ms_done;
+    for (size_t i = 0; i < ch->scan_ev_used; ++i) {
+      float ms = 0.f;
+      BMG_CUDA(cudaEventElapsedTime(&ms, ch->scan_ev[2 * i], ch->scan_ev[2 * i + 1]));
+      tot += ms;
+    }
+    ch->scan_ms_done = tot;
+    ch->scan_launches_done += (int64_t)ch->scan_ev_used;
+    ch->scan_ev_used = 0;
+    if (ms_total) *ms_total = ch->scan_ms_done;
+    if (launches) *launches = ch->scan_launches_done;
+  }
+  if (reset) { ch->scan_ms_done = 0.0; ch->scan_launches_done = 0; ch->scan_ev_used = 0; }
   BMG_CATCH
 }
 BMG_API int bmg_chain_adapt(bmg_chain* c, int update_rao, int64_t n_rao_mean, int update_proposal, int64_t n_prop_mean,
@@ -319,7 +347,7 @@ BMG_API int bmg_chain_get_array(bmg_chain* c, int which, double* out)
   BMG_REQUIRE(out && which >= 0 && which <= 4, "bmg_chain_get_array: bad arguments");
   const double* src[5] = {ch->p_r.p, ch->p_rao.p, ch->p_proposal.p, ch->q_add.p, ch->q_rem.p};
   BMG_CUDA(cudaSetDevice(ch->store->device));
-  BMG_CUDA(cudaMemcpyAsync(out, src[which], ch->store->m * sizeof(double), cudaMemcpyDeviceToHost, ch->stream));
+  bmg::copy_d2h(out, src[which], ch->store->m * sizeof(double), ch->stream);
   BMG_CUDA(cudaStreamSynchronize(ch->stream));
   BMG_CATCH
 }
@@ -330,8 +358,8 @@ BMG_API int bmg_chain_partial_cdf(bmg_chain* c, int64_t* n_blocks, int64_t* bloc
   BMG_CUDA(cudaSetDevice(ch->store->device));
   if (n_blocks) *n_blocks = ch->cdf_blocks;
   if (block_size) *block_size = ch->cdf_block;
-  if (add_sums) BMG_CUDA(cudaMemcpyAsync(add_sums, ch->cdf_add.p, ch->cdf_blocks * sizeof(double), cudaMemcpyDeviceToHost, ch->stream));
-  if (rem_sums) BMG_CUDA(cudaMemcpyAsync(rem_sums, ch->cdf_rem.p, ch->cdf_blocks * sizeof(double), cudaMemcpyDeviceToHost, ch->stream));
+  if (add_sums) bmg::copy_d2h(add_sums, ch->cdf_add.p, ch->cdf_blocks * sizeof(double), ch->stream);
+  if (rem_sums) bmg::copy_d2h(rem_sums, ch->cdf_rem.p, ch->cdf_blocks * sizeof(double), ch->stream);
   BMG_CUDA(cudaStreamSynchronize(ch->stream));
   BMG_CATCH
 }
@@ -375,7 +403,7 @@ BMG_API int bmg_chain_get_phenotype(bmg_chain* c, double* y_out)
   Chain* ch = Cn(c);
   BMG_REQUIRE(y_out, "bmg_chain_get_phenotype: null argument");
   BMG_CUDA(cudaSetDevice(ch->store->device));
-  BMG_CUDA(cudaMemcpyAsync(y_out, ch->y.p, ch->store->n * sizeof(double), cudaMemcpyDeviceToHost, ch->stream));
+  bmg::copy_d2h(y_out, ch->y.p, ch->store->n * sizeof(double), ch->stream);
   BMG_CUDA(cudaStreamSynchronize(ch->stream));
   BMG_CATCH
 }

@@ -181,7 +181,7 @@ void chain_column_stats(Chain* c, const int64_t* cand, int m_c, const int64_t* l
     hp[m_c + k + i] = j;
     if (j >= 0 && s->h_miss_off[j + 1] > s->h_miss_off[j]) any_missing = true;
   }
-  BMG_CUDA(cudaMemcpyAsync(c->cs_idx.p, hp, n_ptr * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  bmg::copy_h2d(c->cs_idx.p, hp, n_ptr * sizeof(int64_t), st);
   ColStatArgs a;
   a.cand_cols = reinterpret_cast<const uint32_t* const*>(c->cs_idx.p);
   a.model_cols = reinterpret_cast<const uint32_t* const*>(c->cs_idx.p + m_c);
@@ -205,7 +205,7 @@ void chain_column_stats(Chain* c, const int64_t* cand, int m_c, const int64_t* l
     count_launch();
   }
   BMG_CUDA(cudaGetLastError());
-  BMG_CUDA(cudaMemcpyAsync(c->h_cs.p, fin, (size_t)m_c * n_tasks * sizeof(double), cudaMemcpyDeviceToHost, st));
+  bmg::copy_d2h(c->h_cs.p, fin, (size_t)m_c * n_tasks * sizeof(double), st);
   BMG_CUDA(cudaStreamSynchronize(st));
   for (int ci = 0; ci < m_c; ++ci) {
     const double* row = c->h_cs.p + (size_t)ci * n_tasks;
@@ -266,14 +266,14 @@ void chain_probit_update(Chain* c, const uint8_t* is_case, const double* u01, ui
   cudaStream_t st = c->stream;
   if (is_case) {
     if (c->is_case.n == 0) c->is_case.alloc(s->n);
-    BMG_CUDA(cudaMemcpyAsync(c->is_case.p, is_case, s->n, cudaMemcpyHostToDevice, st));
+    bmg::copy_h2d(c->is_case.p, is_case, s->n, st);
     c->have_case = true;
   }
   BMG_REQUIRE(c->have_case, "bmg_chain_probit_update: case/control labels were never set");
   DevBuf<double> u_dev;
   if (u01) {
     u_dev.alloc(s->n);
-    BMG_CUDA(cudaMemcpyAsync(u_dev.p, u01, s->n * sizeof(double), cudaMemcpyHostToDevice, st));
+    bmg::copy_h2d(u_dev.p, u01, s->n * sizeof(double), st);
   }
   const int blocks = (int)std::min<int64_t>(1024, (s->n + 255) / 256);
   k_probit<<<blocks, 256, 0, st>>>(c->yhat_e.p, c->yhat_g.p, c->is_case.p, u01 ? u_dev.p : nullptr, seed, counter, s->n, c->y.p,
@@ -281,7 +281,7 @@ void chain_probit_update(Chain* c, const uint8_t* is_case, const double* u01, ui
   k_reduce_final2<<<1, 32, 0, st>>>(c->red_partial.p, blocks, 2, c->red_out.p);
   count_launch(2);
   BMG_CUDA(cudaGetLastError());
-  BMG_CUDA(cudaMemcpyAsync(c->h_red.p, c->red_out.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  bmg::copy_d2h(c->h_red.p, c->red_out.p, 2 * sizeof(double), st);
   BMG_CUDA(cudaStreamSynchronize(st));
   c->residual_valid = false;  // the phenotype changed: the residual must be rebuilt
   if (stats2) { stats2[0] = c->h_red.p[0]; stats2[1] = c->h_red.p[1]; }

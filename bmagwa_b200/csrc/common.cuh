@@ -32,8 +32,30 @@ void set_last_error(const std::string& m);
     if (!(cond)) throw ::bmg::Error(msg);      \
   } while (0)
 
-extern std::atomic<uint64_t> g_launches;
+extern std::atomic<uint64_t> g_launches, g_h2d_bytes, g_d2h_bytes;
 inline void count_launch(int n = 1) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+// every host<->device copy of the library goes through these, so traffic can be reported (bench.py e2e)
+inline void copy_h2d(void* dst, const void* src, size_t bytes, cudaStream_t st)
+{
+  g_h2d_bytes.fetch_add(bytes, std::memory_order_relaxed);
+  BMG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+}
+inline void copy_d2h(void* dst, const void* src, size_t bytes, cudaStream_t st)
+{
+  g_d2h_bytes.fetch_add(bytes, std::memory_order_relaxed);
+  BMG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
+}
+inline void copy_h2d_sync(void* dst, const void* src, size_t bytes)
+{
+  g_h2d_bytes.fetch_add(bytes, std::memory_order_relaxed);
+  BMG_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+}
+inline void copy_d2h_sync(void* dst, const void* src, size_t bytes)
+{
+  g_d2h_bytes.fetch_add(bytes, std::memory_order_relaxed);
+  BMG_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+}
 
 template <class T>
 struct DevBuf {

@@ -272,11 +272,10 @@ void Sampler::refresh_weights_from_device(bool first)
 {
   Chain* c = chain_;
   BMG_CUDA(cudaSetDevice(store_->device));
-  BMG_CUDA(cudaMemcpyAsync(h_w_.p, c->q_add_io.p, m_g_ * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  BMG_CUDA(cudaMemcpyAsync(h_w_.p + m_g_, c->q_rem_io.p, m_g_ * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  BMG_CUDA(cudaMemcpyAsync(h_cdf_.data(), c->cdf_add.p, c->cdf_blocks * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  BMG_CUDA(cudaMemcpyAsync(h_cdf_.data() + c->cdf_blocks, c->cdf_rem.p, c->cdf_blocks * sizeof(double), cudaMemcpyDeviceToHost,
-                           c->stream));
+  bmg::copy_d2h(h_w_.p, c->q_add_io.p, m_g_ * sizeof(double), c->stream);
+  bmg::copy_d2h(h_w_.p + m_g_, c->q_rem_io.p, m_g_ * sizeof(double), c->stream);
+  bmg::copy_d2h(h_cdf_.data(), c->cdf_add.p, c->cdf_blocks * sizeof(double), c->stream);
+  bmg::copy_d2h(h_cdf_.data() + c->cdf_blocks, c->cdf_rem.p, c->cdf_blocks * sizeof(double), c->stream);
   BMG_CUDA(cudaStreamSynchronize(c->stream));
   if (first) {
     dd_add_.update(h_w_.p, h_cdf_.data(), true, std::vector<uint32_t>());
@@ -502,7 +501,7 @@ void Sampler::end()
   // _rao.dat (sampler.cpp:847-849): the running mean kept on the device
   p_rao_.assign(m_g_, 0.0);
   BMG_CUDA(cudaSetDevice(store_->device));
-  BMG_CUDA(cudaMemcpyAsync(h_w_.p, chain_->p_rao.p, m_g_ * sizeof(double), cudaMemcpyDeviceToHost, chain_->stream));
+  bmg::copy_d2h(h_w_.p, chain_->p_rao.p, m_g_ * sizeof(double), chain_->stream);
   BMG_CUDA(cudaStreamSynchronize(chain_->stream));
   std::copy(h_w_.p, h_w_.p + m_g_, p_rao_.begin());
   {

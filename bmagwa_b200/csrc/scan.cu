@@ -601,6 +601,7 @@ void chain_destroy(Chain* c)
   if (!c) return;
   cudaSetDevice(c->store->device);
   if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+  for (cudaEvent_t e : c->scan_ev) cudaEventDestroy(e);
   delete c;
 }
 
@@ -613,7 +614,7 @@ void chain_set_missing(Chain* c, int64_t snp, const int8_t* vals, int64_t count)
   if (cnt == 0) return;
   for (int64_t q = 0; q < cnt; ++q) BMG_REQUIRE(vals[q] >= 0 && vals[q] <= 2, "bmg_chain_set_missing: values must be 0, 1 or 2");
   BMG_CUDA(cudaSetDevice(s->device));
-  BMG_CUDA(cudaMemcpyAsync(c->miss_val.p + lo, vals, (size_t)cnt, cudaMemcpyHostToDevice, c->stream));
+  bmg::copy_h2d(c->miss_val.p + lo, vals, (size_t)cnt, c->stream);
   BMG_CUDA(cudaStreamSynchronize(c->stream));
 }
 
@@ -629,9 +630,9 @@ static void upload_model(Chain* c, const int64_t* loci, const double* beta_g, co
     c->h_stage.p[l] = beta_g ? beta_g[l] : 0.0;
     c->h_stage.p[2048 + l] = tau_g ? tau_g[l] : 0.0;
   }
-  BMG_CUDA(cudaMemcpyAsync(c->loci_dev.p, c->h_stage_i.p, k * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
-  BMG_CUDA(cudaMemcpyAsync(c->beta_dev.p, c->h_stage.p, k * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  BMG_CUDA(cudaMemcpyAsync(c->taug_dev.p, c->h_stage.p + 2048, k * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  bmg::copy_h2d(c->loci_dev.p, c->h_stage_i.p, k * sizeof(int64_t), c->stream);
+  bmg::copy_h2d(c->beta_dev.p, c->h_stage.p, k * sizeof(double), c->stream);
+  bmg::copy_h2d(c->taug_dev.p, c->h_stage.p + 2048, k * sizeof(double), c->stream);
 }
 
 void chain_residual(Chain* c, const int64_t* loci, const double* beta_e, const double* beta_g, int k, double* stats9)
@@ -644,11 +645,11 @@ void chain_residual(Chain* c, const int64_t* loci, const double* beta_e, const d
   // beta_e and column pointers
   BMG_CUDA(cudaStreamSynchronize(st));
   for (int j = 0; j < s->m_e; ++j) c->h_stage.p[4096 + j] = beta_e[j];
-  BMG_CUDA(cudaMemcpyAsync(c->beta_dev.p + 2048, c->h_stage.p + 4096, s->m_e * sizeof(double), cudaMemcpyHostToDevice, st));
+  bmg::copy_h2d(c->beta_dev.p + 2048, c->h_stage.p + 4096, s->m_e * sizeof(double), st);
   static_assert(sizeof(const uint32_t*) == sizeof(int64_t), "pointer size");
   for (int l = 0; l < k; ++l) c->h_stage_i.p[2048 + l] = (int64_t)(uintptr_t)s->column_ptr(loci[l]);
   if (c->cs_idx.n < 4096) c->cs_idx.alloc(4096);
-  if (k) BMG_CUDA(cudaMemcpyAsync(c->cs_idx.p, c->h_stage_i.p + 2048, k * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  if (k) bmg::copy_h2d(c->cs_idx.p, c->h_stage_i.p + 2048, k * sizeof(int64_t), st);
   YhatArgs ya;
   ya.cols = reinterpret_cast<const uint32_t* const*>(c->cs_idx.p);
   ya.beta_g = c->beta_dev.p; ya.beta_e = c->beta_dev.p + 2048; ya.e = s->e.p;
@@ -672,7 +673,7 @@ void chain_residual(Chain* c, const int64_t* loci, const double* beta_e, const d
   k_reduce_final<<<1, 32, 0, st>>>(c->red_partial.p, blocks, kRed, c->red_out.p);
   count_launch();
   BMG_CUDA(cudaGetLastError());
-  BMG_CUDA(cudaMemcpyAsync(c->h_red.p, c->red_out.p, kRed * sizeof(double), cudaMemcpyDeviceToHost, st));
+  bmg::copy_d2h(c->h_red.p, c->red_out.p, kRed * sizeof(double), st);
   BMG_CUDA(cudaStreamSynchronize(st));
   c->sum_r = c->h_red.p[0];
   c->residual_valid = true;
@@ -689,11 +690,36 @@ void chain_scan_dots(Chain* c)
   a.chunk_words = (int)c->scan_chunk_words; a.n_chunks = c->scan_chunks;
   a.tiles = (s->m + kTileSnps - 1) / kTileSnps; a.slices = c->scan_ctas_per_chunk; a.out = c->dot_partial.p;
   const unsigned grid = (unsigned)(c->scan_chunks * c->scan_ctas_per_chunk);
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (c->time_scan) {
+    if (c->scan_ev_used >= 4096) {   // fold finished pairs into the running total
+      BMG_CUDA(cudaStreamSynchronize(c->stream));
+      for (size_t i = 0; i < c->scan_ev_used; ++i) {
+        float ms = 0.f;
+        BMG_CUDA(cudaEventElapsedTime(&ms, c->scan_ev[2 * i], c->scan_ev[2 * i + 1]));
+        c->scan_ms_done += ms;
+      }
+      c->scan_launches_done += (int64_t)c->scan_ev_used;
+      c->scan_ev_used = 0;
+    }
+    while (c->scan_ev.size() < 2 * (c->scan_ev_used + 1)) {
+      cudaEvent_t e;
+      BMG_CUDA(cudaEventCreate(&e));
+      c->scan_ev.push_back(e);
+    }
+    ev0 = c->scan_ev[2 * c->scan_ev_used];
+    ev1 = c->scan_ev[2 * c->scan_ev_used + 1];
+    BMG_CUDA(cudaEventRecord(ev0, c->stream));
+  }
   if (c->scan_variant == 1)
     k_scan_dots_tma<<<grid, 32 * c->scan_warps, scan_smem_bytes(c), c->stream>>>(a);
   else
     k_scan_dots_ldg<<<grid, 32 * c->scan_warps, 0, c->stream>>>(a);
   count_launch();
+  if (ev1) {
+    BMG_CUDA(cudaEventRecord(ev1, c->stream));
+    ++c->scan_ev_used;
+  }
   BMG_CUDA(cudaGetLastError());
 }
 
@@ -710,7 +736,7 @@ void chain_scan(Chain* c, const int64_t* loci, const double* beta_g, const doubl
   if (prm->tau_mode == 1) {
     BMG_REQUIRE(prm->tau_host != nullptr, "bmg_chain_scan: tau_host required for tau_mode 1");
     if (c->tau_dev.n < (size_t)s->m) c->tau_dev.alloc(s->m);
-    BMG_CUDA(cudaMemcpyAsync(c->tau_dev.p, prm->tau_host, s->m * sizeof(double), cudaMemcpyHostToDevice, st));
+    bmg::copy_h2d(c->tau_dev.p, prm->tau_host, s->m * sizeof(double), st);
   }
   chain_scan_dots(c);
   if (s->n_missing > 0) {
@@ -730,7 +756,7 @@ void chain_scan(Chain* c, const int64_t* loci, const double* beta_g, const doubl
   count_launch();
   BMG_CUDA(cudaGetLastError());
   if (p_r_host) {
-    BMG_CUDA(cudaMemcpyAsync(p_r_host, c->p_r.p, s->m * sizeof(double), cudaMemcpyDeviceToHost, st));
+    bmg::copy_d2h(p_r_host, c->p_r.p, s->m * sizeof(double), st);
     BMG_CUDA(cudaStreamSynchronize(st));
   }
 }

@@ -229,7 +229,7 @@ Store* store_create(const uint8_t* bed, bool on_device, int64_t n, int64_t m_g, 
   const uint8_t* raw = bed;
   if (!on_device) {
     raw_own.alloc((size_t)(m * B));
-    BMG_CUDA(cudaMemcpy(raw_own.p, bed, (size_t)(m * B), cudaMemcpyHostToDevice));
+    bmg::copy_h2d_sync(raw_own.p, bed, (size_t)(m * B));
     raw = raw_own.p;
   }
   s->codes.alloc((size_t)(m * s->Wp + 4096));  // slack: tiles may over-read past the last column
@@ -247,14 +247,14 @@ Store* store_create(const uint8_t* bed, bool on_device, int64_t n, int64_t m_g, 
 
   // missing index: exclusive scan of the counts on the host (m ints), then one extraction kernel
   std::vector<int32_t> h_nmiss(m);
-  BMG_CUDA(cudaMemcpy(h_nmiss.data(), s->nmiss.p, m * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  bmg::copy_d2h_sync(h_nmiss.data(), s->nmiss.p, m * sizeof(int32_t));
   s->h_miss_off.resize(m + 1);
   int64_t tot = 0;
   for (int64_t j = 0; j < m; ++j) { s->h_miss_off[j] = tot; tot += h_nmiss[j]; }
   s->h_miss_off[m] = tot;
   s->n_missing = tot;
   s->miss_off.alloc(m + 1);
-  BMG_CUDA(cudaMemcpy(s->miss_off.p, s->h_miss_off.data(), (m + 1) * sizeof(int64_t), cudaMemcpyHostToDevice));
+  bmg::copy_h2d_sync(s->miss_off.p, s->h_miss_off.data(), (m + 1) * sizeof(int64_t));
   if (tot > 0) {
     s->miss_idx.alloc((size_t)tot);
     const int threads = 128;
@@ -266,8 +266,8 @@ Store* store_create(const uint8_t* bed, bool on_device, int64_t n, int64_t m_g, 
 
   // Data::compute_g_var_and_mean: sequential sums over SNPs in index order, as the reference does
   std::vector<double> hm(m), hv(m);
-  BMG_CUDA(cudaMemcpy(hm.data(), snp_mean.p, m * sizeof(double), cudaMemcpyDeviceToHost));
-  BMG_CUDA(cudaMemcpy(hv.data(), snp_var.p, m * sizeof(double), cudaMemcpyDeviceToHost));
+  bmg::copy_d2h_sync(hm.data(), snp_mean.p, m * sizeof(double));
+  bmg::copy_d2h_sync(hv.data(), snp_var.p, m * sizeof(double));
   double tm = 0, tv = 0, nm = 0, nv = 0;
   for (int64_t j = 0; j < m; ++j) {
     const int ng = (int)n - h_nmiss[j];
@@ -278,7 +278,7 @@ Store* store_create(const uint8_t* bed, bool on_device, int64_t n, int64_t m_g, 
 
   build_inorder_permutation(m, s->h_inorder);
   s->inorder.alloc(m);
-  BMG_CUDA(cudaMemcpy(s->inorder.p, s->h_inorder.data(), m * sizeof(int32_t), cudaMemcpyHostToDevice));
+  bmg::copy_h2d_sync(s->inorder.p, s->h_inorder.data(), m * sizeof(int32_t));
   BMG_CUDA(cudaDeviceSynchronize());
   return s.release();
 }
@@ -290,8 +290,8 @@ void store_set_phenotype(Store* s, const double* y, const double* e, int m_e)
   s->m_e = m_e;
   s->y.alloc(s->n);
   s->e.alloc((size_t)s->n * m_e);
-  BMG_CUDA(cudaMemcpy(s->y.p, y, s->n * sizeof(double), cudaMemcpyHostToDevice));
-  BMG_CUDA(cudaMemcpy(s->e.p, e, (size_t)s->n * m_e * sizeof(double), cudaMemcpyHostToDevice));
+  bmg::copy_h2d_sync(s->y.p, y, s->n * sizeof(double));
+  bmg::copy_h2d_sync(s->e.p, e, (size_t)s->n * m_e * sizeof(double));
   s->h_y.assign(y, y + s->n);
   // Data ctor (data.hpp:67-70): yy = y'y (ddot), var_y = VectorView::var (vector.cpp:112-123)
   double sq = 0, sum = 0;
@@ -320,7 +320,7 @@ void store_get_column(const Store* s, int64_t snp, int type, const int8_t* miss_
     count_launch();
   }
   BMG_CUDA(cudaGetLastError());
-  BMG_CUDA(cudaMemcpyAsync(out_host, out.p, s->n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  bmg::copy_d2h(out_host, out.p, s->n * sizeof(double), st);
   BMG_CUDA(cudaStreamSynchronize(st));
 }
 

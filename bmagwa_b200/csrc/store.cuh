@@ -18,6 +18,12 @@ struct Chain {
   Store* store = nullptr;
   cudaStream_t stream = nullptr;
   int scan_variant = 1;
+  // optional CUDA-event timing of the scan's reduction kernel (bench.py roofline): pairs of events
+  bool time_scan = false;
+  std::vector<cudaEvent_t> scan_ev;
+  size_t scan_ev_used = 0;
+  double scan_ms_done = 0.0;
+  int64_t scan_launches_done = 0;
   // scan geometry (chosen once per chain from n and the SM count)
   int scan_warps = 0;        // warps per CTA
   int64_t scan_chunk_words = 0;  // words of each column one CTA covers

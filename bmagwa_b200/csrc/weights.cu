@@ -187,7 +187,7 @@ void chain_sample(Chain* c, int which, double u01, int64_t* snp, double* total)
   k_sample<<<1, 256, 0, c->stream>>>(q, z, s->inorder.p, eff, s->m, c->cdf_blocks, u01, c->sample_out.p);
   count_launch();
   BMG_CUDA(cudaGetLastError());
-  BMG_CUDA(cudaMemcpyAsync(c->h_sample.p, c->sample_out.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  bmg::copy_d2h(c->h_sample.p, c->sample_out.p, 2 * sizeof(double), c->stream);
   BMG_CUDA(cudaStreamSynchronize(c->stream));
   const double j = c->h_sample.p[0];
   BMG_REQUIRE(j >= 0, "bmg_chain_sample: every item is zeroed");

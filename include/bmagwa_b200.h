@@ -42,6 +42,8 @@ const char* bmg_last_error(void);
 int bmg_device_count(void);
 /* Counter of kernels launched by this library in this process (for bench.py's gpu_launches). */
 uint64_t bmg_launch_count(void);
+/* Bytes this library has copied host->device / device->host in this process (bench.py's e2e). */
+void bmg_transfer_bytes(uint64_t* h2d, uint64_t* d2h);
 
 /* ---- genotype store: Data::Data + read_g + recode + handle_missing_g + var/mean --------
  * (data.hpp:45-72, data.cpp:245-273,324-376,403-434) and PrecomputedSNPCovariances
@@ -136,6 +138,12 @@ int bmg_chain_scan_dots(bmg_chain* c, double* dot_host);
 /* Kernel variant used by bmg_chain_scan/_dots: 0 = direct vectorised global loads,
  * 1 = bulk-async (TMA) staging through shared memory.  Default chosen by the library. */
 int bmg_chain_set_scan_variant(bmg_chain* c, int variant);
+
+/* CUDA-event timing of the scan's reduction kernel on the chain's stream (bench.py roofline).
+ * enable != 0 turns recording on for later launches; ms_total / launches (may be NULL) receive the
+ * sum of launch durations and the number of launches recorded so far (this synchronises the
+ * stream); reset != 0 clears the totals afterwards. */
+int bmg_chain_scan_kernel_time(bmg_chain* c, int enable, double* ms_total, int64_t* launches, int reset);
 
 /* The scan epilogue of Sampler::sample (sampler.cpp:739-803): running means and weights.
  *   update_rao:      p_rao      = running mean of p_r (n_rao_mean samples so far)

@@ -35,11 +35,13 @@ def lib():
         L.refd_open.restype = C.c_void_p
         L.refd_open.argtypes = [C.c_char_p, C.c_int]
         for f in ("refd_get_genotype", "refd_prior_log_add", "refd_prior_log_rem", "refd_prior_log_model",
-                  "refd_model_loglik", "refd_scan_time", "refd_run_chain", "refd_rng_u01", "refd_rng_normal",
+                  "refd_model_loglik", "refd_scan_time", "refd_run_chain", "refd_continue_chain", "refd_rng_u01", "refd_rng_normal",
                   "refd_rng_sinvchi2_1", "refd_rng_sinvchi2_2", "refd_dd_total", "refd_gammaln"):
             getattr(L, f).restype = C.c_double
         L.refd_missing.restype = C.c_long
         L.refd_dd_sample.restype = C.c_long
+        L.refd_open_chain.restype = C.c_void_p
+        L.refd_open_chain.argtypes = [C.c_void_p, C.c_int]
         L.refd_rng_new.restype = C.c_void_p
         L.refd_dd_new.restype = C.c_void_p
         L.refd_set_blas_threads(1)
@@ -54,9 +56,12 @@ def _p(a, t=C.c_double):
 class Ref:
     """One reference chain context: Options + Data + moment cache + Sampler (main.cpp:47-76)."""
 
-    def __init__(self, ini_path, chain_index=0):
+    def __init__(self, ini_path, chain_index=0, parent=None):
         self.L = lib()
-        self.h = self.L.refd_open(str(ini_path).encode(), chain_index)
+        if parent is not None:
+            self.h = self.L.refd_open_chain(parent.h, chain_index)
+        else:
+            self.h = self.L.refd_open(str(ini_path).encode(), chain_index)
         if not self.h:
             raise RuntimeError(self.L.refd_last_error().decode())
         self.h = C.c_void_p(self.h)
@@ -210,6 +215,15 @@ class Ref:
 
     def run_chain(self):
         t = self.L.refd_run_chain(self.h)
+        if t < 0:
+            raise RuntimeError(self.L.refd_last_error().decode())
+        return t
+
+    def set_do_n_iter(self, n):
+        self.L.refd_set_do_n_iter(self.h, C.c_long(n))
+
+    def continue_chain(self):
+        t = self.L.refd_continue_chain(self.h)
         if t < 0:
             raise RuntimeError(self.L.refd_last_error().decode())
         return t

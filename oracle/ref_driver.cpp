@@ -34,6 +34,7 @@ struct RefCtx {
   PrecomputedSNPCovariances* pre;
   Sampler* sampler;
   std::string err;
+  bool shares_data;
 };
 
 static thread_local std::string g_err;
@@ -65,6 +66,24 @@ void* refd_open(const char* ini, int chain_index)
     delete tmp;
     c->opt = c->opt0->clone(chain_index);
     c->sampler = new Sampler(*c->opt, c->data, c->pre);
+    c->shares_data = false;
+    return c;
+  } catch (std::exception& e) {
+    g_err = e.what();
+    return NULL;
+  }
+}
+
+/* a further chain over the SAME Data / moment cache, as main.cpp:70-76 does for n_threads > 1 */
+void* refd_open_chain(void* parent, int chain_index)
+{
+  try {
+    RefCtx* p = (RefCtx*)parent;
+    RefCtx* c = new RefCtx();
+    c->opt0 = p->opt0; c->data = p->data; c->pre = p->pre;
+    c->opt = c->opt0->clone(chain_index);
+    c->sampler = new Sampler(*c->opt, c->data, c->pre);
+    c->shares_data = true;
     return c;
   } catch (std::exception& e) {
     g_err = e.what();
@@ -77,10 +96,31 @@ void refd_close(void* h)
   RefCtx* c = (RefCtx*)h;
   delete c->sampler;
   delete c->opt;
-  delete c->pre;
-  delete c->data;
-  delete c->opt0;
+  if (!c->shares_data) {
+    delete c->pre;
+    delete c->data;
+    delete c->opt0;
+  }
   delete c;
+}
+
+/* number of iterations of the next sample() call (Sampler::do_n_iter, sampler.hpp:397) */
+void refd_set_do_n_iter(void* h, long n) { ((RefCtx*)h)->sampler->do_n_iter = (size_t)n; }
+
+/* sample() again on a sampler that already ran (sampler.cpp:625,835 continue from n_iter); wall seconds */
+double refd_continue_chain(void* h)
+{
+  RefCtx* c = (RefCtx*)h;
+  struct timespec t0, t1;
+  try {
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    c->sampler->sample();
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+  } catch (std::exception& e) {
+    g_err = e.what();
+    return -1.0;
+  }
+  return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
 }
 
 /* ---- Data / DataModel (data.hpp:75-88, data_model.hpp:101-140) ---- */

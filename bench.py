@@ -43,6 +43,28 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+class stdout_to_stderr:
+    """The native libraries (ours and the reference) print option warnings on fd 1; keep fd 1 clean so that the
+    JSON line is the only thing on stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        try:
+            import ctypes
+            ctypes.CDLL(None).fflush(None)
+        except Exception:
+            pass
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
 def dataset_dir(w, n_threads):
     base = os.environ.get("BMAGWA_BENCH_DIR", os.path.join(tempfile.gettempdir(), "bmagwa_bench"))
     return os.path.join(base, "%s_n%d_m%d_t%d" % (w, WORKLOADS[w]["n"], WORKLOADS[w]["m_g"], n_threads))
@@ -167,7 +189,7 @@ def run_reference_chains(ini, n_chains, n_rao, warmup, steps):
 
 def reference_arm(args, rank, world):
     if rank != 0:
-        return
+        return None
     from oracle import ref
     spec = WORKLOADS[args.workload]
     n_chains = max(1, args.gpus)
@@ -176,8 +198,7 @@ def reference_arm(args, rank, world):
            "dtype": "f64", "data": "synthetic"}
     if not ref.available():
         out["unavailable"] = "oracle/_ref (the reference compiled against the shims) is not present on this box"
-        print(json.dumps(out))
-        return
+        return out
     with tempfile.TemporaryDirectory() as tmp:
         ini, _ = prepare_dataset(args.workload, args.n_rao, n_chains, tmp, args.n_rao)
         t0 = time.time()
@@ -198,7 +219,7 @@ def reference_arm(args, rank, world):
         "e2e": {"value": value, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     })
-    print(json.dumps(out))
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -307,7 +328,7 @@ def ours_arm(args, rank, local_rank, world):
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
-        return
+        return None
     iters = world * args.steps * args.n_rao
     value = iters / (elapsed_ms * 1e-3)
     peak, peak_src = measured_peak()
@@ -333,14 +354,14 @@ def ours_arm(args, rank, local_rank, world):
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": scan_traffic(args.workload),
                      "bytes_per_launch": bytes_scan, "avg_launch_ms": scan_ms, "launches_timed": int(n_l.value), "peak_source": peak_src},
         "clocks": clk,
-        "breakdown": {"move_seconds": st["move_seconds"], "scan_seconds": st["scan_seconds"], "scans": st["scans"],
+        "breakdown": {"move_seconds": st["move_seconds"], "scan_seconds": st["scan_seconds"], "scans": st["scans"], "column_stats_seconds": st["column_stats_seconds"],
                       "h2d_bytes_per_step_resident": (h2d1 - h2d0) / args.steps, "d2h_bytes_per_step_resident": (d2h1 - d2h0) / args.steps},
     }
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args, spec)
-    print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
+    return out
 
 
 def cpu_baseline(args, spec):
@@ -376,12 +397,12 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.impl == "reference":
-        reference_arm(args, rank, world)
-    else:
-        if world != args.gpus and world == 1 and args.gpus > 1:
-            raise SystemExit("launch with torch.distributed.run --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
-        ours_arm(args, rank, local_rank, world)
+    if world != args.gpus and world == 1 and args.gpus > 1 and args.impl == "ours":
+        raise SystemExit("launch with torch.distributed.run --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    with stdout_to_stderr():
+        line = reference_arm(args, rank, world) if args.impl == "reference" else ours_arm(args, rank, local_rank, world)
+    if line is not None:
+        print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":

@@ -293,7 +293,7 @@ class Sampler:
     def stats(self):
         out = np.zeros(8)
         check(self.L.bmg_sampler_stats(self.h, _pf(out)))
-        keys = ("iterations", "accepted", "model_size", "log_likelihood", "move_seconds", "scan_seconds", "scans", "launches")
+        keys = ("iterations", "accepted", "model_size", "log_likelihood", "move_seconds", "scan_seconds", "scans", "column_stats_seconds")
         return dict(zip(keys, out))
 
     def chain_stream(self):

@@ -9,6 +9,7 @@
 #include "common.cuh"
 #include "store.cuh"
 #include "philox.cuh"
+#include <stdlib.h>
 
 namespace bmg {
 
@@ -73,6 +74,77 @@ __global__ void __launch_bounds__(256) k_column_stats(const ColStatArgs a)
       res = (double)acc;
     }
     if (lane == 0) out[task] = res;
+  }
+}
+
+// ---- latency path: pointers passed BY VALUE in the kernel parameters, results written straight into mapped
+// pinned host memory, completion published by the last CTA through a sequence number the host spins on.
+// One launch per move, no cudaMemcpy and no stream synchronisation on the per-iteration path.
+constexpr int kInlinePtrs = 96;
+struct ColStatInline {
+  const uint32_t* cols[kInlinePtrs];  // m_c candidate columns, then k model columns
+  int m_c, k, m_e;
+  int64_t n, W;
+  int n_seg;
+  const double* y;
+  const double* e;
+  double* out_host;          // [m_c][n_seg][n_tasks] in mapped host memory
+  unsigned int* done_count;  // device counter, reset by the last CTA
+  volatile unsigned int* flag_host;
+  unsigned int seq;
+};
+
+__global__ void __launch_bounds__(256) k_column_stats_inline(const __grid_constant__ ColStatInline a)
+{
+  __shared__ uint32_t cw[kSegWords];
+  const int c = blockIdx.x, seg = blockIdx.y;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nw = blockDim.x >> 5;
+  const int64_t w0 = (int64_t)seg * kSegWords;
+  const int nwords = (int)min((int64_t)kSegWords, a.W - w0);
+  const uint32_t* col = a.cols[c];
+  for (int w = t; w < nwords; w += blockDim.x) cw[w] = col[w0 + w];
+  __syncthreads();
+  const int n_tasks = a.m_e + 1 + a.k + a.m_c;
+  double* out = a.out_host + ((int64_t)c * a.n_seg + seg) * n_tasks;
+  for (int task = warp; task < n_tasks; task += nw) {
+    double res;
+    if (task <= a.m_e) {
+      const double* vec = task == 0 ? a.y : a.e + (int64_t)(task - 1) * a.n;
+      double acc = 0.0;
+      for (int w = lane; w < nwords; w += 32) {
+        const uint32_t word = cw[w];
+        if (word == 0) continue;
+        const int64_t i0 = 16 * (w0 + w);
+#pragma unroll
+        for (int p = 0; p < 16; ++p) {
+          const int64_t i = i0 + p;
+          const double g = (double)((word >> (2 * p)) & 3u);
+          if (i < a.n) acc = fma(g, vec[i], acc);
+        }
+      }
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      res = acc;
+    } else {
+      const int q = task - a.m_e - 1;
+      const uint32_t* other = q < a.k ? a.cols[a.m_c + q] : a.cols[q - a.k];
+      int acc = 0;
+      for (int w = lane; w < nwords; w += 32) acc += packed_dot(cw[w], other[w0 + w]);
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      res = (double)acc;
+    }
+    if (lane == 0) out[task] = res;
+  }
+  // publish: every CTA fences its host writes, the last one to arrive raises the flag
+  __syncthreads();
+  if (t == 0) {
+    __threadfence_system();
+    const unsigned int total = gridDim.x * gridDim.y;
+    const unsigned int prev = atomicAdd(a.done_count, 1u);
+    if (prev == total - 1) {
+      *a.done_count = 0;
+      __threadfence_system();
+      *a.flag_host = a.seq;
+    }
   }
 }
 
@@ -166,6 +238,54 @@ void chain_column_stats(Chain* c, const int64_t* cand, int m_c, const int64_t* l
   cudaStream_t st = c->stream;
   const int n_tasks = s->m_e + 1 + k + m_c;
   const int n_seg = (int)((s->W + kSegWords - 1) / kSegWords);
+  bool any_missing_fast = false;
+  if (s->n_missing > 0)
+    for (int i = 0; i < m_c + k && !any_missing_fast; ++i) {
+      const int64_t snp = i < m_c ? cand[i] : loci[i - m_c];
+      if (s->is_local(snp) && s->h_miss_off[snp - s->lo + 1] > s->h_miss_off[snp - s->lo]) any_missing_fast = true;
+    }
+  if (m_c + k <= kInlinePtrs && !any_missing_fast && getenv("BMG_COLSTATS_SLOW") == nullptr) {
+    const size_t need_fast = (size_t)m_c * n_tasks * n_seg;
+    if (c->cs_map.n < need_fast + 8) {
+      BMG_CUDA(cudaStreamSynchronize(st));
+      c->cs_map.alloc(need_fast * 2 + 64);
+      if (c->cs_done.n == 0) { c->cs_done.alloc(1); BMG_CUDA(cudaMemset(c->cs_done.p, 0, sizeof(unsigned int))); }
+      if (c->cs_flag.n == 0) { c->cs_flag.alloc(16); c->cs_flag.p[0] = 0; }
+    }
+    ColStatInline a;
+    for (int i = 0; i < m_c + k; ++i) a.cols[i] = s->column_ptr(i < m_c ? cand[i] : loci[i - m_c]);
+    a.m_c = m_c; a.k = k; a.m_e = s->m_e; a.n = s->n; a.W = s->W; a.n_seg = n_seg; a.y = c->y.p; a.e = s->e.p;
+    a.out_host = c->cs_map.p; a.done_count = c->cs_done.p;
+    a.flag_host = reinterpret_cast<volatile unsigned int*>(c->cs_flag.p);
+    a.seq = ++c->cs_seq;
+    k_column_stats_inline<<<dim3(m_c, n_seg), 256, 0, st>>>(a);
+    count_launch();
+    g_d2h_bytes.fetch_add(need_fast * sizeof(double), std::memory_order_relaxed);
+    g_h2d_bytes.fetch_add(sizeof(ColStatInline), std::memory_order_relaxed);
+    const cudaError_t le = cudaGetLastError();
+    if (le != cudaSuccess) throw Error(std::string("k_column_stats_inline launch: ") + cudaGetErrorString(le));
+    volatile unsigned int* flag = reinterpret_cast<volatile unsigned int*>(c->cs_flag.p);
+    unsigned long spins = 0;
+    while (*flag != a.seq) {
+      if ((++spins & 0xFFFFF) == 0 && cudaStreamQuery(st) != cudaErrorNotReady) {   // finished (or failed) without raising the flag?
+        if (*flag == a.seq) break;
+        BMG_CUDA(cudaStreamSynchronize(st));
+        if (*flag != a.seq) throw Error("k_column_stats_inline finished without publishing its results");
+      }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    for (int ci = 0; ci < m_c; ++ci) {
+      for (int task = 0; task < n_tasks; ++task) {
+        double v = 0.0;
+        for (int g = 0; g < n_seg; ++g) v += c->cs_map.p[((size_t)ci * n_seg + g) * n_tasks + task];
+        if (task == 0) { if (xy) xy[ci] = v; }
+        else if (task <= s->m_e) { if (xe) xe[(size_t)ci * s->m_e + task - 1] = v; }
+        else if (task <= s->m_e + k) { if (xx_model) xx_model[(size_t)ci * k + task - 1 - s->m_e] = v; }
+        else if (xx_cand) xx_cand[(size_t)ci * m_c + task - 1 - s->m_e - k] = v;
+      }
+    }
+    return;
+  }
   const size_t need = (size_t)m_c * n_tasks * (n_seg + 1);
   if (c->cs_out.n < need) { c->cs_out.alloc(need * 2); c->h_cs.alloc(need * 2); }
   const size_t n_ptr = (size_t)(m_c + k) * 2;

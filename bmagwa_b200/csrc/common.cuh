@@ -94,7 +94,7 @@ struct PinnedBuf {
   {
     release();
     n = count;
-    if (count) BMG_CUDA(cudaHostAlloc((void**)&p, count * sizeof(T), cudaHostAllocDefault));
+    if (count) BMG_CUDA(cudaHostAlloc((void**)&p, count * sizeof(T), cudaHostAllocMapped));
   }
   void release()
   {

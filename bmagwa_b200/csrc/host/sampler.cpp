@@ -208,8 +208,10 @@ void Sampler::fetch_gram(const std::vector<uint32_t>& cand)
   gram_.xe.assign(cand.size() * m_e_, 0.0);
   gram_.xm.assign(cand.size() * std::max<size_t>(1, l64.size()), 0.0);
   gram_.xc.assign(cand.size() * cand.size(), 0.0);
+  const double t0 = wall_seconds();
   chain_column_stats(chain_, c64.data(), (int)c64.size(), l64.data(), (int)l64.size(), gram_.xy.data(), gram_.xe.data(),
                      gram_.xm.data(), gram_.xc.data());
+  device_wait_seconds_ += wall_seconds() - t0;
 }
 
 // Model::add_term for a candidate SNP of this move (model.hpp:453-470 supplies the column; here it comes from gram_)
@@ -516,7 +518,7 @@ void Sampler::end()
 void Sampler::stats(double* out8) const
 {
   out8[0] = (double)n_iter_; out8[1] = (double)n_accepted_; out8[2] = (double)current_.size(); out8[3] = current_.log_likelihood;
-  out8[4] = move_seconds_; out8[5] = scan_seconds_; out8[6] = (double)n_scans_; out8[7] = (double)g_launches.load();
+  out8[4] = move_seconds_; out8[5] = scan_seconds_; out8[6] = (double)n_scans_; out8[7] = device_wait_seconds_;
 }
 
 // ------------------------------------------------------------------------------------------------

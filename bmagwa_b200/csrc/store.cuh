@@ -66,6 +66,10 @@ struct Chain {
   PinnedBuf<double> h_cs;
   DevBuf<int64_t> cs_idx;
   size_t cs_cap = 0;
+  PinnedBuf<double> cs_map;                     // results written by the kernel straight into host memory
+  PinnedBuf<unsigned int> cs_flag;              // completion sequence number (host-visible)
+  DevBuf<unsigned int> cs_done;                 // CTA arrival counter
+  unsigned int cs_seq = 0;
 };
 
 Chain* chain_create(Store* s);

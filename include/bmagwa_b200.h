@@ -202,7 +202,7 @@ int bmg_sampler_run(bmg_sampler* sp, int64_t n_iter);
 /* Writes _rao.dat, _samplerstats.txt, closes files (sampler.cpp:836-879). */
 int bmg_sampler_end(bmg_sampler* sp);
 /* stats: {iterations done, accepted, model size, log likelihood, seconds in moves,
- * seconds in scans, scans done, kernels launched}. */
+ * seconds in scans, scans done, seconds of the move time spent waiting for per-proposal column statistics}. */
 int bmg_sampler_stats(bmg_sampler* sp, double* out8);
 bmg_store* bmg_sampler_store(bmg_sampler* sp);
 bmg_chain* bmg_sampler_chain(bmg_sampler* sp);

@@ -97,6 +97,7 @@ struct ColStatInline {
 __global__ void __launch_bounds__(256) k_column_stats_inline(const __grid_constant__ ColStatInline a)
 {
   __shared__ uint32_t cw[kSegWords];
+  __shared__ double fpart[8][8];   // [warp][fp task], up to 8 fp tasks (y + 7 covariate columns) on the fast path
   const int c = blockIdx.x, seg = blockIdx.y;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nw = blockDim.x >> 5;
   const int64_t w0 = (int64_t)seg * kSegWords;
@@ -104,35 +105,51 @@ __global__ void __launch_bounds__(256) k_column_stats_inline(const __grid_consta
   const uint32_t* col = a.cols[c];
   for (int w = t; w < nwords; w += blockDim.x) cw[w] = col[w0 + w];
   __syncthreads();
-  const int n_tasks = a.m_e + 1 + a.k + a.m_c;
+  const int n_fp = a.m_e + 1;
+  const int n_tasks = n_fp + a.k + a.m_c;
   double* out = a.out_host + ((int64_t)c * a.n_seg + seg) * n_tasks;
-  for (int task = warp; task < n_tasks; task += nw) {
-    double res;
-    if (task <= a.m_e) {
-      const double* vec = task == 0 ? a.y : a.e + (int64_t)(task - 1) * a.n;
-      double acc = 0.0;
-      for (int w = lane; w < nwords; w += 32) {
-        const uint32_t word = cw[w];
-        if (word == 0) continue;
-        const int64_t i0 = 16 * (w0 + w);
+
+  // (1) x_c'y and x_c'E_j: ALL warps sweep the individuals of the segment with coalesced loads
+  //     (lane <-> individual), each warp a contiguous slice; partial sums meet in shared memory.
+  {
+    const int64_t i_lo = 16 * w0, i_hi = min(a.n, i_lo + 16 * (int64_t)nwords);
+    const int64_t span = (i_hi - i_lo + nw - 1) / nw;
+    const int64_t my_lo = i_lo + warp * span, my_hi = min(i_hi, my_lo + span);
+    double acc[8];
 #pragma unroll
-        for (int p = 0; p < 16; ++p) {
-          const int64_t i = i0 + p;
-          const double g = (double)((word >> (2 * p)) & 3u);
-          if (i < a.n) acc = fma(g, vec[i], acc);
-        }
+    for (int q = 0; q < 8; ++q) acc[q] = 0.0;
+    for (int64_t i = my_lo + lane; i < my_hi; i += 32) {
+      const uint32_t word = cw[(i - i_lo) >> 4];
+      const uint32_t f = (word >> (2 * ((i - i_lo) & 15))) & 3u;
+      if (f) {
+        const double g = f == 1 ? 1.0 : 2.0;
+        acc[0] = fma(g, a.y[i], acc[0]);
+#pragma unroll
+        for (int q = 1; q < 8; ++q)
+          if (q < n_fp) acc[q] = fma(g, a.e[(int64_t)(q - 1) * a.n + i], acc[q]);
       }
-      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      res = acc;
-    } else {
-      const int q = task - a.m_e - 1;
-      const uint32_t* other = q < a.k ? a.cols[a.m_c + q] : a.cols[q - a.k];
-      int acc = 0;
-      for (int w = lane; w < nwords; w += 32) acc += packed_dot(cw[w], other[w0 + w]);
-      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      res = (double)acc;
     }
-    if (lane == 0) out[task] = res;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      double v = acc[q];
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) fpart[warp][q] = v;
+    }
+  }
+  // (2) x_c'x_l for model columns and other candidates: exact integer popcount arithmetic, one task per warp
+  for (int task = n_fp + warp; task < n_tasks; task += nw) {
+    const int q = task - n_fp;
+    const uint32_t* other = q < a.k ? a.cols[a.m_c + q] : a.cols[q - a.k];
+    int acc = 0;
+    for (int w = lane; w < nwords; w += 32) acc += packed_dot(cw[w], other[w0 + w]);
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[task] = (double)acc;
+  }
+  __syncthreads();
+  if (t < n_fp) {
+    double v = 0.0;
+    for (int wv = 0; wv < nw; ++wv) v += fpart[wv][t];
+    out[t] = v;
   }
   // publish: every CTA fences its host writes, the last one to arrive raises the flag
   __syncthreads();
@@ -244,7 +261,7 @@ void chain_column_stats(Chain* c, const int64_t* cand, int m_c, const int64_t* l
       const int64_t snp = i < m_c ? cand[i] : loci[i - m_c];
       if (s->is_local(snp) && s->h_miss_off[snp - s->lo + 1] > s->h_miss_off[snp - s->lo]) any_missing_fast = true;
     }
-  if (m_c + k <= kInlinePtrs && !any_missing_fast && getenv("BMG_COLSTATS_SLOW") == nullptr) {
+  if (m_c + k <= kInlinePtrs && s->m_e + 1 <= 8 && !any_missing_fast && getenv("BMG_COLSTATS_SLOW") == nullptr) {
     const size_t need_fast = (size_t)m_c * n_tasks * n_seg;
     if (c->cs_map.n < need_fast + 8) {
       BMG_CUDA(cudaStreamSynchronize(st));

@@ -185,6 +185,19 @@ struct Model {
   int cols() const { return m_e + (int)loci.size(); }
   size_t size() const { return loci.size(); }
 
+  // Model::operator= (model.hpp:115-162): O(k^2) bytes -- only the used upper triangles are copied
+  void assign(const Model& o)
+  {
+    m_e = o.m_e;
+    loci = o.loci;
+    xx.copy_upper_from(o.xx);
+    l.copy_upper_from(o.l);
+    xy = o.xy; v = o.v; inv_tau2_alpha2 = o.inv_tau2_alpha2; beta = o.beta; mu_beta = o.mu_beta;
+    sigma2 = o.sigma2; syx_plus_vs2 = o.syx_plus_vs2; log_det_invQ = o.log_det_invQ;
+    log_det_invQ_plus_xx = o.log_det_invQ_plus_xx; log_likelihood = o.log_likelihood;
+    mu_beta_computed = o.mu_beta_computed; prior = o.prior;
+  }
+
   // Model::Model (model.hpp:49-113): covariate columns only; exx = E'E (upper), exy = E'y
   void init(int m_e_, const UpperMat& exx, const std::vector<double>& exy, const Prior* p)
   {

@@ -7,6 +7,7 @@
 #include <iomanip>
 #include <iostream>
 #include <sstream>
+#include <cstdlib>
 
 namespace bmg {
 
@@ -185,13 +186,13 @@ void Sampler::print_prior()
 void Sampler::copy_proposal_to_current()
 {
   for (uint32_t s : current_.loci) pos_in_current_[s] = -1;
-  current_ = proposal_;
+  current_.assign(proposal_);
   for (size_t i = 0; i < current_.loci.size(); ++i) pos_in_current_[current_.loci[i]] = (int32_t)i;
 }
 void Sampler::copy_current_to_proposal()
 {
   for (uint32_t s : proposal_.loci) pos_in_proposal_[s] = -1;
-  proposal_ = current_;
+  proposal_.assign(current_);
   for (size_t i = 0; i < proposal_.loci.size(); ++i) pos_in_proposal_[proposal_.loci[i]] = (int32_t)i;
 }
 
@@ -500,6 +501,10 @@ void Sampler::end()
       << "p_movesize " << p_move_size_ << std::endl;
   }
   f.log << "Elapsed time: " << wall_seconds() - t_start_ << " seconds." << std::endl;
+  if (getenv("BMG_TIMING"))
+    std::cerr << "[bmg timing] iterations " << n_iter_ << " moves " << move_seconds_ << " s, of which column-stats wait "
+              << device_wait_seconds_ << " s, move-0 delayed rejection " << dr_seconds_ << " s (" << n_dr_ << " events); scans "
+              << scan_seconds_ << " s" << std::endl;
   // _rao.dat (sampler.cpp:847-849): the running mean kept on the device
   p_rao_.assign(m_g_, 0.0);
   BMG_CUDA(cudaSetDevice(store_->device));
@@ -638,7 +643,13 @@ unsigned char Sampler::do_multistep_additions_and_removals()
     if (delay_rejection_ != 0) r_move_size_sum_[movesize_ - 1] += 1.0;
     return movesize_;
   }
-  if (movesize_ <= delay_rejection_ && movesize_ > 1) return delayed_rejection_move0(ms_rem, log_r, log_q_forward, log_q_backward);
+  if (movesize_ <= delay_rejection_ && movesize_ > 1) {
+    const double t0 = wall_seconds();
+    const unsigned char moved = delayed_rejection_move0(ms_rem, log_r, log_q_forward, log_q_backward);
+    dr_seconds_ += wall_seconds() - t0;
+    ++n_dr_;
+    return moved;
+  }
   copy_current_to_proposal();
   undo_move0_flags();
   return 0;

@@ -86,7 +86,8 @@ class Sampler {
   MoveGram gram_;
   // ---- book-keeping (samplerstats.hpp)
   unsigned long n_upd_add_ = 0, n_upd_rem_ = 0, n_comp_ = 0;
-  double move_seconds_ = 0.0, scan_seconds_ = 0.0, device_wait_seconds_ = 0.0;
+  double move_seconds_ = 0.0, scan_seconds_ = 0.0, device_wait_seconds_ = 0.0, dr_seconds_ = 0.0;
+  size_t n_dr_ = 0;
   size_t n_scans_ = 0;
   double t_start_ = 0.0;
   double pves_[3] = {0, 0, 0};

@@ -85,7 +85,7 @@ struct ColStatInline {
   const uint32_t* cols[kInlinePtrs];  // m_c candidate columns, then k model columns
   int m_c, k, m_e;
   int64_t n, W;
-  int n_seg;
+  int n_seg, seg_words;
   const double* y;
   const double* e;
   double* out_host;          // [m_c][n_seg][n_tasks] in mapped host memory
@@ -94,40 +94,39 @@ struct ColStatInline {
   unsigned int seq;
 };
 
+constexpr int kFastSegMax = 256;   // words per CTA on the latency path (64 or 256)
+
 __global__ void __launch_bounds__(256) k_column_stats_inline(const __grid_constant__ ColStatInline a)
 {
-  __shared__ uint32_t cw[kSegWords];
+  __shared__ uint32_t cw[kFastSegMax];
   __shared__ double fpart[8][8];   // [warp][fp task], up to 8 fp tasks (y + 7 covariate columns) on the fast path
   const int c = blockIdx.x, seg = blockIdx.y;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nw = blockDim.x >> 5;
-  const int64_t w0 = (int64_t)seg * kSegWords;
-  const int nwords = (int)min((int64_t)kSegWords, a.W - w0);
+  const int seg_words = a.seg_words;
+  const int64_t w0 = (int64_t)seg * seg_words;
+  const int nwords = (int)min((int64_t)seg_words, a.W - w0);
   const uint32_t* col = a.cols[c];
-  for (int w = t; w < nwords; w += blockDim.x) cw[w] = col[w0 + w];
+  if (t < nwords) cw[t] = col[w0 + t];
   __syncthreads();
   const int n_fp = a.m_e + 1;
   const int n_tasks = n_fp + a.k + a.m_c;
   double* out = a.out_host + ((int64_t)c * a.n_seg + seg) * n_tasks;
 
-  // (1) x_c'y and x_c'E_j: ALL warps sweep the individuals of the segment with coalesced loads
-  //     (lane <-> individual), each warp a contiguous slice; partial sums meet in shared memory.
+  // (1) x_c'y and x_c'E_j: thread <-> individual (coalesced, unconditional loads so that they all issue at once);
+  //     a thread covers individuals i_lo + t + 256 j.
   {
     const int64_t i_lo = 16 * w0, i_hi = min(a.n, i_lo + 16 * (int64_t)nwords);
-    const int64_t span = (i_hi - i_lo + nw - 1) / nw;
-    const int64_t my_lo = i_lo + warp * span, my_hi = min(i_hi, my_lo + span);
     double acc[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) acc[q] = 0.0;
-    for (int64_t i = my_lo + lane; i < my_hi; i += 32) {
+#pragma unroll 4
+    for (int64_t i = i_lo + t; i < i_hi; i += 256) {
       const uint32_t word = cw[(i - i_lo) >> 4];
-      const uint32_t f = (word >> (2 * ((i - i_lo) & 15))) & 3u;
-      if (f) {
-        const double g = f == 1 ? 1.0 : 2.0;
-        acc[0] = fma(g, a.y[i], acc[0]);
+      const double g = (double)((word >> (2 * ((i - i_lo) & 15))) & 3u);
+      acc[0] = fma(g, a.y[i], acc[0]);
 #pragma unroll
-        for (int q = 1; q < 8; ++q)
-          if (q < n_fp) acc[q] = fma(g, a.e[(int64_t)(q - 1) * a.n + i], acc[q]);
-      }
+      for (int q = 1; q < 8; ++q)
+        if (q < n_fp) acc[q] = fma(g, a.e[(int64_t)(q - 1) * a.n + i], acc[q]);
     }
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
@@ -136,14 +135,44 @@ __global__ void __launch_bounds__(256) k_column_stats_inline(const __grid_consta
       if (lane == 0) fpart[warp][q] = v;
     }
   }
-  // (2) x_c'x_l for model columns and other candidates: exact integer popcount arithmetic, one task per warp
-  for (int task = n_fp + warp; task < n_tasks; task += nw) {
-    const int q = task - n_fp;
-    const uint32_t* other = q < a.k ? a.cols[a.m_c + q] : a.cols[q - a.k];
-    int acc = 0;
-    for (int w = lane; w < nwords; w += 32) acc += packed_dot(cw[w], other[w0 + w]);
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) out[task] = (double)acc;
+  // (2) x_c'x_l for model columns and other candidates: exact integer popcount arithmetic.  A warp takes tasks
+  //     warp, warp+8, ...; the words of FOUR tasks are loaded before any is used (one memory round per group).
+  if (seg_words <= 64) {
+    for (int task0 = n_fp + warp; task0 < n_tasks; task0 += 4 * nw) {
+      uint32_t ow[4][2];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int task = task0 + u * nw;
+        const int q = task - n_fp;
+        const uint32_t* other = task < n_tasks ? (q < a.k ? a.cols[a.m_c + q] : a.cols[q - a.k]) + w0 : nullptr;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) ow[u][j] = (other != nullptr && lane + 32 * j < nwords) ? other[lane + 32 * j] : 0u;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int task = task0 + u * nw;
+        int acc = 0;
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          if (lane + 32 * j < nwords) acc += packed_dot(cw[lane + 32 * j], ow[u][j]);
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0 && task < n_tasks) out[task] = (double)acc;
+      }
+    }
+  } else {
+    for (int task = n_fp + warp; task < n_tasks; task += nw) {
+      const int q = task - n_fp;
+      const uint32_t* other = (q < a.k ? a.cols[a.m_c + q] : a.cols[q - a.k]) + w0;
+      uint32_t ow[kFastSegMax / 32];
+#pragma unroll
+      for (int j = 0; j < kFastSegMax / 32; ++j) ow[j] = (lane + 32 * j < nwords) ? other[lane + 32 * j] : 0u;
+      int acc = 0;
+#pragma unroll
+      for (int j = 0; j < kFastSegMax / 32; ++j)
+        if (lane + 32 * j < nwords) acc += packed_dot(cw[lane + 32 * j], ow[j]);
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) out[task] = (double)acc;
+    }
   }
   __syncthreads();
   if (t < n_fp) {
@@ -245,42 +274,15 @@ __global__ void k_sum_segments(const double* __restrict__ seg_out, int m_c, int 
   out[gid] = s;
 }
 
-void chain_column_stats(Chain* c, const int64_t* cand, int m_c, const int64_t* loci, int k, double* xy, double* xe,
-                        double* xx_model, double* xx_cand)
+// second half of the latency path: spin on the completion flag, then reduce the per-slice partials on the host
+void chain_column_stats_wait(Chain* c, double* xy, double* xe, double* xx_model, double* xx_cand)
 {
+  if (!c->cs_pending) return;
   Store* s = c->store;
-  BMG_REQUIRE(m_c >= 1 && m_c <= 256, "bmg_chain_column_stats: 1..256 candidates per call");
-  BMG_REQUIRE(k >= 0 && k <= 2048, "bmg_chain_column_stats: model size must be <= 2048");
-  BMG_CUDA(cudaSetDevice(s->device));
   cudaStream_t st = c->stream;
+  const int m_c = c->cs_p_mc, k = c->cs_p_k, n_seg = c->cs_p_nseg;
   const int n_tasks = s->m_e + 1 + k + m_c;
-  const int n_seg = (int)((s->W + kSegWords - 1) / kSegWords);
-  bool any_missing_fast = false;
-  if (s->n_missing > 0)
-    for (int i = 0; i < m_c + k && !any_missing_fast; ++i) {
-      const int64_t snp = i < m_c ? cand[i] : loci[i - m_c];
-      if (s->is_local(snp) && s->h_miss_off[snp - s->lo + 1] > s->h_miss_off[snp - s->lo]) any_missing_fast = true;
-    }
-  if (m_c + k <= kInlinePtrs && s->m_e + 1 <= 8 && !any_missing_fast && getenv("BMG_COLSTATS_SLOW") == nullptr) {
-    const size_t need_fast = (size_t)m_c * n_tasks * n_seg;
-    if (c->cs_map.n < need_fast + 8) {
-      BMG_CUDA(cudaStreamSynchronize(st));
-      c->cs_map.alloc(need_fast * 2 + 64);
-      if (c->cs_done.n == 0) { c->cs_done.alloc(1); BMG_CUDA(cudaMemset(c->cs_done.p, 0, sizeof(unsigned int))); }
-      if (c->cs_flag.n == 0) { c->cs_flag.alloc(16); c->cs_flag.p[0] = 0; }
-    }
-    ColStatInline a;
-    for (int i = 0; i < m_c + k; ++i) a.cols[i] = s->column_ptr(i < m_c ? cand[i] : loci[i - m_c]);
-    a.m_c = m_c; a.k = k; a.m_e = s->m_e; a.n = s->n; a.W = s->W; a.n_seg = n_seg; a.y = c->y.p; a.e = s->e.p;
-    a.out_host = c->cs_map.p; a.done_count = c->cs_done.p;
-    a.flag_host = reinterpret_cast<volatile unsigned int*>(c->cs_flag.p);
-    a.seq = ++c->cs_seq;
-    k_column_stats_inline<<<dim3(m_c, n_seg), 256, 0, st>>>(a);
-    count_launch();
-    g_d2h_bytes.fetch_add(need_fast * sizeof(double), std::memory_order_relaxed);
-    g_h2d_bytes.fetch_add(sizeof(ColStatInline), std::memory_order_relaxed);
-    const cudaError_t le = cudaGetLastError();
-    if (le != cudaSuccess) throw Error(std::string("k_column_stats_inline launch: ") + cudaGetErrorString(le));
+  struct { unsigned int seq; } a = {c->cs_p_seq};
     volatile unsigned int* flag = reinterpret_cast<volatile unsigned int*>(c->cs_flag.p);
     unsigned long spins = 0;
     while (*flag != a.seq) {
@@ -301,6 +303,60 @@ void chain_column_stats(Chain* c, const int64_t* cand, int m_c, const int64_t* l
         else if (xx_cand) xx_cand[(size_t)ci * m_c + task - 1 - s->m_e - k] = v;
       }
     }
+  c->cs_pending = false;
+}
+
+void chain_column_stats(Chain* c, const int64_t* cand, int m_c, const int64_t* loci, int k, double* xy, double* xe,
+                        double* xx_model, double* xx_cand)
+{
+  chain_column_stats_launch(c, cand, m_c, loci, k, xy, xe, xx_model, xx_cand, false);
+}
+
+// launch_only: on the latency path return right after the launch (results via chain_column_stats_wait); the
+// general path always completes before returning
+void chain_column_stats_launch(Chain* c, const int64_t* cand, int m_c, const int64_t* loci, int k, double* xy, double* xe,
+                               double* xx_model, double* xx_cand, bool launch_only)
+{
+  BMG_REQUIRE(!c->cs_pending, "column statistics: a previous launch has not been collected");
+  Store* s = c->store;
+  BMG_REQUIRE(m_c >= 1 && m_c <= 256, "bmg_chain_column_stats: 1..256 candidates per call");
+  BMG_REQUIRE(k >= 0 && k <= 2048, "bmg_chain_column_stats: model size must be <= 2048");
+  BMG_CUDA(cudaSetDevice(s->device));
+  cudaStream_t st = c->stream;
+  const int n_tasks = s->m_e + 1 + k + m_c;
+  const int n_seg = (int)((s->W + kSegWords - 1) / kSegWords);
+  bool any_missing_fast = false;
+  if (s->n_missing > 0)
+    for (int i = 0; i < m_c + k && !any_missing_fast; ++i) {
+      const int64_t snp = i < m_c ? cand[i] : loci[i - m_c];
+      if (s->is_local(snp) && s->h_miss_off[snp - s->lo + 1] > s->h_miss_off[snp - s->lo]) any_missing_fast = true;
+    }
+  if (m_c + k <= kInlinePtrs && s->m_e + 1 <= 8 && !any_missing_fast && getenv("BMG_COLSTATS_SLOW") == nullptr) {
+    // many small CTAs (one per candidate and 1024- or 4096-individual slice): one round of memory latency each
+    const int seg_words = s->W <= 4096 ? 64 : kFastSegMax;
+    const int n_seg = (int)((s->W + seg_words - 1) / seg_words);
+    const size_t need_fast = (size_t)m_c * n_tasks * n_seg;
+    if (c->cs_map.n < need_fast + 8) {
+      BMG_CUDA(cudaStreamSynchronize(st));
+      c->cs_map.alloc(need_fast * 2 + 64);
+      if (c->cs_done.n == 0) { c->cs_done.alloc(1); BMG_CUDA(cudaMemset(c->cs_done.p, 0, sizeof(unsigned int))); }
+      if (c->cs_flag.n == 0) { c->cs_flag.alloc(16); c->cs_flag.p[0] = 0; }
+    }
+    ColStatInline a;
+    for (int i = 0; i < m_c + k; ++i) a.cols[i] = s->column_ptr(i < m_c ? cand[i] : loci[i - m_c]);
+    a.m_c = m_c; a.k = k; a.m_e = s->m_e; a.n = s->n; a.W = s->W; a.n_seg = n_seg; a.seg_words = seg_words; a.y = c->y.p; a.e = s->e.p;
+    a.out_host = c->cs_map.p; a.done_count = c->cs_done.p;
+    a.flag_host = reinterpret_cast<volatile unsigned int*>(c->cs_flag.p);
+    a.seq = ++c->cs_seq;
+    k_column_stats_inline<<<dim3(m_c, n_seg), 256, 0, st>>>(a);
+    count_launch();
+    g_d2h_bytes.fetch_add(need_fast * sizeof(double), std::memory_order_relaxed);
+    g_h2d_bytes.fetch_add(sizeof(ColStatInline), std::memory_order_relaxed);
+    const cudaError_t le = cudaGetLastError();
+    if (le != cudaSuccess) throw Error(std::string("k_column_stats_inline launch: ") + cudaGetErrorString(le));
+    c->cs_pending = true;
+    c->cs_p_mc = m_c; c->cs_p_k = k; c->cs_p_nseg = n_seg; c->cs_p_seq = a.seq;
+    if (!launch_only) chain_column_stats_wait(c, xy, xe, xx_model, xx_cand);
     return;
   }
   const size_t need = (size_t)m_c * n_tasks * (n_seg + 1);

@@ -70,16 +70,29 @@ class Prior {
   const std::vector<double>& inv_tau2_e() const { return inv_tau2_e_; }
   double e_g() const { return g_a_ / (g_a_ + g_b_) * (double)m_g_; }
 
-  // prior.hpp:144-167 with Ns = number of type-A terms = L
+  // prior.hpp:144-167 with Ns = number of type-A terms = L.  The values depend on L only, so they are tabulated
+  // on first use (the delayed-rejection enumeration asks for them 2^ms times per event).
   double log_change_on_add(int L) const
   {
-    return (std::log(g_a_ + L) - std::log(g_b_ + (double)m_g_ - L - 1)) +
-           (std::log(types_prior_[kA] + L) - std::log(types_prior_sum_ + L));
+    if (L >= 0 && L < (int)add_tab_.size() && add_tab_[L] == add_tab_[L]) return add_tab_[L];
+    const double v = (std::log(g_a_ + L) - std::log(g_b_ + (double)m_g_ - L - 1)) +
+                     (std::log(types_prior_[kA] + L) - std::log(types_prior_sum_ + L));
+    if (L >= 0 && L < kMaxModelColumns + 2) {
+      if ((int)add_tab_.size() <= L) add_tab_.resize(L + 1, NAN);
+      add_tab_[L] = v;
+    }
+    return v;
   }
   double log_change_on_rem(int L) const
   {
-    return (std::log(g_b_ + (double)m_g_ - L) - std::log(g_a_ + L - 1)) +
-           (std::log(types_prior_sum_ + L - 1) - std::log(types_prior_[kA] + L - 1));
+    if (L >= 0 && L < (int)rem_tab_.size() && rem_tab_[L] == rem_tab_[L]) return rem_tab_[L];
+    const double v = (std::log(g_b_ + (double)m_g_ - L) - std::log(g_a_ + L - 1)) +
+                     (std::log(types_prior_sum_ + L - 1) - std::log(types_prior_[kA] + L - 1));
+    if (L >= 0 && L < kMaxModelColumns + 2) {
+      if ((int)rem_tab_.size() <= L) rem_tab_.resize(L + 1, NAN);
+      rem_tab_[L] = v;
+    }
+    return v;
   }
   double log_model(int L) const
   {
@@ -130,6 +143,7 @@ class Prior {
   double inv_tau2_alpha2_;
   double types_prior_[5];
   double types_prior_sum_;
+  mutable std::vector<double> add_tab_, rem_tab_;
 
   double sample_alpha(Model* model, ChainRng& rng);  // prior.cpp:30-69
   void sample_tau2(Model* model, ChainRng& rng);     // prior.cpp:71-114
@@ -436,6 +450,7 @@ struct ExhModel {
   int m_e = 0;
   UpperMat l;
   std::vector<double> xy, v, inv_tau2_alpha2;
+  std::vector<double> log_diag, log_tau;   // log l(i,i) and log inv_tau2_alpha2[i], kept in step with the swaps
   double syx_plus_vs2 = 0, log_det_invQ = 0, log_det_invQ_plus_xx = 0, log_likelihood = 0, log_model_prior = 0;
   int model_size = 0, v_size = 0, n_terms = 0;
 
@@ -450,15 +465,20 @@ struct ExhModel {
     xy = src.xy;
     v = src.v;
     inv_tau2_alpha2 = src.inv_tau2_alpha2;
+    const int k = src.cols();
+    log_diag.resize(k);
+    log_tau.resize(k);
+    for (int i = 0; i < k; ++i) log_diag[i] = std::log(l(i, i));
+    for (int i = m_e; i < k; ++i) log_tau[i] = std::log(inv_tau2_alpha2[i]);
     model_size = const_loci;
     v_size = m_e + const_loci;
     double vv = 0.0;
     for (int i = 0; i < v_size; ++i) vv += v[i] * v[i];
     syx_plus_vs2 = prior->nus2_plus_yy - vv;
     log_det_invQ_plus_xx = 0.0;
-    for (int i = 0; i < v_size; ++i) log_det_invQ_plus_xx += std::log(l(i, i));
+    for (int i = 0; i < v_size; ++i) log_det_invQ_plus_xx += log_diag[i];
     log_det_invQ = prior->log_det_invQ_e();
-    for (int i = m_e; i < v_size; ++i) log_det_invQ += std::log(inv_tau2_alpha2[i]);
+    for (int i = m_e; i < v_size; ++i) log_det_invQ += log_tau[i];
     log_det_invQ *= 0.5;
     refresh();
     log_model_prior = 0.0;
@@ -468,8 +488,8 @@ struct ExhModel {
   double update_on_add()  // model.hpp:673-704
   {
     syx_plus_vs2 -= v[v_size] * v[v_size];
-    log_det_invQ += 0.5 * std::log(inv_tau2_alpha2[v_size]);
-    log_det_invQ_plus_xx += std::log(l(v_size, v_size));
+    log_det_invQ += 0.5 * log_tau[v_size];
+    log_det_invQ_plus_xx += log_diag[v_size];
     ++v_size;
     refresh();
     log_model_prior += prior->log_change_on_add(model_size);
@@ -482,17 +502,20 @@ struct ExhModel {
     --model_size;
     --v_size;  // the kept variable
     syx_plus_vs2 += v[v_size] * v[v_size];
-    log_det_invQ_plus_xx -= std::log(l(v_size, v_size));
+    log_det_invQ_plus_xx -= log_diag[v_size];
     --v_size;  // the removed variable
     syx_plus_vs2 += v[v_size] * v[v_size];
-    log_det_invQ -= 0.5 * std::log(inv_tau2_alpha2[v_size]);
-    log_det_invQ_plus_xx -= std::log(l(v_size, v_size));
+    log_det_invQ -= 0.5 * log_tau[v_size];
+    log_det_invQ_plus_xx -= log_diag[v_size];
     const int ind_keep = m_e + model_size, ind_rem = m_e + model_size - 1;
     l.swap_adjacent(ind_rem, v.data());
+    log_diag[ind_rem] = std::log(l(ind_rem, ind_rem));
+    log_diag[ind_keep] = std::log(l(ind_keep, ind_keep));
     std::swap(xy[ind_keep], xy[ind_rem]);
     std::swap(inv_tau2_alpha2[ind_keep], inv_tau2_alpha2[ind_rem]);
+    std::swap(log_tau[ind_keep], log_tau[ind_rem]);
     syx_plus_vs2 -= v[v_size] * v[v_size];
-    log_det_invQ_plus_xx += std::log(l(v_size, v_size));
+    log_det_invQ_plus_xx += log_diag[v_size];
     ++v_size;
     refresh();
     log_model_prior += prior->log_change_on_rem(model_size + 1);

@@ -196,23 +196,38 @@ void Sampler::copy_current_to_proposal()
   for (size_t i = 0; i < proposal_.loci.size(); ++i) pos_in_proposal_[proposal_.loci[i]] = (int32_t)i;
 }
 
-// one device launch: statistics of every SNP the move wants to add against y, E, the current model and each other
-void Sampler::fetch_gram(const std::vector<uint32_t>& cand)
+// one device launch: statistics of every SNP the move wants to add against y, E, the current model and each other.
+// begin_gram() returns as soon as the kernel is queued; finish_gram() collects the numbers, so host work that does
+// not need them (the removals of the move) overlaps the device round trip.
+void Sampler::begin_gram(const std::vector<uint32_t>& cand)
 {
   gram_.m_e = (int)m_e_;
   gram_.k_cur = (int)current_.loci.size();
   gram_.m_c = (int)cand.size();
   gram_.cand = cand;
   if (cand.empty()) return;
-  std::vector<int64_t> c64(cand.begin(), cand.end()), l64(current_.loci.begin(), current_.loci.end());
+  gram_c64_.assign(cand.begin(), cand.end());
+  gram_l64_.assign(current_.loci.begin(), current_.loci.end());
   gram_.xy.assign(cand.size(), 0.0);
   gram_.xe.assign(cand.size() * m_e_, 0.0);
-  gram_.xm.assign(cand.size() * std::max<size_t>(1, l64.size()), 0.0);
+  gram_.xm.assign(cand.size() * std::max<size_t>(1, gram_l64_.size()), 0.0);
   gram_.xc.assign(cand.size() * cand.size(), 0.0);
   const double t0 = wall_seconds();
-  chain_column_stats(chain_, c64.data(), (int)c64.size(), l64.data(), (int)l64.size(), gram_.xy.data(), gram_.xe.data(),
-                     gram_.xm.data(), gram_.xc.data());
+  chain_column_stats_launch(chain_, gram_c64_.data(), (int)gram_c64_.size(), gram_l64_.data(), (int)gram_l64_.size(),
+                            gram_.xy.data(), gram_.xe.data(), gram_.xm.data(), gram_.xc.data(), true);
   device_wait_seconds_ += wall_seconds() - t0;
+}
+void Sampler::finish_gram()
+{
+  if (gram_.m_c == 0) return;
+  const double t0 = wall_seconds();
+  chain_column_stats_wait(chain_, gram_.xy.data(), gram_.xe.data(), gram_.xm.data(), gram_.xc.data());
+  device_wait_seconds_ += wall_seconds() - t0;
+}
+void Sampler::fetch_gram(const std::vector<uint32_t>& cand)
+{
+  begin_gram(cand);
+  finish_gram();
 }
 
 // Model::add_term for a candidate SNP of this move (model.hpp:453-470 supplies the column; here it comes from gram_)
@@ -596,7 +611,7 @@ void Sampler::do_addrem(double& log_q_forward, double& log_q_backward, double& l
   std::vector<uint32_t> cand;
   for (unsigned char i = 0; i < ms; ++i)
     if (move_isadd_[i]) cand.push_back((uint32_t)move_inds_[i]);
-  fetch_gram(cand);
+  begin_gram(cand);
   for (unsigned char i = 0; i < ms; ++i) {   // removals first
     if (move_isadd_[i]) continue;
     const size_t ind = move_inds_[i];
@@ -607,6 +622,7 @@ void Sampler::do_addrem(double& log_q_forward, double& log_q_backward, double& l
     log_mpc += prior_->log_change_on_rem((int)proposal_.size());
     remove_from_proposal(model_ind);
   }
+  finish_gram();
   for (unsigned char i = 0; i < ms; ++i) {   // then additions
     if (!move_isadd_[i]) continue;
     const size_t ind = move_inds_[i];
@@ -844,13 +860,14 @@ unsigned char Sampler::do_statechange_of_nearby_snps()
   }
   std::vector<uint32_t> cand(ms_add);
   for (unsigned char i = 0; i < ms_add; ++i) cand[i] = (uint32_t)move_inds_add_[i];
-  fetch_gram(cand);
+  begin_gram(cand);
   double log_mpc = 0.0;
   for (unsigned char i = 0; i < ms_rem; ++i) {
     const int model_ind_rem = pos_in_proposal_[move_inds_rem_[i]];
     log_mpc += prior_->log_change_on_rem((int)proposal_.size());
     remove_from_proposal(model_ind_rem);
   }
+  finish_gram();
   for (unsigned char i = 0; i < ms_add; ++i) {
     log_mpc += prior_->log_change_on_add((int)proposal_.size());
     const double tau = prior_->draw_inv_tau2_alpha2(rng_);
@@ -1013,7 +1030,11 @@ void compute_proposal_probs_for_exh_modelset(int n_inds, const unsigned char* bi
                                              const double* q_rem, double z_add, double z_rem, size_t const_loci, size_t m_g,
                                              double* log_prop_probs)
 {
-  std::vector<char> isadd(n_inds);
+  // sampler.cpp:982-1049.  Same sequence of factors as the reference; the logs of the ms weights are taken once
+  // and the normalising totals are multiplied up and logged once per sub-model instead of once per step.
+  char isadd[256];
+  double lq_add[256], lq_rem[256];
+  for (int j = 0; j < n_inds; ++j) { lq_add[j] = std::log(q_add[j]); lq_rem[j] = std::log(q_rem[j]); }
   const unsigned long nmodels = 1ul << n_inds;
   for (unsigned long i = 0; i < nmodels; ++i) {
     size_t max_adds = m_g - const_loci, max_rems = const_loci;
@@ -1030,21 +1051,25 @@ void compute_proposal_probs_for_exh_modelset(int n_inds, const unsigned char* bi
         isadd[nind] = 1;
       }
     }
-    int last_rem_pos = n_inds - 1;
+    int last_rem_pos = n_inds - 1, n_half = 0;
+    double sum_log_q = 0.0, prod_z = 1.0;
     for (int j = 0; j < n_inds; ++j) {
-      if (max_adds > 0 && max_rems > 0) log_prop_probs[i] += kLogHalf;
+      if (max_adds > 0 && max_rems > 0) ++n_half;
       if (isadd[j]) {
         --max_adds;
-        log_prop_probs[i] += std::log(q_add[j]) - std::log(z_a);
+        sum_log_q += lq_add[j];
+        prod_z *= z_a;
         z_a -= q_add[j];
       } else {
         --max_rems;
         while (isadd[last_rem_pos]) --last_rem_pos;
-        log_prop_probs[i] += std::log(q_rem[last_rem_pos]) - std::log(z_r);
+        sum_log_q += lq_rem[last_rem_pos];
+        prod_z *= z_r;
         z_r -= q_rem[last_rem_pos];
         --last_rem_pos;
       }
     }
+    log_prop_probs[i] += (double)n_half * kLogHalf + sum_log_q - std::log(prod_z);
   }
 }
 

@@ -109,6 +109,9 @@ class Sampler {
   void copy_proposal_to_current();
   void copy_current_to_proposal();
   void fetch_gram(const std::vector<uint32_t>& cand);
+  void begin_gram(const std::vector<uint32_t>& cand);
+  void finish_gram();
+  std::vector<int64_t> gram_c64_, gram_l64_;
   void add_to_proposal(uint32_t snp, double inv_tau2_alpha2);
   void readd_to_proposal(uint32_t snp);
   void remove_from_proposal(int model_ind);

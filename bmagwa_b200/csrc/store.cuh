@@ -70,6 +70,9 @@ struct Chain {
   PinnedBuf<unsigned int> cs_flag;              // completion sequence number (host-visible)
   DevBuf<unsigned int> cs_done;                 // CTA arrival counter
   unsigned int cs_seq = 0;
+  bool cs_pending = false;
+  int cs_p_mc = 0, cs_p_k = 0, cs_p_nseg = 0;
+  unsigned int cs_p_seq = 0;
 };
 
 Chain* chain_create(Store* s);
@@ -88,6 +91,9 @@ void chain_set_zeroed(Chain* c, int which, int64_t snp, int flag);
 void chain_fill_zeroed(Chain* c, int which, int flag);
 void chain_column_stats(Chain* c, const int64_t* cand, int m_c, const int64_t* loci, int k, double* xy, double* xe,
                         double* xx_model, double* xx_cand);
+void chain_column_stats_launch(Chain* c, const int64_t* cand, int m_c, const int64_t* loci, int k, double* xy, double* xe,
+                               double* xx_model, double* xx_cand, bool launch_only);
+void chain_column_stats_wait(Chain* c, double* xy, double* xe, double* xx_model, double* xx_cand);
 void chain_probit_update(Chain* c, const uint8_t* is_case, const double* u01, uint64_t seed, uint64_t counter,
                          double* stats2);
 

@@ -286,12 +286,12 @@ BMG_API int bmg_chain_scan_dots(bmg_chain* c, double* dot_host)
   if (dot_host) {
     // sum the per-chunk partials on the host side of the copy (tests / roofline probe only)
     const int64_t m = ch->store->m;
-    std::vector<double> tmp((size_t)ch->scan_chunks * m);
-    bmg::copy_d2h(tmp.data(), ch->dot_partial.p, tmp.size() * sizeof(double), ch->stream);
+    std::vector<double> tmp((size_t)ch->last_chunks * m);
+    bmg::copy_d2h(tmp.data(), ch->last_partial, tmp.size() * sizeof(double), ch->stream);
     BMG_CUDA(cudaStreamSynchronize(ch->stream));
     for (int64_t j = 0; j < m; ++j) {
       double s = 0.0;
-      for (int q = 0; q < ch->scan_chunks; ++q) s += tmp[(size_t)q * m + j];
+      for (int q = 0; q < ch->last_chunks; ++q) s += tmp[(size_t)q * m + j];
       dot_host[j] = s;
     }
   }
@@ -300,7 +300,7 @@ BMG_API int bmg_chain_scan_dots(bmg_chain* c, double* dot_host)
 BMG_API int bmg_chain_set_scan_variant(bmg_chain* c, int variant)
 {
   BMG_TRY
-  BMG_REQUIRE(variant == 0 || variant == 1, "bmg_chain_set_scan_variant: variant must be 0 or 1");
+  BMG_REQUIRE(variant >= 0 && variant <= 2, "bmg_chain_set_scan_variant: variant must be 0, 1 or 2");
   Cn(c)->scan_variant = variant;
   BMG_CATCH
 }

@@ -477,6 +477,7 @@ void chain_probit_update(Chain* c, const uint8_t* is_case, const double* u01, ui
   bmg::copy_d2h(c->h_red.p, c->red_out.p, 2 * sizeof(double), st);
   BMG_CUDA(cudaStreamSynchronize(st));
   c->residual_valid = false;  // the phenotype changed: the residual must be rebuilt
+  c->imma_q_valid = false;
   if (stats2) { stats2[0] = c->h_red.p[0]; stats2[1] = c->h_red.p[1]; }
 }
 

@@ -551,6 +551,10 @@ Chain* chain_create(Store* s)
   BMG_CUDA(cudaSetDevice(s->device));
   std::unique_ptr<Chain> c(new Chain());
   c->store = s;
+  if (const char* env = getenv("BMG_SCAN_VARIANT")) {
+    const int v = atoi(env);
+    if (v >= 0 && v <= 2) c->scan_variant = v;
+  }
   BMG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   choose_scan_geometry(c.get());
   const int64_t n = s->n, m = s->m;
@@ -677,6 +681,7 @@ void chain_residual(Chain* c, const int64_t* loci, const double* beta_e, const d
   BMG_CUDA(cudaStreamSynchronize(st));
   c->sum_r = c->h_red.p[0];
   c->residual_valid = true;
+  c->imma_q_valid = false;
   if (stats9) for (int q = 0; q < kRed; ++q) stats9[q] = c->h_red.p[q];
 }
 
@@ -690,6 +695,7 @@ void chain_scan_dots(Chain* c)
   a.chunk_words = (int)c->scan_chunk_words; a.n_chunks = c->scan_chunks;
   a.tiles = (s->m + kTileSnps - 1) / kTileSnps; a.slices = c->scan_ctas_per_chunk; a.out = c->dot_partial.p;
   const unsigned grid = (unsigned)(c->scan_chunks * c->scan_ctas_per_chunk);
+  if (c->scan_variant == 2) imma_quantize(c);   // residual -> fixed-point limbs, outside the timed pair
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   if (c->time_scan) {
     if (c->scan_ev_used >= 4096) {   // fold finished pairs into the running total
@@ -711,11 +717,17 @@ void chain_scan_dots(Chain* c)
     ev1 = c->scan_ev[2 * c->scan_ev_used + 1];
     BMG_CUDA(cudaEventRecord(ev0, c->stream));
   }
-  if (c->scan_variant == 1)
-    k_scan_dots_tma<<<grid, 32 * c->scan_warps, scan_smem_bytes(c), c->stream>>>(a);
-  else
-    k_scan_dots_ldg<<<grid, 32 * c->scan_warps, 0, c->stream>>>(a);
-  count_launch();
+  if (c->scan_variant == 2) {
+    imma_launch(c);
+  } else {
+    if (c->scan_variant == 1)
+      k_scan_dots_tma<<<grid, 32 * c->scan_warps, scan_smem_bytes(c), c->stream>>>(a);
+    else
+      k_scan_dots_ldg<<<grid, 32 * c->scan_warps, 0, c->stream>>>(a);
+    count_launch();
+    c->last_partial = c->dot_partial.p;
+    c->last_chunks = c->scan_chunks;
+  }
   if (ev1) {
     BMG_CUDA(cudaEventRecord(ev1, c->stream));
     ++c->scan_ev_used;
@@ -745,7 +757,7 @@ void chain_scan(Chain* c, const int64_t* loci, const double* beta_g, const doubl
     count_launch();
   }
   FinalizeArgs f;
-  f.dot_partial = c->dot_partial.p; f.n_chunks = c->scan_chunks; f.m = s->m; f.lo = s->lo; f.n = s->n;
+  f.dot_partial = c->last_partial; f.n_chunks = c->last_chunks; f.m = s->m; f.lo = s->lo; f.n = s->n;
   f.n1 = s->n1.p; f.n2 = s->n2.p; f.miss_corr = s->n_missing > 0 ? c->miss_corr.p : nullptr;
   f.loci = c->loci_dev.p; f.beta_g = c->beta_dev.p; f.tau_g = c->taug_dev.p; f.k = k;
   f.sum_r = c->sum_r; f.sigma2 = prm->sigma2; f.lmp_add = prm->lmp_add; f.lmp_rem = prm->lmp_rem;

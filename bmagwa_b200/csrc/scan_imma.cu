@@ -1,0 +1,296 @@
+// scan_imma.cu -- the genotype scan on the integer tensor cores (scan variant 2).
+//
+// Same contract as k_scan_dots_tma in scan.cu -- dot_j = sum_i x_ij r_i for every SNP of the shard,
+// each packed byte read once -- but the multiply-adds leave the FP64 pipe, which caps a
+// one-DFMA-per-genotype kernel at ~1/3 of HBM bandwidth on B200 (profiles/round1_notes.md):
+//
+//   * the residual is converted ONCE per scan to 62-bit fixed point, q_i = round(r_i 2^S) with
+//     S chosen from max|r|, and split into eight signed base-256 digits ("limbs"),
+//       q_i = sum_b d_ib 256^b,  d_ib in [-128, 127];
+//   * a tile of 16 SNPs x 32 individuals (int8 genotypes 0/1/2) times 32 individuals x 8 limbs is one
+//     mma.sync.aligned.m16n8k32.s8.s8.s32 (SASS IMMA.16832.S8.S8): the 8 limb sums per SNP accumulate
+//     exactly in int32; dot_j = 2^-S sum_b D_jb 256^b.  Integer arithmetic is associative, so the
+//     result is independent of tiling, warp order and chunking (bit-reproducible), and its only error
+//     is the 2^-62 max|r| quantisation -- smaller than the rounding of an fp64 accumulation.
+//   * per thread, the limb fragments of its 512-individual slice stay in registers for the whole
+//     kernel (8 x uint4); genotype words come from the bulk-async (TMA) stage ring; the 2-bit -> int8
+//     expansion is one shared-memory look-up per packed byte in a 32-way replicated (bank-conflict
+//     free) 256-entry table.  Instruction budget: 28 per warp per 1024 genotypes.
+//
+// This is not a GEMM re-shaping of the problem: the "N" dimension of the MMA is the eight digits of ONE
+// right-hand side, which is what makes a single-RHS GEMV fill the 16x8 tile.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdlib.h>
+#include "common.cuh"
+#include "store.cuh"
+
+namespace bmg {
+
+constexpr int kImmaTile = 16;     // SNPs per tile = M of the MMA
+constexpr int kImmaStages = 3;
+constexpr int kImmaGroups = 8;    // 64-individual groups per warp kept in registers
+constexpr int kImmaWarpWords = 4 * kImmaGroups;   // 32 packed words = 512 individuals per warp
+constexpr int kImmaMaxWarps = 16;
+
+__device__ __forceinline__ uint32_t smem_u32i(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init_i(uint64_t* bar, uint32_t count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32i(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx_i(uint64_t* bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32i(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_i(uint64_t* bar, uint32_t parity)
+{
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32i(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_i(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32i(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32i(bar))
+               : "memory");
+}
+__device__ __forceinline__ void imma16832(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1)
+{
+  asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// ---- residual -> fixed point limbs ------------------------------------------------------------
+// out[0] = S (as int), chosen so that |r_i| 2^S < 2^61 for every i
+__global__ void __launch_bounds__(1024) k_absmax_exp(const double* __restrict__ r, int64_t n, int* __restrict__ scale_exp)
+{
+  __shared__ double sm[32];
+  double mx = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) mx = fmax(mx, fabs(r[i]));
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) mx = fmax(mx, sm[w]);
+    int s = 0;
+    if (mx > 0.0 && isfinite(mx)) s = 60 - ilogb(mx);
+    scale_exp[0] = s;
+  }
+}
+
+// Q layout: [word][limb 0..7][16 individuals] bytes, i.e. one uint4 per (word, limb)
+__global__ void k_quantize(const double* __restrict__ r, int64_t n, int64_t n_pad, const int* __restrict__ scale_exp,
+                           int8_t* __restrict__ q)
+{
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n_pad) return;
+  long long v = 0;
+  if (i < n) v = __double2ll_rn(scalbn(r[i], scale_exp[0]));
+  int8_t* dst = q + ((i >> 4) * 8) * 16 + (i & 15);
+#pragma unroll
+  for (int b = 0; b < 8; ++b) {
+    const int8_t d = (int8_t)(v & 0xFF);   // low byte read as signed
+    dst[b * 16] = d;
+    v = (v - (long long)d) >> 8;
+  }
+}
+
+struct ImmaArgs {
+  const uint32_t* codes;
+  int64_t Wp, m;
+  const uint4* q;          // [words][8]
+  const int* scale_exp;
+  int chunk_words;         // 32 * warps
+  int n_chunks;
+  int64_t tiles;
+  int slices;
+  int row_stride;          // shared-memory row stride in words (chunk_words + 4: conflict-free for the 8 x 4 word pattern)
+  double* out;             // [n_chunks][m]
+};
+
+// dynamic smem: LUT (256*32 words) | kImmaStages * 16 * row_stride words | int acc[2][16][8] | mbarriers
+__global__ void __launch_bounds__(32 * kImmaMaxWarps, 1) k_scan_dots_imma(const __grid_constant__ ImmaArgs a)
+{
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int g = lane >> 2, tig = lane & 3;
+  const int chunk = blockIdx.x % a.n_chunks, slice = blockIdx.x / a.n_chunks;
+  const int64_t c0 = (int64_t)chunk * a.chunk_words;
+  const int row_copy_words = (int)min((int64_t)a.chunk_words, a.Wp - c0);
+  const int RS = a.row_stride;
+  const int stage_words = kImmaTile * RS;
+
+  uint32_t* lut = reinterpret_cast<uint32_t*>(smem_raw);
+  uint32_t* stage0 = lut + 256 * 32;
+  int* acc = reinterpret_cast<int*>(stage0 + (size_t)kImmaStages * stage_words);
+  uint64_t* full = reinterpret_cast<uint64_t*>(acc + 2 * kImmaTile * 8);
+
+  const int64_t tile_lo = a.tiles * slice / a.slices, tile_hi = a.tiles * (slice + 1) / a.slices;
+  const int64_t my_tiles = tile_hi - tile_lo;
+
+  if (t == 0) {
+    for (int s = 0; s < kImmaStages; ++s) mbar_init_i(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // expansion table: packed byte (four value-coded 2-bit fields) -> four int8, replicated once per lane
+  for (int idx = t; idx < 256 * 32; idx += blockDim.x) {
+    const uint32_t b = (uint32_t)idx >> 5;
+    uint32_t v = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t f = (b >> (2 * j)) & 3u;
+      v |= (f == 3u ? 0u : f) << (8 * j);
+    }
+    lut[idx] = v;
+  }
+  for (int idx = t; idx < 2 * kImmaTile * 8; idx += blockDim.x) acc[idx] = 0;
+  __syncthreads();
+
+  auto issue = [&](int64_t it) {
+    const int s = (int)(it % kImmaStages);
+    const int64_t snp0 = (tile_lo + it) * kImmaTile;
+    const int rows = (int)min((int64_t)kImmaTile, a.m - snp0);
+    uint32_t* dst = stage0 + (size_t)s * stage_words;
+    const uint32_t rb = (uint32_t)row_copy_words * 4u;
+    mbar_expect_tx_i(&full[s], rb * (uint32_t)rows);
+    for (int rr = 0; rr < rows; ++rr) bulk_g2s_i(dst + (size_t)rr * RS, a.codes + (snp0 + rr) * a.Wp + c0, rb, &full[s]);
+  };
+  if (t == 0)
+    for (int64_t it = 0; it < min((int64_t)kImmaStages, my_tiles); ++it) issue(it);
+
+  // limb fragments of this thread: limb g of the 16 individuals of word (c0 + 32 warp + 4 grp + tig)
+  uint4 bq[kImmaGroups];
+#pragma unroll
+  for (int grp = 0; grp < kImmaGroups; ++grp) bq[grp] = a.q[(c0 + warp * kImmaWarpWords + 4 * grp + tig) * 8 + g];
+  const int scale_exp = a.scale_exp[0];
+  const uint32_t* lut_lane = lut + lane;
+  const int word_off = warp * kImmaWarpWords + tig;
+
+  for (int64_t it = 0; it < my_tiles; ++it) {
+    const int s = (int)(it % kImmaStages);
+    mbar_wait_i(&full[s], (uint32_t)((it / kImmaStages) & 1));
+    const uint32_t* row_lo = stage0 + (size_t)s * stage_words + (size_t)g * RS + word_off;
+    const uint32_t* row_hi = row_lo + 8 * RS;
+    int c[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int grp = 0; grp < kImmaGroups; ++grp) {
+      const uint32_t wl = row_lo[4 * grp], wh = row_hi[4 * grp];
+      const uint32_t a0 = lut_lane[(wl & 0xFFu) << 5], a2 = lut_lane[((wl >> 8) & 0xFFu) << 5];
+      const uint32_t a1 = lut_lane[(wh & 0xFFu) << 5], a3 = lut_lane[((wh >> 8) & 0xFFu) << 5];
+      imma16832(c, a0, a1, a2, a3, bq[grp].x, bq[grp].y);
+      const uint32_t e0 = lut_lane[((wl >> 16) & 0xFFu) << 5], e2 = lut_lane[(wl >> 24) << 5];
+      const uint32_t e1 = lut_lane[((wh >> 16) & 0xFFu) << 5], e3 = lut_lane[(wh >> 24) << 5];
+      imma16832(c, e0, e1, e2, e3, bq[grp].z, bq[grp].w);
+    }
+    int* tile_acc = acc + (it & 1) * kImmaTile * 8;
+    atomicAdd(&tile_acc[g * 8 + 2 * tig], c[0]);
+    atomicAdd(&tile_acc[g * 8 + 2 * tig + 1], c[1]);
+    atomicAdd(&tile_acc[(g + 8) * 8 + 2 * tig], c[2]);
+    atomicAdd(&tile_acc[(g + 8) * 8 + 2 * tig + 1], c[3]);
+    __syncthreads();   // limb sums complete; every thread is done reading stage s
+    if (t == 0 && it + kImmaStages < my_tiles) issue(it + kImmaStages);
+    if (t < kImmaTile) {
+      const int64_t snp = (tile_lo + it) * kImmaTile + t;
+      int* d = tile_acc + t * 8;
+      const long long lo = (long long)d[0] + ((long long)d[1] << 8) + ((long long)d[2] << 16) + ((long long)d[3] << 24);
+      const long long hi = (long long)d[4] + ((long long)d[5] << 8) + ((long long)d[6] << 16) + ((long long)d[7] << 24);
+#pragma unroll
+      for (int b = 0; b < 8; ++b) d[b] = 0;   // this buffer is used again two tiles later (a barrier lies in between)
+      if (snp < a.m) a.out[(int64_t)chunk * a.m + snp] = scalbn(fma((double)hi, 4294967296.0, (double)lo), -scale_exp);
+    }
+  }
+}
+
+// ---- host side ----------------------------------------------------------------------------------
+void imma_choose_geometry(Chain* c)
+{
+  const int64_t W = c->store->W;
+  double best = -1.0;
+  int best_nw = 1;
+  for (int nw = 1; nw <= kImmaMaxWarps; ++nw) {
+    const int64_t chunks = (W + (int64_t)kImmaWarpWords * nw - 1) / ((int64_t)kImmaWarpWords * nw);
+    double eff = (double)W / (double)(chunks * kImmaWarpWords * nw);
+    if (nw < 4) eff *= 0.9;   // very small CTAs: the 32 KB table and the barriers weigh more
+    if (eff > best + 1e-9 || (eff > best - 1e-9 && nw > best_nw && nw <= 12)) { best = eff; best_nw = nw; }
+  }
+  if (const char* env = getenv("BMG_IMMA_WARPS")) {
+    const int v = atoi(env);
+    if (v >= 1 && v <= kImmaMaxWarps) best_nw = v;
+  }
+  c->imma_warps = best_nw;
+  c->imma_chunk_words = kImmaWarpWords * best_nw;
+  c->imma_chunks = (int)((W + c->imma_chunk_words - 1) / c->imma_chunk_words);
+}
+
+static size_t imma_smem_bytes(const Chain* c)
+{
+  const int RS = (int)c->imma_chunk_words + 4;
+  return (size_t)256 * 32 * 4 + (size_t)kImmaStages * kImmaTile * RS * 4 + 2 * kImmaTile * 8 * sizeof(int) + kImmaStages * sizeof(uint64_t);
+}
+
+void imma_prepare(Chain* c)
+{
+  Store* s = c->store;
+  imma_choose_geometry(c);
+  const int64_t n_pad = 16 * (int64_t)c->imma_chunks * c->imma_chunk_words;
+  c->imma_q.alloc((size_t)n_pad * 8);
+  c->imma_exp.alloc(4);
+  if ((int64_t)c->imma_partial.n < (int64_t)c->imma_chunks * s->m) c->imma_partial.alloc((size_t)c->imma_chunks * s->m);
+  const size_t smem = imma_smem_bytes(c);
+  BMG_REQUIRE(smem <= 227 * 1024, "IMMA scan tile does not fit in shared memory");
+  BMG_CUDA(cudaFuncSetAttribute(k_scan_dots_imma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 1;
+  BMG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan_dots_imma, 32 * c->imma_warps, smem));
+  if (per_sm < 1) per_sm = 1;
+  if (const char* env = getenv("BMG_IMMA_CTAS_PER_SM")) {
+    const int v = atoi(env);
+    if (v >= 1 && v <= per_sm) per_sm = v;
+  }
+  const int64_t tiles = (s->m + kImmaTile - 1) / kImmaTile;
+  int64_t slices = ((int64_t)per_sm * s->sm_count) / c->imma_chunks;
+  if (slices < 1) slices = 1;
+  if (slices > tiles) slices = tiles;
+  c->imma_slices = (int)slices;
+  c->imma_ready = true;
+}
+
+// quantise the current residual into limbs (once per residual)
+void imma_quantize(Chain* c)
+{
+  Store* s = c->store;
+  if (!c->imma_ready) imma_prepare(c);
+  if (c->imma_q_valid) return;
+  cudaStream_t st = c->stream;
+  const int64_t n_pad = 16 * (int64_t)c->imma_chunks * c->imma_chunk_words;
+  k_absmax_exp<<<1, 1024, 0, st>>>(c->r.p, s->n, c->imma_exp.p);
+  k_quantize<<<(unsigned)((n_pad + 255) / 256), 256, 0, st>>>(c->r.p, s->n, n_pad, c->imma_exp.p,
+                                                              reinterpret_cast<int8_t*>(c->imma_q.p));
+  count_launch(2);
+  c->imma_q_valid = true;
+}
+
+// the tensor-core scan into imma_partial ([chunks][m] doubles)
+void imma_launch(Chain* c)
+{
+  Store* s = c->store;
+  ImmaArgs a;
+  a.codes = s->codes.p; a.Wp = s->Wp; a.m = s->m; a.q = reinterpret_cast<const uint4*>(c->imma_q.p); a.scale_exp = c->imma_exp.p;
+  a.chunk_words = (int)c->imma_chunk_words; a.n_chunks = c->imma_chunks; a.tiles = (s->m + kImmaTile - 1) / kImmaTile;
+  a.slices = c->imma_slices; a.row_stride = (int)c->imma_chunk_words + 4; a.out = c->imma_partial.p;
+  k_scan_dots_imma<<<(unsigned)(c->imma_chunks * c->imma_slices), 32 * c->imma_warps, imma_smem_bytes(c), c->stream>>>(a);
+  count_launch();
+  c->last_partial = c->imma_partial.p;
+  c->last_chunks = c->imma_chunks;
+}
+
+}  // namespace bmg

@@ -29,6 +29,15 @@ struct Chain {
   int64_t scan_chunk_words = 0;  // words of each column one CTA covers
   int scan_chunks = 0;       // CTAs along the individual axis
   int scan_ctas_per_chunk = 0;
+  // variant 2 (integer tensor cores, scan_imma.cu)
+  bool imma_ready = false, imma_q_valid = false;
+  int imma_warps = 0, imma_chunks = 0, imma_slices = 0;
+  int64_t imma_chunk_words = 0;
+  DevBuf<unsigned char> imma_q;                 // residual limbs [word][8][16]
+  DevBuf<int> imma_exp;                         // fixed-point exponent S
+  DevBuf<double> imma_partial;                  // [imma_chunks][m]
+  const double* last_partial = nullptr;         // per-chunk dots of the most recent scan
+  int last_chunks = 0;
   // phenotype the chain works on (a copy of the store's y; the probit update overwrites it)
   DevBuf<double> y;
   DevBuf<uint8_t> is_case;
@@ -80,6 +89,9 @@ void chain_destroy(Chain* c);
 void chain_set_missing(Chain* c, int64_t snp, const int8_t* vals, int64_t count);
 void chain_residual(Chain* c, const int64_t* loci, const double* beta_e, const double* beta_g, int k, double* stats9);
 void chain_scan_dots(Chain* c);
+void imma_prepare(Chain* c);
+void imma_quantize(Chain* c);
+void imma_launch(Chain* c);
 void chain_scan(Chain* c, const int64_t* loci, const double* beta_g, const double* tau_g, int k,
                 const bmg_scan_params* prm, double* p_r_host);
 void chain_adapt(Chain* c, int update_rao, int64_t n_rao_mean, int update_prop, int64_t n_prop_mean, double q_add_min,

@@ -135,8 +135,9 @@ int bmg_chain_scan(bmg_chain* c, const int64_t* loci, const double* beta_g, cons
                    const bmg_scan_params* prm, double* p_r_host);
 /* Only the x_j . r reductions of the scan (dot[local m]); the roofline kernel in isolation. */
 int bmg_chain_scan_dots(bmg_chain* c, double* dot_host);
-/* Kernel variant used by bmg_chain_scan/_dots: 0 = direct vectorised global loads,
- * 1 = bulk-async (TMA) staging through shared memory.  Default chosen by the library. */
+/* Kernel variant used by bmg_chain_scan/_dots: 0 = fp64, direct vectorised global loads;
+ * 1 = fp64, bulk-async (TMA) staging through shared memory; 2 = exact fixed-point limbs on the
+ * integer tensor cores (IMMA) with TMA staging.  Default chosen by the library. */
 int bmg_chain_set_scan_variant(bmg_chain* c, int variant);
 
 /* CUDA-event timing of the scan's reduction kernel on the chain's stream (bench.py roofline).

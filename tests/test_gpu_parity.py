@@ -127,7 +127,7 @@ def oracle_yhat(bed, n, loci, beta_e, beta_g, E, miss=None):
     return ye, yg
 
 
-@pytest.mark.parametrize("variant", [1, 0])
+@pytest.mark.parametrize("variant", [2, 1, 0])
 @pytest.mark.parametrize("n,m,k,miss,tau_mode", [
     (30, 7, 2, 0.0, 0), (203, 300, 3, 0.01, 1), (1000, 500, 0, 0.0, 0), (1000, 500, 5, 0.0, 1),
     (5000, 1000, 4, 0.0, 0), (5000, 333, 3, 0.003, 1), (10007, 120, 2, 0.0, 0), (50000, 64, 3, 0.0, 1),
@@ -370,6 +370,11 @@ def test_scan_full_size_linearity_and_checksum(api):
     ch.set_scan_variant(0)
     d0 = ch.scan_dots()
     assert np.abs(d1 - d0).max() <= 1e-12 * np.abs(d1).max()
+    ch.set_scan_variant(2)
+    d2 = ch.scan_dots()
+    assert np.abs(d2 - d0).max() <= 1e-12 * np.abs(d1).max()
+    assert np.array_equal(d2, ch.scan_dots())   # integer accumulation: bit-reproducible
+    ch.set_scan_variant(1)
     # linearity: residual scaled by -2.5 (beta_e = 3.5 on an all-ones covariate gives y - 3.5; use y2 = a*y instead)
     st2 = api.GenotypeStore(None, n, m, recode_to_minor=True, payload_device_ptr=raw.data_ptr())
     st2.set_phenotype(-2.5 * y)

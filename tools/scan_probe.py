@@ -40,7 +40,7 @@ def main():
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
     bytes_scan = m * B
     out = {}
-    for variant in (1, 0):
+    for variant in (2, 1, 0):
         ch.set_scan_variant(variant)
         for _ in range(3):
             ch.scan_dots(fetch=False)
@@ -60,12 +60,13 @@ def main():
         out[variant] = t
         print("variant %d: median %.3f ms  min %.3f ms  -> %.1f GB/s packed (%.1f%% of measured %.0f GB/s)" % (
             variant, t, min(times), bytes_scan / t / 1e6, 100 * bytes_scan / t / 1e6 / peak, peak))
-    d1 = None
     ch.set_scan_variant(1)
     d1 = ch.scan_dots()
     ch.set_scan_variant(0)
     d0 = ch.scan_dots()
-    print("variants agree:", float(np.abs(d1 - d0).max()), "max|dot|", float(np.abs(d1).max()))
+    ch.set_scan_variant(2)
+    d2 = ch.scan_dots()
+    print("variants agree: |v1-v0| %.3g |v2-v0| %.3g max|dot| %.3g" % (float(np.abs(d1 - d0).max()), float(np.abs(d2 - d0).max()), float(np.abs(d1).max())))
 
 
 if __name__ == "__main__":

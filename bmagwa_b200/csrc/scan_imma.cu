@@ -63,6 +63,19 @@ __device__ __forceinline__ void bulk_g2s_i(void* dst_smem, const void* src_gmem,
                "l"(src_gmem), "r"(bytes), "r"(smem_u32i(bar))
                : "memory");
 }
+// expansion look-up of packed byte `j` of word w: one PRMT (ALU pipe) to isolate the byte, one IMAD (FMA pipe) to form
+// the shared-memory address byte * 128 + (table base + 4 * lane), one LDS.  Keeping the address arithmetic off the
+// half-rate ALU pipe is what the kernel's throughput hinges on (profiles/round1_notes.md).
+template <int J>
+__device__ __forceinline__ uint32_t expand_byte(uint32_t w, uint32_t lut_lane_addr)
+{
+  uint32_t b, addr, v;
+  asm("prmt.b32 %0, %1, 0, %2;" : "=r"(b) : "r"(w), "n"(0x4440 + J));
+  asm("mad.lo.u32 %0, %1, 128, %2;" : "=r"(addr) : "r"(b), "r"(lut_lane_addr));
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+
 __device__ __forceinline__ void imma16832(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1)
 {
   asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -173,7 +186,7 @@ __global__ void __launch_bounds__(32 * kImmaMaxWarps, 1) k_scan_dots_imma(const 
 #pragma unroll
   for (int grp = 0; grp < kImmaGroups; ++grp) bq[grp] = a.q[(c0 + warp * kImmaWarpWords + 4 * grp + tig) * 8 + g];
   const int scale_exp = a.scale_exp[0];
-  const uint32_t* lut_lane = lut + lane;
+  const uint32_t lut_lane = smem_u32i(lut + lane);
   const int word_off = warp * kImmaWarpWords + tig;
 
   for (int64_t it = 0; it < my_tiles; ++it) {
@@ -185,11 +198,11 @@ __global__ void __launch_bounds__(32 * kImmaMaxWarps, 1) k_scan_dots_imma(const 
 #pragma unroll
     for (int grp = 0; grp < kImmaGroups; ++grp) {
       const uint32_t wl = row_lo[4 * grp], wh = row_hi[4 * grp];
-      const uint32_t a0 = lut_lane[(wl & 0xFFu) << 5], a2 = lut_lane[((wl >> 8) & 0xFFu) << 5];
-      const uint32_t a1 = lut_lane[(wh & 0xFFu) << 5], a3 = lut_lane[((wh >> 8) & 0xFFu) << 5];
+      const uint32_t a0 = expand_byte<0>(wl, lut_lane), a2 = expand_byte<1>(wl, lut_lane);
+      const uint32_t a1 = expand_byte<0>(wh, lut_lane), a3 = expand_byte<1>(wh, lut_lane);
       imma16832(c, a0, a1, a2, a3, bq[grp].x, bq[grp].y);
-      const uint32_t e0 = lut_lane[((wl >> 16) & 0xFFu) << 5], e2 = lut_lane[(wl >> 24) << 5];
-      const uint32_t e1 = lut_lane[((wh >> 16) & 0xFFu) << 5], e3 = lut_lane[(wh >> 24) << 5];
+      const uint32_t e0 = expand_byte<2>(wl, lut_lane), e2 = expand_byte<3>(wl, lut_lane);
+      const uint32_t e1 = expand_byte<2>(wh, lut_lane), e3 = expand_byte<3>(wh, lut_lane);
       imma16832(c, e0, e1, e2, e3, bq[grp].z, bq[grp].w);
     }
     int* tile_acc = acc + (it & 1) * kImmaTile * 8;

@@ -233,8 +233,15 @@ void imma_choose_geometry(Chain* c)
   for (int nw = 1; nw <= kImmaMaxWarps; ++nw) {
     const int64_t chunks = (W + (int64_t)kImmaWarpWords * nw - 1) / ((int64_t)kImmaWarpWords * nw);
     double eff = (double)W / (double)(chunks * kImmaWarpWords * nw);
-    if (nw < 4) eff *= 0.9;   // very small CTAs: the 32 KB table and the barriers weigh more
-    if (eff > best + 1e-9 || (eff > best - 1e-9 && nw > best_nw && nw <= 12)) { best = eff; best_nw = nw; }
+    // resident warps per SM: 80 registers/thread and ~(32 KB table + stages) of shared memory per CTA
+    const int by_regs = 65536 / (80 * 32 * nw);
+    const size_t smem = (size_t)256 * 32 * 4 + (size_t)kImmaStages * kImmaTile * (kImmaWarpWords * nw + 4) * 4 + 2048;
+    const int by_smem = (int)((227 * 1024) / smem);
+    const int ctas = by_regs < by_smem ? by_regs : by_smem;
+    if (ctas < 1) continue;
+    const double occ = (double)(ctas * nw) / 20.0;
+    eff *= occ < 1.0 ? occ : 1.0;
+    if (eff > best + 1e-9) { best = eff; best_nw = nw; }
   }
   if (const char* env = getenv("BMG_IMMA_WARPS")) {
     const int v = atoi(env);

@@ -17,7 +17,7 @@ void store_get_column(const Store* s, int64_t snp, int type, const int8_t* miss_
 struct Chain {
   Store* store = nullptr;
   cudaStream_t stream = nullptr;
-  int scan_variant = 1;
+  int scan_variant = 2;   // 2 = integer tensor cores (default), 1 = fp64 + TMA staging, 0 = fp64 + direct loads
   // optional CUDA-event timing of the scan's reduction kernel (bench.py roofline): pairs of events
   bool time_scan = false;
   std::vector<cudaEvent_t> scan_ev;

@@ -13,9 +13,12 @@
 //     result is independent of tiling, warp order and chunking (bit-reproducible), and its only error
 //     is the 2^-62 max|r| quantisation -- smaller than the rounding of an fp64 accumulation.
 //   * per thread, the limb fragments of its 512-individual slice stay in registers for the whole
-//     kernel (8 x uint4); genotype words come from the bulk-async (TMA) stage ring; the 2-bit -> int8
-//     expansion is one shared-memory look-up per packed byte in a 32-way replicated (bank-conflict
-//     free) 256-entry table.  Instruction budget: 28 per warp per 1024 genotypes.
+//     kernel (8 x uint4); genotype words come from the bulk-async (TMA) stage ring;
+//   * the 2-bit -> 8-bit expansion costs TWO integer instructions per packed byte and no memory access:
+//     PRMT replicates the byte into the four byte lanes, LOP3 masks lane p with 3 << 2p, which leaves
+//     f_p 4^p in lane p (an unsigned byte, <= 128: the MMA's A operand is .u8).  The factor 4^p is paid
+//     back in the quantisation: the individual at position p of its packed byte is quantised with
+//     exponent S - 2p, so every product still carries 2^S.  Costs 6 of the 62 fixed-point bits.
 //
 // This is not a GEMM re-shaping of the problem: the "N" dimension of the MMA is the eight digits of ONE
 // right-hand side, which is what makes a single-RHS GEMV fill the 16x8 tile.
@@ -63,22 +66,18 @@ __device__ __forceinline__ void bulk_g2s_i(void* dst_smem, const void* src_gmem,
                "l"(src_gmem), "r"(bytes), "r"(smem_u32i(bar))
                : "memory");
 }
-// expansion look-up of packed byte `j` of word w: one PRMT (ALU pipe) to isolate the byte, one IMAD (FMA pipe) to form
-// the shared-memory address byte * 128 + (table base + 4 * lane), one LDS.  Keeping the address arithmetic off the
-// half-rate ALU pipe is what the kernel's throughput hinges on (profiles/round1_notes.md).
+// packed byte J of word w -> four unsigned bytes (f_0, 4 f_1, 16 f_2, 64 f_3): PRMT + LOP3, both on the ALU pipe
 template <int J>
-__device__ __forceinline__ uint32_t expand_byte(uint32_t w, uint32_t lut_lane_addr)
+__device__ __forceinline__ uint32_t expand_byte(uint32_t w)
 {
-  uint32_t b, addr, v;
-  asm("prmt.b32 %0, %1, 0, %2;" : "=r"(b) : "r"(w), "n"(0x4440 + J));
-  asm("mad.lo.u32 %0, %1, 128, %2;" : "=r"(addr) : "r"(b), "r"(lut_lane_addr));
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
-  return v;
+  uint32_t rep;
+  asm("prmt.b32 %0, %1, 0, %2;" : "=r"(rep) : "r"(w), "n"(0x1111 * J));
+  return rep & 0xC0300C03u;
 }
 
 __device__ __forceinline__ void imma16832(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1)
 {
-  asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+  asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
@@ -108,7 +107,7 @@ __global__ void k_quantize(const double* __restrict__ r, int64_t n, int64_t n_pa
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n_pad) return;
   long long v = 0;
-  if (i < n) v = __double2ll_rn(scalbn(r[i], scale_exp[0]));
+  if (i < n) v = __double2ll_rn(scalbn(r[i], scale_exp[0] - 2 * (int)(i & 3)));   // 4^p is carried by the genotype operand
   int8_t* dst = q + ((i >> 4) * 8) * 16 + (i & 15);
 #pragma unroll
   for (int b = 0; b < 8; ++b) {
@@ -131,7 +130,7 @@ struct ImmaArgs {
   double* out;             // [n_chunks][m]
 };
 
-// dynamic smem: LUT (256*32 words) | kImmaStages * 16 * row_stride words | int acc[2][16][8] | mbarriers
+// dynamic smem: kImmaStages * 16 * row_stride words | int acc[2][16][8] | mbarriers
 __global__ void __launch_bounds__(32 * kImmaMaxWarps, 1) k_scan_dots_imma(const __grid_constant__ ImmaArgs a)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -143,8 +142,7 @@ __global__ void __launch_bounds__(32 * kImmaMaxWarps, 1) k_scan_dots_imma(const 
   const int RS = a.row_stride;
   const int stage_words = kImmaTile * RS;
 
-  uint32_t* lut = reinterpret_cast<uint32_t*>(smem_raw);
-  uint32_t* stage0 = lut + 256 * 32;
+  uint32_t* stage0 = reinterpret_cast<uint32_t*>(smem_raw);
   int* acc = reinterpret_cast<int*>(stage0 + (size_t)kImmaStages * stage_words);
   uint64_t* full = reinterpret_cast<uint64_t*>(acc + 2 * kImmaTile * 8);
 
@@ -154,17 +152,6 @@ __global__ void __launch_bounds__(32 * kImmaMaxWarps, 1) k_scan_dots_imma(const 
   if (t == 0) {
     for (int s = 0; s < kImmaStages; ++s) mbar_init_i(&full[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  // expansion table: packed byte (four value-coded 2-bit fields) -> four int8, replicated once per lane
-  for (int idx = t; idx < 256 * 32; idx += blockDim.x) {
-    const uint32_t b = (uint32_t)idx >> 5;
-    uint32_t v = 0;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const uint32_t f = (b >> (2 * j)) & 3u;
-      v |= (f == 3u ? 0u : f) << (8 * j);
-    }
-    lut[idx] = v;
   }
   for (int idx = t; idx < 2 * kImmaTile * 8; idx += blockDim.x) acc[idx] = 0;
   __syncthreads();
@@ -186,7 +173,6 @@ __global__ void __launch_bounds__(32 * kImmaMaxWarps, 1) k_scan_dots_imma(const 
 #pragma unroll
   for (int grp = 0; grp < kImmaGroups; ++grp) bq[grp] = a.q[(c0 + warp * kImmaWarpWords + 4 * grp + tig) * 8 + g];
   const int scale_exp = a.scale_exp[0];
-  const uint32_t lut_lane = smem_u32i(lut + lane);
   const int word_off = warp * kImmaWarpWords + tig;
 
   for (int64_t it = 0; it < my_tiles; ++it) {
@@ -198,11 +184,11 @@ __global__ void __launch_bounds__(32 * kImmaMaxWarps, 1) k_scan_dots_imma(const 
 #pragma unroll
     for (int grp = 0; grp < kImmaGroups; ++grp) {
       const uint32_t wl = row_lo[4 * grp], wh = row_hi[4 * grp];
-      const uint32_t a0 = expand_byte<0>(wl, lut_lane), a2 = expand_byte<1>(wl, lut_lane);
-      const uint32_t a1 = expand_byte<0>(wh, lut_lane), a3 = expand_byte<1>(wh, lut_lane);
+      const uint32_t a0 = expand_byte<0>(wl), a2 = expand_byte<1>(wl);
+      const uint32_t a1 = expand_byte<0>(wh), a3 = expand_byte<1>(wh);
       imma16832(c, a0, a1, a2, a3, bq[grp].x, bq[grp].y);
-      const uint32_t e0 = expand_byte<2>(wl, lut_lane), e2 = expand_byte<3>(wl, lut_lane);
-      const uint32_t e1 = expand_byte<2>(wh, lut_lane), e3 = expand_byte<3>(wh, lut_lane);
+      const uint32_t e0 = expand_byte<2>(wl), e2 = expand_byte<3>(wl);
+      const uint32_t e1 = expand_byte<2>(wh), e3 = expand_byte<3>(wh);
       imma16832(c, e0, e1, e2, e3, bq[grp].z, bq[grp].w);
     }
     int* tile_acc = acc + (it & 1) * kImmaTile * 8;
@@ -233,9 +219,9 @@ void imma_choose_geometry(Chain* c)
   for (int nw = 1; nw <= kImmaMaxWarps; ++nw) {
     const int64_t chunks = (W + (int64_t)kImmaWarpWords * nw - 1) / ((int64_t)kImmaWarpWords * nw);
     double eff = (double)W / (double)(chunks * kImmaWarpWords * nw);
-    // resident warps per SM: 80 registers/thread and ~(32 KB table + stages) of shared memory per CTA
+    // resident warps per SM: 80 registers/thread and the stage ring in shared memory
     const int by_regs = 65536 / (80 * 32 * nw);
-    const size_t smem = (size_t)256 * 32 * 4 + (size_t)kImmaStages * kImmaTile * (kImmaWarpWords * nw + 4) * 4 + 2048;
+    const size_t smem = (size_t)kImmaStages * kImmaTile * (kImmaWarpWords * nw + 4) * 4 + 2048;
     const int by_smem = (int)((227 * 1024) / smem);
     const int ctas = by_regs < by_smem ? by_regs : by_smem;
     if (ctas < 1) continue;
@@ -255,7 +241,7 @@ void imma_choose_geometry(Chain* c)
 static size_t imma_smem_bytes(const Chain* c)
 {
   const int RS = (int)c->imma_chunk_words + 4;
-  return (size_t)256 * 32 * 4 + (size_t)kImmaStages * kImmaTile * RS * 4 + 2 * kImmaTile * 8 * sizeof(int) + kImmaStages * sizeof(uint64_t);
+  return (size_t)kImmaStages * kImmaTile * RS * 4 + 2 * kImmaTile * 8 * sizeof(int) + kImmaStages * sizeof(uint64_t);
 }
 
 void imma_prepare(Chain* c)

@@ -31,7 +31,7 @@
 namespace bmg {
 
 constexpr int kImmaTile = 16;     // SNPs per tile = M of the MMA
-constexpr int kImmaStages = 3;
+constexpr int kImmaStages = 4;
 constexpr int kImmaGroups = 8;    // 64-individual groups per warp kept in registers
 constexpr int kImmaWarpWords = 4 * kImmaGroups;   // 32 packed words = 512 individuals per warp
 constexpr int kImmaMaxWarps = 16;
@@ -130,11 +130,22 @@ struct ImmaArgs {
   double* out;             // [n_chunks][m]
 };
 
-// dynamic smem: kImmaStages * 16 * row_stride words | int acc[2][16][8] | mbarriers
-__global__ void __launch_bounds__(32 * kImmaMaxWarps, 1) k_scan_dots_imma(const __grid_constant__ ImmaArgs a)
+__device__ __forceinline__ void mbar_arrive_i(uint64_t* bar)
+{
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32i(bar)) : "memory");
+}
+
+constexpr int kImmaAccBufs = kImmaStages + 1;
+
+// Warp-specialised: blockDim = 32 * (consumer warps + 1).  The last warp is the producer (one lane issues the
+// bulk-async copies, gated by per-stage "empty" mbarriers); consumer warps never meet at a CTA barrier: each adds its
+// int32 limb sums into a shared accumulator and the LAST warp to finish a tile (atomic ticket) combines and stores it.
+// dynamic smem: kImmaStages * 16 * row_stride words | int acc[kImmaAccBufs][16][8] | int ticket[kImmaAccBufs] | mbarriers
+__global__ void __launch_bounds__(32 * (kImmaMaxWarps + 1), 1) k_scan_dots_imma(const __grid_constant__ ImmaArgs a)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int n_cons = (blockDim.x >> 5) - 1;
   const int g = lane >> 2, tig = lane & 3;
   const int chunk = blockIdx.x % a.n_chunks, slice = blockIdx.x / a.n_chunks;
   const int64_t c0 = (int64_t)chunk * a.chunk_words;
@@ -144,30 +155,38 @@ __global__ void __launch_bounds__(32 * kImmaMaxWarps, 1) k_scan_dots_imma(const 
 
   uint32_t* stage0 = reinterpret_cast<uint32_t*>(smem_raw);
   int* acc = reinterpret_cast<int*>(stage0 + (size_t)kImmaStages * stage_words);
-  uint64_t* full = reinterpret_cast<uint64_t*>(acc + 2 * kImmaTile * 8);
+  int* ticket = acc + kImmaAccBufs * kImmaTile * 8;
+  uint64_t* full = reinterpret_cast<uint64_t*>(ticket + 8);
+  uint64_t* empty = full + kImmaStages;
 
   const int64_t tile_lo = a.tiles * slice / a.slices, tile_hi = a.tiles * (slice + 1) / a.slices;
   const int64_t my_tiles = tile_hi - tile_lo;
 
   if (t == 0) {
-    for (int s = 0; s < kImmaStages; ++s) mbar_init_i(&full[s], 1);
+    for (int s = 0; s < kImmaStages; ++s) { mbar_init_i(&full[s], 1); mbar_init_i(&empty[s], (uint32_t)n_cons); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int idx = t; idx < 2 * kImmaTile * 8; idx += blockDim.x) acc[idx] = 0;
+  for (int idx = t; idx < kImmaAccBufs * kImmaTile * 8 + 8; idx += blockDim.x) acc[idx] = 0;   // accumulators and tickets
   __syncthreads();
 
-  auto issue = [&](int64_t it) {
-    const int s = (int)(it % kImmaStages);
-    const int64_t snp0 = (tile_lo + it) * kImmaTile;
-    const int rows = (int)min((int64_t)kImmaTile, a.m - snp0);
-    uint32_t* dst = stage0 + (size_t)s * stage_words;
-    const uint32_t rb = (uint32_t)row_copy_words * 4u;
-    mbar_expect_tx_i(&full[s], rb * (uint32_t)rows);
-    for (int rr = 0; rr < rows; ++rr) bulk_g2s_i(dst + (size_t)rr * RS, a.codes + (snp0 + rr) * a.Wp + c0, rb, &full[s]);
-  };
-  if (t == 0)
-    for (int64_t it = 0; it < min((int64_t)kImmaStages, my_tiles); ++it) issue(it);
+  if (warp == n_cons) {
+    // ---------------- producer warp ----------------
+    if (lane == 0) {
+      const uint32_t rb = (uint32_t)row_copy_words * 4u;
+      for (int64_t it = 0; it < my_tiles; ++it) {
+        const int s = (int)(it % kImmaStages);
+        if (it >= kImmaStages) mbar_wait_i(&empty[s], (uint32_t)(((it / kImmaStages) - 1) & 1));
+        const int64_t snp0 = (tile_lo + it) * kImmaTile;
+        const int rows = (int)min((int64_t)kImmaTile, a.m - snp0);
+        uint32_t* dst = stage0 + (size_t)s * stage_words;
+        mbar_expect_tx_i(&full[s], rb * (uint32_t)rows);
+        for (int rr = 0; rr < rows; ++rr) bulk_g2s_i(dst + (size_t)rr * RS, a.codes + (snp0 + rr) * a.Wp + c0, rb, &full[s]);
+      }
+    }
+    return;
+  }
 
+  // ---------------- consumer warps ----------------
   // limb fragments of this thread: limb g of the 16 individuals of word (c0 + 32 warp + 4 grp + tig)
   uint4 bq[kImmaGroups];
 #pragma unroll
@@ -180,32 +199,45 @@ __global__ void __launch_bounds__(32 * kImmaMaxWarps, 1) k_scan_dots_imma(const 
     mbar_wait_i(&full[s], (uint32_t)((it / kImmaStages) & 1));
     const uint32_t* row_lo = stage0 + (size_t)s * stage_words + (size_t)g * RS + word_off;
     const uint32_t* row_hi = row_lo + 8 * RS;
+    uint32_t wl[kImmaGroups], wh[kImmaGroups];
+#pragma unroll
+    for (int grp = 0; grp < kImmaGroups; ++grp) { wl[grp] = row_lo[4 * grp]; wh[grp] = row_hi[4 * grp]; }
+    __syncwarp();
+    if (lane == 0) mbar_arrive_i(&empty[s]);   // this warp's words are in registers: the stage may be refilled
     int c[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int grp = 0; grp < kImmaGroups; ++grp) {
-      const uint32_t wl = row_lo[4 * grp], wh = row_hi[4 * grp];
-      const uint32_t a0 = expand_byte<0>(wl), a2 = expand_byte<1>(wl);
-      const uint32_t a1 = expand_byte<0>(wh), a3 = expand_byte<1>(wh);
+      const uint32_t a0 = expand_byte<0>(wl[grp]), a2 = expand_byte<1>(wl[grp]);
+      const uint32_t a1 = expand_byte<0>(wh[grp]), a3 = expand_byte<1>(wh[grp]);
       imma16832(c, a0, a1, a2, a3, bq[grp].x, bq[grp].y);
-      const uint32_t e0 = expand_byte<2>(wl), e2 = expand_byte<3>(wl);
-      const uint32_t e1 = expand_byte<2>(wh), e3 = expand_byte<3>(wh);
+      const uint32_t e0 = expand_byte<2>(wl[grp]), e2 = expand_byte<3>(wl[grp]);
+      const uint32_t e1 = expand_byte<2>(wh[grp]), e3 = expand_byte<3>(wh[grp]);
       imma16832(c, e0, e1, e2, e3, bq[grp].z, bq[grp].w);
     }
-    int* tile_acc = acc + (it & 1) * kImmaTile * 8;
+    const int buf = (int)(it % kImmaAccBufs);
+    int* tile_acc = acc + buf * kImmaTile * 8;
     atomicAdd(&tile_acc[g * 8 + 2 * tig], c[0]);
     atomicAdd(&tile_acc[g * 8 + 2 * tig + 1], c[1]);
     atomicAdd(&tile_acc[(g + 8) * 8 + 2 * tig], c[2]);
     atomicAdd(&tile_acc[(g + 8) * 8 + 2 * tig + 1], c[3]);
-    __syncthreads();   // limb sums complete; every thread is done reading stage s
-    if (t == 0 && it + kImmaStages < my_tiles) issue(it + kImmaStages);
-    if (t < kImmaTile) {
-      const int64_t snp = (tile_lo + it) * kImmaTile + t;
-      int* d = tile_acc + t * 8;
-      const long long lo = (long long)d[0] + ((long long)d[1] << 8) + ((long long)d[2] << 16) + ((long long)d[3] << 24);
-      const long long hi = (long long)d[4] + ((long long)d[5] << 8) + ((long long)d[6] << 16) + ((long long)d[7] << 24);
+    __threadfence_block();
+    __syncwarp();
+    int last = 0;
+    if (lane == 0) last = (atomicAdd(&ticket[buf], 1) == n_cons - 1);
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (last) {   // every other warp's sums are in (their fences precede their tickets)
+      __threadfence_block();
+      if (lane < kImmaTile) {
+        const int64_t snp = (tile_lo + it) * kImmaTile + lane;
+        volatile int* d = tile_acc + lane * 8;
+        const long long lo = (long long)d[0] + ((long long)d[1] << 8) + ((long long)d[2] << 16) + ((long long)d[3] << 24);
+        const long long hi = (long long)d[4] + ((long long)d[5] << 8) + ((long long)d[6] << 16) + ((long long)d[7] << 24);
 #pragma unroll
-      for (int b = 0; b < 8; ++b) d[b] = 0;   // this buffer is used again two tiles later (a barrier lies in between)
-      if (snp < a.m) a.out[(int64_t)chunk * a.m + snp] = scalbn(fma((double)hi, 4294967296.0, (double)lo), -scale_exp);
+        for (int b = 0; b < 8; ++b) d[b] = 0;
+        if (snp < a.m) a.out[(int64_t)chunk * a.m + snp] = scalbn(fma((double)hi, 4294967296.0, (double)lo), -scale_exp);
+      }
+      __syncwarp();
+      if (lane == 0) { __threadfence_block(); ticket[buf] = 0; }
     }
   }
 }
@@ -220,7 +252,7 @@ void imma_choose_geometry(Chain* c)
     const int64_t chunks = (W + (int64_t)kImmaWarpWords * nw - 1) / ((int64_t)kImmaWarpWords * nw);
     double eff = (double)W / (double)(chunks * kImmaWarpWords * nw);
     // resident warps per SM: 80 registers/thread and the stage ring in shared memory
-    const int by_regs = 65536 / (80 * 32 * nw);
+    const int by_regs = 65536 / (80 * 32 * (nw + 1));
     const size_t smem = (size_t)kImmaStages * kImmaTile * (kImmaWarpWords * nw + 4) * 4 + 2048;
     const int by_smem = (int)((227 * 1024) / smem);
     const int ctas = by_regs < by_smem ? by_regs : by_smem;
@@ -241,7 +273,7 @@ void imma_choose_geometry(Chain* c)
 static size_t imma_smem_bytes(const Chain* c)
 {
   const int RS = (int)c->imma_chunk_words + 4;
-  return (size_t)kImmaStages * kImmaTile * RS * 4 + 2 * kImmaTile * 8 * sizeof(int) + kImmaStages * sizeof(uint64_t);
+  return (size_t)kImmaStages * kImmaTile * RS * 4 + (size_t)(kImmaStages + 1) * kImmaTile * 8 * sizeof(int) + 8 * sizeof(int) + 2 * kImmaStages * sizeof(uint64_t);
 }
 
 void imma_prepare(Chain* c)
@@ -256,7 +288,7 @@ void imma_prepare(Chain* c)
   BMG_REQUIRE(smem <= 227 * 1024, "IMMA scan tile does not fit in shared memory");
   BMG_CUDA(cudaFuncSetAttribute(k_scan_dots_imma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1;
-  BMG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan_dots_imma, 32 * c->imma_warps, smem));
+  BMG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan_dots_imma, 32 * (c->imma_warps + 1), smem));
   if (per_sm < 1) per_sm = 1;
   if (const char* env = getenv("BMG_IMMA_CTAS_PER_SM")) {
     const int v = atoi(env);
@@ -293,7 +325,7 @@ void imma_launch(Chain* c)
   a.codes = s->codes.p; a.Wp = s->Wp; a.m = s->m; a.q = reinterpret_cast<const uint4*>(c->imma_q.p); a.scale_exp = c->imma_exp.p;
   a.chunk_words = (int)c->imma_chunk_words; a.n_chunks = c->imma_chunks; a.tiles = (s->m + kImmaTile - 1) / kImmaTile;
   a.slices = c->imma_slices; a.row_stride = (int)c->imma_chunk_words + 4; a.out = c->imma_partial.p;
-  k_scan_dots_imma<<<(unsigned)(c->imma_chunks * c->imma_slices), 32 * c->imma_warps, imma_smem_bytes(c), c->stream>>>(a);
+  k_scan_dots_imma<<<(unsigned)(c->imma_chunks * c->imma_slices), 32 * (c->imma_warps + 1), imma_smem_bytes(c), c->stream>>>(a);
   count_launch();
   c->last_partial = c->imma_partial.p;
   c->last_chunks = c->imma_chunks;

@@ -14,11 +14,13 @@
 //     is the 2^-62 max|r| quantisation -- smaller than the rounding of an fp64 accumulation.
 //   * per thread, the limb fragments of its 512-individual slice stay in registers for the whole
 //     kernel (8 x uint4); genotype words come from the bulk-async (TMA) stage ring;
-//   * the 2-bit -> 8-bit expansion costs TWO integer instructions per packed byte and no memory access:
-//     PRMT replicates the byte into the four byte lanes, LOP3 masks lane p with 3 << 2p, which leaves
-//     f_p 4^p in lane p (an unsigned byte, <= 128: the MMA's A operand is .u8).  The factor 4^p is paid
-//     back in the quantisation: the individual at position p of its packed byte is quantised with
-//     exponent S - 2p, so every product still carries 2^S.  Costs 6 of the 62 fixed-point bits.
+//   * the 2-bit -> 8-bit expansion costs ONE integer instruction per four genotypes and no memory access:
+//     w & (0x03030303 << 2p) leaves, in byte lane b, field p of packed byte b times 4^p (an unsigned byte
+//     <= 128: the MMA's A operand is .u8).  Which individual sits at which k of the MMA is free as long as
+//     the limb operand agrees, so the limb bytes of a word are stored in the order the four masks produce
+//     (individuals 0,4,8,12 | 1,5,9,13 | 2,6,10,14 | 3,7,11,15).  The factor 4^p is paid back in the
+//     quantisation: the individual at position p of its packed byte is quantised with exponent S - 2p,
+//     so every product still carries 2^S.  Costs 6 of the 62 fixed-point bits.
 //
 // This is not a GEMM re-shaping of the problem: the "N" dimension of the MMA is the eight digits of ONE
 // right-hand side, which is what makes a single-RHS GEMV fill the 16x8 tile.
@@ -66,14 +68,9 @@ __device__ __forceinline__ void bulk_g2s_i(void* dst_smem, const void* src_gmem,
                "l"(src_gmem), "r"(bytes), "r"(smem_u32i(bar))
                : "memory");
 }
-// packed byte J of word w -> four unsigned bytes (f_0, 4 f_1, 16 f_2, 64 f_3): PRMT + LOP3, both on the ALU pipe
-template <int J>
-__device__ __forceinline__ uint32_t expand_byte(uint32_t w)
-{
-  uint32_t rep;
-  asm("prmt.b32 %0, %1, 0, %2;" : "=r"(rep) : "r"(w), "n"(0x1111 * J));
-  return rep & 0xC0300C03u;
-}
+// field P of each of the four packed bytes of w, scaled by 4^P, one per byte lane: a single LOP3
+template <int P>
+__device__ __forceinline__ uint32_t expand_field(uint32_t w) { return w & (0x03030303u << (2 * P)); }
 
 __device__ __forceinline__ void imma16832(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1)
 {
@@ -100,7 +97,8 @@ __global__ void __launch_bounds__(1024) k_absmax_exp(const double* __restrict__ 
   }
 }
 
-// Q layout: [word][limb 0..7][16 individuals] bytes, i.e. one uint4 per (word, limb)
+// Q layout: [word][limb 0..7][16 slots] bytes, i.e. one uint4 per (word, limb); individual j = 4 b + p of the word
+// (packed byte b, position p) sits in slot 4 p + b, the order expand_field<0..3> delivers them
 __global__ void k_quantize(const double* __restrict__ r, int64_t n, int64_t n_pad, const int* __restrict__ scale_exp,
                            int8_t* __restrict__ q)
 {
@@ -108,7 +106,7 @@ __global__ void k_quantize(const double* __restrict__ r, int64_t n, int64_t n_pa
   if (i >= n_pad) return;
   long long v = 0;
   if (i < n) v = __double2ll_rn(scalbn(r[i], scale_exp[0] - 2 * (int)(i & 3)));   // 4^p is carried by the genotype operand
-  int8_t* dst = q + ((i >> 4) * 8) * 16 + (i & 15);
+  int8_t* dst = q + ((i >> 4) * 8) * 16 + (4 * (i & 3) + ((i >> 2) & 3));
 #pragma unroll
   for (int b = 0; b < 8; ++b) {
     const int8_t d = (int8_t)(v & 0xFF);   // low byte read as signed
@@ -126,7 +124,7 @@ struct ImmaArgs {
   int n_chunks;
   int64_t tiles;
   int slices;
-  int row_stride;          // shared-memory row stride in words (chunk_words + 4: conflict-free for the 8 x 4 word pattern)
+  int row_stride;          // shared-memory row stride in words (chunk_words + 16: two rows x 16 words per LDS.128 phase hit 32 banks)
   double* out;             // [n_chunks][m]
 };
 
@@ -136,12 +134,13 @@ __device__ __forceinline__ void mbar_arrive_i(uint64_t* bar)
 }
 
 constexpr int kImmaAccBufs = kImmaStages + 1;
+__device__ __forceinline__ void fence_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
 
 // Warp-specialised: blockDim = 32 * (consumer warps + 1).  The last warp is the producer (one lane issues the
 // bulk-async copies, gated by per-stage "empty" mbarriers); consumer warps never meet at a CTA barrier: each adds its
 // int32 limb sums into a shared accumulator and the LAST warp to finish a tile (atomic ticket) combines and stores it.
 // dynamic smem: kImmaStages * 16 * row_stride words | int acc[kImmaAccBufs][16][8] | int ticket[kImmaAccBufs] | mbarriers
-__global__ void __launch_bounds__(32 * (kImmaMaxWarps + 1), 1) k_scan_dots_imma(const __grid_constant__ ImmaArgs a)
+__global__ void __maxnreg__(80) k_scan_dots_imma(const __grid_constant__ ImmaArgs a)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -160,7 +159,7 @@ __global__ void __launch_bounds__(32 * (kImmaMaxWarps + 1), 1) k_scan_dots_imma(
   uint64_t* empty = full + kImmaStages;
 
   const int64_t tile_lo = a.tiles * slice / a.slices, tile_hi = a.tiles * (slice + 1) / a.slices;
-  const int64_t my_tiles = tile_hi - tile_lo;
+  const int my_tiles = (int)(tile_hi - tile_lo);
 
   if (t == 0) {
     for (int s = 0; s < kImmaStages; ++s) { mbar_init_i(&full[s], 1); mbar_init_i(&empty[s], (uint32_t)n_cons); }
@@ -173,60 +172,68 @@ __global__ void __launch_bounds__(32 * (kImmaMaxWarps + 1), 1) k_scan_dots_imma(
     // ---------------- producer warp ----------------
     if (lane == 0) {
       const uint32_t rb = (uint32_t)row_copy_words * 4u;
-      for (int64_t it = 0; it < my_tiles; ++it) {
-        const int s = (int)(it % kImmaStages);
-        if (it >= kImmaStages) mbar_wait_i(&empty[s], (uint32_t)(((it / kImmaStages) - 1) & 1));
+      int s = 0;
+      uint32_t round = 0;   // number of times the ring has wrapped
+      for (int it = 0; it < my_tiles; ++it) {
+        if (round) mbar_wait_i(&empty[s], (round - 1) & 1);
         const int64_t snp0 = (tile_lo + it) * kImmaTile;
         const int rows = (int)min((int64_t)kImmaTile, a.m - snp0);
         uint32_t* dst = stage0 + (size_t)s * stage_words;
         mbar_expect_tx_i(&full[s], rb * (uint32_t)rows);
         for (int rr = 0; rr < rows; ++rr) bulk_g2s_i(dst + (size_t)rr * RS, a.codes + (snp0 + rr) * a.Wp + c0, rb, &full[s]);
+        if (++s == kImmaStages) { s = 0; ++round; }
       }
     }
     return;
   }
 
   // ---------------- consumer warps ----------------
-  // limb fragments of this thread: limb g of the 16 individuals of word (c0 + 32 warp + 4 grp + tig)
+  // this thread's words of a warp slice: 16 x + 4 tig + e (x < 2, e < 4) = one uint4 per x; limb g of each
   uint4 bq[kImmaGroups];
 #pragma unroll
-  for (int grp = 0; grp < kImmaGroups; ++grp) bq[grp] = a.q[(c0 + warp * kImmaWarpWords + 4 * grp + tig) * 8 + g];
+  for (int grp = 0; grp < kImmaGroups; ++grp)
+    bq[grp] = a.q[(c0 + warp * kImmaWarpWords + 16 * (grp >> 2) + 4 * tig + (grp & 3)) * 8 + g];
   const int scale_exp = a.scale_exp[0];
-  const int word_off = warp * kImmaWarpWords + tig;
+  const int word_off = warp * kImmaWarpWords + 4 * tig;
 
-  for (int64_t it = 0; it < my_tiles; ++it) {
-    const int s = (int)(it % kImmaStages);
-    mbar_wait_i(&full[s], (uint32_t)((it / kImmaStages) & 1));
+  int s = 0, buf = 0;
+  uint32_t phase = 0;
+  for (int it = 0; it < my_tiles; ++it) {
+    mbar_wait_i(&full[s], phase);
     const uint32_t* row_lo = stage0 + (size_t)s * stage_words + (size_t)g * RS + word_off;
     const uint32_t* row_hi = row_lo + 8 * RS;
     uint32_t wl[kImmaGroups], wh[kImmaGroups];
 #pragma unroll
-    for (int grp = 0; grp < kImmaGroups; ++grp) { wl[grp] = row_lo[4 * grp]; wh[grp] = row_hi[4 * grp]; }
+    for (int x = 0; x < kImmaGroups / 4; ++x) {
+      const uint4 vl = *reinterpret_cast<const uint4*>(row_lo + 16 * x);
+      const uint4 vh = *reinterpret_cast<const uint4*>(row_hi + 16 * x);
+      wl[4 * x] = vl.x; wl[4 * x + 1] = vl.y; wl[4 * x + 2] = vl.z; wl[4 * x + 3] = vl.w;
+      wh[4 * x] = vh.x; wh[4 * x + 1] = vh.y; wh[4 * x + 2] = vh.z; wh[4 * x + 3] = vh.w;
+    }
     __syncwarp();
     if (lane == 0) mbar_arrive_i(&empty[s]);   // this warp's words are in registers: the stage may be refilled
-    int c[4] = {0, 0, 0, 0};
+    int c[4] = {0, 0, 0, 0}, c2[4] = {0, 0, 0, 0};   // two independent IMMA chains
 #pragma unroll
     for (int grp = 0; grp < kImmaGroups; ++grp) {
-      const uint32_t a0 = expand_byte<0>(wl[grp]), a2 = expand_byte<1>(wl[grp]);
-      const uint32_t a1 = expand_byte<0>(wh[grp]), a3 = expand_byte<1>(wh[grp]);
-      imma16832(c, a0, a1, a2, a3, bq[grp].x, bq[grp].y);
-      const uint32_t e0 = expand_byte<2>(wl[grp]), e2 = expand_byte<3>(wl[grp]);
-      const uint32_t e1 = expand_byte<2>(wh[grp]), e3 = expand_byte<3>(wh[grp]);
-      imma16832(c, e0, e1, e2, e3, bq[grp].z, bq[grp].w);
+      imma16832(c, expand_field<0>(wl[grp]), expand_field<0>(wh[grp]), expand_field<1>(wl[grp]), expand_field<1>(wh[grp]),
+                bq[grp].x, bq[grp].y);
+      imma16832(c2, expand_field<2>(wl[grp]), expand_field<2>(wh[grp]), expand_field<3>(wl[grp]), expand_field<3>(wh[grp]),
+                bq[grp].z, bq[grp].w);
     }
-    const int buf = (int)(it % kImmaAccBufs);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) c[e] += c2[e];
     int* tile_acc = acc + buf * kImmaTile * 8;
     atomicAdd(&tile_acc[g * 8 + 2 * tig], c[0]);
     atomicAdd(&tile_acc[g * 8 + 2 * tig + 1], c[1]);
     atomicAdd(&tile_acc[(g + 8) * 8 + 2 * tig], c[2]);
     atomicAdd(&tile_acc[(g + 8) * 8 + 2 * tig + 1], c[3]);
-    __threadfence_block();
+    fence_cta();
     __syncwarp();
     int last = 0;
     if (lane == 0) last = (atomicAdd(&ticket[buf], 1) == n_cons - 1);
     last = __shfl_sync(0xffffffffu, last, 0);
     if (last) {   // every other warp's sums are in (their fences precede their tickets)
-      __threadfence_block();
+      fence_cta();
       if (lane < kImmaTile) {
         const int64_t snp = (tile_lo + it) * kImmaTile + lane;
         volatile int* d = tile_acc + lane * 8;
@@ -234,11 +241,16 @@ __global__ void __launch_bounds__(32 * (kImmaMaxWarps + 1), 1) k_scan_dots_imma(
         const long long hi = (long long)d[4] + ((long long)d[5] << 8) + ((long long)d[6] << 16) + ((long long)d[7] << 24);
 #pragma unroll
         for (int b = 0; b < 8; ++b) d[b] = 0;
-        if (snp < a.m) a.out[(int64_t)chunk * a.m + snp] = scalbn(fma((double)hi, 4294967296.0, (double)lo), -scale_exp);
+        // 2^-S in two always-normal factors (S spans about +-1100)
+        const int h0 = scale_exp / 2, h1 = scale_exp - h0;
+        const double f0 = __hiloint2double((1023 - h0) << 20, 0), f1 = __hiloint2double((1023 - h1) << 20, 0);
+        if (snp < a.m) a.out[(int64_t)chunk * a.m + snp] = fma((double)hi, 4294967296.0, (double)lo) * f0 * f1;
       }
       __syncwarp();
-      if (lane == 0) { __threadfence_block(); ticket[buf] = 0; }
+      if (lane == 0) { fence_cta(); ticket[buf] = 0; }
     }
+    if (++s == kImmaStages) { s = 0; phase ^= 1u; }
+    if (++buf == kImmaAccBufs) buf = 0;
   }
 }
 
@@ -253,7 +265,7 @@ void imma_choose_geometry(Chain* c)
     double eff = (double)W / (double)(chunks * kImmaWarpWords * nw);
     // resident warps per SM: 80 registers/thread and the stage ring in shared memory
     const int by_regs = 65536 / (80 * 32 * (nw + 1));
-    const size_t smem = (size_t)kImmaStages * kImmaTile * (kImmaWarpWords * nw + 4) * 4 + 2048;
+    const size_t smem = (size_t)kImmaStages * kImmaTile * (kImmaWarpWords * nw + 16) * 4 + 2048;
     const int by_smem = (int)((227 * 1024) / smem);
     const int ctas = by_regs < by_smem ? by_regs : by_smem;
     if (ctas < 1) continue;
@@ -272,7 +284,7 @@ void imma_choose_geometry(Chain* c)
 
 static size_t imma_smem_bytes(const Chain* c)
 {
-  const int RS = (int)c->imma_chunk_words + 4;
+  const int RS = (int)c->imma_chunk_words + 16;
   return (size_t)kImmaStages * kImmaTile * RS * 4 + (size_t)(kImmaStages + 1) * kImmaTile * 8 * sizeof(int) + 8 * sizeof(int) + 2 * kImmaStages * sizeof(uint64_t);
 }
 
@@ -324,7 +336,7 @@ void imma_launch(Chain* c)
   ImmaArgs a;
   a.codes = s->codes.p; a.Wp = s->Wp; a.m = s->m; a.q = reinterpret_cast<const uint4*>(c->imma_q.p); a.scale_exp = c->imma_exp.p;
   a.chunk_words = (int)c->imma_chunk_words; a.n_chunks = c->imma_chunks; a.tiles = (s->m + kImmaTile - 1) / kImmaTile;
-  a.slices = c->imma_slices; a.row_stride = (int)c->imma_chunk_words + 4; a.out = c->imma_partial.p;
+  a.slices = c->imma_slices; a.row_stride = (int)c->imma_chunk_words + 16; a.out = c->imma_partial.p;
   k_scan_dots_imma<<<(unsigned)(c->imma_chunks * c->imma_slices), 32 * (c->imma_warps + 1), imma_smem_bytes(c), c->stream>>>(a);
   count_launch();
   c->last_partial = c->imma_partial.p;

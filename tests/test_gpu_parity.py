@@ -350,6 +350,33 @@ def test_probit_latent_update_matches_oracle(api):
     st.close()
 
 
+@pytest.mark.parametrize("n,m", [(5120, 20000), (5000, 20000), (3000, 50000), (8192, 50000), (50000, 20000)])
+def test_scan_imma_repeated_launches_are_bit_identical(api, n, m):
+    """The tensor-core scan accumulates in integers, so every launch on the same residual must give the same
+    bits whatever the timing (launch after an idle GPU, cache-resident store, ragged last chunk): a regression
+    guard for the producer/consumer stage ring.  The fp64 kernel is the cross-check."""
+    import torch
+    B = (n + 3) // 4
+    g = torch.Generator(device="cuda").manual_seed(n + m)
+    raw = torch.randint(0, 256, (m * B,), dtype=torch.uint8, device="cuda", generator=g)
+    raw &= 0b10111011
+    y = np.random.default_rng(n).normal(size=n)
+    st = api.GenotypeStore(None, n, m, recode_to_minor=True, payload_device_ptr=raw.data_ptr())
+    del raw
+    st.set_phenotype(y)
+    ch = api.Chain(st)
+    ch.residual([], [0.0], [])
+    ch.set_scan_variant(0)
+    d0 = ch.scan_dots()
+    ch.set_scan_variant(2)
+    first = ch.scan_dots()
+    assert np.abs(first - d0).max() <= 1e-12 * np.abs(d0).max()
+    for _ in range(6):
+        torch.cuda.synchronize()
+        assert np.array_equal(ch.scan_dots(), first)
+    ch.close(); st.close()
+
+
 # ------------------------------------------------------- full-size property checks (BASELINE C2)
 def test_scan_full_size_linearity_and_checksum(api):
     """n=5000 x m=100000 (BASELINE config 2): size-independent properties instead of an oracle pass:

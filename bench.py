@@ -157,18 +157,33 @@ def scan_traffic(workload):
 # reference arm: the unmodified reference sampler on the host cores (oracle/_ref)
 # ------------------------------------------------------------------------------------------------
 def run_reference_chains(ini, n_chains, n_rao, warmup, steps):
-    """Returns (seconds of the timed K steps, per-chain stats).  One pthread-like host thread per chain over one
-    shared Data, as main.cpp does."""
+    """Returns (seconds of the K timed steps, per-chain wall times).  One host thread per chain over one shared
+    Data, as main.cpp does.  The reference's Sampler::sample() cannot be re-entered on a non-empty model (it rebuilds
+    its removal distribution as if the model were empty, sampler.cpp:599-606), so "W warm-up steps, then K timed"
+    is measured as two deterministic runs of the same seeded chains: T(W + K steps) - T(W steps)."""
     from oracle import ref
-    parent = ref.Ref(ini, 0)
-    chains = [parent] + [ref.Ref(ini, t, parent=parent) for t in range(1, n_chains)]
+    parent = ref.Ref(ini, 0)   # owns the Data; its own sampler is chain 0 of the first set
+    opened = [parent]
+    parent_used = [False]
 
-    def phase(fn_name, iters):
+    def fresh_set():
+        cs = []
+        for t in range(n_chains):
+            if t == 0 and not parent_used[0]:
+                parent_used[0] = True
+                cs.append(parent)
+            else:
+                c = ref.Ref(ini, t, parent=parent)
+                opened.append(c)
+                cs.append(c)
+        return cs
+
+    def phase(chains, iters):
         res = [None] * n_chains
 
         def work(i):
             chains[i].set_do_n_iter(iters)
-            res[i] = getattr(chains[i], fn_name)()
+            res[i] = chains[i].run_chain()
         th = [threading.Thread(target=work, args=(i,)) for i in range(n_chains)]
         t0 = time.perf_counter()
         for t in th:
@@ -177,14 +192,13 @@ def run_reference_chains(ini, n_chains, n_rao, warmup, steps):
             t.join()
         return time.perf_counter() - t0, res
 
+    t_w = 0.0
     if warmup > 0:
-        phase("run_chain", warmup * n_rao)
-        secs, per = phase("continue_chain", steps * n_rao)
-    else:
-        secs, per = phase("run_chain", steps * n_rao)
-    for c in reversed(chains):
+        t_w, _ = phase(fresh_set(), warmup * n_rao)
+    t_wk, per = phase(fresh_set(), (warmup + steps) * n_rao)
+    for c in reversed(opened):
         c.close()
-    return secs, per
+    return t_wk - t_w, per
 
 
 def reference_arm(args, rank, world):
@@ -213,8 +227,9 @@ def reference_arm(args, rank, world):
                    % (args.workload, spec["desc"], n_chains), "n": spec["n"], "m_g": spec["m_g"], "n_rao": args.n_rao,
                    "step": "%d MCMC iterations incl. one all-SNP scan" % args.n_rao},
         "cpu_baseline": {"value": value, "unit": "iterations/s", "cores": n_chains, "kind": "reference",
-                         "sample": "%d timed iterations per chain after %d warm-up, unmodified reference sources built against "
-                                   "oracle/shim (OpenBLAS 1 thread per chain), host has %s cores"
+                         "sample": "%d timed iterations per chain after %d warm-up (T(W+K) - T(W) of the same seeded chain), "
+                                   "unmodified reference sources built against oracle/shim (OpenBLAS 1 thread per chain), "
+                                   "host has %s cores"
                                    % (args.steps * args.n_rao, args.warmup * args.n_rao, cores)},
         "e2e": {"value": value, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -373,7 +388,7 @@ def cpu_baseline(args, spec):
     with tempfile.TemporaryDirectory() as tmp:
         ini, _ = prepare_dataset(args.workload, args.n_rao, 1, tmp, args.n_rao)
         t0 = time.time()
-        secs, _ = run_reference_chains(ini, 1, args.n_rao, 1, 2)
+        secs, _ = run_reference_chains(ini, 1, args.n_rao, 1, 2)   # T(3 steps) - T(1 step)
         log("[bench] cpu_baseline total %.1f s (timed %.2f s)" % (time.time() - t0, secs))
     return {"value": 2 * args.n_rao / secs, "unit": "iterations/s", "cores": 1, "kind": "reference",
             "sample": "%d timed iterations (2 steps) after one warm-up step of one chain of the unmodified reference sampler "

@@ -88,11 +88,20 @@ struct ColStatInline {
   int n_seg, seg_words;
   const double* y;
   const double* e;
-  double* out_host;          // [m_c][n_seg][n_tasks] in mapped host memory
-  unsigned int* done_count;  // device counter, reset by the last CTA
-  volatile unsigned int* flag_host;
-  unsigned int seq;
+  ulonglong2* out_host;      // [m_c][n_seg][n_tasks] tagged results in mapped host memory
+  unsigned int seq;          // launch sequence number = the tag
 };
+
+// A result travels to the host as two 8-byte words, each carrying half of the double and the launch's sequence
+// number in its upper half, written by ONE 16-byte store.  Every word validates itself, so the kernel needs no
+// completion flag, no CTA counter and no system-scope fence (each of which costs a PCIe round trip): the host polls
+// the words until they carry the expected tag.
+__device__ __forceinline__ void publish_tagged(ulonglong2* slot, double v, unsigned int seq)
+{
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v), tag = (unsigned long long)seq << 32;
+  const unsigned long long w0 = (b & 0xFFFFFFFFull) | tag, w1 = (b >> 32) | tag;
+  asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"(w0), "l"(w1) : "memory");
+}
 
 constexpr int kFastSegMax = 256;   // words per CTA on the latency path (64 or 256)
 
@@ -110,7 +119,7 @@ __global__ void __launch_bounds__(256) k_column_stats_inline(const __grid_consta
   __syncthreads();
   const int n_fp = a.m_e + 1;
   const int n_tasks = n_fp + a.k + a.m_c;
-  double* out = a.out_host + ((int64_t)c * a.n_seg + seg) * n_tasks;
+  ulonglong2* out = a.out_host + ((int64_t)c * a.n_seg + seg) * n_tasks;
 
   // (1) x_c'y and x_c'E_j: thread <-> individual (coalesced, unconditional loads so that they all issue at once);
   //     a thread covers individuals i_lo + t + 256 j.
@@ -156,7 +165,7 @@ __global__ void __launch_bounds__(256) k_column_stats_inline(const __grid_consta
         for (int j = 0; j < 2; ++j)
           if (lane + 32 * j < nwords) acc += packed_dot(cw[lane + 32 * j], ow[u][j]);
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0 && task < n_tasks) out[task] = (double)acc;
+        if (lane == 0 && task < n_tasks) publish_tagged(out + task, (double)acc, a.seq);
       }
     }
   } else {
@@ -171,26 +180,14 @@ __global__ void __launch_bounds__(256) k_column_stats_inline(const __grid_consta
       for (int j = 0; j < kFastSegMax / 32; ++j)
         if (lane + 32 * j < nwords) acc += packed_dot(cw[lane + 32 * j], ow[j]);
       for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (lane == 0) out[task] = (double)acc;
+      if (lane == 0) publish_tagged(out + task, (double)acc, a.seq);
     }
   }
   __syncthreads();
   if (t < n_fp) {
     double v = 0.0;
     for (int wv = 0; wv < nw; ++wv) v += fpart[wv][t];
-    out[t] = v;
-  }
-  // publish: every CTA fences its host writes, the last one to arrive raises the flag
-  __syncthreads();
-  if (t == 0) {
-    __threadfence_system();
-    const unsigned int total = gridDim.x * gridDim.y;
-    const unsigned int prev = atomicAdd(a.done_count, 1u);
-    if (prev == total - 1) {
-      *a.done_count = 0;
-      __threadfence_system();
-      *a.flag_host = a.seq;
-    }
+    publish_tagged(out + t, v, a.seq);
   }
 }
 
@@ -282,27 +279,38 @@ void chain_column_stats_wait(Chain* c, double* xy, double* xe, double* xx_model,
   cudaStream_t st = c->stream;
   const int m_c = c->cs_p_mc, k = c->cs_p_k, n_seg = c->cs_p_nseg;
   const int n_tasks = s->m_e + 1 + k + m_c;
-  struct { unsigned int seq; } a = {c->cs_p_seq};
-    volatile unsigned int* flag = reinterpret_cast<volatile unsigned int*>(c->cs_flag.p);
-    unsigned long spins = 0;
-    while (*flag != a.seq) {
-      if ((++spins & 0xFFFFF) == 0 && cudaStreamQuery(st) != cudaErrorNotReady) {   // finished (or failed) without raising the flag?
-        if (*flag == a.seq) break;
-        BMG_CUDA(cudaStreamSynchronize(st));
-        if (*flag != a.seq) throw Error("k_column_stats_inline finished without publishing its results");
+  const unsigned long long tag = (unsigned long long)c->cs_p_seq << 32;
+  const volatile unsigned long long* words = reinterpret_cast<const volatile unsigned long long*>(c->cs_map.p);
+  unsigned long spins = 0;
+  for (int ci = 0; ci < m_c; ++ci) {
+    for (int task = 0; task < n_tasks; ++task) {
+      double v = 0.0;
+      for (int g = 0; g < n_seg; ++g) {
+        const size_t slot = ((size_t)ci * n_seg + g) * n_tasks + task;
+        unsigned long long w0, w1;
+        for (;;) {
+          w0 = words[2 * slot];
+          w1 = words[2 * slot + 1];
+          if ((w0 & 0xFFFFFFFF00000000ull) == tag && (w1 & 0xFFFFFFFF00000000ull) == tag) break;
+          if ((++spins & 0xFFFFF) == 0 && cudaStreamQuery(st) != cudaErrorNotReady) {   // finished (or failed) without publishing?
+            BMG_CUDA(cudaStreamSynchronize(st));
+            w0 = words[2 * slot];
+            w1 = words[2 * slot + 1];
+            if ((w0 & 0xFFFFFFFF00000000ull) == tag && (w1 & 0xFFFFFFFF00000000ull) == tag) break;
+            throw Error("k_column_stats_inline finished without publishing its results");
+          }
+        }
+        const unsigned long long bits = (w0 & 0xFFFFFFFFull) | (w1 << 32);
+        double part;
+        memcpy(&part, &bits, sizeof(part));
+        v += part;
       }
+      if (task == 0) { if (xy) xy[ci] = v; }
+      else if (task <= s->m_e) { if (xe) xe[(size_t)ci * s->m_e + task - 1] = v; }
+      else if (task <= s->m_e + k) { if (xx_model) xx_model[(size_t)ci * k + task - 1 - s->m_e] = v; }
+      else if (xx_cand) xx_cand[(size_t)ci * m_c + task - 1 - s->m_e - k] = v;
     }
-    std::atomic_thread_fence(std::memory_order_acquire);
-    for (int ci = 0; ci < m_c; ++ci) {
-      for (int task = 0; task < n_tasks; ++task) {
-        double v = 0.0;
-        for (int g = 0; g < n_seg; ++g) v += c->cs_map.p[((size_t)ci * n_seg + g) * n_tasks + task];
-        if (task == 0) { if (xy) xy[ci] = v; }
-        else if (task <= s->m_e) { if (xe) xe[(size_t)ci * s->m_e + task - 1] = v; }
-        else if (task <= s->m_e + k) { if (xx_model) xx_model[(size_t)ci * k + task - 1 - s->m_e] = v; }
-        else if (xx_cand) xx_cand[(size_t)ci * m_c + task - 1 - s->m_e - k] = v;
-      }
-    }
+  }
   c->cs_pending = false;
 }
 
@@ -336,21 +344,20 @@ void chain_column_stats_launch(Chain* c, const int64_t* cand, int m_c, const int
     const int seg_words = s->W <= 4096 ? 64 : kFastSegMax;
     const int n_seg = (int)((s->W + seg_words - 1) / seg_words);
     const size_t need_fast = (size_t)m_c * n_tasks * n_seg;
-    if (c->cs_map.n < need_fast + 8) {
+    if (c->cs_map.n < 2 * need_fast + 8 || c->cs_seq == 0xFFFFFFFFu) {   // (re)allocate; also before the tag wraps around
       BMG_CUDA(cudaStreamSynchronize(st));
-      c->cs_map.alloc(need_fast * 2 + 64);
-      if (c->cs_done.n == 0) { c->cs_done.alloc(1); BMG_CUDA(cudaMemset(c->cs_done.p, 0, sizeof(unsigned int))); }
-      if (c->cs_flag.n == 0) { c->cs_flag.alloc(16); c->cs_flag.p[0] = 0; }
+      if (c->cs_map.n < 2 * need_fast + 8) c->cs_map.alloc(need_fast * 4 + 64);
+      memset(c->cs_map.p, 0, c->cs_map.n * sizeof(double));   // tag 0 is never used by a launch
+      if (c->cs_seq == 0xFFFFFFFFu) c->cs_seq = 0;
     }
     ColStatInline a;
     for (int i = 0; i < m_c + k; ++i) a.cols[i] = s->column_ptr(i < m_c ? cand[i] : loci[i - m_c]);
     a.m_c = m_c; a.k = k; a.m_e = s->m_e; a.n = s->n; a.W = s->W; a.n_seg = n_seg; a.seg_words = seg_words; a.y = c->y.p; a.e = s->e.p;
-    a.out_host = c->cs_map.p; a.done_count = c->cs_done.p;
-    a.flag_host = reinterpret_cast<volatile unsigned int*>(c->cs_flag.p);
+    a.out_host = reinterpret_cast<ulonglong2*>(c->cs_map.p);
     a.seq = ++c->cs_seq;
     k_column_stats_inline<<<dim3(m_c, n_seg), 256, 0, st>>>(a);
     count_launch();
-    g_d2h_bytes.fetch_add(need_fast * sizeof(double), std::memory_order_relaxed);
+    g_d2h_bytes.fetch_add(need_fast * 2 * sizeof(double), std::memory_order_relaxed);
     g_h2d_bytes.fetch_add(sizeof(ColStatInline), std::memory_order_relaxed);
     const cudaError_t le = cudaGetLastError();
     if (le != cudaSuccess) throw Error(std::string("k_column_stats_inline launch: ") + cudaGetErrorString(le));

@@ -223,6 +223,7 @@ class Ref:
         self.L.refd_set_do_n_iter(self.h, C.c_long(n))
 
     def continue_chain(self):
+        # reference limitation: only safe while the model is empty (see ref_driver.cpp)
         t = self.L.refd_continue_chain(self.h)
         if t < 0:
             raise RuntimeError(self.L.refd_last_error().decode())

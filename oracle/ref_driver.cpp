@@ -107,7 +107,10 @@ void refd_close(void* h)
 /* number of iterations of the next sample() call (Sampler::do_n_iter, sampler.hpp:397) */
 void refd_set_do_n_iter(void* h, long n) { ((RefCtx*)h)->sampler->do_n_iter = (size_t)n; }
 
-/* sample() again on a sampler that already ran (sampler.cpp:625,835 continue from n_iter); wall seconds */
+/* sample() again on a sampler that already ran (sampler.cpp:625,835 continue from n_iter); wall seconds.
+   ONLY valid while the model is still empty: sample() rebuilds dd_rem with every SNP zeroed (sampler.cpp:599-606),
+   so re-entering with SNPs in the model corrupts the removal proposal and eventually crashes.  bench.py therefore
+   never continues a chain; kept for the empty-model case only. */
 double refd_continue_chain(void* h)
 {
   RefCtx* c = (RefCtx*)h;

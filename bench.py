@@ -327,12 +327,17 @@ def ours_arm(args, rank, local_rank, world):
     t0 = time.perf_counter()
     s2 = api.Sampler(ini, rank, dev, tau_rng=args.tau_rng)
     s2.set_option("basename", os.path.join(tmp, "e2e%d" % rank))
+    t1 = time.perf_counter()
     s2.begin()
+    t2 = time.perf_counter()
     for _ in range(args.steps):
         s2.run(args.n_rao)
+    t3 = time.perf_counter()
     s2.end()
     torch.cuda.synchronize()
     e2e_secs = time.perf_counter() - t0
+    log("[bench] e2e phases: create %.3f s, begin %.3f s, %d steps %.3f s, end %.3f s"
+        % (t1 - t0, t2 - t1, args.steps, t3 - t2, t0 + e2e_secs - t3))
     h2d_b, d2h_b = transfers()
     s2.close()
     if dist is not None:

@@ -66,8 +66,9 @@ class stdout_to_stderr:
 
 
 def dataset_dir(w, n_threads):
+    """The data files do not depend on the number of chains (only the INI written per run does)."""
     base = os.environ.get("BMAGWA_BENCH_DIR", os.path.join(tempfile.gettempdir(), "bmagwa_bench"))
-    return os.path.join(base, "%s_n%d_m%d_t%d" % (w, WORKLOADS[w]["n"], WORKLOADS[w]["m_g"], n_threads))
+    return os.path.join(base, "%s_n%d_m%d" % (w, WORKLOADS[w]["n"], WORKLOADS[w]["m_g"]))
 
 
 def prepare_dataset(w, n_rao, n_threads, out_dir, do_n_iter):

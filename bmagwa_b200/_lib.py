@@ -28,6 +28,7 @@ SIGNATURES = {
     "bmg_launch_count": (u64, []),
     "bmg_transfer_bytes": (None, [C.POINTER(u64), C.POINTER(u64)]),
     "bmg_store_create": (C.c_int, [vp, C.c_int, i64, i64, i64, i64, C.c_int, C.c_int, C.POINTER(vp)]),
+    "bmg_store_create_from_bed": (C.c_int, [C.c_char_p, i64, i64, i64, i64, C.c_int, C.c_int, C.POINTER(vp)]),
     "bmg_store_destroy": (C.c_int, [vp]),
     "bmg_store_set_phenotype": (C.c_int, [vp, f64p, f64p, C.c_int]),
     "bmg_store_dims": (C.c_int, [vp, i64p, i64p, i64p, i64p, C.POINTER(C.c_int), i64p]),

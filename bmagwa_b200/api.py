@@ -9,6 +9,7 @@ Names follow the reference classes they stand in for:
 All arguments are HOST numpy arrays; every call goes through libbmagwa_b200.so.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -49,12 +50,15 @@ def read_bed_payload(path, n, m_g):
 
 class GenotypeStore:
     def __init__(self, bed_payload, n, m_g, recode_to_minor=False, device=0, snp_lo=0, snp_hi=None,
-                 payload_device_ptr=None):
+                 payload_device_ptr=None, bed_path=None):
         self.L = _lib.lib()
         snp_hi = m_g if snp_hi is None else snp_hi
         self.n, self.m_g, self.lo, self.hi, self.m = n, m_g, snp_lo, snp_hi, snp_hi - snp_lo
         h = vp()
-        if payload_device_ptr is not None:
+        if bed_path is not None:   # streamed straight from the PLINK file
+            check(self.L.bmg_store_create_from_bed(os.fsencode(bed_path), n, m_g, snp_lo, snp_hi, int(recode_to_minor), device,
+                                                   C.byref(h)))
+        elif payload_device_ptr is not None:
             check(self.L.bmg_store_create(vp(payload_device_ptr), 1, n, m_g, snp_lo, snp_hi, int(recode_to_minor), device,
                                           C.byref(h)))
         else:

@@ -74,6 +74,14 @@ BMG_API int bmg_store_create(const uint8_t* bed_payload, int payload_on_device, 
   BMG_CATCH
 }
 
+BMG_API int bmg_store_create_from_bed(const char* bed_path, int64_t n, int64_t m_g, int64_t snp_lo, int64_t snp_hi,
+                                      int recode_to_minor, int device, bmg_store** out)
+{
+  BMG_TRY
+  BMG_REQUIRE(out != nullptr && bed_path != nullptr, "bmg_store_create_from_bed: null argument");
+  *out = reinterpret_cast<bmg_store*>(store_create_from_bed(bed_path, n, m_g, snp_lo, snp_hi, recode_to_minor != 0, device));
+  BMG_CATCH
+}
 BMG_API int bmg_store_destroy(bmg_store* s)
 {
   BMG_TRY

@@ -47,15 +47,15 @@ SamplerHandle* make(const char* ini, int chain_index, int device, Store* existin
   h->opt.reset(new Options(ini, /*quiet=*/chain_index != 0));
   const Options& o = *h->opt;
   BMG_REQUIRE(chain_index >= 0 && (size_t)chain_index < o.n_threads, "bmg_sampler_create: chain_index must be < thread.n_threads");
-  h->data.reset(new Dataset(o.n, o.m_g, o.m_e, o.file_fam, o.file_g, o.file_e, o.file_y, existing == nullptr));
+  h->data.reset(new Dataset(o.n, o.m_g, o.m_e, o.file_fam, o.file_g, o.file_e, o.file_y, /*load_bed=*/false));
   if (existing) {
     BMG_REQUIRE(existing->n == (int64_t)o.n && existing->m_g == (int64_t)o.m_g, "bmg_sampler_create_on_store: store dimensions differ from the INI file");
     h->store = existing;
   } else {
-    h->store = store_create(h->data->bed.data(), false, (int64_t)o.n, (int64_t)o.m_g, 0, (int64_t)o.m_g,
-                            o.recode_g_to_minor_allele_count, device >= 0 ? device : o.device);
+    // the packed genotypes are streamed from the file to the device and live there only
+    h->store = store_create_from_bed(o.file_g.c_str(), (int64_t)o.n, (int64_t)o.m_g, 0, (int64_t)o.m_g,
+                                     o.recode_g_to_minor_allele_count, device >= 0 ? device : o.device);
     h->owns_store = true;
-    std::vector<uint8_t>().swap(h->data->bed);   // the packed genotypes now live on the device only
     store_set_phenotype(h->store, h->data->y.data(), h->data->e.data(), (int)h->data->m_e);
   }
   const double* sm = h->store->summaries;

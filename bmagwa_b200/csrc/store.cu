@@ -201,8 +201,7 @@ const uint32_t* Store::column_ptr(int64_t snp) const
   throw Error("SNP " + std::to_string(snp) + " is neither in the local shard nor in an attached peer shard");
 }
 
-Store* store_create(const uint8_t* bed, bool on_device, int64_t n, int64_t m_g, int64_t lo, int64_t hi, bool recode,
-                    int device)
+static std::unique_ptr<Store> store_open(int64_t n, int64_t m_g, int64_t lo, int64_t hi, bool recode, int device)
 {
   BMG_REQUIRE(n > 0 && m_g > 0 && lo >= 0 && hi > lo && hi <= m_g, "bmg_store_create: invalid sizes");
   BMG_REQUIRE(n < (int64_t)1 << 31, "bmg_store_create: n must be < 2^31");
@@ -222,8 +221,16 @@ Store* store_create(const uint8_t* bed, bool on_device, int64_t n, int64_t m_g, 
   s->n = n; s->m_g = m_g; s->lo = lo; s->hi = hi; s->m = hi - lo;
   s->W = words_for(n); s->Wp = stride_words_for(n);
   s->recode = recode;
-  const int64_t m = s->m, B = (n + 3) / 4;
+  return s;
+}
 
+static Store* store_build(std::unique_ptr<Store> s, const uint8_t* raw);
+
+Store* store_create(const uint8_t* bed, bool on_device, int64_t n, int64_t m_g, int64_t lo, int64_t hi, bool recode,
+                    int device)
+{
+  std::unique_ptr<Store> s = store_open(n, m_g, lo, hi, recode, device);
+  const int64_t m = s->m, B = (n + 3) / 4;
   // raw upload (freed at the end of this function)
   DevBuf<uint8_t> raw_own;
   const uint8_t* raw = bed;
@@ -232,6 +239,59 @@ Store* store_create(const uint8_t* bed, bool on_device, int64_t n, int64_t m_g, 
     bmg::copy_h2d_sync(raw_own.p, bed, (size_t)(m * B));
     raw = raw_own.p;
   }
+  return store_build(std::move(s), raw);
+}
+
+// The .bed file streamed to the device: two pinned 8 MiB buffers, the read of block b+1 overlaps the copy of
+// block b, and no host copy of the payload is ever held (data.cpp:245-273 reads it genotype by genotype into
+// n x m_g doubles).  Header checks as Data::read_g (data.cpp:250-262).
+Store* store_create_from_bed(const char* path, int64_t n, int64_t m_g, int64_t lo, int64_t hi, bool recode, int device)
+{
+  BMG_REQUIRE(path != nullptr, "bmg_store_create_from_bed: null path");
+  FILE* f = fopen(path, "rb");
+  if (!f) throw Error("BED file could not be opened");
+  struct Closer { FILE* f; ~Closer() { fclose(f); } } closer{f};
+  unsigned char hdr[3] = {0, 0, 0};
+  if (fread(hdr, 1, 3, f) != 3 || hdr[0] != 0x6C || hdr[1] != 0x1B) throw Error("BED file not recognised (magic number does not match)");
+  if (hdr[2] != 0x01) throw Error("BED file not in snp-major format");
+  std::unique_ptr<Store> s = store_open(n, m_g, lo, hi, recode, device);
+  const int64_t m = s->m, B = (n + 3) / 4;
+  const size_t total = (size_t)(m * B);
+  if (fseeko(f, (off_t)(3 + lo * B), SEEK_SET) != 0) throw Error("Reading the BED file failed");
+  DevBuf<uint8_t> raw_own;
+  raw_own.alloc(total);
+  const size_t kBlock = (size_t)8 << 20;
+  PinnedBuf<uint8_t> stage[2];
+  cudaEvent_t done[2];
+  cudaStream_t up;
+  BMG_CUDA(cudaStreamCreateWithFlags(&up, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    stage[i].alloc(std::min(kBlock, total));
+    BMG_CUDA(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+  }
+  bool ok = true;
+  size_t off = 0;
+  for (int b = 0; off < total; ++b) {
+    const int i = b & 1;
+    if (b >= 2) BMG_CUDA(cudaEventSynchronize(done[i]));
+    const size_t len = std::min(kBlock, total - off);
+    if (fread(stage[i].p, 1, len, f) != len) { ok = false; break; }
+    BMG_CUDA(cudaMemcpyAsync(raw_own.p + off, stage[i].p, len, cudaMemcpyHostToDevice, up));
+    BMG_CUDA(cudaEventRecord(done[i], up));
+    g_h2d_bytes.fetch_add(len, std::memory_order_relaxed);
+    off += len;
+  }
+  BMG_CUDA(cudaStreamSynchronize(up));
+  for (int i = 0; i < 2; ++i) cudaEventDestroy(done[i]);
+  cudaStreamDestroy(up);
+  if (!ok) throw Error("Reading the BED file failed");
+  return store_build(std::move(s), raw_own.p);
+}
+
+static Store* store_build(std::unique_ptr<Store> s, const uint8_t* raw)
+{
+  const int64_t n = s->n, m = s->m, B = (n + 3) / 4;
+  const bool recode = s->recode;
   s->codes.alloc((size_t)(m * s->Wp + 4096));  // slack: tiles may over-read past the last column
   BMG_CUDA(cudaMemset(s->codes.p + m * s->Wp, 0, 4096 * sizeof(uint32_t)));
   s->n1.alloc(m); s->n2.alloc(m); s->nmiss.alloc(m); s->swapped.alloc(m); s->mom.alloc(2 * m);

@@ -7,6 +7,7 @@
 namespace bmg {
 
 // ---- store.cu
+Store* store_create_from_bed(const char* path, int64_t n, int64_t m_g, int64_t lo, int64_t hi, bool recode, int device);
 Store* store_create(const uint8_t* bed, bool on_device, int64_t n, int64_t m_g, int64_t lo, int64_t hi, bool recode,
                     int device);
 void store_set_phenotype(Store* s, const double* y, const double* e, int m_e);

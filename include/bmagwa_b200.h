@@ -57,6 +57,13 @@ void bmg_transfer_bytes(uint64_t* h2d, uint64_t* d2h);
  * payload_on_device != 0: bed_payload is a device pointer (data generated or staged on the GPU). */
 int bmg_store_create(const uint8_t* bed_payload, int payload_on_device, int64_t n, int64_t m_g,
                      int64_t snp_lo, int64_t snp_hi, int recode_to_minor, int device, bmg_store** out);
+/* Same store built straight from a PLINK .bed FILE (Data::read_g, data.cpp:245-273: header 0x6C 0x1B 0x01 then
+ * SNP-major payload): the SNPs [snp_lo, snp_hi) are streamed to the device through two pinned staging buffers
+ * (file read of block b+1 overlaps the H2D copy of block b); no host copy of the payload is kept.  Errors carry
+ * the reference's messages ("BED file could not be opened", "BED file not recognised (magic number does not
+ * match)", "BED file not in snp-major format", "Reading the BED file failed"). */
+int bmg_store_create_from_bed(const char* bed_path, int64_t n, int64_t m_g, int64_t snp_lo, int64_t snp_hi,
+                              int recode_to_minor, int device, bmg_store** out);
 int bmg_store_destroy(bmg_store* s);
 
 /* Phenotype and covariates (Data::_y, Data::_e; data.hpp:75-76).  e is n x m_e column-major and

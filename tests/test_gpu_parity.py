@@ -101,6 +101,48 @@ def test_store_reference_fixtures_bit_exact(api, ref_tests, golden, golden_data_
     st.close()
 
 
+def test_store_streamed_from_bed_file_equals_store_from_payload(api, golden_data_dir, tmp_path):
+    """bmg_store_create_from_bed (file -> pinned staging -> device) builds the same store as the in-memory
+    payload path, for the whole file, for an SNP shard and for a file larger than one 8 MiB staging block; the
+    header checks carry the reference's messages (data.cpp:250-262)."""
+    from bmagwa_b200 import synth
+    path = os.path.join(golden_data_dir, "plinktest.bed")
+    raw = cpu.read_bed(path, 5, 10)
+    a = api.GenotypeStore(raw, 5, 10, recode_to_minor=True)
+    b = api.GenotypeStore(None, 5, 10, recode_to_minor=True, bed_path=path)
+    for j in range(10):
+        assert np.array_equal(a.get_column(j, 0), b.get_column(j, 0))
+    assert np.array_equal(a.moments(), b.moments())
+    for x, y in zip(a.missing(), b.missing()):
+        assert np.array_equal(x, y)
+    a.close(); b.close()
+    n, m = 4001, 20000   # 1001 bytes per SNP -> 20 MB payload = three staging blocks, ragged last byte
+    payload, _ = synth.make_genotypes(n, m, seed=9, miss_rate=0.01)
+    big = tmp_path / "big.bed"
+    with open(big, "wb") as fh:
+        fh.write(bytes([0x6C, 0x1B, 0x01]))
+        fh.write(payload.tobytes())
+    a = api.GenotypeStore(payload.reshape(m, -1)[5000:17000].copy(), n, m, recode_to_minor=True, snp_lo=5000, snp_hi=17000)
+    b = api.GenotypeStore(None, n, m, recode_to_minor=True, snp_lo=5000, snp_hi=17000, bed_path=str(big))
+    assert all(np.array_equal(x, y) for x, y in zip(a.counts(), b.counts()))
+    assert np.array_equal(a.moments(), b.moments())
+    for j in (5000, 11111, 16999):
+        assert np.array_equal(a.get_column(j, 0), b.get_column(j, 0))
+    for x, y in zip(a.missing(), b.missing()):
+        assert np.array_equal(x, y)
+    a.close(); b.close()
+    bad = tmp_path / "bad.bed"
+    bad.write_bytes(bytes([0x6C, 0x1B, 0x00]) + payload.tobytes()[:100])
+    with pytest.raises(RuntimeError, match="BED file not in snp-major format"):
+        api.GenotypeStore(None, n, m, bed_path=str(bad))
+    with pytest.raises(RuntimeError, match="BED file could not be opened"):
+        api.GenotypeStore(None, n, m, bed_path=str(tmp_path / "absent.bed"))
+    short = tmp_path / "short.bed"
+    short.write_bytes(bytes([0x6C, 0x1B, 0x01]) + payload.tobytes()[:1000])
+    with pytest.raises(RuntimeError, match="Reading the BED file failed"):
+        api.GenotypeStore(None, n, m, bed_path=str(short))
+
+
 # ------------------------------------------------------------------- residual + scan (a5, a9)
 def random_state(n, m, m_e, k, seed):
     rs = np.random.default_rng(seed)

@@ -63,6 +63,7 @@ SIGNATURES = {
     "bmg_chain_get_phenotype": (C.c_int, [vp, f64p]),
     "bmg_sampler_create": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.POINTER(vp)]),
     "bmg_sampler_create_on_store": (C.c_int, [C.c_char_p, C.c_int, vp, C.POINTER(vp)]),
+    "bmg_sampler_create_sharded": (C.c_int, [C.c_char_p, C.c_int, vp, vp, C.POINTER(vp)]),
     "bmg_sampler_set_option": (C.c_int, [vp, C.c_char_p, C.c_char_p]),
     "bmg_sampler_begin": (C.c_int, [vp]),
     "bmg_sampler_run": (C.c_int, [vp, i64]),
@@ -72,6 +73,14 @@ SIGNATURES = {
     "bmg_sampler_chain": (vp, [vp]),
     "bmg_sampler_destroy": (C.c_int, [vp]),
 }
+
+
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p)
+
+
+class ShardCommStruct(C.Structure):
+    """struct bmg_shard_comm (include/bmagwa_b200.h)."""
+    _fields_ = [("world", C.c_int), ("rank", C.c_int), ("snp_stride", C.c_int64), ("allgather", ALLGATHER_FN), ("ctx", C.c_void_p)]
 
 
 class BmgError(RuntimeError):

@@ -271,10 +271,13 @@ class Chain:
 class Sampler:
     """The MH driver (src/sampler.cpp:551-880) behind bmg_sampler_*; reads the reference's INI file."""
 
-    def __init__(self, ini_path, chain_index=0, device=0, store=None, **options):
+    def __init__(self, ini_path, chain_index=0, device=0, store=None, comm=None, **options):
         self.L = _lib.lib()
         h = vp()
-        if store is None:
+        self._comm = comm   # keeps the callback object alive as long as the sampler
+        if comm is not None:
+            check(self.L.bmg_sampler_create_sharded(str(ini_path).encode(), chain_index, store.h, C.byref(comm.struct), C.byref(h)))
+        elif store is None:
             check(self.L.bmg_sampler_create(str(ini_path).encode(), chain_index, device, C.byref(h)))
         else:
             check(self.L.bmg_sampler_create_on_store(str(ini_path).encode(), chain_index, store.h, C.byref(h)))

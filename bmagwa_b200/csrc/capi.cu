@@ -355,7 +355,7 @@ BMG_API int bmg_chain_get_array(bmg_chain* c, int which, double* out)
   BMG_REQUIRE(out && which >= 0 && which <= 4, "bmg_chain_get_array: bad arguments");
   const double* src[5] = {ch->p_r.p, ch->p_rao.p, ch->p_proposal.p, ch->q_add.p, ch->q_rem.p};
   BMG_CUDA(cudaSetDevice(ch->store->device));
-  bmg::copy_d2h(out, src[which], ch->store->m * sizeof(double), ch->stream);
+  bmg::copy_d2h(out, src[which], ch->mw * sizeof(double), ch->stream);
   BMG_CUDA(cudaStreamSynchronize(ch->stream));
   BMG_CATCH
 }

@@ -140,6 +140,7 @@ struct Store {
   DevBuf<int32_t> n1, n2, nmiss;            // per local SNP
   DevBuf<uint8_t> swapped;
   DevBuf<double> mom;                       // 2 per local SNP: (s, v)
+  DevBuf<double> snp_mean, snp_var;         // per local SNP mean and unbiased variance (Data::compute_g_var_and_mean terms)
   DevBuf<int64_t> miss_off;                 // m + 1
   DevBuf<int32_t> miss_idx;                 // total missing cells
   std::vector<int64_t> h_miss_off;          // host mirror

@@ -68,7 +68,7 @@ struct Sampler::Files {
 // construction (sampler.hpp:107-282)
 // ------------------------------------------------------------------------------------------------
 Sampler::Sampler(const Options& opts, int chain_index, Store* store, const std::vector<double>& y, const std::vector<double>& e,
-                 double var_y, double yy, double var_x, double mean_x)
+                 double var_y, double yy, double var_x, double mean_x, const ShardComm* comm)
 : opt_(opts), basename_(opts.basename + std::to_string(chain_index)), seed_(opts.seeds.at(chain_index)), n_(opts.n),
   m_g_(opts.m_g), m_e_(opts.m_e + 1), n_rao_(opts.n_rao), n_rao_burnin_(opts.n_rao_burnin),
   n_sample_tau2_and_missing_(opts.n_sample_tau2_and_missing), thin_(opts.thin), verbosity_(opts.verbosity),
@@ -81,8 +81,11 @@ Sampler::Sampler(const Options& opts, int chain_index, Store* store, const std::
 {
   if (opts.sampler_type != 0) throw std::runtime_error("this build implements the PMV sampler only (sampler.type = PMV)");
   if (opts.types.size() != 1 || opts.types[0] != kA) throw std::runtime_error("this build implements effect type A only (model.types = A)");
-  if (store_->lo != 0 || store_->hi != (int64_t)m_g_)
-    throw std::runtime_error("the host sampler needs the whole SNP range on its store (multi-GPU chains attach peer shards)");
+  if (comm == nullptr && (store_->lo != 0 || store_->hi != (int64_t)m_g_))
+    throw std::runtime_error("the host sampler needs the whole SNP range on its store (multi-GPU chains: bmg_sampler_create_sharded)");
+  if (comm != nullptr) {
+    for (int64_t snp : {(int64_t)0, (int64_t)m_g_ - 1}) (void)store_->column_ptr(snp);   // throws unless every shard is attached
+  }
   if (store_->n_missing > 0)
     throw std::runtime_error("genotype data contains missing calls: the missing-genotype Gibbs step (sampler.cpp:264-453) is "
                              "not implemented in this build");
@@ -123,8 +126,9 @@ Sampler::Sampler(const Options& opts, int chain_index, Store* store, const std::
   pos_in_proposal_.assign(m_g_, -1);
 
   chain_ = chain_create(store_);
-  dd_add_.init(&store_->h_inorder, (int)chain_->cdf_block);
-  dd_rem_.init(&store_->h_inorder, (int)chain_->cdf_block);
+  if (comm != nullptr) chain_set_sharded(chain_, comm->world, comm->rank, comm->stride, comm->allgather, comm->ctx);
+  dd_add_.init(&chain_->inorder_host(), (int)chain_->cdf_block);
+  dd_rem_.init(&chain_->inorder_host(), (int)chain_->cdf_block);
   h_w_.alloc(2 * m_g_);
   h_cdf_.assign(2 * chain_->cdf_blocks, 0.0);
 

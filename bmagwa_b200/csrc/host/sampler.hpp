@@ -28,8 +28,10 @@ namespace bmg {
 class Sampler {
  public:
   // Takes ownership of nothing: store and dataset summaries must outlive the sampler.
+  // SNP-sharded chain: `store` holds rank's SNP block (peers attached), the same sampler runs in lockstep on every rank
+  struct ShardComm { int world = 1, rank = 0; int64_t stride = 0; AllGatherFn allgather = nullptr; void* ctx = nullptr; };
   Sampler(const Options& opts, int chain_index, Store* store, const std::vector<double>& y, const std::vector<double>& e,
-          double var_y, double yy, double var_x, double mean_x);
+          double var_y, double yy, double var_x, double mean_x, const ShardComm* comm = nullptr);
   ~Sampler();
 
   void set_option(const std::string& key, const std::string& value);

@@ -39,7 +39,44 @@ SamplerHandle* H(bmg_sampler* sp)
   return reinterpret_cast<SamplerHandle*>(sp);
 }
 
-SamplerHandle* make(const char* ini, int chain_index, int device, Store* existing)
+// var_x / mean_x of a SNP-sharded data set exactly as the unsharded store computes them (store.cu, as
+// Data::compute_g_var_and_mean): per-SNP means, variances and missing counts are all-gathered and summed on the
+// host in SNP order.
+static void global_summaries(Store* st, const Sampler::ShardComm& cm, double* out4)
+{
+  BMG_CUDA(cudaSetDevice(st->device));
+  const int64_t total = (int64_t)cm.world * cm.stride, off = (int64_t)cm.rank * cm.stride;
+  DevBuf<double> buf; buf.alloc(total);
+  DevBuf<int32_t> ibuf; ibuf.alloc(total);
+  cudaStream_t stm;
+  BMG_CUDA(cudaStreamCreateWithFlags(&stm, cudaStreamNonBlocking));
+  std::vector<double> hm(total), hv(total);
+  std::vector<int32_t> hn(total);
+  auto gather_d = [&](const double* local, std::vector<double>& host) {
+    BMG_CUDA(cudaMemsetAsync(buf.p, 0, total * sizeof(double), stm));
+    BMG_CUDA(cudaMemcpyAsync(buf.p + off, local, st->m * sizeof(double), cudaMemcpyDeviceToDevice, stm));
+    if (cm.allgather(cm.ctx, buf.p, cm.stride, (int)sizeof(double), (void*)stm) != 0) throw Error("sharded sampler: all-gather callback failed");
+    BMG_CUDA(cudaMemcpyAsync(host.data(), buf.p, total * sizeof(double), cudaMemcpyDeviceToHost, stm));
+    BMG_CUDA(cudaStreamSynchronize(stm));
+  };
+  gather_d(st->snp_mean.p, hm);
+  gather_d(st->snp_var.p, hv);
+  BMG_CUDA(cudaMemsetAsync(ibuf.p, 0, total * sizeof(int32_t), stm));
+  BMG_CUDA(cudaMemcpyAsync(ibuf.p + off, st->nmiss.p, st->m * sizeof(int32_t), cudaMemcpyDeviceToDevice, stm));
+  if (cm.allgather(cm.ctx, ibuf.p, cm.stride, (int)sizeof(int32_t), (void*)stm) != 0) throw Error("sharded sampler: all-gather callback failed");
+  BMG_CUDA(cudaMemcpyAsync(hn.data(), ibuf.p, total * sizeof(int32_t), cudaMemcpyDeviceToHost, stm));
+  BMG_CUDA(cudaStreamSynchronize(stm));
+  cudaStreamDestroy(stm);
+  double tm = 0, tv = 0, nm = 0, nv = 0;
+  for (int64_t j = 0; j < st->m_g; ++j) {
+    const int ng = (int)st->n - hn[j];
+    if (ng > 1) { tm += hm[j]; tv += hv[j]; nm += 1; nv += 1; }
+    else if (ng == 1) { tm += hm[j]; nm += 1; }
+  }
+  out4[0] = tm; out4[1] = nm; out4[2] = tv; out4[3] = nv;
+}
+
+SamplerHandle* make(const char* ini, int chain_index, int device, Store* existing, const Sampler::ShardComm* comm = nullptr)
 {
   BMG_REQUIRE(ini != nullptr, "bmg_sampler_create: null ini path");
   std::unique_ptr<SamplerHandle> h(new SamplerHandle());
@@ -58,9 +95,15 @@ SamplerHandle* make(const char* ini, int chain_index, int device, Store* existin
     h->owns_store = true;
     store_set_phenotype(h->store, h->data->y.data(), h->data->e.data(), (int)h->data->m_e);
   }
-  const double* sm = h->store->summaries;
+  double sm[6];
+  for (int i = 0; i < 6; ++i) sm[i] = h->store->summaries[i];
+  if (comm != nullptr) {
+    BMG_REQUIRE(existing != nullptr, "bmg_sampler_create_sharded: a shard store is required");
+    BMG_REQUIRE(existing->m_e >= 1, "bmg_sampler_create_sharded: call bmg_store_set_phenotype on the shard first");
+    global_summaries(h->store, *comm, sm);
+  }
   const double mean_x = sm[0] / sm[1], var_x = sm[2] / sm[3];
-  h->sampler.reset(new Sampler(o, chain_index, h->store, h->data->y, h->data->e, sm[4], sm[5], var_x, mean_x));
+  h->sampler.reset(new Sampler(o, chain_index, h->store, h->data->y, h->data->e, sm[4], sm[5], var_x, mean_x, comm));
   return h.release();
 }
 }  // namespace
@@ -85,6 +128,18 @@ BMG_API int bmg_sampler_create(const char* ini_path, int chain_index, int device
   BMG_TRY
   BMG_REQUIRE(out != nullptr, "bmg_sampler_create: null argument");
   *out = reinterpret_cast<bmg_sampler*>(make(ini_path, chain_index, device, nullptr));
+  BMG_CATCH
+}
+BMG_API int bmg_sampler_create_sharded(const char* ini_path, int chain_index, bmg_store* shard, const bmg_shard_comm* comm,
+                                       bmg_sampler** out)
+{
+  BMG_TRY
+  BMG_REQUIRE(out != nullptr && shard != nullptr && comm != nullptr, "bmg_sampler_create_sharded: null argument");
+  BMG_REQUIRE(comm->allgather != nullptr && comm->world >= 1 && comm->rank >= 0 && comm->rank < comm->world && comm->snp_stride > 0,
+              "bmg_sampler_create_sharded: invalid communicator");
+  Sampler::ShardComm cm;
+  cm.world = comm->world; cm.rank = comm->rank; cm.stride = comm->snp_stride; cm.allgather = comm->allgather; cm.ctx = comm->ctx;
+  *out = reinterpret_cast<bmg_sampler*>(make(ini_path, chain_index, -1, reinterpret_cast<Store*>(shard), &cm));
   BMG_CATCH
 }
 BMG_API int bmg_sampler_create_on_store(const char* ini_path, int chain_index, bmg_store* s, bmg_sampler** out)

@@ -545,6 +545,51 @@ static size_t scan_smem_bytes(const Chain* c)
   return (size_t)kStages * kTileSnps * row_words * 4 + 2 * kMaxWarps * kTileSnps * sizeof(double) + kStages * sizeof(uint64_t);
 }
 
+// the per-SNP proposal / Rao-Blackwell arrays over [0, mw) (see Chain)
+static void alloc_weight_arrays(Chain* c)
+{
+  const int64_t ma = c->mw_alloc, mw = c->mw;
+  c->p_r.alloc(ma); c->p_rao.alloc(ma); c->p_proposal.alloc(ma); c->q_add.alloc(ma); c->q_rem.alloc(ma);
+  BMG_CUDA(cudaMemset(c->p_r.p, 0, ma * sizeof(double)));
+  BMG_CUDA(cudaMemset(c->p_rao.p, 0, ma * sizeof(double)));
+  BMG_CUDA(cudaMemset(c->p_proposal.p, 0, ma * sizeof(double)));
+  BMG_CUDA(cudaMemset(c->q_add.p, 0, ma * sizeof(double)));
+  BMG_CUDA(cudaMemset(c->q_rem.p, 0, ma * sizeof(double)));
+  c->cdf_blocks = (mw + c->cdf_block - 1) / c->cdf_block;
+  c->cdf_add.alloc(c->cdf_blocks); c->cdf_rem.alloc(c->cdf_blocks);
+  c->zero_add.alloc(mw); c->zero_rem.alloc(mw);
+  BMG_CUDA(cudaMemset(c->zero_add.p, 0, mw));
+  BMG_CUDA(cudaMemset(c->zero_rem.p, 0, mw));
+  c->q_add_io.release(); c->q_rem_io.release(); c->cdf_eff_add.release(); c->cdf_eff_rem.release();
+}
+
+// SNP-sharded chain: rank r of `world` holds the packed SNPs [r stride, min(m_g, (r+1) stride)); the weight arrays
+// are re-created over all m_g SNPs (padded to world x stride for the all-gather) with the GLOBAL in-order permutation.
+void chain_set_sharded(Chain* c, int world, int rank, int64_t stride, AllGatherFn fn, void* ctx)
+{
+  Store* s = c->store;
+  BMG_REQUIRE(world >= 1 && rank >= 0 && rank < world && stride > 0 && fn != nullptr, "sharded chain: invalid communicator");
+  BMG_REQUIRE((int64_t)world * stride >= s->m_g, "sharded chain: world x stride does not cover m_g");
+  BMG_REQUIRE(s->lo == std::min(s->m_g, (int64_t)rank * stride) && s->hi == std::min(s->m_g, (int64_t)(rank + 1) * stride),
+              "sharded chain: the store's SNP range is not this rank's shard");
+  BMG_CUDA(cudaSetDevice(s->device));
+  c->world = world; c->rank = rank; c->shard_stride = stride; c->gather = fn; c->gather_ctx = ctx;
+  c->mw = s->m_g; c->w_off = s->lo; c->mw_alloc = (int64_t)world * stride;
+  alloc_weight_arrays(c);
+  build_inorder_permutation(c->mw, c->h_inorder_own);
+  c->inorder_own.alloc(c->mw);
+  bmg::copy_h2d_sync(c->inorder_own.p, c->h_inorder_own.data(), c->mw * sizeof(int32_t));
+  BMG_CUDA(cudaDeviceSynchronize());
+}
+
+// every rank contributes elems [rank stride, (rank+1) stride) of dev_buffer (world x stride elements) in place
+void chain_allgather(Chain* c, void* dev_buffer, int elem_bytes)
+{
+  if (c->world <= 1) return;
+  const int rc = c->gather(c->gather_ctx, dev_buffer, c->shard_stride, elem_bytes, (void*)c->stream);
+  if (rc != 0) throw Error("sharded chain: the host's all-gather callback failed");
+}
+
 Chain* chain_create(Store* s)
 {
   BMG_REQUIRE(s->m_e >= 1, "bmg_chain_create: call bmg_store_set_phenotype first");
@@ -570,20 +615,12 @@ Chain* chain_create(Store* s)
     BMG_CUDA(cudaMemset(c->miss_corr.p, 0, 3 * m * sizeof(double)));
   }
   c->dot_partial.alloc((size_t)c->scan_chunks * m);
-  c->dot.alloc(m); c->p_r.alloc(m); c->p_rao.alloc(m); c->p_proposal.alloc(m); c->q_add.alloc(m); c->q_rem.alloc(m);
-  BMG_CUDA(cudaMemset(c->p_r.p, 0, m * sizeof(double)));
-  BMG_CUDA(cudaMemset(c->p_rao.p, 0, m * sizeof(double)));
-  BMG_CUDA(cudaMemset(c->p_proposal.p, 0, m * sizeof(double)));
-  BMG_CUDA(cudaMemset(c->q_add.p, 0, m * sizeof(double)));
-  BMG_CUDA(cudaMemset(c->q_rem.p, 0, m * sizeof(double)));
+  c->dot.alloc(m);
   c->loci_dev.alloc(2048); c->beta_dev.alloc(2048 + 64); c->taug_dev.alloc(2048);
   c->h_stage.alloc(8192); c->h_stage_i.alloc(4096);
-  c->cdf_blocks = (m + c->cdf_block - 1) / c->cdf_block;
-  c->cdf_add.alloc(c->cdf_blocks); c->cdf_rem.alloc(c->cdf_blocks);
-  c->zero_add.alloc(m); c->zero_rem.alloc(m);
-  BMG_CUDA(cudaMemset(c->zero_add.p, 0, m));
-  BMG_CUDA(cudaMemset(c->zero_rem.p, 0, m));
   c->sample_out.alloc(4); c->h_sample.alloc(4);
+  c->mw = m; c->w_off = 0; c->mw_alloc = m;
+  alloc_weight_arrays(c.get());
   const size_t smem = scan_smem_bytes(c.get());
   BMG_REQUIRE(smem <= 227 * 1024, "scan tile does not fit in shared memory");
   BMG_CUDA(cudaFuncSetAttribute(k_scan_dots_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -748,7 +785,7 @@ void chain_scan(Chain* c, const int64_t* loci, const double* beta_g, const doubl
   if (prm->tau_mode == 1) {
     BMG_REQUIRE(prm->tau_host != nullptr, "bmg_chain_scan: tau_host required for tau_mode 1");
     if (c->tau_dev.n < (size_t)s->m) c->tau_dev.alloc(s->m);
-    bmg::copy_h2d(c->tau_dev.p, prm->tau_host, s->m * sizeof(double), st);
+    bmg::copy_h2d(c->tau_dev.p, prm->tau_host + c->w_off, s->m * sizeof(double), st);   // tau_host covers [0, mw)
   }
   chain_scan_dots(c);
   if (s->n_missing > 0) {
@@ -763,12 +800,13 @@ void chain_scan(Chain* c, const int64_t* loci, const double* beta_g, const doubl
   f.sum_r = c->sum_r; f.sigma2 = prm->sigma2; f.lmp_add = prm->lmp_add; f.lmp_rem = prm->lmp_rem;
   f.tau_mode = prm->tau_mode; f.tau_shared = prm->tau_shared; f.tau_snp = c->tau_dev.p;
   f.seed = prm->tau_seed; f.counter = prm->tau_counter; f.nu_tau2 = prm->nu_tau2; f.s2_tau2 = prm->s2_tau2; f.alpha2 = prm->alpha2;
-  f.dot = c->dot.p; f.p_r = c->p_r.p;
+  f.dot = c->dot.p; f.p_r = c->p_r.p + c->w_off;
   k_scan_finalize<<<(unsigned)((s->m + 255) / 256), 256, 0, st>>>(f);
   count_launch();
   BMG_CUDA(cudaGetLastError());
+  chain_allgather(c, c->p_r.p, (int)sizeof(double));   // no-op unless SNP-sharded
   if (p_r_host) {
-    bmg::copy_d2h(p_r_host, c->p_r.p, s->m * sizeof(double), st);
+    bmg::copy_d2h(p_r_host, c->p_r.p, c->mw * sizeof(double), st);
     BMG_CUDA(cudaStreamSynchronize(st));
   }
 }
@@ -780,7 +818,7 @@ void chain_adapt(Chain* c, int update_rao, int64_t n_rao_mean, int update_prop, 
   BMG_CUDA(cudaSetDevice(s->device));
   const double rz1 = (double)(n_rao_mean + 1), rz2 = (double)n_rao_mean / rz1;      // sampler.cpp:740-741
   const double pz1 = (double)(n_prop_mean + 1), pz2 = (double)n_prop_mean / pz1;    // sampler.cpp:762-763
-  k_adapt<<<(unsigned)((s->m + 255) / 256), 256, 0, c->stream>>>(c->p_r.p, s->m, update_rao, rz1, rz2, update_prop, pz1, pz2,
+  k_adapt<<<(unsigned)((c->mw + 255) / 256), 256, 0, c->stream>>>(c->p_r.p, c->mw, update_rao, rz1, rz2, update_prop, pz1, pz2,
                                                                  q_add_min, q_rem_min, c->p_rao.p, c->p_proposal.p,
                                                                  c->q_add.p, c->q_rem.p);
   count_launch();
@@ -792,7 +830,7 @@ void chain_init_flat(Chain* c, double value, double q_add_min, double q_rem_min)
 {
   Store* s = c->store;
   BMG_CUDA(cudaSetDevice(s->device));
-  k_fill_flat<<<(unsigned)((s->m + 255) / 256), 256, 0, c->stream>>>(s->m, value, q_add_min, q_rem_min, c->p_proposal.p,
+  k_fill_flat<<<(unsigned)((c->mw + 255) / 256), 256, 0, c->stream>>>(c->mw, value, q_add_min, q_rem_min, c->p_proposal.p,
                                                                      c->q_add.p, c->q_rem.p, c->p_rao.p);
   count_launch();
   BMG_CUDA(cudaGetLastError());

@@ -299,7 +299,8 @@ static Store* store_build(std::unique_ptr<Store> s, const uint8_t* raw)
                                           s->nmiss.p, s->swapped.p);
   count_launch();
   BMG_CUDA(cudaGetLastError());
-  DevBuf<double> snp_mean, snp_var;
+  DevBuf<double>& snp_mean = s->snp_mean;
+  DevBuf<double>& snp_var = s->snp_var;
   snp_mean.alloc(m); snp_var.alloc(m);
   k_moments<<<(unsigned)((m + 255) / 256), 256>>>(s->n1.p, s->n2.p, s->nmiss.p, n, m, s->mom.p, snp_mean.p, snp_var.p);
   count_launch();

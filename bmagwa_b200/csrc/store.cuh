@@ -15,9 +15,25 @@ void store_get_column(const Store* s, int64_t snp, int type, const int8_t* miss_
                       double* out_host, cudaStream_t st);
 
 // ---- chain state (scan.cu, colstats.cu, weights.cu, probit.cu)
+// host-supplied all-gather over the ranks of a SNP-sharded chain (include/bmagwa_b200.h: bmg_allgather_fn)
+typedef int (*AllGatherFn)(void* ctx, void* dev_buffer, int64_t elems_per_rank, int elem_bytes, void* cuda_stream);
+
 struct Chain {
   Store* store = nullptr;
   cudaStream_t stream = nullptr;
+  // Range of the per-SNP proposal / Rao-Blackwell arrays (p_r, p_rao, p_proposal, q_add, q_rem, zero flags, CDF
+  // blocks).  Unsharded: mw = store->m, w_off = 0.  SNP-sharded chain: every rank keeps them for ALL m_g SNPs
+  // (8 B per SNP each) and only the packed genotypes and the scan are sharded; the local shard's p_r lands at w_off
+  // and is all-gathered (chain_scan), everything downstream is replicated and identical on every rank.
+  int64_t mw = 0, w_off = 0, mw_alloc = 0;
+  int world = 1, rank = 0;
+  int64_t shard_stride = 0;
+  AllGatherFn gather = nullptr;
+  void* gather_ctx = nullptr;
+  DevBuf<int32_t> inorder_own;              // in-order permutation over mw when it differs from the store's
+  std::vector<int32_t> h_inorder_own;
+  const int32_t* inorder_dev() const { return inorder_own.n ? inorder_own.p : store->inorder.p; }
+  const std::vector<int32_t>& inorder_host() const { return h_inorder_own.empty() ? store->h_inorder : h_inorder_own; }
   int scan_variant = 2;   // 2 = integer tensor cores (default), 1 = fp64 + TMA staging, 0 = fp64 + direct loads
   // optional CUDA-event timing of the scan's reduction kernel (bench.py roofline): pairs of events
   bool time_scan = false;
@@ -90,6 +106,8 @@ void chain_destroy(Chain* c);
 void chain_set_missing(Chain* c, int64_t snp, const int8_t* vals, int64_t count);
 void chain_residual(Chain* c, const int64_t* loci, const double* beta_e, const double* beta_g, int k, double* stats9);
 void chain_scan_dots(Chain* c);
+void chain_set_sharded(Chain* c, int world, int rank, int64_t stride, AllGatherFn fn, void* ctx);
+void chain_allgather(Chain* c, void* dev_buffer, int elem_bytes);
 void imma_prepare(Chain* c);
 void imma_quantize(Chain* c);
 void imma_launch(Chain* c);

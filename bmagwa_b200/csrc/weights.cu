@@ -133,11 +133,11 @@ void chain_partial_cdf(Chain* c)
   BMG_CUDA(cudaSetDevice(s->device));
   if (c->cdf_eff_add.n == 0) {
     c->cdf_eff_add.alloc(c->cdf_blocks); c->cdf_eff_rem.alloc(c->cdf_blocks);
-    c->q_add_io.alloc(s->m); c->q_rem_io.alloc(s->m);
+    c->q_add_io.alloc(c->mw); c->q_rem_io.alloc(c->mw);
   }
-  k_block_sums<<<(unsigned)c->cdf_blocks, 256, 0, c->stream>>>(c->q_add.p, c->zero_add.p, s->inorder.p, s->m, c->cdf_add.p,
+  k_block_sums<<<(unsigned)c->cdf_blocks, 256, 0, c->stream>>>(c->q_add.p, c->zero_add.p, c->inorder_dev(), c->mw, c->cdf_add.p,
                                                               c->cdf_eff_add.p, c->q_add_io.p);
-  k_block_sums<<<(unsigned)c->cdf_blocks, 256, 0, c->stream>>>(c->q_rem.p, c->zero_rem.p, s->inorder.p, s->m, c->cdf_rem.p,
+  k_block_sums<<<(unsigned)c->cdf_blocks, 256, 0, c->stream>>>(c->q_rem.p, c->zero_rem.p, c->inorder_dev(), c->mw, c->cdf_rem.p,
                                                               c->cdf_eff_rem.p, c->q_rem_io.p);
   count_launch(2);
   BMG_CUDA(cudaGetLastError());
@@ -147,18 +147,19 @@ void chain_set_zeroed(Chain* c, int which, int64_t snp, int flag)
 {
   Store* s = c->store;
   BMG_REQUIRE(which == 0 || which == 1, "which must be 0 (dd_add) or 1 (dd_rem)");
-  BMG_REQUIRE(s->is_local(snp), "bmg_chain_set_zeroed: SNP not in the local shard");
+  const int64_t base = s->lo - c->w_off;   // global index of element 0 of the weight arrays
+  BMG_REQUIRE(snp >= base && snp < base + c->mw, "bmg_chain_set_zeroed: SNP outside the chain's weight arrays");
   BMG_CUDA(cudaSetDevice(s->device));
   if (c->cdf_eff_add.n == 0) chain_partial_cdf(c);
   uint8_t* z = which == 0 ? c->zero_add.p : c->zero_rem.p;
-  k_set_zero<<<1, 1, 0, c->stream>>>(z, snp - s->lo, flag ? 1 : 0);
+  k_set_zero<<<1, 1, 0, c->stream>>>(z, snp - base, flag ? 1 : 0);
   count_launch();
   // refresh the zero-aware partial sums (all blocks: m/256 tiny CTAs; keeps the kernel count at two)
   if (which == 0)
-    k_block_sums<<<(unsigned)c->cdf_blocks, 256, 0, c->stream>>>(c->q_add.p, c->zero_add.p, s->inorder.p, s->m, c->cdf_add.p,
+    k_block_sums<<<(unsigned)c->cdf_blocks, 256, 0, c->stream>>>(c->q_add.p, c->zero_add.p, c->inorder_dev(), c->mw, c->cdf_add.p,
                                                                 c->cdf_eff_add.p, c->q_add_io.p);
   else
-    k_block_sums<<<(unsigned)c->cdf_blocks, 256, 0, c->stream>>>(c->q_rem.p, c->zero_rem.p, s->inorder.p, s->m, c->cdf_rem.p,
+    k_block_sums<<<(unsigned)c->cdf_blocks, 256, 0, c->stream>>>(c->q_rem.p, c->zero_rem.p, c->inorder_dev(), c->mw, c->cdf_rem.p,
                                                                 c->cdf_eff_rem.p, c->q_rem_io.p);
   count_launch();
   BMG_CUDA(cudaGetLastError());
@@ -170,7 +171,7 @@ void chain_fill_zeroed(Chain* c, int which, int flag)
   BMG_REQUIRE(which == 0 || which == 1, "which must be 0 (dd_add) or 1 (dd_rem)");
   BMG_CUDA(cudaSetDevice(s->device));
   uint8_t* z = which == 0 ? c->zero_add.p : c->zero_rem.p;
-  BMG_CUDA(cudaMemsetAsync(z, flag ? 1 : 0, s->m, c->stream));
+  BMG_CUDA(cudaMemsetAsync(z, flag ? 1 : 0, c->mw, c->stream));
   chain_partial_cdf(c);
 }
 
@@ -184,14 +185,14 @@ void chain_sample(Chain* c, int which, double u01, int64_t* snp, double* total)
   const double* q = which == 0 ? c->q_add.p : c->q_rem.p;
   const uint8_t* z = which == 0 ? c->zero_add.p : c->zero_rem.p;
   const double* eff = which == 0 ? c->cdf_eff_add.p : c->cdf_eff_rem.p;
-  k_sample<<<1, 256, 0, c->stream>>>(q, z, s->inorder.p, eff, s->m, c->cdf_blocks, u01, c->sample_out.p);
+  k_sample<<<1, 256, 0, c->stream>>>(q, z, c->inorder_dev(), eff, c->mw, c->cdf_blocks, u01, c->sample_out.p);
   count_launch();
   BMG_CUDA(cudaGetLastError());
   bmg::copy_d2h(c->h_sample.p, c->sample_out.p, 2 * sizeof(double), c->stream);
   BMG_CUDA(cudaStreamSynchronize(c->stream));
   const double j = c->h_sample.p[0];
   BMG_REQUIRE(j >= 0, "bmg_chain_sample: every item is zeroed");
-  *snp = (int64_t)j + s->lo;
+  *snp = (int64_t)j + (s->lo - c->w_off);
   if (total) *total = c->h_sample.p[1];
 }
 

@@ -1,0 +1,91 @@
+"""One chain over a SNP-sharded store: host-side plumbing for bmg_sampler_create_sharded.
+
+One process per GPU (torchrun).  Rank r builds the store of SNPs [r*stride, (r+1)*stride), exports its packed shard
+over CUDA IPC, attaches every peer's shard (column statistics read remote columns over NVLink), and runs the same
+seeded sampler as every other rank; the only collective on the data path is the all-gather of the scan's per-SNP
+result (8 B per SNP, once per scan), supplied here through torch.distributed (NCCL: plumbing, not product)."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib, api
+
+
+def shard_range(m_g, world, rank, multiple=16):
+    """Equal-stride contiguous SNP blocks (stride a multiple of the scan's 16-SNP tile)."""
+    stride = -(-m_g // world)
+    stride = -(-stride // multiple) * multiple
+    lo = min(m_g, rank * stride)
+    return stride, lo, min(m_g, lo + stride)
+
+
+class _DevicePtr:
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+class ShardComm:
+    """The bmg_shard_comm of this rank.  backend 'nccl': in-place all_gather_into_tensor on the chain's stream;
+    'gloo' (tests: several ranks sharing one GPU, which NCCL refuses): staged through host memory."""
+
+    def __init__(self, dist, world, rank, stride, device):
+        self.dist, self.world, self.rank, self.stride, self.device = dist, world, rank, stride, device
+        self.backend = dist.get_backend()
+        self.calls = 0
+        self.bytes = 0
+        self._cb = _lib.ALLGATHER_FN(self._allgather)
+        self.struct = _lib.ShardCommStruct(world, rank, stride, self._cb, None)
+
+    def _allgather(self, ctx, buf, elems, elem_bytes, stream):
+        try:
+            per = int(elems) * int(elem_bytes)
+            full = torch.as_tensor(_DevicePtr(buf, per * self.world), device=torch.device("cuda", self.device))
+            mine = full[self.rank * per:(self.rank + 1) * per]
+            ext = torch.cuda.ExternalStream(int(stream or 0), device=torch.device("cuda", self.device))
+            with torch.cuda.stream(ext):
+                if self.backend == "nccl":
+                    self.dist.all_gather_into_tensor(full, mine)
+                else:
+                    ext.synchronize()
+                    host = mine.cpu()
+                    parts = [torch.empty_like(host) for _ in range(self.world)]
+                    self.dist.all_gather(parts, host)
+                    full.copy_(torch.cat(parts).to(full.device))
+                    ext.synchronize()
+            self.calls += 1
+            self.bytes += per * (self.world - 1)
+            return 0
+        except Exception as e:   # never let an exception cross the C boundary
+            import sys
+            print("[bmagwa_b200.sharded] all-gather failed: %r" % (e,), file=sys.stderr)
+            return 1
+
+
+def attach_all_peers(dist, store, world, rank, lo, hi):
+    """Exchange the IPC handles of the packed shards and map every peer's shard into this rank's store."""
+    handle, _ = store.export()
+    mine = (bytes(handle), int(lo), int(hi))
+    everyone = [None] * world
+    dist.all_gather_object(everyone, mine)
+    for r, (h, plo, phi) in enumerate(everyone):
+        if r != rank and phi > plo:
+            store.attach_peer(np.frombuffer(h, dtype=np.uint8), plo, phi)
+
+
+def create_sharded_sampler(dist, ini_path, n, m_g, bed_path, device, y, covariates=None, recode_to_minor=True,
+                           payload_device_ptr=None, **options):
+    """Builds shard store + peers + sampler for this rank.  Returns (sampler, store, comm)."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    stride, lo, hi = shard_range(m_g, world, rank)
+    if payload_device_ptr is not None:
+        store = api.GenotypeStore(None, n, m_g, recode_to_minor=recode_to_minor, device=device, snp_lo=lo, snp_hi=hi,
+                                  payload_device_ptr=payload_device_ptr)
+    else:
+        store = api.GenotypeStore(None, n, m_g, recode_to_minor=recode_to_minor, device=device, snp_lo=lo, snp_hi=hi,
+                                  bed_path=bed_path)
+    store.set_phenotype(y, covariates)
+    attach_all_peers(dist, store, world, rank, lo, hi)
+    comm = ShardComm(dist, world, rank, stride, device)
+    sampler = api.Sampler(ini_path, 0, device, store=store, comm=comm, **options)
+    return sampler, store, comm

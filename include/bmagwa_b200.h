@@ -201,6 +201,27 @@ int bmg_chain_get_phenotype(bmg_chain* c, double* y_out);
 int bmg_sampler_create(const char* ini_path, int chain_index, int device, bmg_sampler** out);
 /* Same, over a store that already exists (chains share it, main.cpp:54-76). */
 int bmg_sampler_create_on_store(const char* ini_path, int chain_index, bmg_store* s, bmg_sampler** out);
+
+/* One chain over a SNP-SHARDED store on the G GPUs of a box (the reference has no counterpart: its
+ * only parallelism is one thread per chain, main.cpp:70-95).  One process per GPU; rank r holds the packed SNPs
+ * [r*snp_stride, min(m_g, (r+1)*snp_stride)) in `shard` (bmg_store_create / _from_bed with that range, phenotype set,
+ * every other rank's shard attached with bmg_store_attach_peer so that column statistics can read any SNP's packed
+ * column over NVLink).  Every rank runs the SAME seeded sampler in lockstep: only the genotype scan is sharded; its
+ * per-SNP result (8 bytes per SNP) is all-gathered through `allgather`, everything downstream is replicated and
+ * bit-identical, so the chain equals the single-GPU chain draw for draw.
+ * allgather(ctx, dev_buffer, elems_per_rank, elem_bytes, cuda_stream): dev_buffer holds world*elems_per_rank elements;
+ * rank r's block [r*elems_per_rank, (r+1)*elems_per_rank) is valid on entry, all blocks must be valid after the
+ * work enqueued on cuda_stream (ncclAllGather in place, or torch.distributed.all_gather_into_tensor).  Returns 0 on
+ * success.  Called from the thread inside bmg_sampler_create_sharded / bmg_sampler_run. */
+typedef int (*bmg_allgather_fn)(void* ctx, void* dev_buffer, int64_t elems_per_rank, int elem_bytes, void* cuda_stream);
+struct bmg_shard_comm {
+  int world, rank;
+  int64_t snp_stride;
+  bmg_allgather_fn allgather;
+  void* ctx;
+};
+int bmg_sampler_create_sharded(const char* ini_path, int chain_index, bmg_store* shard, const struct bmg_shard_comm* comm,
+                               bmg_sampler** out);
 /* key=value overrides applied after the INI file (e.g. "tau_rng=device", "do_n_iter=1000"). */
 int bmg_sampler_set_option(bmg_sampler* sp, const char* key, const char* value);
 /* Opens output files, initialises the chain (sampler.cpp:592-620). */

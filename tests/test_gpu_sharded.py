@@ -1,0 +1,34 @@
+"""one chain over a SNP-sharded store.  Two ranks (sharing the one GPU of the test box; gloo for the
+plumbing because NCCL refuses two ranks on one device) must reproduce the single-GPU chain byte for byte."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tau_rng", ["host", "device"])
+def test_sharded_chain_equals_single_gpu_chain(tmp_path, tau_rng):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29%03d" % (os.getpid() % 1000), os.path.join(ROOT, "tests", "sharded_worker.py"), str(tmp_path),
+           tau_rng, "1200"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "SHARDED_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_shard_range_covers_all_snps():
+    from bmagwa_b200.sharded import shard_range
+    for m_g in (1, 15, 16, 17, 3000, 100000, 1000003):
+        for world in (1, 2, 3, 8):
+            got = []
+            for r in range(world):
+                stride, lo, hi = shard_range(m_g, world, r)
+                assert stride % 16 == 0 and stride * world >= m_g and lo == min(m_g, r * stride)
+                got += list(range(lo, hi)) if m_g <= 3000 else [lo, hi]
+            if m_g <= 3000:
+                assert got == list(range(m_g))
+            else:
+                assert got[0] == 0 and got[-1] == m_g and all(got[2 * i + 1] == got[2 * i + 2] for i in range(world - 1))

@@ -34,6 +34,8 @@ WORKLOADS = {
     "C1s": dict(n=1000, m_g=10000, m_e=2, desc="synthetic stand-in for testdata/testdata.ini (n=1,000 x p=10,000)"),
     "C2": dict(n=5000, m_g=100000, m_e=2, desc="synthetic linear GWAS n=5,000 x p=100,000 SNPs, single chain"),
     "C2x": dict(n=5000, m_g=1000000, m_e=2, desc="synthetic linear GWAS n=5,000 x p=1,000,000 SNPs"),
+    "C4": dict(n=50000, m_g=1000000, m_e=2, desc="synthetic linear n=50,000 x p=1,000,000 (12.5 GB packed)"),
+    "C4s": dict(n=50000, m_g=200000, m_e=2, desc="synthetic linear n=50,000 x p=200,000 (2.5 GB packed; C4 at one fifth of the SNPs)"),
 }
 GEN_SEED = 20121101
 CHAIN_SEEDS = [1234, 2345, 3456, 4567, 5678, 6789, 7890, 8901]
@@ -385,6 +387,175 @@ def ours_arm(args, rank, local_rank, world):
     return out
 
 
+# ------------------------------------------------------------------------------------------------
+# --sharded: ONE chain over a SNP-sharded store (BASELINE configs[3]); strong scaling
+# ------------------------------------------------------------------------------------------------
+def device_payload(n, snp_lo, snp_hi, seed, device, block=2048):
+    """Seeded PLINK payload of the SNPs [snp_lo, snp_hi) generated on the device: codes 00/10/11 only (no missing
+    calls), Binomial(2, f_j) genotypes with f_j ~ U(0.02, 0.95).  Every block of `block` SNPs has its own generator
+    seed, so the data do not depend on how the SNP axis is sharded.  Returns a uint8 tensor of
+    (snp_hi - snp_lo) * ceil(n/4) bytes."""
+    import torch
+    B = (n + 3) // 4
+    out = torch.empty((snp_hi - snp_lo) * B, dtype=torch.uint8, device=device)
+    for blk in range(snp_lo // block, (snp_hi + block - 1) // block):
+        g = torch.Generator(device=device).manual_seed(seed * 1000003 + blk)
+        f = torch.rand((block, 1), generator=g, device=device) * 0.93 + 0.02
+        byte = torch.zeros((block, B), dtype=torch.uint8, device=device)
+        for p in range(4):
+            a = (torch.rand((block, B), generator=g, device=device) < f).to(torch.uint8)
+            b = (torch.rand((block, B), generator=g, device=device) < f).to(torch.uint8)
+            x = a + b                            # Binomial(2, f)
+            code = x + (x > 0).to(torch.uint8)   # 0 -> 00, 1 -> 10, 2 -> 11
+            byte |= code << (2 * p)
+        r0, r1 = max(snp_lo, blk * block), min(snp_hi, (blk + 1) * block)
+        out[(r0 - snp_lo) * B:(r1 - snp_lo) * B] = byte[r0 - blk * block:r1 - blk * block].reshape(-1)
+    return out
+
+
+def sharded_arm(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from bmagwa_b200 import _lib, sharded, synth
+    import ctypes as C
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = local_rank
+    if not dist.is_initialized():
+        if world == 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29577")
+            os.environ.setdefault("RANK", "0"); os.environ.setdefault("WORLD_SIZE", "1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    L = _lib.lib()
+    spec = WORKLOADS[args.workload]
+    n, m, m_e = spec["n"], spec["m_g"], spec["m_e"]
+    stride, lo, hi = sharded.shard_range(m, world, rank)
+    t0 = time.perf_counter()
+    payload = device_payload(n, lo, hi, GEN_SEED, torch.device("cuda", dev))
+    store, stride, lo, hi = sharded.create_shard_store(dist, n, m, dev, payload_device_ptr=payload.data_ptr())
+    del payload
+    torch.cuda.empty_cache()
+    # phenotype: 20 causal SNPs spread over the genome; each owner contributes its columns
+    rs = np.random.default_rng(GEN_SEED)
+    causal = np.linspace(0, m - 1, 20).astype(np.int64)
+    contrib = np.zeros(n)
+    swapped = store.counts()[3]
+    for j in causal:
+        if lo <= j < hi:
+            x = store.get_column(int(j), 0)
+            if swapped[j - lo]:
+                x = 2.0 - x   # effects are positive on the file's allele coding, as in synth.make_phenotype (mixed signs on
+                              # the minor-allele coding; same-sign effects make the reference's model grow to > 100 SNPs)
+            contrib += 0.14 * (x - x.mean()) / max(x.std(), 1e-9)
+    t = torch.from_numpy(contrib).cuda()
+    dist.all_reduce(t)
+    y = t.cpu().numpy() + rs.normal(size=n) * np.sqrt(0.6)
+    E = rs.uniform(0.0, 1.0, size=(n, m_e))
+    tmp = tempfile.mkdtemp(prefix="bmagwa_shard_r%d_" % rank)
+    shared = os.path.join(tempfile.gettempdir(), "bmagwa_shard_job")
+    if rank == 0:
+        os.makedirs(shared, exist_ok=True)
+        base = os.path.join(shared, "syn")
+        ids = ["per%d per%d" % (i, i) for i in range(n)]
+        with open(base + ".fam", "w") as fh:
+            fh.write("".join("%s 0 0 1 %.10g\n" % (ident, v) for ident, v in zip(ids, y)))
+        with open(base + ".y", "w") as fh:
+            fh.write("".join("%s %.17g\n" % (ident, v) for ident, v in zip(ids, y)))
+        with open(base + ".e", "w") as fh:
+            fh.write("".join("%s %s\n" % (ident, " ".join("%.17g" % v for v in row)) for ident, row in zip(ids, E)))
+        open(base + ".bed", "wb").write(bytes([0x6C, 0x1B, 0x01]))   # never read: the shards were generated on the devices
+        cfg = dict(base=base, recode=1, n=n, m_g=m, m_e=m_e, save_beta=0, do_n_iter=args.n_rao, n_rao=args.n_rao, n_rao_burnin=1000,
+                   thin=10, n_sample_tau2_and_missing=10, delay_rejection=10, max_move_size=20, use_individual_tau2=1, e_qg=20,
+                   var_qg=300, n_threads=1, seeds=str(CHAIN_SEEDS[0]), outbase=os.path.join(shared, "chain"), verbosity=0)
+        with open(os.path.join(shared, "bench.ini"), "w") as fh:
+            fh.write(synth.INI_TEMPLATE.format(**cfg))
+    dist.barrier()
+    ini = os.path.join(shared, "bench.ini")
+    s, comm = sharded.finish_sharded_sampler(dist, ini, store, stride, lo, hi, dev, y, E, tau_rng=args.tau_rng)
+    s.set_option("basename", os.path.join(tmp, "bench%d" % rank))
+    log("[bench] rank %d: shard [%d, %d) ready in %.1f s" % (rank, lo, hi, time.perf_counter() - t0))
+    s.begin()
+    chain = L.bmg_sampler_chain(s.h)
+    stream = torch.cuda.ExternalStream(s.chain_stream())
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+
+    def step():
+        with torch.cuda.stream(stream):
+            flush.zero_()
+        s.run(args.n_rao)
+
+    for _ in range(args.warmup):
+        step()
+    L.bmg_chain_scan_kernel_time(chain, 1, None, None, 1)
+    st0 = s.stats()
+    launches_a = int(L.bmg_launch_count())
+    clocks = ClockSampler(dev)
+    if rank == 0:
+        clocks.start()
+    torch.cuda.synchronize(); dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    dist.barrier()
+    clk = clocks.stop() if rank == 0 else None
+    t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    launches_b = int(L.bmg_launch_count())
+    st1 = s.stats()
+    ms_total, n_l = C.c_double(), C.c_int64()
+    L.bmg_chain_scan_kernel_time(chain, 0, C.byref(ms_total), C.byref(n_l), 0)
+    s.end(); s.close(); store.close()
+    try:
+        ms_trace = np.fromfile(os.path.join(tmp, "bench%d_modelsize.dat" % rank), dtype=np.uint32)
+        ms_trace = [int(v) for v in ms_trace[::max(1, len(ms_trace) // 12)]]
+    except Exception:
+        ms_trace = None
+    peak, peak_src = measured_peak()
+    B = (n + 3) // 4
+    bytes_scan = (hi - lo) * B + 8 * (hi - lo) + 8 * n      # this rank's shard
+    out = None
+    if rank == 0:
+        avg_ms = ms_total.value / max(1, n_l.value)
+        iters = args.steps * args.n_rao
+        out = {
+            "metric": "mcmc_iterations_per_sec", "value": iters / (elapsed_ms / 1e3), "unit": "iterations/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s: %s; ONE chain, store SNP-sharded over %d GPU(s) (%d SNPs per shard)"
+                       % (args.workload, spec["desc"], world, stride), "n": n, "m_g": m, "n_rao": args.n_rao,
+                       "step": "%d MCMC iterations incl. one all-SNP scan" % args.n_rao, "tau_rng": args.tau_rng,
+                       "l2": "256 MiB write on the chain's stream before every step, inside the timed region",
+                       "collective": "all-gather of the scan's per-SNP p_r (8 B/SNP) through torch.distributed NCCL, once per scan; "
+                                     "column statistics read remote shards over CUDA IPC peer mappings",
+                       "timing": "CUDA events on the chain's stream, max over ranks; wall %.3f ms/step" % (1e3 * wall / args.steps)},
+            "e2e": {"value": iters / wall, "unit": "iterations/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
+                    "what": "wall clock of the K steps through bmg_sampler_run (per-move results and per-scan weights cross PCIe "
+                            "inside); the shards are generated on the devices, so there is no store upload to time"},
+            "gpu_launches": launches_b - launches_a,
+            "roofline": {"bound": "hbm", "kernel": "k_scan_dots_imma on this rank's shard", "achieved": bytes_scan / (avg_ms * 1e-3) / 1e9,
+                         "peak": peak, "unit": "GB/s", "frac": bytes_scan / (avg_ms * 1e-3) / 1e9 / peak, "traffic": None,
+                         "bytes_per_launch": bytes_scan, "avg_launch_ms": avg_ms, "launches_timed": int(n_l.value), "peak_source": peak_src},
+            "clocks": clk,
+            "breakdown": {"move_seconds": st1["move_seconds"] - st0["move_seconds"], "scan_seconds": st1["scan_seconds"] - st0["scan_seconds"],
+                          "column_stats_seconds": st1["column_stats_seconds"] - st0["column_stats_seconds"],
+                          "allgather_calls": comm.calls, "allgather_bytes_received": comm.bytes, "model_size": st1["model_size"], "model_size_trace": ms_trace},
+            "cpu_baseline": {"value": None, "unit": "iterations/s", "cores": 0, "kind": "reference",
+                             "sample": "not run: the reference needs n x m_g doubles (%.0f GB) in host memory for this workload"
+                                       % (8.0 * n * m / 1e9)},
+        }
+    dist.barrier()
+    dist.destroy_process_group()
+    return out
+
+
 def cpu_baseline(args, spec):
     """The reference sampler (oracle/_ref) on this box's host cores, bounded sample of the same workload."""
     from oracle import ref
@@ -412,6 +583,8 @@ def main():
     ap.add_argument("--n-rao", type=int, default=500, dest="n_rao")
     ap.add_argument("--tau-rng", default="device", choices=["device", "host"], dest="tau_rng")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sharded", action="store_true",
+                    help="ONE chain over a SNP-sharded store (strong scaling) instead of one chain per GPU")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         log("[bench] note: fewer than 3 warm-up steps requested")
@@ -421,7 +594,12 @@ def main():
     if world != args.gpus and world == 1 and args.gpus > 1 and args.impl == "ours":
         raise SystemExit("launch with torch.distributed.run --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
     with stdout_to_stderr():
-        line = reference_arm(args, rank, world) if args.impl == "reference" else ours_arm(args, rank, local_rank, world)
+        if args.impl == "reference":
+            line = reference_arm(args, rank, world)
+        elif args.sharded:
+            line = sharded_arm(args, rank, local_rank, world)
+        else:
+            line = ours_arm(args, rank, local_rank, world)
     if line is not None:
         print(json.dumps(line), flush=True)
 

@@ -544,7 +544,8 @@ class ProposalCdf {
     nb_ = (m_ + block - 1) / block;
     pos_of_.resize(m_);
     for (int64_t p = 0; p < m_; ++p) pos_of_[(*order)[p]] = (int32_t)p;
-    w_.assign(m_, 0.0);
+    w_own_.assign(m_, 0.0);
+    w_ = w_own_.data();
     zeroed_.assign(m_, 0);
     fen_.assign(nb_ + 1, 0.0);
     eff_.assign(nb_, 0.0);
@@ -554,7 +555,7 @@ class ProposalCdf {
   // `mostly_live` (dd_add) or the currently non-zeroed items otherwise (dd_rem).
   void update(const double* w_inorder, const double* block_sums, bool mostly_live, const std::vector<uint32_t>& exceptions)
   {
-    std::copy(w_inorder, w_inorder + m_, w_.begin());
+    w_ = w_inorder;   // borrowed: the caller keeps the buffer alive and unchanged until the next update()
     if (mostly_live) {
       for (int64_t b = 0; b < nb_; ++b) eff_[b] = block_sums[b];
       for (uint32_t it : exceptions) eff_[pos_of_[it] / block_] -= w_[pos_of_[it]];
@@ -646,7 +647,8 @@ class ProposalCdf {
   int64_t m_ = 0, nb_ = 0;
   int block_ = 256;
   std::vector<int32_t> pos_of_;
-  std::vector<double> w_;       // in-order layout
+  const double* w_ = nullptr;      // in-order layout (borrowed from the sampler's pinned staging buffer)
+  std::vector<double> w_own_;      // zeros until the first update()
   std::vector<uint8_t> zeroed_; // by item
   std::vector<double> fen_, eff_;
 };

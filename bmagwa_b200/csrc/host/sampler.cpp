@@ -129,7 +129,8 @@ Sampler::Sampler(const Options& opts, int chain_index, Store* store, const std::
   if (comm != nullptr) chain_set_sharded(chain_, comm->world, comm->rank, comm->stride, comm->allgather, comm->ctx);
   dd_add_.init(&chain_->inorder_host(), (int)chain_->cdf_block);
   dd_rem_.init(&chain_->inorder_host(), (int)chain_->cdf_block);
-  h_w_.alloc(2 * m_g_);
+  h_w_.alloc(m_g_);
+  h_w2_[0].alloc(2 * m_g_); h_w2_[1].alloc(2 * m_g_);
   h_cdf_.assign(2 * chain_->cdf_blocks, 0.0);
 
   move_inds_add_.assign(max_move_size_, 0); move_inds_rem_.assign(max_move_size_, 0); move_inds_.assign(max_move_size_, 0);
@@ -294,20 +295,22 @@ void Sampler::refresh_weights_from_device(bool first)
 {
   Chain* c = chain_;
   BMG_CUDA(cudaSetDevice(store_->device));
-  bmg::copy_d2h(h_w_.p, c->q_add_io.p, m_g_ * sizeof(double), c->stream);
-  bmg::copy_d2h(h_w_.p + m_g_, c->q_rem_io.p, m_g_ * sizeof(double), c->stream);
+  h_w_cur_ ^= 1;   // the CDFs keep reading the previous buffer until update() below
+  double* hw = h_w2_[h_w_cur_].p;
+  bmg::copy_d2h(hw, c->q_add_io.p, m_g_ * sizeof(double), c->stream);
+  bmg::copy_d2h(hw + m_g_, c->q_rem_io.p, m_g_ * sizeof(double), c->stream);
   bmg::copy_d2h(h_cdf_.data(), c->cdf_add.p, c->cdf_blocks * sizeof(double), c->stream);
   bmg::copy_d2h(h_cdf_.data() + c->cdf_blocks, c->cdf_rem.p, c->cdf_blocks * sizeof(double), c->stream);
   BMG_CUDA(cudaStreamSynchronize(c->stream));
   if (first) {
-    dd_add_.update(h_w_.p, h_cdf_.data(), true, std::vector<uint32_t>());
-    dd_rem_.update(h_w_.p + m_g_, h_cdf_.data() + c->cdf_blocks, true, std::vector<uint32_t>());
+    dd_add_.update(hw, h_cdf_.data(), true, std::vector<uint32_t>());
+    dd_rem_.update(hw + m_g_, h_cdf_.data() + c->cdf_blocks, true, std::vector<uint32_t>());
     dd_rem_.zero_all();   // sampler.cpp:601-605
   } else {
     // zero flags are kept (discrete_distribution.hpp:263-314): dd_add has the model's SNPs zeroed,
     // dd_rem has everything but the model's SNPs zeroed
-    dd_add_.update(h_w_.p, h_cdf_.data(), true, current_.loci);
-    dd_rem_.update(h_w_.p + m_g_, h_cdf_.data() + c->cdf_blocks, false, current_.loci);
+    dd_add_.update(hw, h_cdf_.data(), true, current_.loci);
+    dd_rem_.update(hw + m_g_, h_cdf_.data() + c->cdf_blocks, false, current_.loci);
   }
 }
 
@@ -495,8 +498,10 @@ void Sampler::rao_block()
     ++p_proposal_n_;
   }
   if (update_rao || update_prop) {
+    const double t1 = wall_seconds();
     chain_adapt(chain_, update_rao ? 1 : 0, n_rao_mean, update_prop ? 1 : 0, n_prop_mean, q_add_min_, q_rem_min_);
     if (update_prop) refresh_weights_from_device(false);
+    epilogue_seconds_ += wall_seconds() - t1;
   }
 }
 
@@ -523,7 +528,8 @@ void Sampler::end()
   if (getenv("BMG_TIMING"))
     std::cerr << "[bmg timing] iterations " << n_iter_ << " moves " << move_seconds_ << " s, of which column-stats wait "
               << device_wait_seconds_ << " s, move-0 delayed rejection " << dr_seconds_ << " s (" << n_dr_ << " events); scans "
-              << scan_seconds_ << " s" << std::endl;
+              << scan_seconds_ << " s, scan epilogue (adapt + weights to the host, waits for the scan) " << epilogue_seconds_ << " s"
+              << std::endl;
   // _rao.dat (sampler.cpp:847-849): the running mean kept on the device
   p_rao_.assign(m_g_, 0.0);
   BMG_CUDA(cudaSetDevice(store_->device));

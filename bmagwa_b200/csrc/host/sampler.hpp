@@ -67,7 +67,9 @@ class Sampler {
   int p_rao_n_ = 0;
   double q_add_min_, q_rem_min_;
   ProposalCdf dd_add_, dd_rem_;
-  PinnedBuf<double> h_w_;                  // pinned staging of the in-order weights
+  PinnedBuf<double> h_w2_[2];              // pinned in-order weights, double-buffered: the proposal CDFs read them in place
+  int h_w_cur_ = 0;
+  PinnedBuf<double> h_w_;                  // pinned staging (p_rao at the end)
   std::vector<double> h_cdf_;
   // ---- moves (sampler.hpp:442-483)
   double p_moves_[7], p_moves_cumsum_[7];
@@ -88,7 +90,7 @@ class Sampler {
   MoveGram gram_;
   // ---- book-keeping (samplerstats.hpp)
   unsigned long n_upd_add_ = 0, n_upd_rem_ = 0, n_comp_ = 0;
-  double move_seconds_ = 0.0, scan_seconds_ = 0.0, device_wait_seconds_ = 0.0, dr_seconds_ = 0.0;
+  double move_seconds_ = 0.0, scan_seconds_ = 0.0, device_wait_seconds_ = 0.0, dr_seconds_ = 0.0, epilogue_seconds_ = 0.0;
   size_t n_dr_ = 0;
   size_t n_scans_ = 0;
   double t_start_ = 0.0;

@@ -73,19 +73,28 @@ def attach_all_peers(dist, store, world, rank, lo, hi):
             store.attach_peer(np.frombuffer(h, dtype=np.uint8), plo, phi)
 
 
-def create_sharded_sampler(dist, ini_path, n, m_g, bed_path, device, y, covariates=None, recode_to_minor=True,
-                           payload_device_ptr=None, **options):
-    """Builds shard store + peers + sampler for this rank.  Returns (sampler, store, comm)."""
+def create_shard_store(dist, n, m_g, device, bed_path=None, payload_device_ptr=None, recode_to_minor=True):
+    """This rank's SNP block of the store (phenotype not yet set).  Returns (store, stride, lo, hi)."""
     world, rank = dist.get_world_size(), dist.get_rank()
     stride, lo, hi = shard_range(m_g, world, rank)
-    if payload_device_ptr is not None:
-        store = api.GenotypeStore(None, n, m_g, recode_to_minor=recode_to_minor, device=device, snp_lo=lo, snp_hi=hi,
-                                  payload_device_ptr=payload_device_ptr)
-    else:
-        store = api.GenotypeStore(None, n, m_g, recode_to_minor=recode_to_minor, device=device, snp_lo=lo, snp_hi=hi,
-                                  bed_path=bed_path)
+    store = api.GenotypeStore(None, n, m_g, recode_to_minor=recode_to_minor, device=device, snp_lo=lo, snp_hi=hi,
+                              payload_device_ptr=payload_device_ptr, bed_path=bed_path)
+    return store, stride, lo, hi
+
+
+def finish_sharded_sampler(dist, ini_path, store, stride, lo, hi, device, y, covariates=None, **options):
+    """Phenotype, peer shards, communicator and the lockstep sampler.  Returns (sampler, comm)."""
+    world, rank = dist.get_world_size(), dist.get_rank()
     store.set_phenotype(y, covariates)
     attach_all_peers(dist, store, world, rank, lo, hi)
     comm = ShardComm(dist, world, rank, stride, device)
-    sampler = api.Sampler(ini_path, 0, device, store=store, comm=comm, **options)
+    return api.Sampler(ini_path, 0, device, store=store, comm=comm, **options), comm
+
+
+def create_sharded_sampler(dist, ini_path, n, m_g, bed_path, device, y, covariates=None, recode_to_minor=True,
+                           payload_device_ptr=None, **options):
+    """Builds shard store + peers + sampler for this rank.  Returns (sampler, store, comm)."""
+    store, stride, lo, hi = create_shard_store(dist, n, m_g, device, bed_path=bed_path, payload_device_ptr=payload_device_ptr,
+                                               recode_to_minor=recode_to_minor)
+    sampler, comm = finish_sharded_sampler(dist, ini_path, store, stride, lo, hi, device, y, covariates, **options)
     return sampler, store, comm

@@ -419,13 +419,16 @@ void chain_column_stats_launch(Chain* c, const int64_t* cand, int m_c, const int
 // ---------------------------------------------------------------------------------------
 // probit latent update (no reference counterpart)
 // ---------------------------------------------------------------------------------------
+// partial[block][2 + m_e] = { sum z, sum z^2, sum z E_j ... } (m_e <= 8 here; more covariates fall back to 2 sums)
 __global__ void __launch_bounds__(256) k_probit(const double* __restrict__ ye, const double* __restrict__ yg,
                                                 const uint8_t* __restrict__ is_case, const double* __restrict__ u_in,
-                                                uint64_t seed, uint64_t counter, int64_t n, double* __restrict__ y,
-                                                double* __restrict__ partial)
+                                                uint64_t seed, uint64_t counter, int64_t n, const double* __restrict__ e, int m_e,
+                                                double* __restrict__ y, double* __restrict__ partial)
 {
-  __shared__ double sm[2][8];
-  double s1 = 0.0, s2 = 0.0;
+  __shared__ double sm[10][8];
+  double acc[10];
+#pragma unroll
+  for (int q = 0; q < 10; ++q) acc[q] = 0.0;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const double mu = yg[i] + ye[i];
     double u;
@@ -434,17 +437,24 @@ __global__ void __launch_bounds__(256) k_probit(const double* __restrict__ ye, c
     // inverse-CDF draw from N(mu,1) truncated to (0,inf) [case] or (-inf,0] [control], always through the lower tail
     const double z = is_case[i] ? mu - normcdfinv(u * normcdf(mu)) : mu + normcdfinv(u * normcdf(-mu));
     y[i] = z;
-    s1 += z;
-    s2 += z * z;
+    acc[0] += z;
+    acc[1] += z * z;
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      if (q < m_e) acc[2 + q] = fma(z, e[(int64_t)q * n + i], acc[2 + q]);
   }
-  for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) { sm[0][warp] = s1; sm[1][warp] = s2; }
+#pragma unroll
+  for (int q = 0; q < 10; ++q) {
+    double v = acc[q];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) sm[q][warp] = v;
+  }
   __syncthreads();
-  if (threadIdx.x < 2) {
+  if (threadIdx.x < 2 + m_e) {
     double s = 0.0;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += sm[threadIdx.x][w];
-    partial[(int64_t)blockIdx.x * 2 + threadIdx.x] = s;
+    partial[(int64_t)blockIdx.x * (2 + m_e) + threadIdx.x] = s;
   }
 }
 
@@ -457,8 +467,9 @@ __global__ void k_reduce_final2(const double* __restrict__ partial, int blocks, 
   out[q] = s;
 }
 
+// stats: { sum z, sum z^2, E'z (m_e entries, when m_e <= 8) }
 void chain_probit_update(Chain* c, const uint8_t* is_case, const double* u01, uint64_t seed, uint64_t counter,
-                         double* stats2)
+                         double* stats2, double* ez)
 {
   Store* s = c->store;
   BMG_REQUIRE(c->residual_valid, "bmg_chain_probit_update: call bmg_chain_residual first (it leaves the fitted values)");
@@ -476,16 +487,21 @@ void chain_probit_update(Chain* c, const uint8_t* is_case, const double* u01, ui
     bmg::copy_h2d(u_dev.p, u01, s->n * sizeof(double), st);
   }
   const int blocks = (int)std::min<int64_t>(1024, (s->n + 255) / 256);
-  k_probit<<<blocks, 256, 0, st>>>(c->yhat_e.p, c->yhat_g.p, c->is_case.p, u01 ? u_dev.p : nullptr, seed, counter, s->n, c->y.p,
-                                   c->red_partial.p);
-  k_reduce_final2<<<1, 32, 0, st>>>(c->red_partial.p, blocks, 2, c->red_out.p);
+  const int me = s->m_e <= 8 ? s->m_e : 0;
+  k_probit<<<blocks, 256, 0, st>>>(c->yhat_e.p, c->yhat_g.p, c->is_case.p, u01 ? u_dev.p : nullptr, seed, counter, s->n, s->e.p, me,
+                                   c->y.p, c->red_partial.p);
+  k_reduce_final2<<<1, 32, 0, st>>>(c->red_partial.p, blocks, 2 + me, c->red_out.p);
   count_launch(2);
   BMG_CUDA(cudaGetLastError());
-  bmg::copy_d2h(c->h_red.p, c->red_out.p, 2 * sizeof(double), st);
+  bmg::copy_d2h(c->h_red.p, c->red_out.p, (2 + me) * sizeof(double), st);
   BMG_CUDA(cudaStreamSynchronize(st));
   c->residual_valid = false;  // the phenotype changed: the residual must be rebuilt
   c->imma_q_valid = false;
   if (stats2) { stats2[0] = c->h_red.p[0]; stats2[1] = c->h_red.p[1]; }
+  if (ez) {
+    BMG_REQUIRE(me == s->m_e, "probit update: E'z is returned for at most 8 covariate columns");
+    for (int q = 0; q < me; ++q) ez[q] = c->h_red.p[2 + q];
+  }
 }
 
 }  // namespace bmg

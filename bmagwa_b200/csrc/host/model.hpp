@@ -38,6 +38,15 @@ struct Model;
 class Prior {
  public:
   double n_plus_nu, minus_n_plus_nu_2, nus2_plus_yy, mu_alpha;
+  // probit mode (no reference counterpart): the latent phenotype has sigma2 == 1, so the marginal
+  // likelihood keeps -(y'y - v'v)/2 instead of integrating sigma2 out, and y'y changes with every latent sweep
+  bool fixed_sigma2 = false;
+  double residual_term(double syx_plus_vs2) const
+  {
+    return fixed_sigma2 ? -0.5 * syx_plus_vs2 : minus_n_plus_nu_2 * std::log(syx_plus_vs2);
+  }
+  void set_fixed_sigma2(double yy) { fixed_sigma2 = true; nus2_plus_yy = yy; }
+  void set_yy(double yy) { nus2_plus_yy = (fixed_sigma2 ? 0.0 : nu_sigma2_ * s2_sigma2_) + yy; }
   bool use_individual_tau2;
 
   Prior(size_t n, size_t m_g, size_t m_e, double yy, const double* types_prior, double e_qg, double var_qg,
@@ -252,7 +261,7 @@ struct Model {
     syx_plus_vs2 = prior->nus2_plus_yy - vv;
     log_det_invQ_plus_xx = 0.0;
     for (int i = 0; i < k; ++i) log_det_invQ_plus_xx += std::log(l(i, i));
-    log_likelihood = log_det_invQ - log_det_invQ_plus_xx + prior->minus_n_plus_nu_2 * std::log(syx_plus_vs2);
+    log_likelihood = log_det_invQ - log_det_invQ_plus_xx + prior->residual_term(syx_plus_vs2);
     mu_beta_computed = false;
   }
 
@@ -282,7 +291,7 @@ struct Model {
     syx_plus_vs2 -= v[col] * v[col];
     log_det_invQ += 0.5 * std::log(inv_tau2_alpha2_val);
     log_det_invQ_plus_xx += std::log(lcol[col]);
-    log_likelihood = log_det_invQ - log_det_invQ_plus_xx + prior->minus_n_plus_nu_2 * std::log(syx_plus_vs2);
+    log_likelihood = log_det_invQ - log_det_invQ_plus_xx + prior->residual_term(syx_plus_vs2);
   }
 
   // Model::remove_term + update_likelihood_on_remove (model.hpp:270-312,508-556)
@@ -312,7 +321,7 @@ struct Model {
       syx_plus_vs2 = prior->nus2_plus_yy - vv;
     }
     log_det_invQ -= 0.5 * std::log(inv_val);
-    log_likelihood = log_det_invQ - log_det_invQ_plus_xx + prior->minus_n_plus_nu_2 * std::log(syx_plus_vs2);
+    log_likelihood = log_det_invQ - log_det_invQ_plus_xx + prior->residual_term(syx_plus_vs2);
     mu_beta_computed = false;
   }
 
@@ -325,7 +334,7 @@ struct Model {
   }
   void sample_beta_sigma2(ChainRng& rng)  // model.hpp:326-342, rand.hpp:144-168
   {
-    sigma2 = rng.sinvchi2_fixed(syx_plus_vs2 / prior->n_plus_nu);
+    sigma2 = prior->fixed_sigma2 ? 1.0 : rng.sinvchi2_fixed(syx_plus_vs2 / prior->n_plus_nu);
     compute_mu_beta();
     const int k = cols();
     beta.resize(k);
@@ -455,7 +464,7 @@ struct ExhModel {
   int model_size = 0, v_size = 0, n_terms = 0;
 
   double log_prob() const { return log_likelihood + log_model_prior; }
-  void refresh() { log_likelihood = log_det_invQ - log_det_invQ_plus_xx + prior->minus_n_plus_nu_2 * std::log(syx_plus_vs2); }
+  void refresh() { log_likelihood = log_det_invQ - log_det_invQ_plus_xx + prior->residual_term(syx_plus_vs2); }
 
   double update_to_model(const Model& src, int const_loci)  // model.hpp:602-671
   {

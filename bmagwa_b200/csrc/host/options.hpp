@@ -121,6 +121,7 @@ struct Options {
   bool use_individual_tau2 = false;
   size_t delay_rejection = 0;
   // [b200] extensions
+  bool probit = false;            // y holds 0/1 case-control labels; the sampler works on an Albert-Chib latent phenotype
   std::string tau_rng = "host";   // "host": per-SNP tau draws from the chain's stream in reference order (parity);
                                   // "device": counter-based draws on the GPU (throughput)
   int device = 0;
@@ -322,6 +323,7 @@ struct Options {
     const std::string tr = r.get("b200", "tau_rng", "host");
     if (tr != "host" && tr != "device") throw std::runtime_error("Config error: b200.tau_rng must be host or device");
     tau_rng = tr;
+    probit = r.get("b200", "probit", "0") != "0";
     const std::string dv = r.get("b200", "device", "0");
     device = convert<int>(dv);
   }

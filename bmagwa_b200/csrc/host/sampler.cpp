@@ -149,6 +149,71 @@ Sampler::Sampler(const Options& opts, int chain_index, Store* store, const std::
     dr_log_q_add_types_.assign(delay_rejection_, 0.0);
     dr_bit_to_normalized_order_.assign(delay_rejection_, 0);
   }
+  y_host_ = &y; e_host_ = &e;
+  if (opts.probit) enable_probit();
+}
+
+// ------------------------------------------------------------------------------------------------
+// probit mode: Albert & Chib latent phenotype on the device (k_probit), sigma2 == 1
+// ------------------------------------------------------------------------------------------------
+void Sampler::enable_probit()
+{
+  if (probit_) return;
+  if (current_.size() != 0) throw std::runtime_error("probit mode must be enabled before the chain starts");
+  const std::vector<double>& y = *y_host_;
+  const std::vector<double>& e = *e_host_;
+  is_case_.resize(n_);
+  std::vector<double> z(n_);
+  size_t n_case = 0;
+  for (size_t i = 0; i < n_; ++i) {
+    if (y[i] != 0.0 && y[i] != 1.0) throw std::runtime_error("probit mode needs a 0/1 phenotype (file_y)");
+    is_case_[i] = y[i] > 0.5 ? 1 : 0;
+    n_case += is_case_[i];
+    z[i] = is_case_[i] ? 0.7978845608028654 : -0.7978845608028654;   // E|N(0,1)|: start of the latent phenotype
+  }
+  if (n_case == 0 || n_case == n_) throw std::runtime_error("probit mode needs both cases and controls");
+  double yy = 0.0;
+  std::vector<double> exy(m_e_, 0.0);
+  for (size_t i = 0; i < n_; ++i) yy += z[i] * z[i];
+  for (size_t c = 0; c < m_e_; ++c) {
+    double s = 0.0;
+    for (size_t i = 0; i < n_; ++i) s += e[c * n_ + i] * z[i];
+    exy[c] = s;
+  }
+  prior_->set_fixed_sigma2(yy);
+  for (size_t c = 0; c < m_e_; ++c) { current_.xy[c] = exy[c]; proposal_.xy[c] = exy[c]; }
+  current_.sigma2 = 1.0;
+  current_.compute_log_likelihood();
+  proposal_.assign(current_);
+  BMG_CUDA(cudaSetDevice(store_->device));
+  bmg::copy_h2d(chain_->y.p, z.data(), n_ * sizeof(double), chain_->stream);
+  BMG_CUDA(cudaStreamSynchronize(chain_->stream));
+  chain_->residual_valid = false;
+  chain_->imma_q_valid = false;
+  probit_ = true;
+}
+
+void Sampler::probit_sweep()
+{
+  const int k = (int)current_.size();
+  std::vector<int64_t> loci(current_.loci.begin(), current_.loci.end());
+  // fitted values of the CURRENT coefficients (fresh from sample_beta_sigma2), not the quirk-tracked ones of the scan
+  chain_residual(chain_, loci.data(), current_.beta.data(), current_.beta.data() + m_e_, k, nullptr);
+  double st[2];
+  std::vector<double> ez(m_e_, 0.0);
+  chain_probit_update(chain_, probit_labels_sent_ ? nullptr : is_case_.data(), nullptr, (uint64_t)seed_ * 0x9E3779B97F4A7C15ull + 17u,
+                      ++probit_counter_, st, ez.data());
+  probit_labels_sent_ = true;
+  for (size_t c = 0; c < m_e_; ++c) current_.xy[c] = ez[c];
+  for (int done = 0; done < k;) {   // X_gamma' z, 64 model columns per launch
+    const int cnt = std::min(64, k - done);
+    std::vector<double> xy(cnt);
+    chain_column_stats(chain_, loci.data() + done, cnt, nullptr, 0, xy.data(), nullptr, nullptr, nullptr);
+    for (int j = 0; j < cnt; ++j) current_.xy[m_e_ + done + j] = xy[j];
+    done += cnt;
+  }
+  prior_->set_yy(st[1]);
+  ++n_probit_sweeps_;
 }
 
 Sampler::~Sampler()
@@ -168,6 +233,9 @@ void Sampler::set_option(const std::string& key, const std::string& value)
     verbosity_ = (size_t)std::stoul(value);
   } else if (key == "reference_quirks") {
     reference_quirks_ = value != "0";
+  } else if (key == "probit") {
+    if (value != "0") enable_probit();
+    else if (probit_) throw std::runtime_error("probit mode cannot be switched off once enabled");
   } else if (key == "scan_variant") {
     chain_->scan_variant = std::stoi(value);
   } else {
@@ -357,6 +425,7 @@ void Sampler::begin()
   compute_p_moves();
   current_.sample_beta_sigma2(rng_);
   sample_missing();
+  if (probit_) probit_sweep();
   prior_->sample_alpha_and_tau2(&current_, rng_);
   current_.compute_log_likelihood();
   copy_current_to_proposal();
@@ -373,6 +442,7 @@ void Sampler::run(int64_t do_n_iter)
   for (size_t iter = n_iter_; iter < end_iter; ++iter) {
     if ((iter + 1) % n_sample_tau2_and_missing_ == 0) {   // sampler.cpp:628-635
       sample_missing();
+      if (probit_) probit_sweep();   // the latent phenotype moves with the same cadence as tau2 / missing genotypes
       prior_->sample_alpha_and_tau2(&current_, rng_);
       current_.compute_log_likelihood();
       copy_current_to_proposal();

@@ -122,6 +122,15 @@ class Sampler {
   void refresh_weights_from_device(bool first);
   void compute_p_moves();
   void sample_missing() {}   // no missing cells in the supported inputs (checked at construction)
+  // probit mode (no reference counterpart): y = 0/1 labels, the chain's phenotype is the latent z
+  void enable_probit();
+  void probit_sweep();       // z ~ N(X beta, 1) truncated by the labels (device), then y'y, E'z, X_gamma'z refreshed
+  bool probit_ = false, probit_labels_sent_ = false;
+  uint64_t probit_counter_ = 0;
+  int64_t n_probit_sweeps_ = 0;
+  std::vector<uint8_t> is_case_;
+  const std::vector<double>* y_host_ = nullptr;
+  const std::vector<double>* e_host_ = nullptr;
   void rao_block();
   // moves
   unsigned char do_multistep_additions_and_removals();

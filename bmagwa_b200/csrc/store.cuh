@@ -126,6 +126,6 @@ void chain_column_stats_launch(Chain* c, const int64_t* cand, int m_c, const int
                                double* xx_model, double* xx_cand, bool launch_only);
 void chain_column_stats_wait(Chain* c, double* xy, double* xe, double* xx_model, double* xx_cand);
 void chain_probit_update(Chain* c, const uint8_t* is_case, const double* u01, uint64_t seed, uint64_t counter,
-                         double* stats2);
+                         double* stats2, double* ez = nullptr);
 
 }  // namespace bmg

@@ -34,6 +34,7 @@ WORKLOADS = {
     "C1s": dict(n=1000, m_g=10000, m_e=2, desc="synthetic stand-in for testdata/testdata.ini (n=1,000 x p=10,000)"),
     "C2": dict(n=5000, m_g=100000, m_e=2, desc="synthetic linear GWAS n=5,000 x p=100,000 SNPs, single chain"),
     "C2x": dict(n=5000, m_g=1000000, m_e=2, desc="synthetic linear GWAS n=5,000 x p=1,000,000 SNPs"),
+    "C3": dict(n=10000, m_g=500000, m_e=2, desc="synthetic probit case-control n=10,000 x p=500,000 with latent-variable updates (1.25 GB packed)"),
     "C4": dict(n=50000, m_g=1000000, m_e=2, desc="synthetic linear n=50,000 x p=1,000,000 (12.5 GB packed)"),
     "C4s": dict(n=50000, m_g=200000, m_e=2, desc="synthetic linear n=50,000 x p=200,000 (2.5 GB packed; C4 at one fifth of the SNPs)"),
 }
@@ -452,6 +453,8 @@ def sharded_arm(args, rank, local_rank, world):
     t = torch.from_numpy(contrib).cuda()
     dist.all_reduce(t)
     y = t.cpu().numpy() + rs.normal(size=n) * np.sqrt(0.6)
+    if args.probit:
+        y = (y > 0).astype(np.float64)   # case-control labels from the liability
     E = rs.uniform(0.0, 1.0, size=(n, m_e))
     tmp = tempfile.mkdtemp(prefix="bmagwa_shard_r%d_" % rank)
     shared = os.path.join(tempfile.gettempdir(), "bmagwa_shard_job")
@@ -475,6 +478,8 @@ def sharded_arm(args, rank, local_rank, world):
     ini = os.path.join(shared, "bench.ini")
     s, comm = sharded.finish_sharded_sampler(dist, ini, store, stride, lo, hi, dev, y, E, tau_rng=args.tau_rng)
     s.set_option("basename", os.path.join(tmp, "bench%d" % rank))
+    if args.probit:
+        s.set_option("probit", "1")
     log("[bench] rank %d: shard [%d, %d) ready in %.1f s" % (rank, lo, hi, time.perf_counter() - t0))
     s.begin()
     chain = L.bmg_sampler_chain(s.h)
@@ -532,6 +537,7 @@ def sharded_arm(args, rank, local_rank, world):
             "config": {"workload": "%s: %s; ONE chain, store SNP-sharded over %d GPU(s) (%d SNPs per shard)"
                        % (args.workload, spec["desc"], world, stride), "n": n, "m_g": m, "n_rao": args.n_rao,
                        "step": "%d MCMC iterations incl. one all-SNP scan" % args.n_rao, "tau_rng": args.tau_rng,
+                       "likelihood": "probit: latent phenotype redrawn on the device every 10 iterations, sigma2 = 1" if args.probit else "linear",
                        "l2": "256 MiB write on the chain's stream before every step, inside the timed region",
                        "collective": "all-gather of the scan's per-SNP p_r (8 B/SNP) through torch.distributed NCCL, once per scan; "
                                      "column statistics read remote shards over CUDA IPC peer mappings",
@@ -583,6 +589,7 @@ def main():
     ap.add_argument("--n-rao", type=int, default=500, dest="n_rao")
     ap.add_argument("--tau-rng", default="device", choices=["device", "host"], dest="tau_rng")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--probit", action="store_true", help="case-control labels + latent-variable updates (with --sharded; e.g. --workload C3)")
     ap.add_argument("--sharded", action="store_true",
                     help="ONE chain over a SNP-sharded store (strong scaling) instead of one chain per GPU")
     args = ap.parse_args()

@@ -115,27 +115,61 @@ __global__ void __launch_bounds__(256) k_column_stats_inline(const __grid_consta
   const int64_t w0 = (int64_t)seg * seg_words;
   const int nwords = (int)min((int64_t)seg_words, a.W - w0);
   const uint32_t* col = a.cols[c];
-  if (t < nwords) cw[t] = col[w0 + t];
-  __syncthreads();
   const int n_fp = a.m_e + 1;
   const int n_tasks = n_fp + a.k + a.m_c;
   ulonglong2* out = a.out_host + ((int64_t)c * a.n_seg + seg) * n_tasks;
+  const int64_t i_lo = 16 * w0, i_hi = min(a.n, i_lo + 16 * (int64_t)nwords);
+  const bool small = seg_words <= 64;   // 1024 individuals per CTA: 4 per thread, everything this CTA reads issues at once
+  // Every load of the CTA is issued BEFORE the candidate's words are waited for: y / covariates of this thread's
+  // individuals and the first four tasks' words do not depend on them, so the kernel is one memory round trip deep.
+  double yv[4], ev[4][7];
+  uint32_t ow0[4][2];
+  if (small) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t i = i_lo + t + 256 * j;
+      const bool ok = i < i_hi;
+      yv[j] = ok ? a.y[i] : 0.0;
+#pragma unroll
+      for (int q = 1; q < 8; ++q) ev[j][q - 1] = (ok && q < n_fp) ? a.e[(int64_t)(q - 1) * a.n + i] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int task = n_fp + warp + u * nw;
+      const int q = task - n_fp;
+      const uint32_t* other = task < n_tasks ? (q < a.k ? a.cols[a.m_c + q] : a.cols[q - a.k]) + w0 : nullptr;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) ow0[u][j] = (other != nullptr && lane + 32 * j < nwords) ? other[lane + 32 * j] : 0u;
+    }
+  }
+  if (t < nwords) cw[t] = col[w0 + t];
+  __syncthreads();
 
-  // (1) x_c'y and x_c'E_j: thread <-> individual (coalesced, unconditional loads so that they all issue at once);
-  //     a thread covers individuals i_lo + t + 256 j.
+  // (1) x_c'y and x_c'E_j: thread <-> individual (coalesced); a thread covers individuals i_lo + t + 256 j.
   {
-    const int64_t i_lo = 16 * w0, i_hi = min(a.n, i_lo + 16 * (int64_t)nwords);
     double acc[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) acc[q] = 0.0;
-#pragma unroll 4
-    for (int64_t i = i_lo + t; i < i_hi; i += 256) {
-      const uint32_t word = cw[(i - i_lo) >> 4];
-      const double g = (double)((word >> (2 * ((i - i_lo) & 15))) & 3u);
-      acc[0] = fma(g, a.y[i], acc[0]);
+    if (small) {
 #pragma unroll
-      for (int q = 1; q < 8; ++q)
-        if (q < n_fp) acc[q] = fma(g, a.e[(int64_t)(q - 1) * a.n + i], acc[q]);
+      for (int j = 0; j < 4; ++j) {
+        const int li = t + 256 * j;
+        const uint32_t word = cw[(li >> 4) & 63];
+        const double g = (i_lo + li < i_hi) ? (double)((word >> (2 * (li & 15))) & 3u) : 0.0;
+        acc[0] = fma(g, yv[j], acc[0]);
+#pragma unroll
+        for (int q = 1; q < 8; ++q) acc[q] = fma(g, ev[j][q - 1], acc[q]);
+      }
+    } else {
+#pragma unroll 4
+      for (int64_t i = i_lo + t; i < i_hi; i += 256) {
+        const uint32_t word = cw[(i - i_lo) >> 4];
+        const double g = (double)((word >> (2 * ((i - i_lo) & 15))) & 3u);
+        acc[0] = fma(g, a.y[i], acc[0]);
+#pragma unroll
+        for (int q = 1; q < 8; ++q)
+          if (q < n_fp) acc[q] = fma(g, a.e[(int64_t)(q - 1) * a.n + i], acc[q]);
+      }
     }
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
@@ -146,16 +180,21 @@ __global__ void __launch_bounds__(256) k_column_stats_inline(const __grid_consta
   }
   // (2) x_c'x_l for model columns and other candidates: exact integer popcount arithmetic.  A warp takes tasks
   //     warp, warp+8, ...; the words of FOUR tasks are loaded before any is used (one memory round per group).
-  if (seg_words <= 64) {
+  if (small) {
     for (int task0 = n_fp + warp; task0 < n_tasks; task0 += 4 * nw) {
       uint32_t ow[4][2];
+      if (task0 == n_fp + warp) {   // first group: loaded before the barrier
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int task = task0 + u * nw;
-        const int q = task - n_fp;
-        const uint32_t* other = task < n_tasks ? (q < a.k ? a.cols[a.m_c + q] : a.cols[q - a.k]) + w0 : nullptr;
+        for (int u = 0; u < 4; ++u) { ow[u][0] = ow0[u][0]; ow[u][1] = ow0[u][1]; }
+      } else {
 #pragma unroll
-        for (int j = 0; j < 2; ++j) ow[u][j] = (other != nullptr && lane + 32 * j < nwords) ? other[lane + 32 * j] : 0u;
+        for (int u = 0; u < 4; ++u) {
+          const int task = task0 + u * nw;
+          const int q = task - n_fp;
+          const uint32_t* other = task < n_tasks ? (q < a.k ? a.cols[a.m_c + q] : a.cols[q - a.k]) + w0 : nullptr;
+#pragma unroll
+          for (int j = 0; j < 2; ++j) ow[u][j] = (other != nullptr && lane + 32 * j < nwords) ? other[lane + 32 * j] : 0u;
+        }
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {

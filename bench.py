@@ -367,7 +367,11 @@ def ours_arm(args, rank, local_rank, world):
         "config": {"workload": "%s: %s%s" % (args.workload, spec["desc"], "" if world == 1 else "; %d independent chains, one per GPU" % world),
                    "n": n, "m_g": m, "n_rao": args.n_rao, "step": "%d MCMC iterations incl. one all-SNP scan" % args.n_rao,
                    "sampler": "testdata/testdata.ini settings (PMV, thin 10, DR 10, individual tau2)",
-                   "tau_rng": args.tau_rng, "l2": "256 MiB write on the chain's stream before every step, inside the timed region",
+                   "tau_rng": args.tau_rng,
+                   "per_move": ("column statistics served by the persistent k_colstats_server kernel (host mailbox in mapped pinned "
+                                "memory; BMG_COLSTATS_SERVER=0 launches k_column_stats_inline per move instead)")
+                   if os.environ.get("BMG_COLSTATS_SERVER", "1") != "0" else "one k_column_stats_inline launch per move",
+                   "l2": "256 MiB write on the chain's stream before every step, inside the timed region",
                    "timing": "CUDA events on the chain's stream, max over ranks; wall %.3f ms/step" % (1e3 * wall / args.steps)},
         "e2e": {"value": world * args.steps * args.n_rao / e2e_secs, "unit": "iterations/s",
                 "h2d_bytes_per_step": (h2d_b - h2d_a) / args.steps, "d2h_bytes_per_step": (d2h_b - d2h_a) / args.steps,

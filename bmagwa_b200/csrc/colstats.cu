@@ -77,9 +77,9 @@ __global__ void __launch_bounds__(256) k_column_stats(const ColStatArgs a)
   }
 }
 
-// ---- latency path: pointers passed BY VALUE in the kernel parameters, results written straight into mapped
-// pinned host memory, completion published by the last CTA through a sequence number the host spins on.
-// One launch per move, no cudaMemcpy and no stream synchronisation on the per-iteration path.
+// ---- latency path: pointers passed BY VALUE (kernel parameters, or the persistent server's mailbox), results written
+// straight into mapped pinned host memory as self-validating tagged words the host spins on.  No cudaMemcpy and no
+// stream synchronisation on the per-iteration path.
 constexpr int kInlinePtrs = 96;
 struct ColStatInline {
   const uint32_t* cols[kInlinePtrs];  // m_c candidate columns, then k model columns
@@ -100,16 +100,16 @@ __device__ __forceinline__ void publish_tagged(ulonglong2* slot, double v, unsig
 {
   const unsigned long long b = (unsigned long long)__double_as_longlong(v), tag = (unsigned long long)seq << 32;
   const unsigned long long w0 = (b & 0xFFFFFFFFull) | tag, w1 = (b >> 32) | tag;
-  asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"(w0), "l"(w1) : "memory");
+  // .volatile: written through to host memory at once (a plain store may sit in L2 until the kernel ends, which a
+  // persistent kernel never does)
+  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"(w0), "l"(w1) : "memory");
 }
 
 constexpr int kFastSegMax = 256;   // words per CTA on the latency path (64 or 256)
 
-__global__ void __launch_bounds__(256) k_column_stats_inline(const __grid_constant__ ColStatInline a)
+// one (candidate, slice) work item; `a` may live in the kernel parameters or in shared memory
+__device__ __forceinline__ void colstat_item(const ColStatInline& a, const int c, const int seg, uint32_t* cw, double (*fpart)[8])
 {
-  __shared__ uint32_t cw[kFastSegMax];
-  __shared__ double fpart[8][8];   // [warp][fp task], up to 8 fp tasks (y + 7 covariate columns) on the fast path
-  const int c = blockIdx.x, seg = blockIdx.y;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nw = blockDim.x >> 5;
   const int seg_words = a.seg_words;
   const int64_t w0 = (int64_t)seg * seg_words;
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(256) k_column_stats_inline(const __grid_consta
     for (int j = 0; j < 4; ++j) {
       const int64_t i = i_lo + t + 256 * j;
       const bool ok = i < i_hi;
-      yv[j] = ok ? a.y[i] : 0.0;
+      yv[j] = ok ? __ldcg(a.y + i) : 0.0;   // y may be rewritten (probit) while the persistent server runs: bypass L1
 #pragma unroll
       for (int q = 1; q < 8; ++q) ev[j][q - 1] = (ok && q < n_fp) ? a.e[(int64_t)(q - 1) * a.n + i] : 0.0;
     }
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(256) k_column_stats_inline(const __grid_consta
       for (int64_t i = i_lo + t; i < i_hi; i += 256) {
         const uint32_t word = cw[(i - i_lo) >> 4];
         const double g = (double)((word >> (2 * ((i - i_lo) & 15))) & 3u);
-        acc[0] = fma(g, a.y[i], acc[0]);
+        acc[0] = fma(g, __ldcg(a.y + i), acc[0]);
 #pragma unroll
         for (int q = 1; q < 8; ++q)
           if (q < n_fp) acc[q] = fma(g, a.e[(int64_t)(q - 1) * a.n + i], acc[q]);
@@ -227,6 +227,128 @@ __global__ void __launch_bounds__(256) k_column_stats_inline(const __grid_consta
     double v = 0.0;
     for (int wv = 0; wv < nw; ++wv) v += fpart[wv][t];
     publish_tagged(out + t, v, a.seq);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_column_stats_inline(const __grid_constant__ ColStatInline a)
+{
+  __shared__ uint32_t cw[kFastSegMax];
+  __shared__ double fpart[8][8];   // [warp][fp task], up to 8 fp tasks (y + 7 covariate columns) on the fast path
+  colstat_item(a, blockIdx.x, blockIdx.y, cw, fpart);
+}
+
+// ---- persistent server for the latency path ----------------------------------------------------------------
+// A kernel launch costs ~4-5 us before the first instruction runs; with one launch per MCMC move that is a third of
+// the column-statistics round trip.  The server is ONE long-running kernel: CTA 0 polls a mailbox in mapped pinned
+// host memory (the host posts a request by plain stores), forwards the request through device memory to the worker
+// CTAs, and every CTA processes its share of the (candidate, slice) items exactly as k_column_stats_inline does,
+// publishing the same self-validating tagged results.  The mailbox is made of 16-byte chunks that each carry the
+// request's sequence number, so one warp-wide read returns a request that validates itself (no second PCIe round
+// trip).  The server is stopped before every scan (it would take registers from the scan's CTAs) and exits by
+// itself when no request arrives for kServerIdleCycles.
+constexpr int kMailChunks = 1 + kInlinePtrs;            // chunk 0: {seq, m_c, k, n_seg}; chunk 1+i: {ptr lo, ptr hi, seq, 0}
+constexpr unsigned int kServerStop = 0xFFFFFFFFu;
+constexpr long long kServerIdleCycles = 200000000ll;    // ~0.1 s: bounds what an unexpected implicit device synchronisation
+                                                        // (cudaMalloc / cudaFreeHost somewhere in the process) can cost; the
+                                                        // next request restarts the server
+
+struct ServerArgs {
+  const uint4* mail;        // host (mapped, pinned)
+  uint4* dev_req;           // device: [2][kMailChunks]
+  unsigned int* dev_flag;   // device: sequence number of the request in dev_req[seq & 1]
+  ColStatInline base;       // everything but cols / m_c / k / n_seg / seq
+};
+
+__device__ __forceinline__ uint4 ld_sys_v4(const uint4* p)
+{
+  uint4 v;
+  asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p)
+{
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned int* p, unsigned int v)
+{
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(256) k_colstats_server(const __grid_constant__ ServerArgs sa)
+{
+  __shared__ uint32_t cw[kFastSegMax];
+  __shared__ double fpart[8][8];
+  __shared__ ColStatInline req;
+  __shared__ uint4 head;
+  __shared__ unsigned int sh_seq;
+  const int t = threadIdx.x;
+  unsigned int last = ld_acquire_gpu(sa.dev_flag);   // whatever the previous server instance served last
+  long long t_idle = clock64();
+  for (int i = t; i < (int)(sizeof(ColStatInline) / sizeof(uint32_t)); i += blockDim.x)
+    reinterpret_cast<uint32_t*>(&req)[i] = reinterpret_cast<const uint32_t*>(&sa.base)[i];
+  __syncthreads();
+  for (;;) {
+    if (blockIdx.x == 0) {
+      // ---- poller: one read of the mailbox per trip; forward a complete request to the workers
+      for (;;) {
+        uint4 ch = make_uint4(0, 0, 0, 0);
+        if (t < kMailChunks) ch = ld_sys_v4(sa.mail + t);
+        if (t == 0) head = ch;
+        __syncthreads();
+        const uint4 h = head;
+        const unsigned int s = h.x;
+        bool fresh = s != last && s != 0;
+        int ok = 1;
+        if (fresh && s != kServerStop) {
+          const int needed = 1 + (int)h.y + (int)h.z;
+          ok = (t == 0 || t >= needed || ch.z == s) ? 1 : 0;
+        }
+        ok = __syncthreads_and(ok);
+        if (fresh && ok) {
+          if (s != kServerStop) {
+            const int needed = 1 + (int)h.y + (int)h.z;
+            if (t < needed) sa.dev_req[(size_t)(s & 1u) * kMailChunks + t] = ch;
+            __threadfence();
+          }
+          __syncthreads();
+          if (t == 0) st_release_gpu(sa.dev_flag, s);
+          break;
+        }
+        if (clock64() - t_idle > kServerIdleCycles) {   // abandoned: shut the whole server down
+          if (t == 0) st_release_gpu(sa.dev_flag, kServerStop);
+          __syncthreads();
+          break;
+        }
+      }
+    }
+    // ---- every CTA: wait for the forwarded request
+    if (t == 0) {
+      unsigned int s;
+      while ((s = ld_acquire_gpu(sa.dev_flag)) == last) {
+        if (clock64() - t_idle > 2 * kServerIdleCycles) { s = kServerStop; break; }
+      }
+      sh_seq = s;
+    }
+    __syncthreads();
+    const unsigned int s = sh_seq;
+    if (s == kServerStop) return;
+    const uint4* rq = sa.dev_req + (size_t)(s & 1u) * kMailChunks;
+    const uint4 h = __ldcg(rq);   // forwarded through L2: never from a stale L1 line
+    const int m_c = (int)h.y, k = (int)h.z, n_seg = (int)h.w;
+    if (t == 0) { req.m_c = m_c; req.k = k; req.n_seg = n_seg; req.seq = s; }
+    if (t < m_c + k) {
+      const uint4 c4 = __ldcg(rq + 1 + t);
+      req.cols[t] = reinterpret_cast<const uint32_t*>((unsigned long long)c4.x | ((unsigned long long)c4.y << 32));
+    }
+    __syncthreads();
+    for (int item = blockIdx.x; item < m_c * n_seg; item += gridDim.x) {
+      colstat_item(req, item / n_seg, item % n_seg, cw, fpart);
+      __syncthreads();
+    }
+    last = s;
+    t_idle = clock64();
   }
 }
 
@@ -310,6 +432,76 @@ __global__ void k_sum_segments(const double* __restrict__ seg_out, int m_c, int 
   out[gid] = s;
 }
 
+// ---- host side of the persistent server ----------------------------------------------------------------------
+static void server_start(Chain* c, const ColStatInline& base, unsigned int last_served)
+{
+  Store* s = c->store;
+  if (c->server_stream == nullptr) {
+    BMG_CUDA(cudaStreamCreateWithFlags(&c->server_stream, cudaStreamNonBlocking));
+    c->server_mail.alloc(kMailChunks);
+    c->server_req.alloc(2 * kMailChunks);
+    c->server_flag.alloc(1);
+    memset(c->server_mail.p, 0, kMailChunks * sizeof(uint4));
+    c->server_ctas = std::min(64, std::max(8, s->sm_count / 2));
+  }
+  // nothing is "fresh" until the next post: mailbox head and device flag both carry the last served sequence number
+  volatile uint32_t* head = reinterpret_cast<volatile uint32_t*>(c->server_mail.p);
+  head[0] = last_served;
+  std::atomic_thread_fence(std::memory_order_seq_cst);
+  const unsigned int flag0 = last_served;
+  BMG_CUDA(cudaMemcpyAsync(c->server_flag.p, &flag0, sizeof(flag0), cudaMemcpyHostToDevice, c->server_stream));
+  BMG_CUDA(cudaStreamSynchronize(c->server_stream));
+  ServerArgs sa;
+  sa.mail = reinterpret_cast<const uint4*>(c->server_mail.p);
+  sa.dev_req = reinterpret_cast<uint4*>(c->server_req.p);
+  sa.dev_flag = c->server_flag.p;
+  sa.base = base;
+  k_colstats_server<<<c->server_ctas, 256, 0, c->server_stream>>>(sa);
+  count_launch();
+  const cudaError_t le = cudaGetLastError();
+  if (le != cudaSuccess) throw Error(std::string("k_colstats_server launch: ") + cudaGetErrorString(le));
+  c->server_running = true;
+  c->server_base_y = base.y; c->server_seg_words = base.seg_words; c->server_base_out = (const void*)base.out_host;
+}
+
+void chain_server_stop(Chain* c)
+{
+  if (!c->server_running) return;
+  static const bool timing = getenv("BMG_TIMING") != nullptr;
+  struct timespec ta, tb;
+  if (timing) clock_gettime(CLOCK_MONOTONIC, &ta);
+  volatile uint32_t* head = reinterpret_cast<volatile uint32_t*>(c->server_mail.p);
+  head[0] = kServerStop;
+  std::atomic_thread_fence(std::memory_order_seq_cst);
+  cudaStreamSynchronize(c->server_stream);
+  c->server_running = false;
+  if (timing) {
+    clock_gettime(CLOCK_MONOTONIC, &tb);
+    static int shown = 0;
+    if (shown++ < 4) fprintf(stderr, "[bmg timing] column-statistics server stopped in %.1f us after %lld requests\n",
+                             1e6 * ((tb.tv_sec - ta.tv_sec) + 1e-9 * (tb.tv_nsec - ta.tv_nsec)), (long long)c->server_requests);
+  }
+}
+
+static void server_post(Chain* c, const ColStatInline& a)
+{
+  // the server may have timed out while the host was busy elsewhere
+  if (c->server_running && cudaStreamQuery(c->server_stream) != cudaErrorNotReady) c->server_running = false;
+  if (c->server_running && (c->server_base_y != a.y || c->server_seg_words != a.seg_words || c->server_base_out != (const void*)a.out_host))
+    chain_server_stop(c);
+  if (!c->server_running) server_start(c, a, a.seq - 1);   // a.seq is the request about to be posted
+  volatile uint64_t* w = reinterpret_cast<volatile uint64_t*>(c->server_mail.p);
+  const uint64_t tag = (uint64_t)a.seq;
+  for (int i = 0; i < a.m_c + a.k; ++i) {   // pointer half first, tag half second (x86 keeps the store order)
+    w[2 * (1 + i)] = (uint64_t)(uintptr_t)a.cols[i];
+    w[2 * (1 + i) + 1] = tag;
+  }
+  std::atomic_thread_fence(std::memory_order_release);
+  w[1] = (uint64_t)(uint32_t)a.k | ((uint64_t)(uint32_t)a.n_seg << 32);
+  w[0] = tag | ((uint64_t)(uint32_t)a.m_c << 32);   // head last: {seq, m_c} | {k, n_seg}
+  std::atomic_thread_fence(std::memory_order_seq_cst);
+}
+
 // second half of the latency path: spin on the completion flag, then reduce the per-slice partials on the host
 void chain_column_stats_wait(Chain* c, double* xy, double* xe, double* xx_model, double* xx_cand)
 {
@@ -318,6 +510,11 @@ void chain_column_stats_wait(Chain* c, double* xy, double* xe, double* xx_model,
   cudaStream_t st = c->stream;
   const int m_c = c->cs_p_mc, k = c->cs_p_k, n_seg = c->cs_p_nseg;
   const int n_tasks = s->m_e + 1 + k + m_c;
+  static const bool timing = getenv("BMG_TIMING") != nullptr;
+  static long long hist[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  static long long hist_n = 0;
+  struct timespec ta;
+  if (timing) clock_gettime(CLOCK_MONOTONIC, &ta);
   const unsigned long long tag = (unsigned long long)c->cs_p_seq << 32;
   const volatile unsigned long long* words = reinterpret_cast<const volatile unsigned long long*>(c->cs_map.p);
   unsigned long spins = 0;
@@ -331,8 +528,9 @@ void chain_column_stats_wait(Chain* c, double* xy, double* xe, double* xx_model,
           w0 = words[2 * slot];
           w1 = words[2 * slot + 1];
           if ((w0 & 0xFFFFFFFF00000000ull) == tag && (w1 & 0xFFFFFFFF00000000ull) == tag) break;
-          if ((++spins & 0xFFFFF) == 0 && cudaStreamQuery(st) != cudaErrorNotReady) {   // finished (or failed) without publishing?
-            BMG_CUDA(cudaStreamSynchronize(st));
+          cudaStream_t qs = c->server_running ? c->server_stream : st;
+          if ((++spins & 0xFFFFF) == 0 && cudaStreamQuery(qs) != cudaErrorNotReady) {   // finished (or failed) without publishing?
+            BMG_CUDA(cudaStreamSynchronize(qs));
             w0 = words[2 * slot];
             w1 = words[2 * slot + 1];
             if ((w0 & 0xFFFFFFFF00000000ull) == tag && (w1 & 0xFFFFFFFF00000000ull) == tag) break;
@@ -351,6 +549,18 @@ void chain_column_stats_wait(Chain* c, double* xy, double* xe, double* xx_model,
     }
   }
   c->cs_pending = false;
+  if (timing) {
+    struct timespec tb;
+    clock_gettime(CLOCK_MONOTONIC, &tb);
+    const double us = 1e6 * ((tb.tv_sec - ta.tv_sec) + 1e-9 * (tb.tv_nsec - ta.tv_nsec));
+    const double edges[7] = {5, 10, 20, 50, 200, 2000, 50000};
+    int b = 0;
+    while (b < 7 && us >= edges[b]) ++b;
+    ++hist[b];
+    if ((++hist_n % 3000) == 0)
+      fprintf(stderr, "[bmg timing] column-stats wait histogram (us) <5:%lld <10:%lld <20:%lld <50:%lld <200:%lld <2000:%lld <50000:%lld more:%lld\n",
+              hist[0], hist[1], hist[2], hist[3], hist[4], hist[5], hist[6], hist[7]);
+  }
 }
 
 void chain_column_stats(Chain* c, const int64_t* cand, int m_c, const int64_t* loci, int k, double* xy, double* xe,
@@ -383,28 +593,35 @@ void chain_column_stats_launch(Chain* c, const int64_t* cand, int m_c, const int
     const int seg_words = s->W <= 4096 ? 64 : kFastSegMax;
     const int n_seg = (int)((s->W + seg_words - 1) / seg_words);
     const size_t need_fast = (size_t)m_c * n_tasks * n_seg;
-    if (c->cs_map.n < 2 * need_fast + 8 || c->cs_seq == 0xFFFFFFFFu) {   // (re)allocate; also before the tag wraps around
+    if (c->cs_map.n < 2 * need_fast + 8 || c->cs_seq >= 0xFFFFFFF0u) {   // (re)allocate; also before the tag wraps around
+      chain_server_stop(c);   // cudaFreeHost / cudaHostAlloc synchronise the device: a running server would stall them
       BMG_CUDA(cudaStreamSynchronize(st));
       if (c->cs_map.n < 2 * need_fast + 8) c->cs_map.alloc(need_fast * 4 + 64);
       memset(c->cs_map.p, 0, c->cs_map.n * sizeof(double));   // tag 0 is never used by a launch
-      if (c->cs_seq == 0xFFFFFFFFu) c->cs_seq = 0;
+      if (c->cs_seq >= 0xFFFFFFF0u) { chain_server_stop(c); c->cs_seq = 0; }
     }
     ColStatInline a;
     for (int i = 0; i < m_c + k; ++i) a.cols[i] = s->column_ptr(i < m_c ? cand[i] : loci[i - m_c]);
     a.m_c = m_c; a.k = k; a.m_e = s->m_e; a.n = s->n; a.W = s->W; a.n_seg = n_seg; a.seg_words = seg_words; a.y = c->y.p; a.e = s->e.p;
     a.out_host = reinterpret_cast<ulonglong2*>(c->cs_map.p);
     a.seq = ++c->cs_seq;
-    k_column_stats_inline<<<dim3(m_c, n_seg), 256, 0, st>>>(a);
-    count_launch();
+    if (c->server_enabled) {
+      server_post(c, a);
+      ++c->server_requests;
+    } else {
+      k_column_stats_inline<<<dim3(m_c, n_seg), 256, 0, st>>>(a);
+      count_launch();
+      const cudaError_t le = cudaGetLastError();
+      if (le != cudaSuccess) throw Error(std::string("k_column_stats_inline launch: ") + cudaGetErrorString(le));
+    }
     g_d2h_bytes.fetch_add(need_fast * 2 * sizeof(double), std::memory_order_relaxed);
     g_h2d_bytes.fetch_add(sizeof(ColStatInline), std::memory_order_relaxed);
-    const cudaError_t le = cudaGetLastError();
-    if (le != cudaSuccess) throw Error(std::string("k_column_stats_inline launch: ") + cudaGetErrorString(le));
     c->cs_pending = true;
     c->cs_p_mc = m_c; c->cs_p_k = k; c->cs_p_nseg = n_seg; c->cs_p_seq = a.seq;
     if (!launch_only) chain_column_stats_wait(c, xy, xe, xx_model, xx_cand);
     return;
   }
+  chain_server_stop(c);   // the general path allocates and synchronises
   const size_t need = (size_t)m_c * n_tasks * (n_seg + 1);
   if (c->cs_out.n < need) { c->cs_out.alloc(need * 2); c->h_cs.alloc(need * 2); }
   const size_t n_ptr = (size_t)(m_c + k) * 2;

@@ -236,6 +236,8 @@ void Sampler::set_option(const std::string& key, const std::string& value)
   } else if (key == "probit") {
     if (value != "0") enable_probit();
     else if (probit_) throw std::runtime_error("probit mode cannot be switched off once enabled");
+  } else if (key == "colstats_server") {
+    chain_->server_enabled = value != "0";
   } else if (key == "scan_variant") {
     chain_->scan_variant = std::stoi(value);
   } else {
@@ -578,6 +580,8 @@ void Sampler::rao_block()
 void Sampler::end()
 {
   if (!begun_) return;
+  if (getenv("BMG_TIMING")) std::cerr << "[bmg timing] end(): column-statistics server running = " << chain_->server_running << std::endl;
+  chain_server_stop(chain_);
   Files& f = *files_;
   // samplerstats.print (samplerstats.hpp:92-113)
   {

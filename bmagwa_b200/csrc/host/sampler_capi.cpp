@@ -2,6 +2,9 @@
 //
 // bmg_sampler_create does what main() does for one chain (src/main.cpp:47-76): parse the INI file,
 // load .fam/.y/.e/.bed, build the device store (recode, counts, moment cache), construct the sampler.
+#include <time.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <memory>
 #include "../common.cuh"
 #include "../store.cuh"
@@ -79,12 +82,16 @@ static void global_summaries(Store* st, const Sampler::ShardComm& cm, double* ou
 SamplerHandle* make(const char* ini, int chain_index, int device, Store* existing, const Sampler::ShardComm* comm = nullptr)
 {
   BMG_REQUIRE(ini != nullptr, "bmg_sampler_create: null ini path");
+  const bool timing = getenv("BMG_TIMING") != nullptr;
+  auto now = [] { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; };
+  const double t_a = now();
   std::unique_ptr<SamplerHandle> h(new SamplerHandle());
   h->chain_index = chain_index;
   h->opt.reset(new Options(ini, /*quiet=*/chain_index != 0));
   const Options& o = *h->opt;
   BMG_REQUIRE(chain_index >= 0 && (size_t)chain_index < o.n_threads, "bmg_sampler_create: chain_index must be < thread.n_threads");
   h->data.reset(new Dataset(o.n, o.m_g, o.m_e, o.file_fam, o.file_g, o.file_e, o.file_y, /*load_bed=*/false));
+  const double t_b = now();
   if (existing) {
     BMG_REQUIRE(existing->n == (int64_t)o.n && existing->m_g == (int64_t)o.m_g, "bmg_sampler_create_on_store: store dimensions differ from the INI file");
     h->store = existing;
@@ -95,6 +102,7 @@ SamplerHandle* make(const char* ini, int chain_index, int device, Store* existin
     h->owns_store = true;
     store_set_phenotype(h->store, h->data->y.data(), h->data->e.data(), (int)h->data->m_e);
   }
+  const double t_c = now();
   double sm[6];
   for (int i = 0; i < 6; ++i) sm[i] = h->store->summaries[i];
   if (comm != nullptr) {
@@ -104,6 +112,9 @@ SamplerHandle* make(const char* ini, int chain_index, int device, Store* existin
   }
   const double mean_x = sm[0] / sm[1], var_x = sm[2] / sm[3];
   h->sampler.reset(new Sampler(o, chain_index, h->store, h->data->y, h->data->e, sm[4], sm[5], var_x, mean_x, comm));
+  if (timing)
+    fprintf(stderr, "[bmg timing] create: options + fam/y/e files %.1f ms, store (bed -> device, re-coding, counts) %.1f ms, sampler + chain %.1f ms\n",
+            1e3 * (t_b - t_a), 1e3 * (t_c - t_b), 1e3 * (now() - t_c));
   return h.release();
 }
 }  // namespace

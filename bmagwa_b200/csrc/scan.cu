@@ -601,6 +601,7 @@ Chain* chain_create(Store* s)
     if (v >= 0 && v <= 2) c->scan_variant = v;
   }
   BMG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  if (const char* env = getenv("BMG_COLSTATS_SERVER")) c->server_enabled = atoi(env) != 0;
   choose_scan_geometry(c.get());
   const int64_t n = s->n, m = s->m;
   const int64_t n_pad = 16 * (int64_t)c->scan_chunks * c->scan_chunk_words;
@@ -641,6 +642,8 @@ void chain_destroy(Chain* c)
 {
   if (!c) return;
   cudaSetDevice(c->store->device);
+  chain_server_stop(c);
+  if (c->server_stream) cudaStreamDestroy(c->server_stream);
   if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
   for (cudaEvent_t e : c->scan_ev) cudaEventDestroy(e);
   delete c;
@@ -678,6 +681,7 @@ static void upload_model(Chain* c, const int64_t* loci, const double* beta_g, co
 
 void chain_residual(Chain* c, const int64_t* loci, const double* beta_e, const double* beta_g, int k, double* stats9)
 {
+  chain_server_stop(c);   // precedes scans and latent sweeps (which may allocate and want all SMs)
   Store* s = c->store;
   BMG_CUDA(cudaSetDevice(s->device));
   BMG_REQUIRE(k >= 0 && k <= 2048, "bmg_chain_residual: model size must be <= 2048");
@@ -780,6 +784,7 @@ void chain_scan(Chain* c, const int64_t* loci, const double* beta_g, const doubl
   BMG_REQUIRE(prm->tau_mode >= 0 && prm->tau_mode <= 2, "bmg_chain_scan: tau_mode must be 0, 1 or 2");
   BMG_REQUIRE(prm->sigma2 > 0, "bmg_chain_scan: sigma2 must be positive");
   BMG_CUDA(cudaSetDevice(s->device));
+  chain_server_stop(c);   // the scan's CTAs want every SM's registers; the server restarts with the next request
   cudaStream_t st = c->stream;
   upload_model(c, loci, beta_g, tau_g, k);
   if (prm->tau_mode == 1) {

@@ -97,6 +97,16 @@ struct Chain {
   DevBuf<unsigned int> cs_done;                 // CTA arrival counter
   unsigned int cs_seq = 0;
   bool cs_pending = false;
+  // persistent column-statistics server (colstats.cu): one long-running kernel fed through a host mailbox
+  bool server_enabled = true, server_running = false;   // BMG_COLSTATS_SERVER=0 / option colstats_server=0: one launch per move
+  cudaStream_t server_stream = nullptr;
+  PinnedBuf<uint4> server_mail;
+  DevBuf<uint4> server_req;
+  DevBuf<unsigned int> server_flag;
+  int server_ctas = 0, server_seg_words = 0;
+  const double* server_base_y = nullptr;
+  const void* server_base_out = nullptr;
+  int64_t server_requests = 0;
   int cs_p_mc = 0, cs_p_k = 0, cs_p_nseg = 0;
   unsigned int cs_p_seq = 0;
 };
@@ -124,6 +134,7 @@ void chain_column_stats(Chain* c, const int64_t* cand, int m_c, const int64_t* l
                         double* xx_model, double* xx_cand);
 void chain_column_stats_launch(Chain* c, const int64_t* cand, int m_c, const int64_t* loci, int k, double* xy, double* xe,
                                double* xx_model, double* xx_cand, bool launch_only);
+void chain_server_stop(Chain* c);
 void chain_column_stats_wait(Chain* c, double* xy, double* xe, double* xx_model, double* xx_cand);
 void chain_probit_update(Chain* c, const uint8_t* is_case, const double* u01, uint64_t seed, uint64_t counter,
                          double* stats2, double* ez = nullptr);

@@ -222,7 +222,12 @@ struct bmg_shard_comm {
 };
 int bmg_sampler_create_sharded(const char* ini_path, int chain_index, bmg_store* shard, const struct bmg_shard_comm* comm,
                                bmg_sampler** out);
-/* key=value overrides applied after the INI file (e.g. "tau_rng=device", "do_n_iter=1000"). */
+/* Overrides applied after the INI file, before bmg_sampler_begin.  Keys: "tau_rng" = host | device (per-SNP tau2 draws
+ * of the scan from the chain's stream in reference order, or Philox on the device); "basename" (output files);
+ * "verbosity"; "reference_quirks" = 1 | 0 (keep the reference's stale-y_hat behaviour, model.hpp:345-392);
+ * "scan_variant" = 2 | 1 | 0; "probit" = 1 (0/1 phenotype, Albert-Chib latent updates on the device; no reference
+ * counterpart); "colstats_server" = 1 | 0 (serve the per-move column statistics from one persistent kernel fed through
+ * a host mailbox instead of one launch per move).  Unknown keys are an error. */
 int bmg_sampler_set_option(bmg_sampler* sp, const char* key, const char* value);
 /* Opens output files, initialises the chain (sampler.cpp:592-620). */
 int bmg_sampler_begin(bmg_sampler* sp);

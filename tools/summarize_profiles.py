@@ -53,7 +53,9 @@ def launches(tag, rnd):
         tot[k] += v
         cnt[k] += 1
     total = sum(tot.values())
-    lines = ["# %s: kernel launch list of `python bench.py --steps 2 --warmup 1 --no-cpu-baseline`" % rnd, "",
+    lines = ["# %s: kernel launch list of `BMG_COLSTATS_SERVER=0 python bench.py --steps 2 --warmup 1 --no-cpu-baseline`" % rnd, "",
+             "(launch-per-move form of the column statistics: ncu serialises kernels, which the default persistent",
+             "`k_colstats_server` cannot run under; the work items are the same.)", "",
              "Captured with `ncu --metrics gpu__time_duration.sum --clock-control none` (tools/profile_round.sh);",
              "per-launch times under ncu are serialised and cold-cache, so only the SHARES are meaningful.", "",
              "%d launches, %.1f us of kernel time in total." % (sum(cnt.values()), total), "",
@@ -69,6 +71,8 @@ def raw(name, title, rnd, out_name):
     if not os.path.exists(path):
         return None
     rows = list(csv.reader(open(path)))
+    if len(rows) < 3:
+        return None
     hdr, units, r = rows[0], rows[1], rows[2]
     ix = {h: i for i, h in enumerate(hdr)}
     lines = ["# %s: %s" % (rnd, title), "", "`ncu --set full --clock-control none --import-source on`, one launch after warm-up; raw page.",

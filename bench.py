@@ -99,6 +99,31 @@ def prepare_dataset(w, n_rao, n_threads, out_dir, do_n_iter):
     return ini, spec
 
 
+def pin_rank_to_core(local_rank, world):
+    """A block of physical cores (all their hyperthreads) per rank: the chain's host thread spin-waits on device results,
+    and two spinning ranks on sibling hyperthreads slow each other down.  No-op with fewer physical cores than ranks."""
+    try:
+        allowed = sorted(os.sched_getaffinity(0))
+        cores = {}
+        for cpu in allowed:
+            with open("/sys/devices/system/cpu/cpu%d/topology/thread_siblings_list" % cpu) as fh:
+                sib = fh.read().strip()
+            members = set()
+            for part in sib.split(","):
+                lo, _, hi = part.partition("-")
+                members.update(range(int(lo), int(hi or lo) + 1))
+            cores[min(members)] = sorted(members & set(allowed))
+        phys = [cores[k] for k in sorted(cores)]
+        if len(phys) < world:
+            return None
+        per = len(phys) // world   # a contiguous block of physical cores per rank (helper threads keep their own CPUs)
+        mine = sorted(c for core in phys[local_rank * per:(local_rank + 1) * per] for c in core)
+        os.sched_setaffinity(0, mine)
+        return mine
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -259,6 +284,9 @@ def ours_arm(args, rank, local_rank, world):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = local_rank
     torch.cuda.set_device(dev)
+    pinned = pin_rank_to_core(local_rank, world) if world > 1 else None
+    if pinned is not None:
+        log("[bench] rank %d pinned to CPUs %s" % (rank, pinned))
     L = _lib.lib()
     spec = WORKLOADS[args.workload]
     n, m = spec["n"], spec["m_g"]

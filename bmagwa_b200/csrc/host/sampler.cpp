@@ -395,7 +395,6 @@ void Sampler::compute_p_moves()  // sampler.cpp:455-515, PMV with one effect typ
 // ------------------------------------------------------------------------------------------------
 // sample(): set-up, loop, tear-down (sampler.cpp:551-880)
 // ------------------------------------------------------------------------------------------------
-static double g_k_move_size_unused = 0;
 
 void Sampler::begin()
 {
@@ -433,7 +432,6 @@ void Sampler::begin()
   copy_current_to_proposal();
   t_start_ = wall_seconds();
   begun_ = true;
-  (void)g_k_move_size_unused;
 }
 
 void Sampler::run(int64_t do_n_iter)
@@ -519,8 +517,6 @@ void Sampler::track_fitted_values()
 // the rao block of the loop (sampler.cpp:731-811)
 void Sampler::rao_block()
 {
-  static const double kInf = INFINITY;
-  (void)kInf;
   const double k_move_size = 1000.0 / (double)opt_.n_rao_burnin;   // sampler.cpp:558 (initial burn-in length)
   const bool do_scan = !flat_proposal_dist_ || n_rao_burnin_ <= 0;
   if (do_scan) {

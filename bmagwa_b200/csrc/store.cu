@@ -242,7 +242,7 @@ Store* store_create(const uint8_t* bed, bool on_device, int64_t n, int64_t m_g, 
   return store_build(std::move(s), raw);
 }
 
-// The .bed file streamed to the device: two pinned 8 MiB buffers, the read of block b+1 overlaps the copy of
+// The .bed file streamed to the device: two pinned 2 MiB buffers, the read of block b+1 overlaps the copy of
 // block b, and no host copy of the payload is ever held (data.cpp:245-273 reads it genotype by genotype into
 // n x m_g doubles).  Header checks as Data::read_g (data.cpp:250-262).
 Store* store_create_from_bed(const char* path, int64_t n, int64_t m_g, int64_t lo, int64_t hi, bool recode, int device)
@@ -264,7 +264,7 @@ Store* store_create_from_bed(const char* path, int64_t n, int64_t m_g, int64_t l
   DevBuf<uint8_t> raw_own;
   raw_own.alloc(total);
   const double t_b = now();
-  const size_t kBlock = (size_t)8 << 20;
+  const size_t kBlock = (size_t)2 << 20;   // pinning costs ~0.7 ms per MiB: small staging buffers, many blocks
   PinnedBuf<uint8_t> stage[2];
   cudaEvent_t done[2];
   cudaStream_t up;

@@ -103,7 +103,7 @@ def test_store_reference_fixtures_bit_exact(api, ref_tests, golden, golden_data_
 
 def test_store_streamed_from_bed_file_equals_store_from_payload(api, golden_data_dir, tmp_path):
     """bmg_store_create_from_bed (file -> pinned staging -> device) builds the same store as the in-memory
-    payload path, for the whole file, for an SNP shard and for a file larger than one 8 MiB staging block; the
+    payload path, for the whole file, for an SNP shard and for a file larger than one staging block; the
     header checks carry the reference's messages (data.cpp:250-262)."""
     from bmagwa_b200 import synth
     path = os.path.join(golden_data_dir, "plinktest.bed")
@@ -116,7 +116,7 @@ def test_store_streamed_from_bed_file_equals_store_from_payload(api, golden_data
     for x, y in zip(a.missing(), b.missing()):
         assert np.array_equal(x, y)
     a.close(); b.close()
-    n, m = 4001, 20000   # 1001 bytes per SNP -> 20 MB payload = three staging blocks, ragged last byte
+    n, m = 4001, 20000   # 1001 bytes per SNP -> 20 MB payload = many staging blocks, ragged last byte
     payload, _ = synth.make_genotypes(n, m, seed=9, miss_rate=0.01)
     big = tmp_path / "big.bed"
     with open(big, "wb") as fh:

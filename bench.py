@@ -36,6 +36,7 @@ WORKLOADS = {
     "C2x": dict(n=5000, m_g=1000000, m_e=2, desc="synthetic linear GWAS n=5,000 x p=1,000,000 SNPs"),
     "C3": dict(n=10000, m_g=500000, m_e=2, desc="synthetic probit case-control n=10,000 x p=500,000 with latent-variable updates (1.25 GB packed)"),
     "C4": dict(n=50000, m_g=1000000, m_e=2, desc="synthetic linear n=50,000 x p=1,000,000 (12.5 GB packed)"),
+    "C5": dict(n=400000, m_g=600000, m_e=2, desc="biobank-scale synthetic n=400,000 x p=600,000 (60 GB packed)"),
     "C4s": dict(n=50000, m_g=200000, m_e=2, desc="synthetic linear n=50,000 x p=200,000 (2.5 GB packed; C4 at one fifth of the SNPs)"),
 }
 GEN_SEED = 20121101

@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(256) k_column_stats(const ColStatArgs a)
 // ---- latency path: pointers passed BY VALUE (kernel parameters, or the persistent server's mailbox), results written
 // straight into mapped pinned host memory as self-validating tagged words the host spins on.  No cudaMemcpy and no
 // stream synchronisation on the per-iteration path.
-constexpr int kInlinePtrs = 96;
+constexpr int kInlinePtrs = 250;   // candidates + model columns of one request (2 kB of kernel parameters / mailbox)
 struct ColStatInline {
   const uint32_t* cols[kInlinePtrs];  // m_c candidate columns, then k model columns
   int m_c, k, m_e;
@@ -247,6 +247,7 @@ __global__ void __launch_bounds__(256) k_column_stats_inline(const __grid_consta
 // trip).  The server is stopped before every scan (it would take registers from the scan's CTAs) and exits by
 // itself when no request arrives for kServerIdleCycles.
 constexpr int kMailChunks = 1 + kInlinePtrs;            // chunk 0: {seq, m_c, k, n_seg}; chunk 1+i: {ptr lo, ptr hi, seq, 0}
+static_assert(kMailChunks <= 256, "one mailbox chunk per thread of the poller CTA");
 constexpr unsigned int kServerStop = 0xFFFFFFFFu;
 constexpr long long kServerIdleCycles = 200000000ll;    // ~0.1 s: bounds what an unexpected implicit device synchronisation
                                                         // (cudaMalloc / cudaFreeHost somewhere in the process) can cost; the
@@ -293,8 +294,9 @@ __global__ void __launch_bounds__(256) k_colstats_server(const __grid_constant__
     if (blockIdx.x == 0) {
       // ---- poller: one read of the mailbox per trip; forward a complete request to the workers
       for (;;) {
+        // first trip: head + 63 columns (the usual request); a larger request costs a second trip for the rest
         uint4 ch = make_uint4(0, 0, 0, 0);
-        if (t < kMailChunks) ch = ld_sys_v4(sa.mail + t);
+        if (t < 64) ch = ld_sys_v4(sa.mail + t);
         if (t == 0) head = ch;
         __syncthreads();
         const uint4 h = head;
@@ -302,13 +304,14 @@ __global__ void __launch_bounds__(256) k_colstats_server(const __grid_constant__
         bool fresh = s != last && s != 0;
         int ok = 1;
         if (fresh && s != kServerStop) {
-          const int needed = 1 + (int)h.y + (int)h.z;
+          const int needed = min(kMailChunks, 1 + (int)h.y + (int)h.z);
+          if (t >= 64 && t < needed) ch = ld_sys_v4(sa.mail + t);
           ok = (t == 0 || t >= needed || ch.z == s) ? 1 : 0;
         }
         ok = __syncthreads_and(ok);
         if (fresh && ok) {
           if (s != kServerStop) {
-            const int needed = 1 + (int)h.y + (int)h.z;
+            const int needed = min(kMailChunks, 1 + (int)h.y + (int)h.z);
             if (t < needed) sa.dev_req[(size_t)(s & 1u) * kMailChunks + t] = ch;
             __threadfence();
           }

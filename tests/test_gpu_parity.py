@@ -419,6 +419,31 @@ def test_scan_imma_repeated_launches_are_bit_identical(api, n, m):
     ch.close(); st.close()
 
 
+@pytest.mark.parametrize("k,m_c,server", [(30, 1, "1"), (150, 3, "1"), (150, 3, "0"), (240, 10, "1"), (270, 2, "1")])
+def test_column_stats_large_models_all_paths(api, k, m_c, server, monkeypatch):
+    """Model sizes across the fast path's range (<= 250 columns per request, second mailbox trip beyond 63) and the
+    general path beyond it, through the persistent server and through a launch per request: exact integers for
+    genotype x genotype, 1e-12 for x'y."""
+    monkeypatch.setenv("BMG_COLSTATS_SERVER", server)
+    n, m = 3000, 600
+    payload, y, E = make_data(n, m, seed=77, miss_rate=0.0)
+    bed, _ = oracle_store(payload, n, m, True)
+    st = api.GenotypeStore(payload, n, m, recode_to_minor=True)
+    st.set_phenotype(y, E)
+    ch = api.Chain(st)
+    rs = np.random.default_rng(k)
+    perm = rs.permutation(m)
+    loci, cand = perm[:k].astype(np.int64), perm[k:k + m_c].astype(np.int64)
+    G = np.stack([cpu.decode_column(bed, n, int(j), 0) for j in np.concatenate([cand, loci])], axis=1)
+    for rep in range(3):   # repeated requests: the server stays up between them
+        xy, xe, xm, xc = ch.column_stats(cand, loci)
+        assert np.allclose(xy, G[:, :m_c].T @ y, rtol=1e-12, atol=1e-10)
+        assert np.array_equal(xm, G[:, :m_c].T @ G[:, m_c:])
+        assert np.array_equal(xc, G[:, :m_c].T @ G[:, :m_c])
+    ch.close()
+    st.close()
+
+
 # ------------------------------------------------------- full-size property checks (BASELINE C2)
 def test_scan_full_size_linearity_and_checksum(api):
     """n=5000 x m=100000 (BASELINE config 2): size-independent properties instead of an oracle pass:

@@ -64,7 +64,7 @@ def build(force=False, verbose=False):
                 print(" ".join(cmd))
             subprocess.check_call(cmd)
     if force or _newer(LIB, objs):
-        cmd = [_nvcc(), "-ccbin", _ccbin(), "-shared", "-o", LIB] + objs + ["-lpthread"]
+        cmd = [_nvcc(), "-ccbin", _ccbin(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs + ["-lpthread"]
         subprocess.check_call(cmd)
     main = os.path.join(CSRC, "host", "main.cpp")
     if os.path.exists(main) and (force or _newer(CLI, [main, LIB])):

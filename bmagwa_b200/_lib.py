@@ -44,7 +44,9 @@ SIGNATURES = {
     "bmg_chain_sync": (C.c_int, [vp]),
     "bmg_chain_stream": (vp, [vp]),
     "bmg_chain_set_missing": (C.c_int, [vp, i64, i8p, i64]),
+    "bmg_chain_set_missing_all": (C.c_int, [vp, i8p, i64]),
     "bmg_chain_get_column": (C.c_int, [vp, i64, C.c_int, f64p]),
+    "bmg_chain_get_cells": (C.c_int, [vp, i64p, C.c_int, i32p, i64, i8p]),
     "bmg_chain_residual": (C.c_int, [vp, i64p, f64p, f64p, C.c_int, f64p]),
     "bmg_chain_get_residual": (C.c_int, [vp, f64p]),
     "bmg_chain_scan": (C.c_int, [vp, i64p, f64p, f64p, C.c_int, C.POINTER(ScanParams), f64p]),

@@ -164,9 +164,21 @@ class Chain:
         v = np.ascontiguousarray(vals, dtype=np.int8)
         check(self.L.bmg_chain_set_missing(self.h, snp, v.ctypes.data_as(i8p), v.size))
 
+    def set_missing_all(self, vals):
+        v = np.ascontiguousarray(vals, dtype=np.int8)
+        check(self.L.bmg_chain_set_missing_all(self.h, v.ctypes.data_as(i8p), v.size))
+
     def get_column(self, snp, type_=A):
         out = np.zeros(self.store.n)
         check(self.L.bmg_chain_get_column(self.h, snp, type_, _pf(out)))
+        return out
+
+    def get_cells(self, loci, rows):
+        loci = np.ascontiguousarray(loci, dtype=np.int64)
+        rows = np.ascontiguousarray(rows, dtype=np.int32)
+        out = np.zeros((loci.size, rows.size), dtype=np.int8)
+        check(self.L.bmg_chain_get_cells(self.h, _pi(loci), loci.size, rows.ctypes.data_as(i32p), rows.size,
+                                         out.ctypes.data_as(i8p)))
         return out
 
     def residual(self, loci, beta_e, beta_g):

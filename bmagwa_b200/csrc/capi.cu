@@ -252,6 +252,20 @@ BMG_API int bmg_chain_set_missing(bmg_chain* c, int64_t snp, const int8_t* vals,
   chain_set_missing(Cn(c), snp, vals, count);
   BMG_CATCH
 }
+BMG_API int bmg_chain_set_missing_all(bmg_chain* c, const int8_t* vals, int64_t count)
+{
+  BMG_TRY
+  BMG_REQUIRE(vals || count == 0, "bmg_chain_set_missing_all: null argument");
+  chain_set_missing_all(Cn(c), vals, count);
+  BMG_CATCH
+}
+BMG_API int bmg_chain_get_cells(bmg_chain* c, const int64_t* loci, int k, const int32_t* rows, int64_t q, int8_t* out)
+{
+  BMG_TRY
+  BMG_REQUIRE((loci && rows && out) || k == 0 || q == 0, "bmg_chain_get_cells: null argument");
+  chain_get_cells(Cn(c), loci, k, rows, q, out);
+  BMG_CATCH
+}
 BMG_API int bmg_chain_get_column(bmg_chain* c, int64_t snp, int type, double* out)
 {
   BMG_TRY

@@ -1,0 +1,162 @@
+// missing.hpp -- missing genotypes of one chain on the host side: the index, the imputed values and the Gibbs step.
+//
+// What the reference keeps in Data::miss_loc_/miss_prior_ (src/data.cpp:341-376) and DataModel::miss_val_
+// (src/data_model.hpp:75-101), and what Sampler::sample_missing (src/sampler.cpp:264-453),
+// DataModel::sample_missing and sample_missing_single (src/data_model.cpp:78-103) do with them.
+//
+// The reference's Gibbs step walks columns of the n x k design matrix; no such matrix exists here (the packed device
+// store is the column cache).  The step only ever touches the rows of individuals that have a missing call in some
+// in-model SNP, so the sampler gathers exactly those cells from the device (bmg_chain_get_cells) and this file does the
+// reference's arithmetic on them, in the reference's order and with the reference's random-number consumption (one
+// uniform per missing cell).  Everything here is plain host code with no device dependency, so it is unit-tested on the
+// CPU against the unmodified reference (tests/test_cpu_missing_gibbs.py).
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <stdexcept>
+#include <vector>
+#include "model.hpp"
+#include "rng.hpp"
+
+namespace bmg {
+
+// Host mirror of the store's missing index plus the chain's imputed values (CSR over SNPs, rows ascending per SNP)
+struct MissingCells {
+  std::vector<int64_t> off;     // m_g + 1
+  std::vector<int32_t> idx;     // individual of each missing cell
+  std::vector<int8_t> val;      // imputed value 0/1/2, initially 0 (data_model.hpp:80-84)
+  std::vector<double> prior3;   // per SNP: cumulative counts of 0/1/2 among the observed cells (data.cpp:357-372)
+
+  int64_t total() const { return off.empty() ? 0 : off.back(); }
+  int64_t count(size_t snp) const { return off[snp + 1] - off[snp]; }
+  // DataModel::genotype_missing (data_model.hpp:104-117)
+  bool is_missing(int32_t individual, size_t snp) const
+  {
+    const int32_t* b = idx.data() + off[snp];
+    const int32_t* e = idx.data() + off[snp + 1];
+    return std::binary_search(b, e, individual);
+  }
+  // DataModel::sample_missing_single (data_model.cpp:95-103): one uniform per cell through Utils::sample_discrete_naive
+  void draw_from_prior(size_t snp, ChainRng& rng)
+  {
+    const double* cum = &prior3[3 * snp];
+    for (int64_t q = off[snp]; q < off[snp + 1]; ++q) val[q] = (int8_t)draw3(cum, rng);
+  }
+  // DataModel::sample_missing (data_model.cpp:78-90): every SNP that is not in the model, in SNP order
+  template <class InModel>
+  void draw_all_from_prior(InModel in_model, ChainRng& rng)
+  {
+    const size_t m = off.size() - 1;
+    for (size_t snp = 0; snp < m; ++snp) {
+      if (off[snp + 1] == off[snp] || in_model(snp)) continue;
+      draw_from_prior(snp, rng);
+    }
+  }
+  // Utils::sample_discrete_naive (utils.cpp:46-57) for three classes
+  static int draw3(const double* cumsum, ChainRng& rng)
+  {
+    const double r = rng.u01() * cumsum[2];
+    for (int i = 0; i < 3; ++i)
+      if (r < cumsum[i]) return i;
+    throw std::logic_error("sample_discrete_naive reached end, exiting");
+  }
+};
+
+// Individuals (ascending, distinct) that have a missing call in at least one SNP of the model: the rows the Gibbs
+// step needs from the device.
+inline void rows_missing_in_model(const MissingCells& mc, const std::vector<uint32_t>& loci, std::vector<int32_t>& rows)
+{
+  rows.clear();
+  for (uint32_t snp : loci) rows.insert(rows.end(), mc.idx.begin() + mc.off[snp], mc.idx.begin() + mc.off[snp + 1]);
+  std::sort(rows.begin(), rows.end());
+  rows.erase(std::unique(rows.begin(), rows.end()), rows.end());
+}
+
+// Sampler::sample_missing (sampler.cpp:264-453), effect type A.
+//   cur    current model; xx and xy are patched in place (sampler.cpp:393-450), mu_beta_computed is cleared
+//   rows   rows_missing_in_model(...) (q of them); cells = k x q genotype values with the chain's imputed values
+//          applied, as they are BEFORE this update (bmg_chain_get_cells over cur.loci)
+//   y, e   phenotype (n) and covariates (n x m_e, column-major, ones column included)
+//   yy     y'y.  The reference sums the squared residual over all n individuals; here r'r comes from the Gram
+//          matrix, r'r = y'y - 2 b'X'y + b'X'X b (it only enters through differences in which it cancels).
+// On return mc.val holds the new imputed values of the in-model SNPs.
+inline void gibbs_missing_in_model(Model& cur, MissingCells& mc, const std::vector<int32_t>& rows, const int8_t* cells,
+                                   const double* y, const double* e, size_t n, double yy, ChainRng& rng)
+{
+  const int m_e = cur.m_e, cols = cur.cols(), k = (int)cur.size();
+  const size_t q = rows.size();
+  cur.mu_beta_computed = false;   // sampler.cpp:452, unconditional
+  if (q == 0) return;
+  const std::vector<double>& beta = cur.beta;
+  const double sigma2_times_2 = cur.sigma2 * 2;
+
+  // the touched rows of the design matrix, before (xold: the reference's new_model->x) and after (xnew) the update
+  std::vector<double> xold(q * (size_t)cols), y_hat(q), residual(q);
+  for (size_t u = 0; u < q; ++u) {
+    double* row = &xold[u * cols];
+    for (int c = 0; c < m_e; ++c) row[c] = e[(size_t)c * n + rows[u]];
+    for (int l = 0; l < k; ++l) row[m_e + l] = (double)cells[(size_t)l * q + u];
+    double s = 0.0;   // y_hat = X beta, accumulated column by column like the dgemv of Vector::set_to_product
+    for (int c = 0; c < cols; ++c) s += beta[c] * row[c];
+    y_hat[u] = s;
+    residual[u] = y[rows[u]] - s;
+  }
+  std::vector<double> xnew(xold);
+  double r2 = yy;
+  for (int c = 0; c < cols; ++c) r2 -= 2.0 * beta[c] * cur.xy[c];
+  r2 += cur.quad(0, cols);
+
+  auto slot_of = [&](int32_t individual) { return (size_t)(std::lower_bound(rows.begin(), rows.end(), individual) - rows.begin()); };
+
+  double lprior[3], likelihood[3];
+  for (int t = 0; t < k; ++t) {
+    const size_t snp = cur.loci[t];
+    if (mc.count(snp) == 0) continue;
+    const int x_ind = m_e + t;
+    const double* p3 = &mc.prior3[3 * snp];
+    lprior[0] = std::log(p3[0]);
+    lprior[1] = std::log(p3[1] - p3[0]);
+    lprior[2] = std::log(p3[2] - p3[1]);
+    for (int64_t c = mc.off[snp]; c < mc.off[snp + 1]; ++c) {
+      const size_t u = slot_of(mc.idx[c]);
+      double* row = &xnew[u * cols];
+      const double old_term2 = residual[u] * residual[u];
+      for (int g = 0; g < 3; ++g) {
+        const double new_term = residual[u] - beta[x_ind] * ((double)g - row[x_ind]);
+        likelihood[g] = lprior[g] - (r2 + new_term * new_term - old_term2) / sigma2_times_2;
+      }
+      likelihood[1] -= likelihood[0];
+      likelihood[2] -= likelihood[0];
+      likelihood[0] = 1;
+      likelihood[1] = std::exp(likelihood[1]) + likelihood[0];
+      likelihood[2] = std::exp(likelihood[2]) + likelihood[1];
+      const int g = MissingCells::draw3(likelihood, rng);
+      mc.val[c] = (int8_t)g;
+      y_hat[u] += beta[x_ind] * ((double)g - row[x_ind]);
+      row[x_ind] = (double)g;
+      residual[u] = y[mc.idx[c]] - y_hat[u];
+      r2 += residual[u] * residual[u] - old_term2;
+    }
+  }
+
+  // X'y and the upper triangle of X'X follow the changed cells (sampler.cpp:393-427)
+  for (int t = 0; t < k; ++t) {
+    const size_t snp = cur.loci[t];
+    if (mc.count(snp) == 0) continue;
+    const int x_ind = m_e + t;
+    for (int64_t c = mc.off[snp]; c < mc.off[snp + 1]; ++c) {
+      const int32_t i_miss = mc.idx[c];
+      const size_t u = slot_of(i_miss);
+      const double* xn = &xnew[u * cols];
+      const double* xo = &xold[u * cols];
+      cur.xy[x_ind] += y[i_miss] * (xn[x_ind] - xo[x_ind]);
+      int j = 0;
+      for (; j < x_ind; ++j)   // a column that is itself missing here is patched when its own cell comes up
+        if (j < m_e || !mc.is_missing(i_miss, cur.loci[j - m_e])) cur.xx(j, x_ind) += xn[x_ind] * xn[j] - xo[x_ind] * xo[j];
+      for (; j < cols; ++j) cur.xx(x_ind, j) += xn[x_ind] * xn[j] - xo[x_ind] * xo[j];
+    }
+  }
+}
+
+}  // namespace bmg

@@ -86,9 +86,9 @@ Sampler::Sampler(const Options& opts, int chain_index, Store* store, const std::
   if (comm != nullptr) {
     for (int64_t snp : {(int64_t)0, (int64_t)m_g_ - 1}) (void)store_->column_ptr(snp);   // throws unless every shard is attached
   }
-  if (store_->n_missing > 0)
-    throw std::runtime_error("genotype data contains missing calls: the missing-genotype Gibbs step (sampler.cpp:264-453) is "
-                             "not implemented in this build");
+  if (store_->n_missing > 0 && comm != nullptr)
+    throw std::runtime_error("genotype data contains missing calls: not supported by the SNP-sharded chain");
+  yy_ = yy;
   adapt_p_move_size_ = opts.adapt_p_move_size && max_move_size_ > 1;
   delay_rejection_ = (unsigned char)std::min((size_t)max_move_size_, opts.delay_rejection);
 
@@ -150,7 +150,70 @@ Sampler::Sampler(const Options& opts, int chain_index, Store* store, const std::
     dr_bit_to_normalized_order_.assign(delay_rejection_, 0);
   }
   y_host_ = &y; e_host_ = &e;
+  if (store_->n_missing > 0) load_missing_index();
   if (opts.probit) enable_probit();
+}
+
+// ------------------------------------------------------------------------------------------------
+// missing genotypes: Data::miss_loc / miss_prior and DataModel::miss_val mirrored on the host
+// ------------------------------------------------------------------------------------------------
+void Sampler::load_missing_index()
+{
+  BMG_CUDA(cudaSetDevice(store_->device));
+  miss_.off = store_->h_miss_off;
+  miss_.idx.resize((size_t)store_->n_missing);
+  bmg::copy_d2h_sync(miss_.idx.data(), store_->miss_idx.p, miss_.idx.size() * sizeof(int32_t));
+  miss_.val.assign(miss_.idx.size(), 0);   // data_model.hpp:80-84; the chain's device copy starts at 0 as well
+  std::vector<int32_t> n1(m_g_), n2(m_g_), nm(m_g_);
+  bmg::copy_d2h_sync(n1.data(), store_->n1.p, m_g_ * sizeof(int32_t));
+  bmg::copy_d2h_sync(n2.data(), store_->n2.p, m_g_ * sizeof(int32_t));
+  bmg::copy_d2h_sync(nm.data(), store_->nmiss.p, m_g_ * sizeof(int32_t));
+  miss_.prior3.resize(3 * m_g_);
+  for (size_t j = 0; j < m_g_; ++j) {      // cumulative counts of 0/1/2 among the observed cells (data.cpp:357-372)
+    const double c0 = (double)((int64_t)n_ - nm[j] - n1[j] - n2[j]);
+    miss_.prior3[3 * j] = c0;
+    miss_.prior3[3 * j + 1] = c0 + (double)n1[j];
+    miss_.prior3[3 * j + 2] = c0 + (double)n1[j] + (double)n2[j];
+  }
+  have_missing_ = true;
+}
+
+std::vector<double> Sampler::draw_for_additions(const std::vector<uint32_t>& cand)
+{
+  std::vector<double> taus(cand.size());
+  for (size_t i = 0; i < cand.size(); ++i) {
+    const uint32_t snp = cand[i];
+    if (miss_.count(snp) > 0) {   // DataModel::sample_missing_single (data_model.cpp:95-103)
+      miss_.draw_from_prior(snp, rng_);
+      chain_set_missing(chain_, snp, miss_.val.data() + miss_.off[snp], miss_.count(snp));
+    }
+    taus[i] = prior_->draw_inv_tau2_alpha2(rng_);
+  }
+  return taus;
+}
+
+// Sampler::sample_missing (sampler.cpp:264-453): the arithmetic is in missing.hpp; here the few touched rows of the
+// in-model columns are gathered from the device and the new imputed values are sent back
+void Sampler::sample_missing()
+{
+  if (!have_missing_ || current_.size() == 0) return;
+  rows_missing_in_model(miss_, current_.loci, gibbs_rows_);
+  if (gibbs_rows_.empty()) return;
+  const int k = (int)current_.size();
+  std::vector<int64_t> loci(current_.loci.begin(), current_.loci.end());
+  gibbs_cells_.resize((size_t)k * gibbs_rows_.size());
+  chain_get_cells(chain_, loci.data(), k, gibbs_rows_.data(), (int64_t)gibbs_rows_.size(), gibbs_cells_.data());
+  const double* yv = y_host_->data();
+  if (probit_) {   // the working phenotype is the latent z on the device
+    y_work_.resize(n_);
+    BMG_CUDA(cudaSetDevice(store_->device));
+    bmg::copy_d2h(y_work_.data(), chain_->y.p, n_ * sizeof(double), chain_->stream);
+    BMG_CUDA(cudaStreamSynchronize(chain_->stream));
+    yv = y_work_.data();
+  }
+  gibbs_missing_in_model(current_, miss_, gibbs_rows_, gibbs_cells_.data(), yv, e_host_->data(), n_, yy_, rng_);
+  for (uint32_t snp : current_.loci)
+    if (miss_.count(snp) > 0) chain_set_missing(chain_, snp, miss_.val.data() + miss_.off[snp], miss_.count(snp));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -181,6 +244,7 @@ void Sampler::enable_probit()
     exy[c] = s;
   }
   prior_->set_fixed_sigma2(yy);
+  yy_ = yy;
   for (size_t c = 0; c < m_e_; ++c) { current_.xy[c] = exy[c]; proposal_.xy[c] = exy[c]; }
   current_.sigma2 = 1.0;
   current_.compute_log_likelihood();
@@ -213,6 +277,7 @@ void Sampler::probit_sweep()
     done += cnt;
   }
   prior_->set_yy(st[1]);
+  yy_ = st[1];
   ++n_probit_sweeps_;
 }
 
@@ -520,6 +585,10 @@ void Sampler::rao_block()
   const double k_move_size = 1000.0 / (double)opt_.n_rao_burnin;   // sampler.cpp:558 (initial burn-in length)
   const bool do_scan = !flat_proposal_dist_ || n_rao_burnin_ <= 0;
   if (do_scan) {
+    if (have_missing_) {   // DataModel::sample_missing (sampler.cpp:733): every SNP outside the model is imputed again from its prior
+      miss_.draw_all_from_prior([this](size_t snp) { return pos_in_current_[snp] >= 0; }, rng_);
+      chain_set_missing_all(chain_, miss_.val.data(), (int64_t)miss_.val.size());
+    }
     const double t0 = wall_seconds();
     const int k = (int)current_.size();
     std::vector<int64_t> loci(current_.loci.begin(), current_.loci.end());
@@ -691,6 +760,8 @@ void Sampler::do_addrem(double& log_q_forward, double& log_q_backward, double& l
   std::vector<uint32_t> cand;
   for (unsigned char i = 0; i < ms; ++i)
     if (move_isadd_[i]) cand.push_back((uint32_t)move_inds_[i]);
+  std::vector<double> taus;
+  if (have_missing_) taus = draw_for_additions(cand);   // removals draw nothing, so the stream order is the reference's
   begin_gram(cand);
   for (unsigned char i = 0; i < ms; ++i) {   // removals first
     if (move_isadd_[i]) continue;
@@ -703,12 +774,14 @@ void Sampler::do_addrem(double& log_q_forward, double& log_q_backward, double& l
     remove_from_proposal(model_ind);
   }
   finish_gram();
+  size_t n_added = 0;
   for (unsigned char i = 0; i < ms; ++i) {   // then additions
     if (!move_isadd_[i]) continue;
     const size_t ind = move_inds_[i];
     dd_rem_.unzero((uint32_t)ind);
     log_mpc += prior_->log_change_on_add((int)proposal_.size());
-    const double tau = prior_->draw_inv_tau2_alpha2(rng_);   // prepare_add_new_term (sampler.hpp:500-515)
+    const double tau = have_missing_ ? taus[n_added] : prior_->draw_inv_tau2_alpha2(rng_);   // prepare_add_new_term (sampler.hpp:500-515)
+    ++n_added;
     add_to_proposal((uint32_t)ind, tau);
   }
 }
@@ -892,9 +965,11 @@ unsigned char Sampler::do_switch_of_nearby_snps()
     cand[i] = (uint32_t)move_inds_add_[i];
     cur[move_inds_add_[i]] = -1;   // revert the marks before anything reads pos_in_current_ as a map
   }
+  std::vector<double> taus;
+  if (have_missing_) taus = draw_for_additions(cand);
   fetch_gram(cand);
   for (unsigned char i = 0; i < movesize_; ++i) {
-    const double tau = prior_->draw_inv_tau2_alpha2(rng_);
+    const double tau = have_missing_ ? taus[i] : prior_->draw_inv_tau2_alpha2(rng_);
     add_to_proposal((uint32_t)move_inds_add_[i], tau);
   }
   const double log_r = proposal_.log_likelihood - current_.log_likelihood;
@@ -940,6 +1015,8 @@ unsigned char Sampler::do_statechange_of_nearby_snps()
   }
   std::vector<uint32_t> cand(ms_add);
   for (unsigned char i = 0; i < ms_add; ++i) cand[i] = (uint32_t)move_inds_add_[i];
+  std::vector<double> taus;
+  if (have_missing_) taus = draw_for_additions(cand);
   begin_gram(cand);
   double log_mpc = 0.0;
   for (unsigned char i = 0; i < ms_rem; ++i) {
@@ -950,7 +1027,7 @@ unsigned char Sampler::do_statechange_of_nearby_snps()
   finish_gram();
   for (unsigned char i = 0; i < ms_add; ++i) {
     log_mpc += prior_->log_change_on_add((int)proposal_.size());
-    const double tau = prior_->draw_inv_tau2_alpha2(rng_);
+    const double tau = have_missing_ ? taus[i] : prior_->draw_inv_tau2_alpha2(rng_);
     add_to_proposal((uint32_t)move_inds_add_[i], tau);
   }
   double log_r = log_mpc + proposal_.log_likelihood - current_.log_likelihood;

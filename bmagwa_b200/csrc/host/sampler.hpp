@@ -19,6 +19,7 @@
 #include <vector>
 #include "../store.cuh"
 #include "dataset.hpp"
+#include "missing.hpp"
 #include "model.hpp"
 #include "options.hpp"
 #include "rng.hpp"
@@ -121,7 +122,19 @@ class Sampler {
   void remove_from_proposal(int model_ind);
   void refresh_weights_from_device(bool first);
   void compute_p_moves();
-  void sample_missing() {}   // no missing cells in the supported inputs (checked at construction)
+  // missing genotypes (sampler.cpp:264-453, data_model.cpp:78-103): index + imputed values mirrored on the host
+  // (missing.hpp), the device copy follows through bmg_chain_set_missing[_all]
+  MissingCells miss_;
+  bool have_missing_ = false;
+  double yy_ = 0.0;                    // y'y of the working phenotype
+  std::vector<int32_t> gibbs_rows_;
+  std::vector<int8_t> gibbs_cells_;
+  std::vector<double> y_work_;         // probit mode: host copy of the latent phenotype for the Gibbs step
+  void load_missing_index();
+  void sample_missing();               // Sampler::sample_missing: Gibbs update of the in-model SNPs' missing cells
+  // prepare_add_new_term (sampler.hpp:500-515) for the SNPs a move adds, in the move's order: imputed values from the
+  // prior (uploaded before the move's statistics are taken), then the prior precision of the new term
+  std::vector<double> draw_for_additions(const std::vector<uint32_t>& cand);
   // probit mode (no reference counterpart): y = 0/1 labels, the chain's phenotype is the latent z
   void enable_probit();
   void probit_sweep();       // z ~ N(X beta, 1) truncated by the labels (device), then y'y, E'z, X_gamma'z refreshed

@@ -45,7 +45,7 @@ SamplerHandle* H(bmg_sampler* sp)
 // var_x / mean_x of a SNP-sharded data set exactly as the unsharded store computes them (store.cu, as
 // Data::compute_g_var_and_mean): per-SNP means, variances and missing counts are all-gathered and summed on the
 // host in SNP order.
-static void global_summaries(Store* st, const Sampler::ShardComm& cm, double* out4)
+static int64_t global_summaries(Store* st, const Sampler::ShardComm& cm, double* out4)
 {
   BMG_CUDA(cudaSetDevice(st->device));
   const int64_t total = (int64_t)cm.world * cm.stride, off = (int64_t)cm.rank * cm.stride;
@@ -77,6 +77,9 @@ static void global_summaries(Store* st, const Sampler::ShardComm& cm, double* ou
     else if (ng == 1) { tm += hm[j]; nm += 1; }
   }
   out4[0] = tm; out4[1] = nm; out4[2] = tv; out4[3] = nv;
+  int64_t missing = 0;
+  for (int64_t j = 0; j < st->m_g; ++j) missing += hn[j];
+  return missing;   // over all shards: the same number on every rank
 }
 
 SamplerHandle* make(const char* ini, int chain_index, int device, Store* existing, const Sampler::ShardComm* comm = nullptr)
@@ -108,7 +111,10 @@ SamplerHandle* make(const char* ini, int chain_index, int device, Store* existin
   if (comm != nullptr) {
     BMG_REQUIRE(existing != nullptr, "bmg_sampler_create_sharded: a shard store is required");
     BMG_REQUIRE(existing->m_e >= 1, "bmg_sampler_create_sharded: call bmg_store_set_phenotype on the shard first");
-    global_summaries(h->store, *comm, sm);
+    const int64_t missing_cells = global_summaries(h->store, *comm, sm);
+    // every rank sees the same total, so every rank refuses together (no rank is left waiting in a collective)
+    BMG_REQUIRE(missing_cells == 0, "bmg_sampler_create_sharded: genotype data contains missing calls; the SNP-sharded chain keeps the "
+                                    "imputed values of a shard on its owner only (use a single-GPU chain for such data)");
   }
   const double mean_x = sm[0] / sm[1], var_x = sm[2] / sm[3];
   h->sampler.reset(new Sampler(o, chain_index, h->store, h->data->y, h->data->e, sm[4], sm[5], var_x, mean_x, comm));

@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 #include "common.cuh"
 #include "store.cuh"
 #include "philox.cuh"
@@ -660,6 +661,93 @@ void chain_set_missing(Chain* c, int64_t snp, const int8_t* vals, int64_t count)
   BMG_CUDA(cudaSetDevice(s->device));
   bmg::copy_h2d(c->miss_val.p + lo, vals, (size_t)cnt, c->stream);
   BMG_CUDA(cudaStreamSynchronize(c->stream));
+}
+
+// DataModel::sample_missing (data_model.cpp:78-90) draws every cell again before a scan: one upload for the shard
+void chain_set_missing_all(Chain* c, const int8_t* vals, int64_t count)
+{
+  Store* s = c->store;
+  BMG_REQUIRE(count == s->n_missing, "bmg_chain_set_missing_all: count does not match the number of missing cells of the store");
+  if (count == 0) return;
+  unsigned bad = 0;
+  for (int64_t q = 0; q < count; ++q) bad |= (unsigned)((uint8_t)vals[q] > 2);
+  BMG_REQUIRE(bad == 0, "bmg_chain_set_missing_all: values must be 0, 1 or 2");
+  BMG_CUDA(cudaSetDevice(s->device));
+  bmg::copy_h2d(c->miss_val.p, vals, (size_t)count, c->stream);
+  BMG_CUDA(cudaStreamSynchronize(c->stream));
+}
+
+// ---------------------------------------------------------------------------------------
+// a few cells of a few columns, the chain's imputed values applied: what the reference reads as
+// current_model->x(i_miss, col) in the missing-genotype Gibbs step (src/sampler.cpp:304-449)
+// ---------------------------------------------------------------------------------------
+struct CellArgs {
+  const uint32_t* const* cols;   // k packed columns
+  const int64_t* snp_local;      // local index of each column's SNP, -1 for a peer's
+  const int32_t* rows;           // q individuals
+  int k;
+  int64_t q;
+  const int64_t* off;            // store's missing index (CSR)
+  const int32_t* idx;
+  const int8_t* val;             // chain's imputed values
+  int8_t* out;                   // k x q
+};
+
+__global__ void k_gather_cells(const CellArgs a)
+{
+  const int64_t gid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (gid >= (int64_t)a.k * a.q) return;
+  const int l = (int)(gid / a.q);
+  const int32_t i = a.rows[gid - (int64_t)l * a.q];
+  int v = (int)((a.cols[l][i >> 4] >> (2 * (i & 15))) & 3u);
+  const int64_t j = a.snp_local[l];
+  if (j >= 0) {
+    int64_t lo = a.off[j], hi = a.off[j + 1];
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      const int32_t w = a.idx[mid];
+      if (w == i) { v = a.val[mid]; break; }
+      if (w < i) lo = mid + 1; else hi = mid;
+    }
+  }
+  a.out[gid] = (int8_t)v;
+}
+
+void chain_get_cells(Chain* c, const int64_t* loci, int k, const int32_t* rows, int64_t q, int8_t* out)
+{
+  Store* s = c->store;
+  BMG_REQUIRE(k >= 0 && k <= 2048 && q >= 0, "bmg_chain_get_cells: bad sizes");
+  if (k == 0 || q == 0) return;
+  for (int64_t t = 0; t < q; ++t) BMG_REQUIRE(rows[t] >= 0 && rows[t] < s->n, "bmg_chain_get_cells: individual out of range");
+  BMG_CUDA(cudaSetDevice(s->device));
+  cudaStream_t st = c->stream;
+  const size_t cells = (size_t)k * (size_t)q;
+  if (c->gc_meta.n < (size_t)2 * k || c->gc_rows.n < (size_t)q || c->gc_out.n < cells) {
+    chain_server_stop(c);   // allocations synchronise the device: a running server would stall them
+    BMG_CUDA(cudaStreamSynchronize(st));
+    if (c->gc_meta.n < (size_t)2 * k) { c->gc_meta.alloc(4096); c->gc_h_meta.alloc(4096); }
+    if (c->gc_rows.n < (size_t)q) { c->gc_rows.alloc(2 * q + 1024); c->gc_h_rows.alloc(2 * q + 1024); }
+    if (c->gc_out.n < cells) { c->gc_out.alloc(2 * cells + 4096); c->gc_h_out.alloc(2 * cells + 4096); }
+  }
+  for (int l = 0; l < k; ++l) {
+    c->gc_h_meta.p[l] = (int64_t)(uintptr_t)s->column_ptr(loci[l]);
+    const bool local = s->is_local(loci[l]) && s->n_missing > 0;
+    c->gc_h_meta.p[k + l] = local ? loci[l] - s->lo : -1;
+  }
+  memcpy(c->gc_h_rows.p, rows, (size_t)q * sizeof(int32_t));
+  bmg::copy_h2d(c->gc_meta.p, c->gc_h_meta.p, (size_t)2 * k * sizeof(int64_t), st);
+  bmg::copy_h2d(c->gc_rows.p, c->gc_h_rows.p, (size_t)q * sizeof(int32_t), st);
+  CellArgs a;
+  a.cols = reinterpret_cast<const uint32_t* const*>(c->gc_meta.p);
+  a.snp_local = c->gc_meta.p + k;
+  a.rows = c->gc_rows.p; a.k = k; a.q = q;
+  a.off = s->miss_off.p; a.idx = s->miss_idx.p; a.val = c->miss_val.p; a.out = c->gc_out.p;
+  k_gather_cells<<<(unsigned)((cells + 127) / 128), 128, 0, st>>>(a);
+  count_launch();
+  BMG_CUDA(cudaGetLastError());
+  bmg::copy_d2h(c->gc_h_out.p, c->gc_out.p, cells, st);
+  BMG_CUDA(cudaStreamSynchronize(st));
+  memcpy(out, c->gc_h_out.p, cells);
 }
 
 // uploads loci / beta / tau of the current model into the chain's device scratch

@@ -69,6 +69,13 @@ struct Chain {
   // per-chain imputed values of the missing cells (same CSR as the store)
   DevBuf<int8_t> miss_val;
   DevBuf<double> miss_corr;                     // 3 per local SNP: (dot corr, sum val, sum val^2)
+  // scratch of chain_get_cells (values of a few (SNP, individual) cells for the missing-genotype Gibbs step)
+  DevBuf<int64_t> gc_meta;                      // k column pointers, then k local SNP indices
+  DevBuf<int32_t> gc_rows;
+  DevBuf<int8_t> gc_out;
+  PinnedBuf<int64_t> gc_h_meta;
+  PinnedBuf<int32_t> gc_h_rows;
+  PinnedBuf<int8_t> gc_h_out;
   // scan outputs and the per-SNP arrays Sampler keeps (sampler.hpp:201-258)
   DevBuf<double> dot_partial;                   // scan_chunks * m
   DevBuf<double> dot;                           // m
@@ -114,6 +121,8 @@ struct Chain {
 Chain* chain_create(Store* s);
 void chain_destroy(Chain* c);
 void chain_set_missing(Chain* c, int64_t snp, const int8_t* vals, int64_t count);
+void chain_set_missing_all(Chain* c, const int8_t* vals, int64_t count);
+void chain_get_cells(Chain* c, const int64_t* loci, int k, const int32_t* rows, int64_t q, int8_t* out);
 void chain_residual(Chain* c, const int64_t* loci, const double* beta_e, const double* beta_g, int k, double* stats9);
 void chain_scan_dots(Chain* c);
 void chain_set_sharded(Chain* c, int world, int rank, int64_t stride, AllGatherFn fn, void* ctx);

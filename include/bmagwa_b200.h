@@ -106,8 +106,15 @@ void* bmg_chain_stream(bmg_chain* c);
 /* DataModel::miss_val (data_model.hpp:127-131): imputed values (0,1,2) of ALL missing cells of
  * local SNP `snp`, in miss_loc order. */
 int bmg_chain_set_missing(bmg_chain* c, int64_t snp, const int8_t* vals, int64_t count);
+/* DataModel::sample_missing (data_model.cpp:78-90, re-imputation of every SNP before a scan): the imputed values
+ * of ALL missing cells of the local shard in one upload, in the order of bmg_store_missing's idx array. */
+int bmg_chain_set_missing_all(bmg_chain* c, const int8_t* vals, int64_t count);
 /* DataModel::get_genotypes_<type>(snp, v) (data_model.cpp:30-72): overlay applied. */
 int bmg_chain_get_column(bmg_chain* c, int64_t snp, int type, double* out);
+/* The additive value (0, 1, 2; overlay applied) of a few cells: out[l*q + t] = SNP loci[l] at individual rows[t].
+ * This is what the missing-genotype Gibbs step reads as current_model->x(i_miss, col) (sampler.cpp:304-449); the
+ * design matrix itself does not exist here, so the step gathers the few cells it needs. */
+int bmg_chain_get_cells(bmg_chain* c, const int64_t* loci, int k, const int32_t* rows, int64_t q, int8_t* out);
 
 /* Fitted values and residual for the current model (what Model::compute_pve leaves in y_hat,
  * model.hpp:345-392, and RaoBlackwellizer takes r = y - y_hat from, sampler.cpp:48-49):

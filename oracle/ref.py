@@ -110,6 +110,10 @@ class Ref:
     def set_miss_val(self, snp, k, val):
         self.L.refd_set_miss_val(self.h, C.c_long(snp), C.c_long(k), C.c_int(val))
 
+    def get_miss_val(self, snp):
+        cnt = self.L.refd_missing(self.h, C.c_long(snp), None, None)
+        return np.array([self.L.refd_get_miss_val(self.h, C.c_long(snp), C.c_long(k)) for k in range(cnt)], dtype=np.int8)
+
     def moments(self):
         off = self.L.refd_moments_offset(self.h)
         out = np.zeros(self.m_g * off)
@@ -201,6 +205,12 @@ class Ref:
 
     def sample_alpha_and_tau2(self):
         self.L.refd_sample_alpha_and_tau2(self.h)
+
+    def sample_missing(self):
+        self.L.refd_sample_missing(self.h)
+
+    def sample_missing_from_prior(self):
+        self.L.refd_sample_missing_from_prior(self.h)
 
     # ---- scan
     def scan(self, y_hat=None):

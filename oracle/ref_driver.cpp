@@ -252,6 +252,21 @@ void refd_sample_alpha_and_tau2(void* h)
   c->sampler->prior->sample_alpha_and_tau2(c->sampler->current_model, c->sampler->data_model->y(), c->sampler->rng);
 }
 
+/* Sampler::sample_missing (sampler.cpp:264-453) on the current model with the sampler's own random stream; new_model is
+   brought level with current_model first, as it is whenever sample() calls it (sampler.cpp:266) */
+void refd_sample_missing(void* h)
+{
+  Sampler* s = ((RefCtx*)h)->sampler;
+  *s->new_model = *s->current_model;
+  s->sample_missing();
+}
+/* DataModel::sample_missing (data_model.cpp:78-90): every SNP outside the current model, from its prior */
+void refd_sample_missing_from_prior(void* h)
+{
+  Sampler* s = ((RefCtx*)h)->sampler;
+  s->data_model->sample_missing(s->current_model->model_inds, s->rng);
+}
+
 /* ---- the all-SNP scan (sampler.cpp:32-261).  y_hat == NULL -> X*beta of the current model ---- */
 void refd_scan(void* h, const double* y_hat_in, double* p_r, double* p_r_types /* m_g x n_types or NULL */)
 {

@@ -34,6 +34,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
 
 from bmagwa_b200 import synth  # noqa: E402
 from oracle import ref  # noqa: E402
@@ -362,7 +363,30 @@ def run_chains(tmp, out, d):
         out["chainC_%s" % k] = v
 
 
+# data sets with missing genotype calls: the chain exercises DataModel::sample_missing before
+# every scan, sample_missing_single at every proposed addition and the Gibbs step Sampler::sample_missing
+from missing_chains import MISSING_CHAINS  # noqa: E402
+
+
+def run_missing_chains(tmp, out):
+    for tag, kw in MISSING_CHAINS.items():
+        sub = os.path.join(tmp, tag)
+        ds = synth.write_dataset(sub, "syn", outbase=os.path.join(sub, "chain"), **kw)
+        R = ref.Ref(ds["ini"])
+        R.run_chain()
+        R.close()
+        for k, v in read_chain(os.path.join(sub, "chain0")).items():
+            out["%s_%s" % (tag, k)] = v
+
+
 def main():
+    if "--missing-only" in sys.argv:   # only ref_missing_chains.npz (the other fixtures stay as committed)
+        assert ref.available(), "build oracle/_ref first (make -C oracle ref)"
+        out = {}
+        run_missing_chains(tempfile.mkdtemp(), out)
+        np.savez_compressed(os.path.join(HERE, "ref_missing_chains.npz"), **out)
+        print("wrote", len(out), "arrays;", os.path.getsize(os.path.join(HERE, "ref_missing_chains.npz")), "bytes")
+        return
     assert ref.available(), "build oracle/_ref first (make -C oracle ref)"
     d = os.path.join(HERE, "data")
     os.makedirs(d, exist_ok=True)
@@ -381,6 +405,9 @@ def main():
     run_chol(out)
     run_chains(tmp, out, d)
     np.savez_compressed(os.path.join(HERE, "ref_outputs.npz"), **out)
+    out2 = {}
+    run_missing_chains(tmp, out2)
+    np.savez_compressed(os.path.join(HERE, "ref_missing_chains.npz"), **out2)
     print("wrote", len(out), "arrays;", os.path.getsize(os.path.join(HERE, "ref_outputs.npz")), "bytes")
 
 

@@ -324,6 +324,51 @@ def test_adapt_and_partial_cdf_and_device_sampler(api):
     st.close()
 
 
+# ------------------------------------------------------------------------------ missing overlay (a3, f2)
+@pytest.mark.parametrize("n,m,miss", [(203, 300, 0.05), (4097, 64, 0.01), (50, 20, 0.4)])
+def test_bulk_overlay_upload_and_cell_gather_match_oracle(api, n, m, miss):
+    """bmg_chain_set_missing_all (DataModel::sample_missing, data_model.cpp:78-90: all SNPs re-imputed at once) and
+    bmg_chain_get_cells (the cells the Gibbs step reads as current_model->x(i_miss, col), sampler.cpp:304-449): bit-exact
+    against the oracle's overlay decode."""
+    payload, y, E = make_data(n, m, seed=3 * n + 1, miss_rate=miss)
+    bed, _ = oracle_store(payload, n, m, True)
+    st = api.GenotypeStore(payload, n, m, recode_to_minor=True)
+    st.set_phenotype(y, E)
+    ch = api.Chain(st)
+    off, idx, _ = cpu.missing_index(bed, n, m)
+    rs = np.random.default_rng(n)
+    val = rs.integers(0, 3, size=idx.size).astype(np.int8)
+    ch.set_missing_all(val)
+
+    def col(j):
+        return cpu.decode_column_overlay(bed, n, int(j), 0, idx[off[j]:off[j + 1]], val[off[j]:off[j + 1]])
+
+    for j in rs.choice(m, size=5, replace=False):
+        assert np.array_equal(ch.get_column(int(j)), col(j))
+    loci = rs.choice(m, size=min(9, m), replace=False).astype(np.int64)
+    rows = np.unique(np.concatenate([idx[off[j]:off[j + 1]] for j in loci] + [rs.integers(0, n, size=7)])).astype(np.int32)
+    cells = ch.get_cells(loci, rows)
+    assert cells.shape == (loci.size, rows.size)
+    for li, j in enumerate(loci):
+        assert np.array_equal(cells[li], col(j)[rows].astype(np.int8))
+    # a second upload replaces the first; a per-SNP upload then overrides one SNP only
+    val2 = rs.integers(0, 3, size=idx.size).astype(np.int8)
+    ch.set_missing_all(val2)
+    j0 = int(loci[0])
+    ch.set_missing(j0, val[off[j0]:off[j0 + 1]])
+    val2[off[j0]:off[j0 + 1]] = val[off[j0]:off[j0 + 1]]
+    val = val2
+    cells = ch.get_cells(loci, rows)
+    for li, j in enumerate(loci):
+        assert np.array_equal(cells[li], col(j)[rows].astype(np.int8))
+    with pytest.raises(RuntimeError):
+        ch.set_missing_all(val[:-1])
+    with pytest.raises(RuntimeError):
+        ch.get_cells(loci, np.array([n], dtype=np.int32))
+    ch.close()
+    st.close()
+
+
 # ------------------------------------------------------------------------------ column stats (a7)
 @pytest.mark.parametrize("n,m,miss", [(203, 300, 0.02), (5000, 200, 0.0), (40000, 50, 0.001)])
 def test_column_stats_match_oracle(api, n, m, miss):

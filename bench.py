@@ -69,10 +69,14 @@ class stdout_to_stderr:
         return False
 
 
+MISS_RATE = 0.0   # --miss-rate: fraction of genotype calls set missing in the synthetic data (default none, as BASELINE's configs)
+
+
 def dataset_dir(w, n_threads):
     """The data files do not depend on the number of chains (only the INI written per run does)."""
     base = os.environ.get("BMAGWA_BENCH_DIR", os.path.join(tempfile.gettempdir(), "bmagwa_bench"))
-    return os.path.join(base, "%s_n%d_m%d" % (w, WORKLOADS[w]["n"], WORKLOADS[w]["m_g"]))
+    tag = "" if MISS_RATE == 0.0 else "_miss%g" % MISS_RATE
+    return os.path.join(base, "%s_n%d_m%d%s" % (w, WORKLOADS[w]["n"], WORKLOADS[w]["m_g"], tag))
 
 
 def prepare_dataset(w, n_rao, n_threads, out_dir, do_n_iter):
@@ -88,7 +92,7 @@ def prepare_dataset(w, n_rao, n_threads, out_dir, do_n_iter):
                   verbosity=0)
     if not os.path.exists(marker):
         t0 = time.time()
-        synth.write_dataset(d, "syn", n=spec["n"], m_g=spec["m_g"], m_e=spec["m_e"], seed=GEN_SEED, **ini_kw)
+        synth.write_dataset(d, "syn", n=spec["n"], m_g=spec["m_g"], m_e=spec["m_e"], seed=GEN_SEED, miss_rate=MISS_RATE, **ini_kw)
         open(marker, "w").write("ok")
         log("[bench] generated %s in %.1f s" % (d, time.time() - t0))
     base = os.path.join(d, "syn")
@@ -396,7 +400,7 @@ def ours_arm(args, rank, local_rank, world):
         "config": {"workload": "%s: %s%s" % (args.workload, spec["desc"], "" if world == 1 else "; %d independent chains, one per GPU" % world),
                    "n": n, "m_g": m, "n_rao": args.n_rao, "step": "%d MCMC iterations incl. one all-SNP scan" % args.n_rao,
                    "sampler": "testdata/testdata.ini settings (PMV, thin 10, DR 10, individual tau2)",
-                   "tau_rng": args.tau_rng,
+                   "tau_rng": args.tau_rng, "miss_rate": args.miss_rate,
                    "per_move": ("column statistics served by the persistent k_colstats_server kernel (host mailbox in mapped pinned "
                                 "memory; BMG_COLSTATS_SERVER=0 launches k_column_stats_inline per move instead)")
                    if os.environ.get("BMG_COLSTATS_SERVER", "1") != "0" else "one k_column_stats_inline launch per move",
@@ -622,10 +626,14 @@ def main():
     ap.add_argument("--n-rao", type=int, default=500, dest="n_rao")
     ap.add_argument("--tau-rng", default="device", choices=["device", "host"], dest="tau_rng")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--miss-rate", type=float, default=0.0, dest="miss_rate",
+                    help="fraction of genotype calls set missing in the synthetic data (exercises the imputation path; default 0)")
     ap.add_argument("--probit", action="store_true", help="case-control labels + latent-variable updates (with --sharded; e.g. --workload C3)")
     ap.add_argument("--sharded", action="store_true",
                     help="ONE chain over a SNP-sharded store (strong scaling) instead of one chain per GPU")
     args = ap.parse_args()
+    global MISS_RATE
+    MISS_RATE = args.miss_rate
     if args.warmup < 3 and args.impl == "ours":
         log("[bench] note: fewer than 3 warm-up steps requested")
     rank = int(os.environ.get("RANK", "0"))

@@ -45,6 +45,7 @@ SIGNATURES = {
     "bmg_chain_stream": (vp, [vp]),
     "bmg_chain_set_missing": (C.c_int, [vp, i64, i8p, i64]),
     "bmg_chain_set_missing_all": (C.c_int, [vp, i8p, i64]),
+    "bmg_chain_impute_from_prior": (C.c_int, [vp, i64p, C.c_int, u64, u64]),
     "bmg_chain_get_column": (C.c_int, [vp, i64, C.c_int, f64p]),
     "bmg_chain_get_cells": (C.c_int, [vp, i64p, C.c_int, i32p, i64, i8p]),
     "bmg_chain_residual": (C.c_int, [vp, i64p, f64p, f64p, C.c_int, f64p]),
@@ -71,6 +72,7 @@ SIGNATURES = {
     "bmg_sampler_run": (C.c_int, [vp, i64]),
     "bmg_sampler_end": (C.c_int, [vp]),
     "bmg_sampler_stats": (C.c_int, [vp, f64p]),
+    "bmg_sampler_inclusion_counts": (C.c_int, [vp, C.POINTER(C.c_uint32), i64p]),
     "bmg_sampler_store": (vp, [vp]),
     "bmg_sampler_chain": (vp, [vp]),
     "bmg_sampler_destroy": (C.c_int, [vp]),

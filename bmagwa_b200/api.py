@@ -173,6 +173,10 @@ class Chain:
         check(self.L.bmg_chain_get_column(self.h, snp, type_, _pf(out)))
         return out
 
+    def impute_from_prior(self, loci, seed, counter):
+        loci = np.ascontiguousarray(loci, dtype=np.int64)
+        check(self.L.bmg_chain_impute_from_prior(self.h, _pi(loci), loci.size, seed, counter))
+
     def get_cells(self, loci, rows):
         loci = np.ascontiguousarray(loci, dtype=np.int64)
         rows = np.ascontiguousarray(rows, dtype=np.int32)
@@ -314,6 +318,13 @@ class Sampler:
         check(self.L.bmg_sampler_stats(self.h, _pf(out)))
         keys = ("iterations", "accepted", "model_size", "log_likelihood", "move_seconds", "scan_seconds", "scans", "column_stats_seconds")
         return dict(zip(keys, out))
+
+    def inclusion_counts(self, m_g):
+        """(counts[m_g] uint32, number of thinned samples counted): running MCMC inclusion counts of the chain."""
+        counts = np.zeros(m_g, dtype=np.uint32)
+        ns = C.c_int64(0)
+        check(self.L.bmg_sampler_inclusion_counts(self.h, counts.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(ns)))
+        return counts, int(ns.value)
 
     def chain_stream(self):
         return self.L.bmg_chain_stream(self.L.bmg_sampler_chain(self.h))

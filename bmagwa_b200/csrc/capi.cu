@@ -259,6 +259,13 @@ BMG_API int bmg_chain_set_missing_all(bmg_chain* c, const int8_t* vals, int64_t 
   chain_set_missing_all(Cn(c), vals, count);
   BMG_CATCH
 }
+BMG_API int bmg_chain_impute_from_prior(bmg_chain* c, const int64_t* loci, int k, uint64_t seed, uint64_t counter)
+{
+  BMG_TRY
+  BMG_REQUIRE(loci || k == 0, "bmg_chain_impute_from_prior: null argument");
+  chain_impute_from_prior(Cn(c), loci, k, seed, counter);
+  BMG_CATCH
+}
 BMG_API int bmg_chain_get_cells(bmg_chain* c, const int64_t* loci, int k, const int32_t* rows, int64_t q, int8_t* out)
 {
   BMG_TRY

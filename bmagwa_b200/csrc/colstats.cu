@@ -139,10 +139,12 @@ __device__ __forceinline__ void colstat_item(const ColStatInline& a, const int c
       const int q = task - n_fp;
       const uint32_t* other = task < n_tasks ? (q < a.k ? a.cols[a.m_c + q] : a.cols[q - a.k]) + w0 : nullptr;
 #pragma unroll
-      for (int j = 0; j < 2; ++j) ow0[u][j] = (other != nullptr && lane + 32 * j < nwords) ? other[lane + 32 * j] : 0u;
+      for (int j = 0; j < 2; ++j) ow0[u][j] = (other != nullptr && lane + 32 * j < nwords) ? __ldcg(other + lane + 32 * j) : 0u;
     }
   }
-  if (t < nwords) cw[t] = col[w0 + t];
+  // column words bypass L1 (__ldcg): a patched column of the overlay cache is rewritten between requests while the
+  // persistent server keeps running, and L1 lines are only dropped at kernel boundaries
+  if (t < nwords) cw[t] = __ldcg(col + w0 + t);
   __syncthreads();
 
   // (1) x_c'y and x_c'E_j: thread <-> individual (coalesced); a thread covers individuals i_lo + t + 256 j.
@@ -193,7 +195,7 @@ __device__ __forceinline__ void colstat_item(const ColStatInline& a, const int c
           const int q = task - n_fp;
           const uint32_t* other = task < n_tasks ? (q < a.k ? a.cols[a.m_c + q] : a.cols[q - a.k]) + w0 : nullptr;
 #pragma unroll
-          for (int j = 0; j < 2; ++j) ow[u][j] = (other != nullptr && lane + 32 * j < nwords) ? other[lane + 32 * j] : 0u;
+          for (int j = 0; j < 2; ++j) ow[u][j] = (other != nullptr && lane + 32 * j < nwords) ? __ldcg(other + lane + 32 * j) : 0u;
         }
       }
 #pragma unroll
@@ -213,7 +215,7 @@ __device__ __forceinline__ void colstat_item(const ColStatInline& a, const int c
       const uint32_t* other = (q < a.k ? a.cols[a.m_c + q] : a.cols[q - a.k]) + w0;
       uint32_t ow[kFastSegMax / 32];
 #pragma unroll
-      for (int j = 0; j < kFastSegMax / 32; ++j) ow[j] = (lane + 32 * j < nwords) ? other[lane + 32 * j] : 0u;
+      for (int j = 0; j < kFastSegMax / 32; ++j) ow[j] = (lane + 32 * j < nwords) ? __ldcg(other + lane + 32 * j) : 0u;
       int acc = 0;
 #pragma unroll
       for (int j = 0; j < kFastSegMax / 32; ++j)
@@ -353,76 +355,6 @@ __global__ void __launch_bounds__(256) k_colstats_server(const __grid_constant__
     last = s;
     t_idle = clock64();
   }
-}
-
-// ---- sparse corrections for imputed cells (the dense columns hold 0 there) -------------------
-struct ColMissArgs {
-  const int64_t* snp_local;      // m_c + k entries: local index of each involved SNP, -1 if not local
-  const uint32_t* const* cols;   // m_c + k packed columns (candidates first)
-  const int64_t* off; const int32_t* idx; const int8_t* val;
-  int m_c, k, m_e;
-  int64_t n;
-  const double* y; const double* e;
-  double* out;                   // [m_c][n_tasks] final (segment-summed) results, corrected in place
-};
-
-__device__ __forceinline__ double value_with_overlay(const ColMissArgs& a, int which, int64_t i)
-{
-  // genotype of involved SNP `which` at individual i including the chain's imputed value
-  const int64_t j = a.snp_local[which];
-  if (j >= 0) {
-    int64_t lo = a.off[j], hi = a.off[j + 1];
-    while (lo < hi) {
-      const int64_t mid = (lo + hi) >> 1;
-      const int32_t v = a.idx[mid];
-      if (v == (int32_t)i) return (double)a.val[mid];
-      if (v < (int32_t)i) lo = mid + 1; else hi = mid;
-    }
-  }
-  return (double)((a.cols[which][i >> 4] >> (2 * (i & 15))) & 3u);
-}
-
-// one thread per (candidate c, task); serial over the few imputed cells involved
-__global__ void k_column_stats_missfix(const ColMissArgs a)
-{
-  const int n_tasks = a.m_e + 1 + a.k + a.m_c;
-  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= a.m_c * n_tasks) return;
-  const int c = gid / n_tasks, task = gid % n_tasks;
-  const int64_t jc = a.snp_local[c];
-  double corr = 0.0;
-  if (task <= a.m_e) {
-    if (jc >= 0) {
-      const double* vec = task == 0 ? a.y : a.e + (int64_t)(task - 1) * a.n;
-      for (int64_t q = a.off[jc]; q < a.off[jc + 1]; ++q) corr += (double)a.val[q] * vec[a.idx[q]];
-    }
-  } else {
-    const int q2 = task - a.m_e - 1;
-    const int other = q2 < a.k ? a.m_c + q2 : q2 - a.k;   // index into the involved-SNP list
-    const int64_t jo = a.snp_local[other];
-    // cells imputed in c: val_c * x_other(i) (x_other with ITS overlay)
-    if (jc >= 0)
-      for (int64_t q = a.off[jc]; q < a.off[jc + 1]; ++q)
-        if (a.val[q]) corr += (double)a.val[q] * value_with_overlay(a, other, a.idx[q]);
-    // cells imputed in other but observed in c: x_c(i) * val_other
-    if (jo >= 0 && other != c)
-      for (int64_t q = a.off[jo]; q < a.off[jo + 1]; ++q) {
-        if (!a.val[q]) continue;
-        const int64_t i = a.idx[q];
-        bool c_missing = false;
-        if (jc >= 0) {
-          int64_t lo = a.off[jc], hi = a.off[jc + 1];
-          while (lo < hi) {
-            const int64_t mid = (lo + hi) >> 1;
-            const int32_t v = a.idx[mid];
-            if (v == (int32_t)i) { c_missing = true; break; }
-            if (v < (int32_t)i) lo = mid + 1; else hi = mid;
-          }
-        }
-        if (!c_missing) corr += (double)((a.cols[c][i >> 4] >> (2 * (i & 15))) & 3u) * (double)a.val[q];
-      }
-  }
-  if (corr != 0.0) a.out[(int64_t)c * n_tasks + task] += corr;
 }
 
 __global__ void k_sum_segments(const double* __restrict__ seg_out, int m_c, int n_seg, int n_tasks, double* __restrict__ out)
@@ -585,13 +517,15 @@ void chain_column_stats_launch(Chain* c, const int64_t* cand, int m_c, const int
   cudaStream_t st = c->stream;
   const int n_tasks = s->m_e + 1 + k + m_c;
   const int n_seg = (int)((s->W + kSegWords - 1) / kSegWords);
-  bool any_missing_fast = false;
-  if (s->n_missing > 0)
-    for (int i = 0; i < m_c + k && !any_missing_fast; ++i) {
-      const int64_t snp = i < m_c ? cand[i] : loci[i - m_c];
-      if (s->is_local(snp) && s->h_miss_off[snp - s->lo + 1] > s->h_miss_off[snp - s->lo]) any_missing_fast = true;
-    }
-  if (m_c + k <= kInlinePtrs && s->m_e + 1 <= 8 && !any_missing_fast && getenv("BMG_COLSTATS_SLOW") == nullptr) {
+  // columns as the chain sees them: a SNP with missing calls is read from its patched copy (overlay.cu), built here
+  // if it is not cached; every kernel below then treats all columns alike
+  std::vector<int64_t>& involved = c->cs_involved;
+  involved.assign(cand, cand + m_c);
+  involved.insert(involved.end(), loci, loci + k);
+  std::vector<const uint32_t*>& colp = c->cs_colp;
+  colp.resize(m_c + k);
+  const int patched = chain_overlay_columns(c, involved.data(), m_c + k, colp.data());
+  if (m_c + k <= kInlinePtrs && s->m_e + 1 <= 8 && getenv("BMG_COLSTATS_SLOW") == nullptr) {
     // many small CTAs (one per candidate and 1024- or 4096-individual slice): one round of memory latency each
     const int seg_words = s->W <= 4096 ? 64 : kFastSegMax;
     const int n_seg = (int)((s->W + seg_words - 1) / seg_words);
@@ -604,11 +538,12 @@ void chain_column_stats_launch(Chain* c, const int64_t* cand, int m_c, const int
       if (c->cs_seq >= 0xFFFFFFF0u) { chain_server_stop(c); c->cs_seq = 0; }
     }
     ColStatInline a;
-    for (int i = 0; i < m_c + k; ++i) a.cols[i] = s->column_ptr(i < m_c ? cand[i] : loci[i - m_c]);
+    for (int i = 0; i < m_c + k; ++i) a.cols[i] = colp[i];
     a.m_c = m_c; a.k = k; a.m_e = s->m_e; a.n = s->n; a.W = s->W; a.n_seg = n_seg; a.seg_words = seg_words; a.y = c->y.p; a.e = s->e.p;
     a.out_host = reinterpret_cast<ulonglong2*>(c->cs_map.p);
     a.seq = ++c->cs_seq;
     if (c->server_enabled) {
+      if (patched > 0) BMG_CUDA(cudaStreamSynchronize(st));   // the server runs on its own stream: columns must be complete
       server_post(c, a);
       ++c->server_requests;
     } else {
@@ -627,19 +562,12 @@ void chain_column_stats_launch(Chain* c, const int64_t* cand, int m_c, const int
   chain_server_stop(c);   // the general path allocates and synchronises
   const size_t need = (size_t)m_c * n_tasks * (n_seg + 1);
   if (c->cs_out.n < need) { c->cs_out.alloc(need * 2); c->h_cs.alloc(need * 2); }
-  const size_t n_ptr = (size_t)(m_c + k) * 2;
+  const size_t n_ptr = (size_t)(m_c + k);
   if (c->cs_idx.n < n_ptr + 16) c->cs_idx.alloc(n_ptr * 2 + 4096);
   if (c->h_stage_i.n < n_ptr + 16) c->h_stage_i.alloc(n_ptr * 2 + 4096);
   BMG_CUDA(cudaStreamSynchronize(st));
   int64_t* hp = c->h_stage_i.p;
-  bool any_missing = false;
-  for (int i = 0; i < m_c + k; ++i) {
-    const int64_t snp = i < m_c ? cand[i] : loci[i - m_c];
-    hp[i] = (int64_t)(uintptr_t)s->column_ptr(snp);
-    const int64_t j = s->is_local(snp) ? snp - s->lo : -1;
-    hp[m_c + k + i] = j;
-    if (j >= 0 && s->h_miss_off[j + 1] > s->h_miss_off[j]) any_missing = true;
-  }
+  for (int i = 0; i < m_c + k; ++i) hp[i] = (int64_t)(uintptr_t)colp[i];
   bmg::copy_h2d(c->cs_idx.p, hp, n_ptr * sizeof(int64_t), st);
   ColStatArgs a;
   a.cand_cols = reinterpret_cast<const uint32_t* const*>(c->cs_idx.p);
@@ -652,15 +580,6 @@ void chain_column_stats_launch(Chain* c, const int64_t* cand, int m_c, const int
   count_launch();
   if (n_seg > 1) {
     k_sum_segments<<<(m_c * n_tasks + 127) / 128, 128, 0, st>>>(seg_out, m_c, n_seg, n_tasks, fin);
-    count_launch();
-  }
-  if (any_missing) {
-    ColMissArgs ma;
-    ma.snp_local = c->cs_idx.p + (m_c + k);
-    ma.cols = reinterpret_cast<const uint32_t* const*>(c->cs_idx.p);
-    ma.off = s->miss_off.p; ma.idx = s->miss_idx.p; ma.val = c->miss_val.p;
-    ma.m_c = m_c; ma.k = k; ma.m_e = s->m_e; ma.n = s->n; ma.y = c->y.p; ma.e = s->e.p; ma.out = fin;
-    k_column_stats_missfix<<<(m_c * n_tasks + 63) / 64, 64, 0, st>>>(ma);
     count_launch();
   }
   BMG_CUDA(cudaGetLastError());

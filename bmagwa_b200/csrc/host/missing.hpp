@@ -76,13 +76,16 @@ inline void rows_missing_in_model(const MissingCells& mc, const std::vector<uint
 // Sampler::sample_missing (sampler.cpp:264-453), effect type A.
 //   cur    current model; xx and xy are patched in place (sampler.cpp:393-450), mu_beta_computed is cleared
 //   rows   rows_missing_in_model(...) (q of them); cells = k x q genotype values with the chain's imputed values
-//          applied, as they are BEFORE this update (bmg_chain_get_cells over cur.loci)
+//          applied, as they are BEFORE this update, bit 2 set where the cell is a missing call (bmg_chain_get_cells
+//          over cur.loci)
+//   slot   scratch of n entries, all -1 on entry and on return (individual -> position in rows)
 //   y, e   phenotype (n) and covariates (n x m_e, column-major, ones column included)
 //   yy     y'y.  The reference sums the squared residual over all n individuals; here r'r comes from the Gram
 //          matrix, r'r = y'y - 2 b'X'y + b'X'X b (it only enters through differences in which it cancels).
 // On return mc.val holds the new imputed values of the in-model SNPs.
 inline void gibbs_missing_in_model(Model& cur, MissingCells& mc, const std::vector<int32_t>& rows, const int8_t* cells,
-                                   const double* y, const double* e, size_t n, double yy, ChainRng& rng)
+                                   const double* y, const double* e, size_t n, double yy, ChainRng& rng,
+                                   std::vector<int32_t>& slot)
 {
   const int m_e = cur.m_e, cols = cur.cols(), k = (int)cur.size();
   const size_t q = rows.size();
@@ -96,7 +99,7 @@ inline void gibbs_missing_in_model(Model& cur, MissingCells& mc, const std::vect
   for (size_t u = 0; u < q; ++u) {
     double* row = &xold[u * cols];
     for (int c = 0; c < m_e; ++c) row[c] = e[(size_t)c * n + rows[u]];
-    for (int l = 0; l < k; ++l) row[m_e + l] = (double)cells[(size_t)l * q + u];
+    for (int l = 0; l < k; ++l) row[m_e + l] = (double)(cells[(size_t)l * q + u] & 3);
     double s = 0.0;   // y_hat = X beta, accumulated column by column like the dgemv of Vector::set_to_product
     for (int c = 0; c < cols; ++c) s += beta[c] * row[c];
     y_hat[u] = s;
@@ -107,7 +110,9 @@ inline void gibbs_missing_in_model(Model& cur, MissingCells& mc, const std::vect
   for (int c = 0; c < cols; ++c) r2 -= 2.0 * beta[c] * cur.xy[c];
   r2 += cur.quad(0, cols);
 
-  auto slot_of = [&](int32_t individual) { return (size_t)(std::lower_bound(rows.begin(), rows.end(), individual) - rows.begin()); };
+  if (slot.size() != n) slot.assign(n, -1);
+  for (size_t u = 0; u < q; ++u) slot[rows[u]] = (int32_t)u;
+  auto slot_of = [&](int32_t individual) { return (size_t)slot[individual]; };
 
   double lprior[3], likelihood[3];
   for (int t = 0; t < k; ++t) {
@@ -153,10 +158,11 @@ inline void gibbs_missing_in_model(Model& cur, MissingCells& mc, const std::vect
       cur.xy[x_ind] += y[i_miss] * (xn[x_ind] - xo[x_ind]);
       int j = 0;
       for (; j < x_ind; ++j)   // a column that is itself missing here is patched when its own cell comes up
-        if (j < m_e || !mc.is_missing(i_miss, cur.loci[j - m_e])) cur.xx(j, x_ind) += xn[x_ind] * xn[j] - xo[x_ind] * xo[j];
+        if (j < m_e || !(cells[(size_t)(j - m_e) * q + u] & 4)) cur.xx(j, x_ind) += xn[x_ind] * xn[j] - xo[x_ind] * xo[j];
       for (; j < cols; ++j) cur.xx(x_ind, j) += xn[x_ind] * xn[j] - xo[x_ind] * xo[j];
     }
   }
+  for (size_t u = 0; u < q; ++u) slot[rows[u]] = -1;
 }
 
 }  // namespace bmg

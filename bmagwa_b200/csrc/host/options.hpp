@@ -125,6 +125,7 @@ struct Options {
   std::string tau_rng = "host";   // "host": per-SNP tau draws from the chain's stream in reference order (parity);
                                   // "device": counter-based draws on the GPU (throughput)
   int device = 0;
+  size_t pip_burnin = 0;          // thinned samples dropped before the running inclusion counts start ([b200] pip_burnin)
   bool quiet = false;
 
   explicit Options(const std::string& path, bool quiet_ = false) : quiet(quiet_)
@@ -324,6 +325,7 @@ struct Options {
     if (tr != "host" && tr != "device") throw std::runtime_error("Config error: b200.tau_rng must be host or device");
     tau_rng = tr;
     probit = r.get("b200", "probit", "0") != "0";
+    pip_burnin = convert<size_t>(r.get("b200", "pip_burnin", "0"));
     const std::string dv = r.get("b200", "device", "0");
     device = convert<int>(dv);
   }

@@ -124,6 +124,8 @@ Sampler::Sampler(const Options& opts, int chain_index, Store* store, const std::
   proposal_.init((int)m_e_, exx, exy, prior_.get());
   pos_in_current_.assign(m_g_, -1);
   pos_in_proposal_.assign(m_g_, -1);
+  incl_count_.assign(m_g_, 0);
+  pip_burnin_ = (int64_t)opts.pip_burnin;
 
   chain_ = chain_create(store_);
   if (comm != nullptr) chain_set_sharded(chain_, comm->world, comm->rank, comm->stride, comm->allgather, comm->ctx);
@@ -181,14 +183,19 @@ void Sampler::load_missing_index()
 std::vector<double> Sampler::draw_for_additions(const std::vector<uint32_t>& cand)
 {
   std::vector<double> taus(cand.size());
+  std::vector<int64_t> snps;
+  std::vector<const int8_t*> vals;
   for (size_t i = 0; i < cand.size(); ++i) {
     const uint32_t snp = cand[i];
     if (miss_.count(snp) > 0) {   // DataModel::sample_missing_single (data_model.cpp:95-103)
       miss_.draw_from_prior(snp, rng_);
-      chain_set_missing(chain_, snp, miss_.val.data() + miss_.off[snp], miss_.count(snp));
+      snps.push_back(snp);
+      vals.push_back(miss_.val.data() + miss_.off[snp]);
     }
     taus[i] = prior_->draw_inv_tau2_alpha2(rng_);
   }
+  // one launch for the whole move: values to the device and the SNPs' packed columns with the values filled in
+  if (!snps.empty()) chain_set_missing_many(chain_, snps.data(), (int)snps.size(), vals.data());
   return taus;
 }
 
@@ -197,6 +204,8 @@ std::vector<double> Sampler::draw_for_additions(const std::vector<uint32_t>& can
 void Sampler::sample_missing()
 {
   if (!have_missing_ || current_.size() == 0) return;
+  const double t0 = wall_seconds();
+  struct Toc { double& acc; double t0; ~Toc() { acc += wall_seconds() - t0; } } toc{gibbs_seconds_, t0};
   rows_missing_in_model(miss_, current_.loci, gibbs_rows_);
   if (gibbs_rows_.empty()) return;
   const int k = (int)current_.size();
@@ -211,9 +220,12 @@ void Sampler::sample_missing()
     BMG_CUDA(cudaStreamSynchronize(chain_->stream));
     yv = y_work_.data();
   }
-  gibbs_missing_in_model(current_, miss_, gibbs_rows_, gibbs_cells_.data(), yv, e_host_->data(), n_, yy_, rng_);
+  gibbs_missing_in_model(current_, miss_, gibbs_rows_, gibbs_cells_.data(), yv, e_host_->data(), n_, yy_, rng_, gibbs_slot_);
+  std::vector<int64_t> snps;
+  std::vector<const int8_t*> vals;
   for (uint32_t snp : current_.loci)
-    if (miss_.count(snp) > 0) chain_set_missing(chain_, snp, miss_.val.data() + miss_.off[snp], miss_.count(snp));
+    if (miss_.count(snp) > 0) { snps.push_back(snp); vals.push_back(miss_.val.data() + miss_.off[snp]); }
+  chain_set_missing_many(chain_, snps.data(), (int)snps.size(), vals.data());
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -292,6 +304,12 @@ void Sampler::set_option(const std::string& key, const std::string& value)
   if (key == "tau_rng") {
     if (value != "host" && value != "device") throw std::runtime_error("tau_rng must be host or device");
     tau_on_device_ = value == "device";
+  } else if (key == "missing_rng") {
+    if (value != "host" && value != "device") throw std::runtime_error("missing_rng must be host or device");
+    missing_on_device_ = value == "device";
+  } else if (key == "pip_burnin") {
+    pip_burnin_ = (int64_t)std::stoll(value);
+    if (pip_burnin_ < 0) throw std::runtime_error("pip_burnin must be >= 0");
   } else if (key == "basename") {
     basename_ = value;
   } else if (key == "verbosity") {
@@ -539,6 +557,10 @@ void Sampler::run(int64_t do_n_iter)
       const uint32_t n_loci = (uint32_t)current_.size();
       f.modelsize.write(reinterpret_cast<const char*>(&n_loci), sizeof(n_loci));
       f.loci.write(reinterpret_cast<const char*>(current_.loci.data()), n_loci * sizeof(uint32_t));
+      if (thinned_seen_++ >= pip_burnin_) {   // running MCMC inclusion counts (bmagwa_postprocess.py:94-103)
+        ++incl_samples_;
+        for (uint32_t snp : current_.loci) ++incl_count_[snp];
+      }
       f.log_likelihood.write(reinterpret_cast<const char*>(&current_.log_likelihood), sizeof(double));
       const double log_prior = prior_->log_model((int)n_loci);
       f.log_prior.write(reinterpret_cast<const char*>(&log_prior), sizeof(double));
@@ -586,8 +608,16 @@ void Sampler::rao_block()
   const bool do_scan = !flat_proposal_dist_ || n_rao_burnin_ <= 0;
   if (do_scan) {
     if (have_missing_) {   // DataModel::sample_missing (sampler.cpp:733): every SNP outside the model is imputed again from its prior
-      miss_.draw_all_from_prior([this](size_t snp) { return pos_in_current_[snp] >= 0; }, rng_);
-      chain_set_missing_all(chain_, miss_.val.data(), (int64_t)miss_.val.size());
+      const bool on_device = missing_on_device_ < 0 ? tau_on_device_ : missing_on_device_ != 0;
+      if (on_device) {
+        // the host mirror of SNPs outside the model goes stale; it is never read: a SNP entering the model gets fresh
+        // values in draw_for_additions, and the Gibbs step reads its cells from the device
+        std::vector<int64_t> in_model(current_.loci.begin(), current_.loci.end());
+        chain_impute_from_prior(chain_, in_model.data(), (int)in_model.size(), (uint64_t)seed_ * 0x9E3779B97F4A7C15ull + 29u, ++impute_counter_);
+      } else {
+        miss_.draw_all_from_prior([this](size_t snp) { return pos_in_current_[snp] >= 0; }, rng_);
+        chain_set_missing_all(chain_, miss_.val.data(), (int64_t)miss_.val.size());
+      }
     }
     const double t0 = wall_seconds();
     const int k = (int)current_.size();
@@ -667,8 +697,8 @@ void Sampler::end()
   if (getenv("BMG_TIMING"))
     std::cerr << "[bmg timing] iterations " << n_iter_ << " moves " << move_seconds_ << " s, of which column-stats wait "
               << device_wait_seconds_ << " s, move-0 delayed rejection " << dr_seconds_ << " s (" << n_dr_ << " events); scans "
-              << scan_seconds_ << " s, scan epilogue (adapt + weights to the host, waits for the scan) " << epilogue_seconds_ << " s"
-              << std::endl;
+              << scan_seconds_ << " s, scan epilogue (adapt + weights to the host, waits for the scan) " << epilogue_seconds_ << " s; missing-genotype Gibbs step "
+              << gibbs_seconds_ << " s" << std::endl;
   // _rao.dat (sampler.cpp:847-849): the running mean kept on the device
   p_rao_.assign(m_g_, 0.0);
   BMG_CUDA(cudaSetDevice(store_->device));
@@ -682,6 +712,12 @@ void Sampler::end()
   }
   files_.reset();
   begun_ = false;
+}
+
+int64_t Sampler::inclusion_counts(uint32_t* counts) const
+{
+  if (counts) std::copy(incl_count_.begin(), incl_count_.end(), counts);
+  return incl_samples_;
 }
 
 void Sampler::stats(double* out8) const

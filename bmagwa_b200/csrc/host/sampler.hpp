@@ -42,6 +42,9 @@ class Sampler {
   void run(int64_t n_iter);            // sampler.cpp:625-834
   void end();                          // sampler.cpp:836-879
   void stats(double* out8) const;
+  // inclusion counts over the thinned samples after pip_burnin (what bmagwa_postprocess.py mcmcpos recomputes offline
+  // from _loci.dat / _modelsize.dat, bmagwa_postprocess.py:79-123)
+  int64_t inclusion_counts(uint32_t* counts) const;
   Chain* chain() { return chain_; }
   Store* store() { return store_; }
 
@@ -91,11 +94,13 @@ class Sampler {
   MoveGram gram_;
   // ---- book-keeping (samplerstats.hpp)
   unsigned long n_upd_add_ = 0, n_upd_rem_ = 0, n_comp_ = 0;
-  double move_seconds_ = 0.0, scan_seconds_ = 0.0, device_wait_seconds_ = 0.0, dr_seconds_ = 0.0, epilogue_seconds_ = 0.0;
+  double move_seconds_ = 0.0, scan_seconds_ = 0.0, device_wait_seconds_ = 0.0, dr_seconds_ = 0.0, epilogue_seconds_ = 0.0, gibbs_seconds_ = 0.0;
   size_t n_dr_ = 0;
   size_t n_scans_ = 0;
   double t_start_ = 0.0;
   double pves_[3] = {0, 0, 0};
+  std::vector<uint32_t> incl_count_;   // per SNP: thinned samples (after pip_burnin_) with the SNP in the model
+  int64_t incl_samples_ = 0, thinned_seen_ = 0, pip_burnin_ = 0;
   uint64_t tau_counter_ = 0;
   // what Model::compute_pve leaves in y_hat (model.hpp:345-392), tracked as coefficients: y_hat = X[loci] beta_g + E beta_e.
   // Reference quirk kept for drop-in parity: with covariates and NO SNP term in the model compute_pve does not reset
@@ -126,8 +131,10 @@ class Sampler {
   // (missing.hpp), the device copy follows through bmg_chain_set_missing[_all]
   MissingCells miss_;
   bool have_missing_ = false;
+  int missing_on_device_ = -1;         // re-imputation before scans: 0 host stream (parity), 1 device, -1 follow tau_rng
+  uint64_t impute_counter_ = 0;
   double yy_ = 0.0;                    // y'y of the working phenotype
-  std::vector<int32_t> gibbs_rows_;
+  std::vector<int32_t> gibbs_rows_, gibbs_slot_;
   std::vector<int8_t> gibbs_cells_;
   std::vector<double> y_work_;         // probit mode: host copy of the latent phenotype for the Gibbs step
   void load_missing_index();

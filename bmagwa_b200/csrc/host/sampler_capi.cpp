@@ -202,6 +202,13 @@ BMG_API int bmg_sampler_stats(bmg_sampler* sp, double* out8)
   H(sp)->sampler->stats(out8);
   BMG_CATCH
 }
+BMG_API int bmg_sampler_inclusion_counts(bmg_sampler* sp, uint32_t* counts, int64_t* n_samples)
+{
+  BMG_TRY
+  const int64_t ns = H(sp)->sampler->inclusion_counts(counts);
+  if (n_samples) *n_samples = ns;
+  BMG_CATCH
+}
 BMG_API bmg_store* bmg_sampler_store(bmg_sampler* sp) { return sp ? reinterpret_cast<bmg_store*>(reinterpret_cast<SamplerHandle*>(sp)->store) : nullptr; }
 BMG_API bmg_chain* bmg_sampler_chain(bmg_sampler* sp)
 {

@@ -20,6 +20,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 #include "common.cuh"
 #include "store.cuh"
 #include "philox.cuh"
@@ -329,15 +330,6 @@ __global__ void k_yhat(const YhatArgs a)
       a.yhat_g[i] = g[p];
     }
   }
-}
-
-// imputed cells of in-model SNPs (the dense column holds 0 there): yhat_g[idx] += beta * val
-__global__ void k_yhat_missfix(const int32_t* __restrict__ idx, const int8_t* __restrict__ val, int64_t cnt, double beta,
-                               double* __restrict__ yhat_g)
-{
-  const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (q >= cnt) return;
-  if (val[q]) atomicAdd(&yhat_g[idx[q]], beta * (double)val[q]);
 }
 
 constexpr int kRed = 9;
@@ -654,13 +646,10 @@ void chain_set_missing(Chain* c, int64_t snp, const int8_t* vals, int64_t count)
 {
   Store* s = c->store;
   BMG_REQUIRE(s->is_local(snp), "bmg_chain_set_missing: SNP not in the local shard");
-  const int64_t j = snp - s->lo, lo = s->h_miss_off[j], cnt = s->h_miss_off[j + 1] - lo;
+  const int64_t j = snp - s->lo, cnt = s->h_miss_off[j + 1] - s->h_miss_off[j];
   BMG_REQUIRE(cnt == count, "bmg_chain_set_missing: count does not match the number of missing cells of the SNP");
   if (cnt == 0) return;
-  for (int64_t q = 0; q < cnt; ++q) BMG_REQUIRE(vals[q] >= 0 && vals[q] <= 2, "bmg_chain_set_missing: values must be 0, 1 or 2");
-  BMG_CUDA(cudaSetDevice(s->device));
-  bmg::copy_h2d(c->miss_val.p + lo, vals, (size_t)cnt, c->stream);
-  BMG_CUDA(cudaStreamSynchronize(c->stream));
+  chain_set_missing_many(c, &snp, 1, &vals);   // overlay.cu: values to the device + the SNP's patched column, one launch
 }
 
 // DataModel::sample_missing (data_model.cpp:78-90) draws every cell again before a scan: one upload for the shard
@@ -675,6 +664,54 @@ void chain_set_missing_all(Chain* c, const int8_t* vals, int64_t count)
   BMG_CUDA(cudaSetDevice(s->device));
   bmg::copy_h2d(c->miss_val.p, vals, (size_t)count, c->stream);
   BMG_CUDA(cudaStreamSynchronize(c->stream));
+  chain_overlay_invalidate(c, nullptr, 0);   // the caller may have changed any SNP
+}
+
+// DataModel::sample_missing on the device (throughput mode; the parity mode draws on the host from the chain's own
+// stream): one warp per SNP with missing calls, a counter-based uniform per cell, class from the cumulative counts of
+// 0/1/2 among the SNP's observed cells (data.cpp:357-372).  SNPs of the model (sorted list) keep their values.
+__global__ void k_impute_from_prior(const int64_t* __restrict__ off, const int32_t* __restrict__ n1,
+                                    const int32_t* __restrict__ n2, const int32_t* __restrict__ nmiss, int64_t n, int64_t m,
+                                    int64_t snp_lo, const int64_t* __restrict__ model_sorted, int k, uint64_t seed,
+                                    uint64_t counter, int8_t* __restrict__ val)
+{
+  const int64_t j = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (j >= m) return;
+  const int64_t lo = off[j], hi = off[j + 1];
+  if (hi == lo) return;
+  int a = 0, b = k;
+  while (a < b) {
+    const int mid = (a + b) >> 1;
+    const int64_t v = model_sorted[mid];
+    if (v == j + snp_lo) return;   // in the model: left to the Gibbs step
+    if (v < j + snp_lo) a = mid + 1; else b = mid;
+  }
+  const double c0 = (double)(n - nmiss[j] - n1[j] - n2[j]), c1 = c0 + (double)n1[j], c2 = c1 + (double)n2[j];
+  for (int64_t q = lo + lane; q < hi; q += 32) {
+    Philox g(seed, counter, (uint64_t)q);
+    const double r = g.u01() * c2;
+    val[q] = (int8_t)(r < c0 ? 0 : (r < c1 ? 1 : 2));
+  }
+}
+
+void chain_impute_from_prior(Chain* c, const int64_t* loci, int k, uint64_t seed, uint64_t counter)
+{
+  Store* s = c->store;
+  if (s->n_missing == 0) return;
+  BMG_REQUIRE(k >= 0 && k <= 2048, "bmg_chain_impute_from_prior: model size must be <= 2048");
+  BMG_CUDA(cudaSetDevice(s->device));
+  cudaStream_t st = c->stream;
+  BMG_CUDA(cudaStreamSynchronize(st));   // the pinned staging buffer may still be in flight
+  for (int l = 0; l < k; ++l) c->h_stage_i.p[l] = loci[l];
+  std::sort(c->h_stage_i.p, c->h_stage_i.p + k);
+  if (k) bmg::copy_h2d(c->loci_dev.p, c->h_stage_i.p, k * sizeof(int64_t), st);
+  k_impute_from_prior<<<(unsigned)((s->m * 32 + 127) / 128), 128, 0, st>>>(s->miss_off.p, s->n1.p, s->n2.p, s->nmiss.p, s->n, s->m,
+                                                                          s->lo, c->loci_dev.p, k, seed, counter, c->miss_val.p);
+  count_launch();
+  BMG_CUDA(cudaGetLastError());
+  BMG_CUDA(cudaStreamSynchronize(st));   // loci_dev / the staging buffer are reused by the scan that follows
+  chain_overlay_invalidate(c, loci, k);  // the model's SNPs kept their values
 }
 
 // ---------------------------------------------------------------------------------------
@@ -706,7 +743,7 @@ __global__ void k_gather_cells(const CellArgs a)
     while (lo < hi) {
       const int64_t mid = (lo + hi) >> 1;
       const int32_t w = a.idx[mid];
-      if (w == i) { v = a.val[mid]; break; }
+      if (w == i) { v = a.val[mid] | 4; break; }   // bit 2: the cell is a missing call, its value is imputed
       if (w < i) lo = mid + 1; else hi = mid;
     }
   }
@@ -780,7 +817,12 @@ void chain_residual(Chain* c, const int64_t* loci, const double* beta_e, const d
   for (int j = 0; j < s->m_e; ++j) c->h_stage.p[4096 + j] = beta_e[j];
   bmg::copy_h2d(c->beta_dev.p + 2048, c->h_stage.p + 4096, s->m_e * sizeof(double), st);
   static_assert(sizeof(const uint32_t*) == sizeof(int64_t), "pointer size");
-  for (int l = 0; l < k; ++l) c->h_stage_i.p[2048 + l] = (int64_t)(uintptr_t)s->column_ptr(loci[l]);
+  {
+    // columns as the chain sees them: a SNP with missing calls is read from its patched copy (overlay.cu)
+    std::vector<const uint32_t*> cols(k);
+    chain_overlay_columns(c, loci, k, cols.data());
+    for (int l = 0; l < k; ++l) c->h_stage_i.p[2048 + l] = (int64_t)(uintptr_t)cols[l];
+  }
   if (c->cs_idx.n < 4096) c->cs_idx.alloc(4096);
   if (k) bmg::copy_h2d(c->cs_idx.p, c->h_stage_i.p + 2048, k * sizeof(int64_t), st);
   YhatArgs ya;
@@ -789,16 +831,6 @@ void chain_residual(Chain* c, const int64_t* loci, const double* beta_e, const d
   ya.k = k; ya.m_e = s->m_e; ya.n = s->n; ya.W = s->W; ya.yhat_e = c->yhat_e.p; ya.yhat_g = c->yhat_g.p;
   k_yhat<<<(unsigned)((s->W + 127) / 128), 128, 0, st>>>(ya);
   count_launch();
-  if (s->n_missing > 0) {
-    for (int l = 0; l < k; ++l) {
-      if (!s->is_local(loci[l])) continue;  // peers' imputed cells are not visible here (out of scope)
-      const int64_t j = loci[l] - s->lo, lo = s->h_miss_off[j], cnt = s->h_miss_off[j + 1] - lo;
-      if (cnt == 0) continue;
-      k_yhat_missfix<<<(unsigned)((cnt + 127) / 128), 128, 0, st>>>(s->miss_idx.p + lo, c->miss_val.p + lo, cnt, beta_g[l],
-                                                                    c->yhat_g.p);
-      count_launch();
-    }
-  }
   const int64_t n_pad = (int64_t)c->r_scaled.n;
   int blocks = (int)std::min<int64_t>(1024, (n_pad + 255) / 256);
   k_residual<<<blocks, 256, 0, st>>>(c->y.p, c->yhat_e.p, c->yhat_g.p, s->n, n_pad, c->r.p, c->r_scaled.p, c->red_partial.p);

@@ -1,6 +1,8 @@
 // store.cuh -- internal C++ interface between the modules of libbmagwa_b200.so
 #pragma once
 #include <memory>
+#include <unordered_map>
+#include <utility>
 #include "common.cuh"
 #include "../../include/bmagwa_b200.h"
 
@@ -17,6 +19,16 @@ void store_get_column(const Store* s, int64_t snp, int type, const int8_t* miss_
 // ---- chain state (scan.cu, colstats.cu, weights.cu, probit.cu)
 // host-supplied all-gather over the ranks of a SNP-sharded chain (include/bmagwa_b200.h: bmg_allgather_fn)
 typedef int (*AllGatherFn)(void* ctx, void* dev_buffer, int64_t elems_per_rank, int elem_bytes, void* cuda_stream);
+
+// one column to (re)build in the overlay cache (overlay.cu)
+struct PatchDesc {
+  const uint32_t* src;   // store column
+  uint32_t* dst;         // cache slot
+  const int32_t* idx;    // individuals of the SNP's missing cells
+  const int8_t* vals;    // their imputed values: mapped host staging, or the chain's device array
+  int8_t* keep;          // where to store the values on the device (nullptr: they are already there)
+  int64_t cnt;
+};
 
 struct Chain {
   Store* store = nullptr;
@@ -69,6 +81,15 @@ struct Chain {
   // per-chain imputed values of the missing cells (same CSR as the store)
   DevBuf<int8_t> miss_val;
   DevBuf<double> miss_corr;                     // 3 per local SNP: (dot corr, sum val, sum val^2)
+  // packed columns with the imputed values filled in (overlay.cu)
+  DevBuf<uint32_t> pc_cols;                     // pc_slots x store->Wp words
+  int pc_slots = 0, pc_next = 0;
+  unsigned int pc_seq = 0;
+  std::vector<int64_t> pc_snp;                  // slot -> local SNP, -1 free
+  std::vector<unsigned int> pc_use;             // slot -> sequence number of the last request that used it
+  std::unordered_map<int64_t, int> pc_map;      // local SNP -> slot
+  std::vector<PatchDesc> pc_pending;
+  PinnedBuf<int8_t> pc_h_vals;                  // mapped staging of new imputed values, read by k_patch_columns
   // scratch of chain_get_cells (values of a few (SNP, individual) cells for the missing-genotype Gibbs step)
   DevBuf<int64_t> gc_meta;                      // k column pointers, then k local SNP indices
   DevBuf<int32_t> gc_rows;
@@ -95,6 +116,8 @@ struct Chain {
   DevBuf<double> sample_out;                    // {snp, total}
   PinnedBuf<double> h_sample;
   // column statistics scratch
+  std::vector<int64_t> cs_involved;
+  std::vector<const uint32_t*> cs_colp;
   DevBuf<double> cs_out;
   PinnedBuf<double> h_cs;
   DevBuf<int64_t> cs_idx;
@@ -121,7 +144,11 @@ struct Chain {
 Chain* chain_create(Store* s);
 void chain_destroy(Chain* c);
 void chain_set_missing(Chain* c, int64_t snp, const int8_t* vals, int64_t count);
+void chain_set_missing_many(Chain* c, const int64_t* snps, int count, const int8_t* const* vals);
+int chain_overlay_columns(Chain* c, const int64_t* snps, int count, const uint32_t** out, const int8_t* const* host_vals = nullptr);
+void chain_overlay_invalidate(Chain* c, const int64_t* keep, int k);
 void chain_set_missing_all(Chain* c, const int8_t* vals, int64_t count);
+void chain_impute_from_prior(Chain* c, const int64_t* loci, int k, uint64_t seed, uint64_t counter);
 void chain_get_cells(Chain* c, const int64_t* loci, int k, const int32_t* rows, int64_t q, int8_t* out);
 void chain_residual(Chain* c, const int64_t* loci, const double* beta_e, const double* beta_g, int k, double* stats9);
 void chain_scan_dots(Chain* c);

@@ -109,11 +109,18 @@ int bmg_chain_set_missing(bmg_chain* c, int64_t snp, const int8_t* vals, int64_t
 /* DataModel::sample_missing (data_model.cpp:78-90, re-imputation of every SNP before a scan): the imputed values
  * of ALL missing cells of the local shard in one upload, in the order of bmg_store_missing's idx array. */
 int bmg_chain_set_missing_all(bmg_chain* c, const int8_t* vals, int64_t count);
+/* The same re-imputation drawn on the device (throughput mode): every missing cell of every local SNP that is NOT in
+ * loci[0..k) gets a value from its SNP's prior (cumulative counts of 0/1/2 among the observed cells, data.cpp:357-372)
+ * with a counter-based uniform keyed by (seed, counter, cell).  Not the chain's own stream, so traces differ from the
+ * reference's while the stationary distribution is the same. */
+int bmg_chain_impute_from_prior(bmg_chain* c, const int64_t* loci, int k, uint64_t seed, uint64_t counter);
 /* DataModel::get_genotypes_<type>(snp, v) (data_model.cpp:30-72): overlay applied. */
 int bmg_chain_get_column(bmg_chain* c, int64_t snp, int type, double* out);
-/* The additive value (0, 1, 2; overlay applied) of a few cells: out[l*q + t] = SNP loci[l] at individual rows[t].
- * This is what the missing-genotype Gibbs step reads as current_model->x(i_miss, col) (sampler.cpp:304-449); the
- * design matrix itself does not exist here, so the step gathers the few cells it needs. */
+/* The additive value (0, 1, 2; overlay applied) of a few cells: out[l*q + t] = SNP loci[l] at individual rows[t], in
+ * bits 0-1; bit 2 is set when the cell is a missing call (its value is the chain's imputed one), which is
+ * DataModel::genotype_missing (data_model.hpp:104-117).  This is what the missing-genotype Gibbs step reads as
+ * current_model->x(i_miss, col) (sampler.cpp:304-449); the design matrix itself does not exist here, so the step
+ * gathers the few cells it needs. */
 int bmg_chain_get_cells(bmg_chain* c, const int64_t* loci, int k, const int32_t* rows, int64_t q, int8_t* out);
 
 /* Fitted values and residual for the current model (what Model::compute_pve leaves in y_hat,
@@ -230,7 +237,9 @@ struct bmg_shard_comm {
 int bmg_sampler_create_sharded(const char* ini_path, int chain_index, bmg_store* shard, const struct bmg_shard_comm* comm,
                                bmg_sampler** out);
 /* Overrides applied after the INI file, before bmg_sampler_begin.  Keys: "tau_rng" = host | device (per-SNP tau2 draws
- * of the scan from the chain's stream in reference order, or Philox on the device); "basename" (output files);
+ * of the scan from the chain's stream in reference order, or Philox on the device); "missing_rng" = host | device (the
+ * re-imputation of missing calls before each scan likewise; defaults to tau_rng); "pip_burnin" = thinned samples to drop
+ * before the running inclusion counts start (bmg_sampler_inclusion_counts); "basename" (output files);
  * "verbosity"; "reference_quirks" = 1 | 0 (keep the reference's stale-y_hat behaviour, model.hpp:345-392);
  * "scan_variant" = 2 | 1 | 0; "probit" = 1 (0/1 phenotype, Albert-Chib latent updates on the device; no reference
  * counterpart); "colstats_server" = 1 | 0 (serve the per-move column statistics from one persistent kernel fed through
@@ -245,6 +254,12 @@ int bmg_sampler_end(bmg_sampler* sp);
 /* stats: {iterations done, accepted, model size, log likelihood, seconds in moves,
  * seconds in scans, scans done, seconds of the move time spent waiting for per-proposal column statistics}. */
 int bmg_sampler_stats(bmg_sampler* sp, double* out8);
+/* Running MCMC inclusion counts: counts[j] (m_g entries, may be NULL) = number of thinned samples, after the first
+ * "pip_burnin" of them, whose model contains SNP j; n_samples = how many samples were counted.  counts / n_samples is what
+ * `bmagwa_postprocess.py mcmcpos basename m_g burnin 1` recomputes offline from _loci.dat and _modelsize.dat
+ * (bmagwa_postprocess.py:79-123); chains are merged by averaging (ibid. :118-123; bmagwa_b200.postprocess.merge_chains
+ * does it with one all-reduce across the ranks of a chain-per-GPU run). */
+int bmg_sampler_inclusion_counts(bmg_sampler* sp, uint32_t* counts, int64_t* n_samples);
 bmg_store* bmg_sampler_store(bmg_sampler* sp);
 bmg_chain* bmg_sampler_chain(bmg_sampler* sp);
 int bmg_sampler_destroy(bmg_sampler* sp);

@@ -379,7 +379,36 @@ def run_missing_chains(tmp, out):
             out["%s_%s" % (tag, k)] = v
 
 
+def write_chain_files_for_mcmcpos(directory):
+    """_loci.dat / _modelsize.dat of two committed golden chains (chainC: 300 SNPs without missing calls, chainD: 300
+    SNPs with), as chain0 / chain1 of one run."""
+    g = np.load(os.path.join(HERE, "ref_outputs.npz"))
+    g2 = np.load(os.path.join(HERE, "ref_missing_chains.npz"))
+    for i, (src, tag) in enumerate(((g, "chainC"), (g2, "chainD"))):
+        src[tag + "_loci"].astype(np.uint32).tofile(os.path.join(directory, "chain%d_loci.dat" % i))
+        src[tag + "_modelsize"].astype(np.uint32).tofile(os.path.join(directory, "chain%d_modelsize.dat" % i))
+
+
+def run_mcmcpos():
+    """The reference's own post-processing script (bmagwa_postprocess.py mcmcpos) on those files: its text output is
+    the golden for bmagwa_b200.postprocess."""
+    import subprocess
+    tmp = tempfile.mkdtemp()
+    write_chain_files_for_mcmcpos(tmp)
+    args = dict(nsnps=300, burnin=50, thin=2)
+    subprocess.check_call([sys.executable, os.path.join(REF, "bmagwa_postprocess.py"), "mcmcpos", os.path.join(tmp, "chain"),
+                           str(args["nsnps"]), str(args["burnin"]), str(args["thin"])], stdout=subprocess.DEVNULL)
+    out = {"args": args}
+    for name in ("chain0_mcmcpos.txt", "chain1_mcmcpos.txt", "chain_mcmcpos.txt"):
+        out[name] = open(os.path.join(tmp, name)).read()
+    json.dump(out, open(os.path.join(HERE, "ref_mcmcpos.json"), "w"))
+    print("wrote ref_mcmcpos.json")
+
+
 def main():
+    if "--mcmcpos-only" in sys.argv:
+        run_mcmcpos()
+        return
     if "--missing-only" in sys.argv:   # only ref_missing_chains.npz (the other fixtures stay as committed)
         assert ref.available(), "build oracle/_ref first (make -C oracle ref)"
         out = {}
@@ -408,6 +437,7 @@ def main():
     out2 = {}
     run_missing_chains(tmp, out2)
     np.savez_compressed(os.path.join(HERE, "ref_missing_chains.npz"), **out2)
+    run_mcmcpos()
     print("wrote", len(out), "arrays;", os.path.getsize(os.path.join(HERE, "ref_outputs.npz")), "bytes")
 
 

@@ -36,10 +36,13 @@ int harness_gibbs(int m_e, int k, const unsigned* loci, double* xx, double* xy, 
   const size_t q = rows.size();
   std::vector<int8_t> cells((size_t)k * q);
   for (int l = 0; l < k; ++l)
-    for (size_t u = 0; u < q; ++u) cells[(size_t)l * q + u] = (int8_t)xcols[(size_t)l * n + rows[u]];
+    for (size_t u = 0; u < q; ++u)   // value in bits 0-1, bit 2 = the cell is a missing call (as bmg_chain_get_cells returns)
+      cells[(size_t)l * q + u] = (int8_t)((int)xcols[(size_t)l * n + rows[u]] | (mc.is_missing(rows[u], loci[l]) ? 4 : 0));
   ChainRng rng(seed, nu);
   for (int i = 0; i < skip_draws; ++i) rng.u01();
-  gibbs_missing_in_model(cur, mc, rows, cells.data(), y, e, (size_t)n, yy, rng);
+  std::vector<int32_t> slot;
+  gibbs_missing_in_model(cur, mc, rows, cells.data(), y, e, (size_t)n, yy, rng, slot);
+  for (int32_t v : slot) if (v != -1) return -1;   // the scratch must come back clean
   for (int c = 0; c < cols; ++c)
     for (int r = 0; r <= c; ++r) xx[(size_t)c * cols + r] = cur.xx(r, c);
   std::memcpy(xy, cur.xy.data(), sizeof(double) * cols);

@@ -350,7 +350,8 @@ def test_bulk_overlay_upload_and_cell_gather_match_oracle(api, n, m, miss):
     cells = ch.get_cells(loci, rows)
     assert cells.shape == (loci.size, rows.size)
     for li, j in enumerate(loci):
-        assert np.array_equal(cells[li], col(j)[rows].astype(np.int8))
+        assert np.array_equal(cells[li] & 3, col(j)[rows].astype(np.int8))
+        assert np.array_equal((cells[li] & 4) != 0, np.isin(rows, idx[off[j]:off[j + 1]]))   # bit 2: missing call
     # a second upload replaces the first; a per-SNP upload then overrides one SNP only
     val2 = rs.integers(0, 3, size=idx.size).astype(np.int8)
     ch.set_missing_all(val2)
@@ -360,11 +361,52 @@ def test_bulk_overlay_upload_and_cell_gather_match_oracle(api, n, m, miss):
     val = val2
     cells = ch.get_cells(loci, rows)
     for li, j in enumerate(loci):
-        assert np.array_equal(cells[li], col(j)[rows].astype(np.int8))
+        assert np.array_equal(cells[li] & 3, col(j)[rows].astype(np.int8))
     with pytest.raises(RuntimeError):
         ch.set_missing_all(val[:-1])
     with pytest.raises(RuntimeError):
         ch.get_cells(loci, np.array([n], dtype=np.int32))
+    ch.close()
+    st.close()
+
+
+def test_device_imputation_draws_follow_the_prior_and_skip_the_model(api):
+    """bmg_chain_impute_from_prior (throughput mode of DataModel::sample_missing): cells of SNPs in the model keep their
+    values; every other missing cell is drawn from its SNP's observed genotype frequencies."""
+    n, m = 4000, 40
+    payload, y, E = make_data(n, m, seed=77, miss_rate=0.25)
+    bed, _ = oracle_store(payload, n, m, True)
+    st = api.GenotypeStore(payload, n, m, recode_to_minor=True)
+    st.set_phenotype(y, E)
+    ch = api.Chain(st)
+    off, idx, prior3 = cpu.missing_index(bed, n, m)
+    prior3 = np.asarray(prior3).reshape(m, 3)
+    keep = np.array([3, 17, 30], dtype=np.int64)
+    marker = np.full(idx.size, 2, dtype=np.int8)
+    ch.set_missing_all(marker)
+    ch.impute_from_prior(keep[::-1].copy(), 1234, 1)
+    rows_all = np.arange(n, dtype=np.int32)
+    cells = ch.get_cells(np.arange(m, dtype=np.int64), rows_all)
+    z_max = 0.0
+    for j in range(m):
+        v = cells[j, idx[off[j]:off[j + 1]]]
+        assert (v & 4).all()
+        v = v & 3
+        if j in keep:
+            assert (v == 2).all()
+            continue
+        p = np.diff(np.concatenate([[0.0], prior3[j]])) / prior3[j, 2]
+        cnt = np.bincount(v, minlength=3)[:3]
+        assert cnt.sum() == v.size and v.min() >= 0 and v.max() <= 2
+        z = np.abs(cnt - v.size * p) / np.sqrt(np.maximum(v.size * p * (1 - p), 1.0))
+        z_max = max(z_max, z.max())
+    assert z_max < 5.0, z_max
+    # another counter gives other draws; the same (seed, counter) gives the same draws
+    ch.impute_from_prior(keep, 1234, 2)
+    cells2 = ch.get_cells(np.arange(m, dtype=np.int64), rows_all)
+    assert (cells2 != cells).any()
+    ch.impute_from_prior(keep, 1234, 1)
+    assert np.array_equal(ch.get_cells(np.arange(m, dtype=np.int64), rows_all), cells)
     ch.close()
     st.close()
 

@@ -96,7 +96,7 @@ def prepare_dataset(w, n_rao, n_threads, out_dir, do_n_iter):
         open(marker, "w").write("ok")
         log("[bench] generated %s in %.1f s" % (d, time.time() - t0))
     base = os.path.join(d, "syn")
-    cfg = dict(base=base, recode=1, n=spec["n"], m_g=spec["m_g"], m_e=spec["m_e"], save_beta=0)
+    cfg = dict(base=base, recode=1, n=spec["n"], m_g=spec["m_g"], m_e=spec["m_e"], save_beta=0, types="A")
     cfg.update(ini_kw)
     ini = os.path.join(out_dir, "bench.ini")
     with open(ini, "w") as fh:
@@ -506,7 +506,7 @@ def sharded_arm(args, rank, local_rank, world):
         with open(base + ".e", "w") as fh:
             fh.write("".join("%s %s\n" % (ident, " ".join("%.17g" % v for v in row)) for ident, row in zip(ids, E)))
         open(base + ".bed", "wb").write(bytes([0x6C, 0x1B, 0x01]))   # never read: the shards were generated on the devices
-        cfg = dict(base=base, recode=1, n=n, m_g=m, m_e=m_e, save_beta=0, do_n_iter=args.n_rao, n_rao=args.n_rao, n_rao_burnin=1000,
+        cfg = dict(base=base, recode=1, n=n, m_g=m, m_e=m_e, save_beta=0, types="A", do_n_iter=args.n_rao, n_rao=args.n_rao, n_rao_burnin=1000,
                    thin=10, n_sample_tau2_and_missing=10, delay_rejection=10, max_move_size=20, use_individual_tau2=1, e_qg=20,
                    var_qg=300, n_threads=1, seeds=str(CHAIN_SEEDS[0]), outbase=os.path.join(shared, "chain"), verbosity=0)
         with open(os.path.join(shared, "bench.ini"), "w") as fh:

@@ -20,6 +20,11 @@ class ScanParams(C.Structure):
                 ("alpha2", f64)]
 
 
+class ScanTypesParams(C.Structure):
+    _fields_ = [("sigma2", f64), ("n_types", i32), ("types", i32 * 5), ("lmp_add", f64 * 5), ("lmp_rem", f64 * 25),
+                ("tau_mode", i32), ("tau_shared", f64 * 4), ("tau_host", f64p), ("reference_offsets", i32)]
+
+
 # name -> (restype, argtypes); every symbol declared in include/bmagwa_b200.h
 SIGNATURES = {
     "bmg_abi_version": (C.c_int, []),
@@ -49,6 +54,8 @@ SIGNATURES = {
     "bmg_chain_get_column": (C.c_int, [vp, i64, C.c_int, f64p]),
     "bmg_chain_get_cells": (C.c_int, [vp, i64p, C.c_int, i32p, i64, i8p]),
     "bmg_chain_residual": (C.c_int, [vp, i64p, f64p, f64p, C.c_int, f64p]),
+    "bmg_chain_residual_types": (C.c_int, [vp, i64p, i32p, f64p, f64p, C.c_int, f64p]),
+    "bmg_chain_scan_types": (C.c_int, [vp, i64p, i32p, f64p, f64p, C.c_int, C.POINTER(ScanTypesParams), f64p, f64p]),
     "bmg_chain_get_residual": (C.c_int, [vp, f64p]),
     "bmg_chain_scan": (C.c_int, [vp, i64p, f64p, f64p, C.c_int, C.POINTER(ScanParams), f64p]),
     "bmg_chain_scan_dots": (C.c_int, [vp, f64p]),

@@ -193,6 +193,51 @@ class Chain:
         keys = ("sum_r", "sum_e", "sum_e2", "sum_g", "sum_g2", "sum_yhat", "sum_yhat2", "xbxb", "ebxb")
         return dict(zip(keys, stats))
 
+    def residual_types(self, loci, term_types, beta_e, beta_g):
+        """Fitted values / residual of a model of typed terms (an AH SNP = two terms, types 0 and 1)."""
+        loci = np.ascontiguousarray(loci, dtype=np.int64)
+        tt = np.ascontiguousarray(term_types, dtype=np.int32)
+        be, bg = _f64(beta_e), _f64(beta_g)
+        stats = np.zeros(9)
+        check(self.L.bmg_chain_residual_types(self.h, _pi(loci), tt.ctypes.data_as(i32p), _pf(be), _pf(bg), loci.size, _pf(stats)))
+        return stats
+
+    def scan_types(self, types, loci, loci_type, beta2, tau2, sigma2, lmp_add, lmp_rem, tau_shared=None, tau_snp=None,
+                   reference_offsets=True):
+        """(p_r, p_r_types or None): bmg_chain_scan_types.  beta2 / tau2: (k, 2)."""
+        from ._lib import ScanTypesParams
+        prm = ScanTypesParams()
+        prm.sigma2 = sigma2
+        prm.n_types = len(types)
+        for i, t in enumerate(types):
+            prm.types[i] = int(t)
+        la, lr = _f64(lmp_add), _f64(np.asarray(lmp_rem).reshape(-1))
+        for i in range(5):
+            prm.lmp_add[i] = la[i]
+        for i in range(25):
+            prm.lmp_rem[i] = lr[i]
+        keep = None
+        if tau_snp is not None:
+            keep = _f64(np.asarray(tau_snp).reshape(-1))
+            prm.tau_mode = 1
+            prm.tau_host = _pf(keep)
+        else:
+            prm.tau_mode = 0
+            ts = _f64(tau_shared)
+            for i in range(4):
+                prm.tau_shared[i] = ts[i]
+        prm.reference_offsets = 1 if reference_offsets else 0
+        loci = np.ascontiguousarray(loci, dtype=np.int64)
+        lt = np.ascontiguousarray(loci_type, dtype=np.int32)
+        b2 = _f64(np.asarray(beta2, dtype=np.float64).reshape(-1)) if loci.size else np.zeros(2)
+        t2 = _f64(np.asarray(tau2, dtype=np.float64).reshape(-1)) if loci.size else np.zeros(2)
+        m = self.store.m
+        p_r = np.zeros(m)
+        prt = np.zeros((m, len(types))) if len(types) > 1 else None
+        check(self.L.bmg_chain_scan_types(self.h, _pi(loci), lt.ctypes.data_as(i32p), _pf(b2), _pf(t2), loci.size, C.byref(prm),
+                                          _pf(p_r), _pf(prt) if prt is not None else None))
+        return p_r, prt
+
     def get_residual(self):
         r = np.zeros(self.store.n)
         check(self.L.bmg_chain_get_residual(self.h, _pf(r)))

@@ -289,6 +289,23 @@ BMG_API int bmg_chain_residual(bmg_chain* c, const int64_t* loci, const double* 
   chain_residual(Cn(c), loci, beta_e, beta_g, k, stats9);
   BMG_CATCH
 }
+BMG_API int bmg_chain_residual_types(bmg_chain* c, const int64_t* loci, const int32_t* term_type, const double* beta_e,
+                                     const double* beta_g, int k, double* stats9)
+{
+  BMG_TRY
+  BMG_REQUIRE(beta_e && (k == 0 || (loci && beta_g && term_type)), "bmg_chain_residual_types: null argument");
+  chain_residual(Cn(c), loci, beta_e, beta_g, k, stats9, term_type);
+  BMG_CATCH
+}
+BMG_API int bmg_chain_scan_types(bmg_chain* c, const int64_t* loci, const int32_t* loci_type, const double* beta2,
+                                 const double* tau2, int k, const bmg_scan_types_params* prm, double* p_r_host,
+                                 double* p_r_types_host)
+{
+  BMG_TRY
+  BMG_REQUIRE(prm && (k == 0 || (loci && loci_type && beta2 && tau2)), "bmg_chain_scan_types: null argument");
+  chain_scan_types(Cn(c), loci, loci_type, beta2, tau2, k, prm, p_r_host, p_r_types_host);
+  BMG_CATCH
+}
 BMG_API int bmg_chain_get_residual(bmg_chain* c, double* r)
 {
   BMG_TRY

@@ -41,6 +41,15 @@ __global__ void __launch_bounds__(256) k_patch_columns(const __grid_constant__ P
     const int32_t i = d.idx[q];
     if (v) atomicOr(&d.dst[i >> 4], (uint32_t)v << (2 * (i & 15)));
   }
+  if (d.type == 0) return;
+  // typed column (DataModel::get_genotypes_heterozygous / dominant / recessive, data_model.cpp:41-72) as 0/1 fields:
+  // a field is 00, 01 or 10, so [x == 1] is its low bit, [x == 2] its high bit, [x > 0] either
+  __syncthreads();
+  uint32_t* w32 = d.dst;
+  for (int64_t w = threadIdx.x; w < 4 * a.quads; w += blockDim.x) {
+    const uint32_t v = w32[w], lo = v & 0x55555555u, hi = (v >> 1) & 0x55555555u;
+    w32[w] = d.type == 1 ? lo : (d.type == 2 ? (lo | hi) : hi);
+  }
 }
 
 static void overlay_prepare(Chain* c)
@@ -88,10 +97,17 @@ static void overlay_launch(Chain* c, const std::vector<PatchDesc>& pend)
 // columns whose slot is missing are rebuilt from the values on the device.  host_vals[i] != nullptr: SNP i gets these
 // new values (count = its number of missing cells), stored on the device and patched into its slot in the same launch.
 // Returns the number of columns (re)built; the work is queued on the chain's stream.
-int chain_overlay_columns(Chain* c, const int64_t* snps, int count, const uint32_t** out, const int8_t* const* host_vals)
+int chain_overlay_columns(Chain* c, const int64_t* snps, int count, const uint32_t** out, const int8_t* const* host_vals,
+                          const int32_t* types)
 {
   Store* s = c->store;
-  if (s->n_missing == 0) {
+  bool any_typed = false;
+  if (types)
+    for (int i = 0; i < count; ++i) {
+      BMG_REQUIRE(types[i] >= 0 && types[i] <= 3, "effect type of a column must be 0 (A), 1 (H), 2 (D) or 3 (R)");
+      any_typed = any_typed || types[i] != 0;
+    }
+  if (s->n_missing == 0 && !any_typed) {
     for (int i = 0; i < count; ++i) out[i] = s->column_ptr(snps[i]);
     return 0;
   }
@@ -118,10 +134,16 @@ int chain_overlay_columns(Chain* c, const int64_t* snps, int count, const uint32
   for (int i = 0; i < count; ++i) {
     const int64_t snp = snps[i];
     out[i] = nullptr;
-    if (!s->is_local(snp)) { out[i] = s->column_ptr(snp); continue; }   // a peer's column: its imputed values live on its owner
-    const int64_t j = snp - s->lo, lo = s->h_miss_off[j], cnt = s->h_miss_off[j + 1] - lo;
-    if (cnt == 0) { out[i] = s->column_ptr(snp); continue; }
-    auto it = c->pc_map.find(j);
+    if (!s->is_local(snp)) {   // a peer's column: its imputed values live on its owner
+      BMG_REQUIRE(!types || types[i] == 0, "typed columns of a peer shard are not available");
+      out[i] = s->column_ptr(snp);
+      continue;
+    }
+    const int ty = types ? types[i] : 0;
+    BMG_REQUIRE(!(host_vals && host_vals[i] && ty != 0), "new imputed values are given for the additive column");
+    const int64_t j = snp - s->lo, cnt = s->n_missing > 0 ? s->h_miss_off[j + 1] - s->h_miss_off[j] : 0;
+    if (cnt == 0 && ty == 0) { out[i] = s->column_ptr(snp); continue; }
+    auto it = c->pc_map.find(4 * j + ty);
     if (it != c->pc_map.end()) {
       c->pc_use[it->second] = c->pc_seq;
       out[i] = c->pc_cols.p + (size_t)it->second * s->Wp;
@@ -131,21 +153,27 @@ int chain_overlay_columns(Chain* c, const int64_t* snps, int count, const uint32
   for (int i = 0; i < count; ++i) {
     const int64_t snp = snps[i];
     if (!s->is_local(snp)) continue;
-    const int64_t j = snp - s->lo, lo = s->h_miss_off[j], cnt = s->h_miss_off[j + 1] - lo;
-    if (cnt == 0) continue;
+    const int ty = types ? types[i] : 0;
+    const int64_t j = snp - s->lo, lo = s->n_missing > 0 ? s->h_miss_off[j] : 0, cnt = s->n_missing > 0 ? s->h_miss_off[j + 1] - lo : 0;
+    if (cnt == 0 && ty == 0) continue;
     const bool fresh = host_vals != nullptr && host_vals[i] != nullptr;
     if (out[i] != nullptr && !fresh) continue;
+    if (fresh)   // the typed copies of this SNP are stale now: they are rebuilt on their next use
+      for (int t2 = 1; t2 < 4; ++t2) {
+        auto ot = c->pc_map.find(4 * j + t2);
+        if (ot != c->pc_map.end()) { c->pc_snp[ot->second] = -1; c->pc_map.erase(ot); }
+      }
     uint32_t* dst;
     if (out[i] == nullptr) {
-      auto again = c->pc_map.find(j);   // the same SNP twice in one request
+      auto again = c->pc_map.find(4 * j + ty);   // the same column twice in one request
       if (again != c->pc_map.end()) {
         out[i] = c->pc_cols.p + (size_t)again->second * s->Wp;
         if (!fresh) continue;
         dst = const_cast<uint32_t*>(out[i]);
       } else {
         const int slot = overlay_take_slot(c);
-        c->pc_map[j] = slot;
-        c->pc_snp[slot] = j;
+        c->pc_map[4 * j + ty] = slot;
+        c->pc_snp[slot] = 4 * j + ty;
         c->pc_use[slot] = c->pc_seq;
         dst = c->pc_cols.p + (size_t)slot * s->Wp;
         out[i] = dst;
@@ -156,8 +184,9 @@ int chain_overlay_columns(Chain* c, const int64_t* snps, int count, const uint32
     PatchDesc d;
     d.src = s->column_ptr(snp);
     d.dst = dst;
-    d.idx = s->miss_idx.p + lo;
+    d.idx = cnt ? s->miss_idx.p + lo : nullptr;
     d.cnt = cnt;
+    d.type = ty;
     if (fresh) {
       memcpy(c->pc_h_vals.p + staged, host_vals[i], (size_t)cnt);
       d.vals = c->pc_h_vals.p + staged;   // mapped pinned memory: read by the kernel over PCIe, no separate copy
@@ -165,7 +194,7 @@ int chain_overlay_columns(Chain* c, const int64_t* snps, int count, const uint32
       staged += (size_t)cnt;
       g_h2d_bytes.fetch_add((uint64_t)cnt, std::memory_order_relaxed);
     } else {
-      d.vals = c->miss_val.p + lo;
+      d.vals = cnt ? c->miss_val.p + lo : nullptr;
       d.keep = nullptr;
     }
     pend.push_back(d);
@@ -203,8 +232,10 @@ void chain_overlay_invalidate(Chain* c, const int64_t* keep, int k)
   std::vector<std::pair<int64_t, int>> kept;
   for (int l = 0; l < k; ++l) {
     if (!s->is_local(keep[l])) continue;
-    auto it = c->pc_map.find(keep[l] - s->lo);
-    if (it != c->pc_map.end()) kept.push_back(*it);
+    for (int ty = 0; ty < 4; ++ty) {
+      auto it = c->pc_map.find(4 * (keep[l] - s->lo) + ty);
+      if (it != c->pc_map.end()) kept.push_back(*it);
+    }
   }
   c->pc_map.clear();
   std::fill(c->pc_snp.begin(), c->pc_snp.end(), (int64_t)-1);

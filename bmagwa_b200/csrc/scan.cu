@@ -804,7 +804,8 @@ static void upload_model(Chain* c, const int64_t* loci, const double* beta_g, co
   bmg::copy_h2d(c->taug_dev.p, c->h_stage.p + 2048, k * sizeof(double), c->stream);
 }
 
-void chain_residual(Chain* c, const int64_t* loci, const double* beta_e, const double* beta_g, int k, double* stats9)
+void chain_residual(Chain* c, const int64_t* loci, const double* beta_e, const double* beta_g, int k, double* stats9,
+                    const int32_t* term_types)
 {
   chain_server_stop(c);   // precedes scans and latent sweeps (which may allocate and want all SMs)
   Store* s = c->store;
@@ -820,7 +821,7 @@ void chain_residual(Chain* c, const int64_t* loci, const double* beta_e, const d
   {
     // columns as the chain sees them: a SNP with missing calls is read from its patched copy (overlay.cu)
     std::vector<const uint32_t*> cols(k);
-    chain_overlay_columns(c, loci, k, cols.data());
+    chain_overlay_columns(c, loci, k, cols.data(), nullptr, term_types);
     for (int l = 0; l < k; ++l) c->h_stage_i.p[2048 + l] = (int64_t)(uintptr_t)cols[l];
   }
   if (c->cs_idx.n < 4096) c->cs_idx.alloc(4096);
@@ -934,6 +935,265 @@ void chain_scan(Chain* c, const int64_t* loci, const double* beta_g, const doubl
     bmg::copy_d2h(p_r_host, c->p_r.p, c->mw * sizeof(double), st);
     BMG_CUDA(cudaStreamSynchronize(st));
   }
+}
+
+// ---------------------------------------------------------------------------------------
+// the scan with several effect types, or one type other than A (src/sampler.cpp:90-259)
+//
+// Both statistics every type needs come from the packed store: S1 = sum_{x=1} r (the heterozygote-indicator pass of
+// the tensor-core kernel) and the additive dot S1 + 2 S2 (the ordinary pass); A = S1 + 2 S2, H = S1, D = S1 + S2,
+// R = S2, and all moments follow from the genotype counts.
+// ---------------------------------------------------------------------------------------
+// out[4j..] = { sum_{val=1} r, sum_{val=2} r, #val=1, #val=2 } over the imputed cells of SNP j
+__global__ void k_miss_corr4(const int64_t* __restrict__ off, const int32_t* __restrict__ idx, const int8_t* __restrict__ val,
+                             const double* __restrict__ r, int64_t m, double* __restrict__ out)
+{
+  const int64_t j = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (j >= m) return;
+  const int64_t lo = off[j], hi = off[j + 1];
+  if (hi == lo) return;
+  double d1 = 0.0, d2 = 0.0, c1 = 0.0, c2 = 0.0;
+  for (int64_t q = lo + lane; q < hi; q += 32) {
+    const int v = val[q];
+    const double rv = r[idx[q]];
+    if (v == 1) { d1 += rv; c1 += 1.0; }
+    else if (v == 2) { d2 += rv; c2 += 1.0; }
+  }
+  d1 = warp_sum(d1); d2 = warp_sum(d2); c1 = warp_sum(c1); c2 = warp_sum(c2);
+  if (lane == 0) { out[4 * j] = d1; out[4 * j + 1] = d2; out[4 * j + 2] = c1; out[4 * j + 3] = c2; }
+}
+
+struct TypedArgs {
+  const double* part_a; const double* part_h; int n_chunks;
+  int64_t m, lo, n;
+  const int32_t* n1; const int32_t* n2; const int32_t* nmiss;
+  const double* corr4;          // may be null
+  // model: k SNPs, each with its effect type and one or two terms (AH: additive then heterozygous)
+  const int64_t* loci; const int32_t* mtype; const double* mbeta; const double* mtau; int k;   // mbeta/mtau: [k][2]
+  double sum_r, sigma2;
+  int n_types; int types[5];
+  int n_terms; int term_rank[4];  // -1: term not allowed
+  int allow_ah, ref_offsets, tau_mode;
+  double lmp_add[5], lmp_rem[25], tau_shared[4];
+  const double* tau_snp;        // [m][n_terms] when tau_mode == 1
+  double* p_r; double* p_r_types;
+};
+
+// value of a term type on genotype 1 and genotype 2
+__device__ __forceinline__ void type_values(int t, double& a1, double& a2)
+{
+  a1 = (t == 3) ? 0.0 : 1.0;                    // A, H, D count a heterozygote
+  a2 = (t == 0) ? 2.0 : ((t == 1) ? 0.0 : 1.0); // A counts 2, D and R count 1
+}
+
+__global__ void __launch_bounds__(128) k_scan_finalize_types(const __grid_constant__ TypedArgs a)
+{
+  const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (j >= a.m) return;
+  double dot_a = 0.0, dot_h = 0.0;
+  for (int c = 0; c < a.n_chunks; ++c) { dot_a += a.part_a[(int64_t)c * a.m + j]; dot_h += a.part_h[(int64_t)c * a.m + j]; }
+  const double dn = (double)a.n;
+  const double n1 = (double)a.n1[j], n2 = (double)a.n2[j];
+  double s1 = dot_h, s2 = 0.5 * (dot_a - dot_h);   // sums of r over the observed heterozygotes / minor homozygotes
+  double c1 = 0.0, c2 = 0.0;
+  const bool has_missing = a.corr4 != nullptr && a.nmiss[j] > 0;
+  if (has_missing) { s1 += a.corr4[4 * j]; s2 += a.corr4[4 * j + 1]; c1 = a.corr4[4 * j + 2]; c2 = a.corr4[4 * j + 3]; }
+  const double N1 = n1 + c1, N2 = n2 + c2;
+
+  // the moment cache in the reference's layout (precomputed_snp_covariances.hpp:95-131), then update_prexx_cov
+  // (data_model.cpp:105-167) for the imputed values
+  double pre[9];
+  const int offset = 2 * a.n_terms + a.allow_ah;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int rk = a.term_rank[t];
+    if (rk < 0) continue;
+    double a1, a2;
+    type_values(t, a1, a2);
+    const double s0 = a1 * n1 + a2 * n2, ss0 = a1 * a1 * n1 + a2 * a2 * n2;
+    pre[2 * rk] = s0;
+    pre[2 * rk + 1] = ss0 - s0 * s0 / dn;
+  }
+  if (a.allow_ah) pre[offset - 1] = n1 - pre[0] * pre[2] / dn;   // terms A and H are the first two
+  if (has_missing) {
+    const double sa_sh = a.allow_ah ? pre[0] * pre[2] : 0.0;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int rk = a.term_rank[t];
+      if (rk < 0) continue;
+      double a1, a2;
+      type_values(t, a1, a2);
+      const double sv = a1 * c1 + a2 * c2, sv2 = a1 * a1 * c1 + a2 * a2 * c2;
+      const double old = pre[2 * rk];
+      pre[2 * rk] += sv;
+      pre[2 * rk + 1] += sv2 - sv * (old * 2.0 + sv) / dn;
+    }
+    if (a.allow_ah) {
+      pre[offset - 1] += (sa_sh - pre[0] * pre[2]) / dn;
+      pre[offset - 1] += c1;
+    }
+  }
+
+  double tau[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int rk = a.term_rank[t];
+    if (rk < 0) continue;
+    tau[t] = a.tau_mode == 0 ? a.tau_shared[t] : a.tau_snp[j * a.n_terms + rk];
+  }
+  int pos = -1;
+  const int64_t gj = a.lo + j;
+  for (int l = 0; l < a.k; ++l)
+    if (a.loci[l] == gj) pos = l;
+  double mr = a.sum_r / dn;
+  const double* lmp = a.lmp_add;
+  // residual without SNP j (sampler.cpp:116-149): r + b1 x^(U1) + b2 x^(H); its dot with x^(T) and its mean follow from counts
+  double add1 = 0.0, add2 = 0.0;   // what r_om adds to sum_{x=1} and to sum_{x=2}
+  if (pos >= 0) {
+    const int mt = a.mtype[pos];
+    const int u1 = mt == 4 ? 0 : mt;
+    double b1 = a.mbeta[2 * pos], b2 = mt == 4 ? a.mbeta[2 * pos + 1] : 0.0;
+    if (a.tau_mode != 0) {
+      tau[u1] = a.mtau[2 * pos];
+      if (mt == 4) tau[1] = a.mtau[2 * pos + 1];
+    }
+    double u_a1, u_a2;
+    type_values(u1, u_a1, u_a2);
+    add1 = (b1 * u_a1 + b2) * N1;            // the H term is 1 on heterozygotes only
+    add2 = (b1 * u_a2) * N2;
+    mr = (a.sum_r + add1 + add2) / dn;
+    lmp = a.lmp_rem + 5 * mt;
+  }
+  const double S1 = s1 + add1, S2 = s2 + add2;
+
+  double p[5];
+  double max_types = -INFINITY;
+  for (int ti = 0; ti < a.n_types; ++ti) {
+    const int t = a.types[ti];
+    double det, exp_term, sum_log_q;
+    if (t == 4) {
+      const double sa = pre[0], va = pre[1] + tau[0], sh = pre[2], vh = pre[3] + tau[1], vah = pre[offset - 1];
+      sum_log_q = -log(tau[0]) - log(tau[1]);
+      const double rxa = (S1 + 2.0 * S2) - sa * mr, rxh = S1 - sh * mr;
+      det = va * vh - vah * vah;
+      exp_term = (rxa * rxa * vh - 2.0 * rxa * rxh * vah + rxh * rxh * va) / det;
+    } else {
+      const int o = a.ref_offsets ? a.term_rank[t] : 2 * a.term_rank[t];   // see TypedArgs / include/bmagwa_b200.h
+      double a1, a2;
+      type_values(t, a1, a2);
+      const double sT = pre[o];
+      det = pre[o + 1] + tau[t];
+      sum_log_q = -log(tau[t]);
+      const double rx = (a1 * S1 + a2 * S2) - sT * mr;
+      exp_term = (rx * rx) / det;
+    }
+    p[ti] = exp_term / (2.0 * a.sigma2) - 0.5 * (log(det) + sum_log_q) + lmp[t];
+    if (p[ti] > max_types) max_types = p[ti];   // a NaN never wins this comparison (nor does it in the reference)
+  }
+  double* prt = a.p_r_types ? a.p_r_types + j * a.n_types : nullptr;
+  if (a.n_types == 1) {                              // sampler.cpp:199-206
+    const double e = exp(p[0]);
+    a.p_r[j] = isfinite(e) ? e / (1.0 + e) : 1.0;
+    return;
+  }
+  if (!isfinite(max_types)) {                        // sampler.cpp:210-237
+    if (max_types > 0) {
+      double sum = 0.0;
+      for (int ti = 0; ti < a.n_types; ++ti) { prt[ti] = (!isfinite(p[ti]) && p[ti] > 0) ? 1.0 : 0.0; sum += prt[ti]; }
+      for (int ti = 0; ti < a.n_types; ++ti) prt[ti] /= sum;
+      a.p_r[j] = 1.0;
+    } else {
+      for (int ti = 0; ti < a.n_types; ++ti) prt[ti] = 1.0 / a.n_types;
+      a.p_r[j] = 0.0;
+    }
+    return;
+  }
+  double sum_types = 0.0;                            // sampler.cpp:240-257
+  for (int ti = 0; ti < a.n_types; ++ti) { p[ti] = exp(p[ti] - max_types); sum_types += p[ti]; }
+  for (int ti = 0; ti < a.n_types; ++ti) prt[ti] = p[ti] / sum_types;
+  sum_types = exp(log(sum_types) + max_types);
+  a.p_r[j] = isfinite(sum_types) ? sum_types / (1.0 + sum_types) : 1.0;
+}
+
+void chain_scan_types(Chain* c, const int64_t* loci, const int32_t* loci_type, const double* beta2, const double* tau2, int k,
+                      const bmg_scan_types_params* prm, double* p_r_host, double* p_r_types_host)
+{
+  Store* s = c->store;
+  BMG_REQUIRE(prm != nullptr, "bmg_chain_scan_types: params required");
+  BMG_REQUIRE(c->residual_valid, "bmg_chain_scan_types: call bmg_chain_residual[_types] first");
+  BMG_REQUIRE(c->scan_variant == 2, "bmg_chain_scan_types: needs the tensor-core scan (variant 2)");
+  BMG_REQUIRE(c->world == 1, "bmg_chain_scan_types: not available on a SNP-sharded chain");
+  BMG_REQUIRE(prm->n_types >= 1 && prm->n_types <= 5, "bmg_chain_scan_types: n_types must be 1..5");
+  BMG_REQUIRE(prm->tau_mode == 0 || prm->tau_mode == 1, "bmg_chain_scan_types: tau_mode must be 0 (shared) or 1 (host draws)");
+  BMG_REQUIRE(prm->sigma2 > 0, "bmg_chain_scan_types: sigma2 must be positive");
+  BMG_REQUIRE(k >= 0 && k <= 1024, "bmg_chain_scan_types: model size must be <= 1024");
+  TypedArgs a;
+  memset(&a, 0, sizeof(a));
+  bool allow_type[5] = {false, false, false, false, false}, allow_term[4] = {false, false, false, false};
+  for (int i = 0; i < prm->n_types; ++i) {
+    const int t = prm->types[i];
+    BMG_REQUIRE(t >= 0 && t <= 4 && !allow_type[t], "bmg_chain_scan_types: types must be distinct codes 0..4");
+    BMG_REQUIRE(i == 0 || t > prm->types[i - 1], "bmg_chain_scan_types: types must be in increasing order (the reference sorts model.types)");
+    allow_type[t] = true;
+    if (t == 4) allow_term[0] = allow_term[1] = true; else allow_term[t] = true;
+    a.types[i] = t;
+  }
+  a.n_types = prm->n_types;
+  for (int t = 0; t < 4; ++t) a.term_rank[t] = allow_term[t] ? a.n_terms++ : -1;
+  a.allow_ah = allow_type[4] ? 1 : 0;
+  a.ref_offsets = prm->reference_offsets ? 1 : 0;
+  for (int l = 0; l < k; ++l) BMG_REQUIRE(loci_type[l] >= 0 && loci_type[l] <= 4 && allow_type[loci_type[l]], "bmg_chain_scan_types: a model SNP has a type that is not configured");
+  BMG_CUDA(cudaSetDevice(s->device));
+  chain_server_stop(c);
+  cudaStream_t st = c->stream;
+  // model arrays
+  if (c->tm_d.n == 0) { c->tm_d.alloc(4 * 1024); c->tm_i.alloc(1024); c->tm_h.alloc(4 * 1024 + 1024); }
+  BMG_CUDA(cudaStreamSynchronize(st));
+  for (int l = 0; l < k; ++l) {
+    c->h_stage_i.p[l] = loci[l];
+    c->tm_h.p[2 * l] = beta2[2 * l]; c->tm_h.p[2 * l + 1] = beta2[2 * l + 1];
+    c->tm_h.p[2048 + 2 * l] = tau2[2 * l]; c->tm_h.p[2048 + 2 * l + 1] = tau2[2 * l + 1];
+    reinterpret_cast<int32_t*>(c->tm_h.p + 4096)[l] = loci_type[l];
+  }
+  if (k) {
+    bmg::copy_h2d(c->loci_dev.p, c->h_stage_i.p, k * sizeof(int64_t), st);
+    bmg::copy_h2d(c->tm_d.p, c->tm_h.p, 2 * k * sizeof(double), st);
+    bmg::copy_h2d(c->tm_d.p + 2048, c->tm_h.p + 2048, 2 * k * sizeof(double), st);
+    bmg::copy_h2d(c->tm_i.p, c->tm_h.p + 4096, k * sizeof(int32_t), st);
+  }
+  if (prm->tau_mode == 1) {
+    BMG_REQUIRE(prm->tau_host != nullptr, "bmg_chain_scan_types: tau_host required for tau_mode 1");
+    const size_t need = (size_t)s->m * a.n_terms;
+    if (c->tau_dev.n < need) c->tau_dev.alloc(need);
+    bmg::copy_h2d(c->tau_dev.p, prm->tau_host, need * sizeof(double), st);
+  }
+  if (prm->n_types > 1 && c->p_r_types.n < (size_t)s->m * prm->n_types) c->p_r_types.alloc((size_t)s->m * 5);
+  imma_quantize(c);
+  imma_launch(c, false);
+  imma_launch(c, true);
+  if (s->n_missing > 0) {
+    if (c->miss_corr4.n == 0) { c->miss_corr4.alloc(4 * s->m); c->miss_corr4.zero(st); }
+    k_miss_corr4<<<(unsigned)((s->m * 32 + 127) / 128), 128, 0, st>>>(s->miss_off.p, s->miss_idx.p, c->miss_val.p, c->r.p, s->m,
+                                                                      c->miss_corr4.p);
+    count_launch();
+  }
+  a.part_a = c->imma_partial.p; a.part_h = c->imma_partial_h.p; a.n_chunks = c->imma_chunks;
+  a.m = s->m; a.lo = s->lo; a.n = s->n; a.n1 = s->n1.p; a.n2 = s->n2.p; a.nmiss = s->nmiss.p;
+  a.corr4 = s->n_missing > 0 ? c->miss_corr4.p : nullptr;
+  a.loci = c->loci_dev.p; a.mtype = c->tm_i.p; a.mbeta = c->tm_d.p; a.mtau = c->tm_d.p + 2048; a.k = k;
+  a.sum_r = c->sum_r; a.sigma2 = prm->sigma2; a.tau_mode = prm->tau_mode;
+  for (int t = 0; t < 5; ++t) a.lmp_add[t] = prm->lmp_add[t];
+  for (int t = 0; t < 25; ++t) a.lmp_rem[t] = prm->lmp_rem[t];
+  for (int t = 0; t < 4; ++t) a.tau_shared[t] = prm->tau_shared[t];
+  a.tau_snp = c->tau_dev.p;
+  a.p_r = c->p_r.p; a.p_r_types = prm->n_types > 1 ? c->p_r_types.p : nullptr;
+  k_scan_finalize_types<<<(unsigned)((s->m + 127) / 128), 128, 0, st>>>(a);
+  count_launch();
+  BMG_CUDA(cudaGetLastError());
+  if (p_r_host) bmg::copy_d2h(p_r_host, c->p_r.p, s->m * sizeof(double), st);
+  if (p_r_types_host && prm->n_types > 1) bmg::copy_d2h(p_r_types_host, c->p_r_types.p, (size_t)s->m * prm->n_types * sizeof(double), st);
+  BMG_CUDA(cudaStreamSynchronize(st));
 }
 
 void chain_adapt(Chain* c, int update_rao, int64_t n_rao_mean, int update_prop, int64_t n_prop_mean, double q_add_min,

@@ -69,8 +69,11 @@ __device__ __forceinline__ void bulk_g2s_i(void* dst_smem, const void* src_gmem,
                : "memory");
 }
 // field P of each of the four packed bytes of w, scaled by 4^P, one per byte lane: a single LOP3
-template <int P>
-__device__ __forceinline__ uint32_t expand_field(uint32_t w) { return w & (0x03030303u << (2 * P)); }
+// HET: only the low bit of each field, i.e. the heterozygote indicator [x == 1] (fields hold 0, 1 or 2): the same
+// kernel then yields S1 = sum_{x=1} r, from which every effect type follows (A = S1 + 2 S2, H = S1,
+// D = S1 + S2, R = S2)
+template <int P, bool HET>
+__device__ __forceinline__ uint32_t expand_field(uint32_t w) { return w & ((HET ? 0x01010101u : 0x03030303u) << (2 * P)); }
 
 __device__ __forceinline__ void imma16832(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1)
 {
@@ -140,6 +143,7 @@ __device__ __forceinline__ void fence_cta() { asm volatile("fence.acq_rel.cta;" 
 // bulk-async copies, gated by per-stage "empty" mbarriers); consumer warps never meet at a CTA barrier: each adds its
 // int32 limb sums into a shared accumulator and the LAST warp to finish a tile (atomic ticket) combines and stores it.
 // dynamic smem: kImmaStages * 16 * row_stride words | int acc[kImmaAccBufs][16][8] | int ticket[kImmaAccBufs] | mbarriers
+template <bool HET>
 __global__ void __maxnreg__(80) k_scan_dots_imma(const __grid_constant__ ImmaArgs a)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -215,10 +219,10 @@ __global__ void __maxnreg__(80) k_scan_dots_imma(const __grid_constant__ ImmaArg
     int c[4] = {0, 0, 0, 0}, c2[4] = {0, 0, 0, 0};   // two independent IMMA chains
 #pragma unroll
     for (int grp = 0; grp < kImmaGroups; ++grp) {
-      imma16832(c, expand_field<0>(wl[grp]), expand_field<0>(wh[grp]), expand_field<1>(wl[grp]), expand_field<1>(wh[grp]),
-                bq[grp].x, bq[grp].y);
-      imma16832(c2, expand_field<2>(wl[grp]), expand_field<2>(wh[grp]), expand_field<3>(wl[grp]), expand_field<3>(wh[grp]),
-                bq[grp].z, bq[grp].w);
+      imma16832(c, expand_field<0, HET>(wl[grp]), expand_field<0, HET>(wh[grp]), expand_field<1, HET>(wl[grp]),
+                expand_field<1, HET>(wh[grp]), bq[grp].x, bq[grp].y);
+      imma16832(c2, expand_field<2, HET>(wl[grp]), expand_field<2, HET>(wh[grp]), expand_field<3, HET>(wl[grp]),
+                expand_field<3, HET>(wh[grp]), bq[grp].z, bq[grp].w);
     }
 #pragma unroll
     for (int e = 0; e < 4; ++e) c[e] += c2[e];
@@ -298,9 +302,10 @@ void imma_prepare(Chain* c)
   if ((int64_t)c->imma_partial.n < (int64_t)c->imma_chunks * s->m) c->imma_partial.alloc((size_t)c->imma_chunks * s->m);
   const size_t smem = imma_smem_bytes(c);
   BMG_REQUIRE(smem <= 227 * 1024, "IMMA scan tile does not fit in shared memory");
-  BMG_CUDA(cudaFuncSetAttribute(k_scan_dots_imma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  BMG_CUDA(cudaFuncSetAttribute(k_scan_dots_imma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  BMG_CUDA(cudaFuncSetAttribute(k_scan_dots_imma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1;
-  BMG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan_dots_imma, 32 * (c->imma_warps + 1), smem));
+  BMG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan_dots_imma<false>, 32 * (c->imma_warps + 1), smem));
   if (per_sm < 1) per_sm = 1;
   if (const char* env = getenv("BMG_IMMA_CTAS_PER_SM")) {
     const int v = atoi(env);
@@ -329,15 +334,27 @@ void imma_quantize(Chain* c)
   c->imma_q_valid = true;
 }
 
-// the tensor-core scan into imma_partial ([chunks][m] doubles)
-void imma_launch(Chain* c)
+// the tensor-core scan into imma_partial ([chunks][m] doubles); het: the heterozygote-indicator pass into imma_partial_h
+void imma_launch(Chain* c, bool het)
 {
   Store* s = c->store;
   ImmaArgs a;
   a.codes = s->codes.p; a.Wp = s->Wp; a.m = s->m; a.q = reinterpret_cast<const uint4*>(c->imma_q.p); a.scale_exp = c->imma_exp.p;
   a.chunk_words = (int)c->imma_chunk_words; a.n_chunks = c->imma_chunks; a.tiles = (s->m + kImmaTile - 1) / kImmaTile;
-  a.slices = c->imma_slices; a.row_stride = (int)c->imma_chunk_words + 16; a.out = c->imma_partial.p;
-  k_scan_dots_imma<<<(unsigned)(c->imma_chunks * c->imma_slices), 32 * (c->imma_warps + 1), imma_smem_bytes(c), c->stream>>>(a);
+  a.slices = c->imma_slices; a.row_stride = (int)c->imma_chunk_words + 16;
+  const unsigned grid = (unsigned)(c->imma_chunks * c->imma_slices);
+  if (het) {
+    if ((int64_t)c->imma_partial_h.n < (int64_t)c->imma_chunks * s->m) {
+      BMG_CUDA(cudaStreamSynchronize(c->stream));
+      c->imma_partial_h.alloc((size_t)c->imma_chunks * s->m);
+    }
+    a.out = c->imma_partial_h.p;
+    k_scan_dots_imma<true><<<grid, 32 * (c->imma_warps + 1), imma_smem_bytes(c), c->stream>>>(a);
+    count_launch();
+    return;
+  }
+  a.out = c->imma_partial.p;
+  k_scan_dots_imma<false><<<grid, 32 * (c->imma_warps + 1), imma_smem_bytes(c), c->stream>>>(a);
   count_launch();
   c->last_partial = c->imma_partial.p;
   c->last_chunks = c->imma_chunks;

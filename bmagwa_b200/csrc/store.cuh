@@ -28,6 +28,7 @@ struct PatchDesc {
   const int8_t* vals;    // their imputed values: mapped host staging, or the chain's device array
   int8_t* keep;          // where to store the values on the device (nullptr: they are already there)
   int64_t cnt;
+  int type;              // 0 additive values; 1 H [x == 1], 2 D [x > 0], 3 R [x == 2] written as 0/1 fields
 };
 
 struct Chain {
@@ -65,6 +66,7 @@ struct Chain {
   DevBuf<unsigned char> imma_q;                 // residual limbs [word][8][16]
   DevBuf<int> imma_exp;                         // fixed-point exponent S
   DevBuf<double> imma_partial;                  // [imma_chunks][m]
+  DevBuf<double> imma_partial_h;                // same for the heterozygote-indicator pass of the typed scan
   const double* last_partial = nullptr;         // per-chunk dots of the most recent scan
   int last_chunks = 0;
   // phenotype the chain works on (a copy of the store's y; the probit update overwrites it)
@@ -81,13 +83,18 @@ struct Chain {
   // per-chain imputed values of the missing cells (same CSR as the store)
   DevBuf<int8_t> miss_val;
   DevBuf<double> miss_corr;                     // 3 per local SNP: (dot corr, sum val, sum val^2)
+  DevBuf<double> miss_corr4;                    // typed scan: (sum_{val=1} r, sum_{val=2} r, #val=1, #val=2)
+  DevBuf<double> p_r_types;                     // typed scan: m x n_types
+  DevBuf<double> tm_d;                          // typed scan: model betas [k][2] | taus [k][2]
+  DevBuf<int32_t> tm_i;                         // typed scan: model effect types
+  PinnedBuf<double> tm_h;
   // packed columns with the imputed values filled in (overlay.cu)
   DevBuf<uint32_t> pc_cols;                     // pc_slots x store->Wp words
   int pc_slots = 0, pc_next = 0;
   unsigned int pc_seq = 0;
-  std::vector<int64_t> pc_snp;                  // slot -> local SNP, -1 free
+  std::vector<int64_t> pc_snp;                  // slot -> key (4 * local SNP + type), -1 free
   std::vector<unsigned int> pc_use;             // slot -> sequence number of the last request that used it
-  std::unordered_map<int64_t, int> pc_map;      // local SNP -> slot
+  std::unordered_map<int64_t, int> pc_map;      // 4 * local SNP + effect type -> slot
   std::vector<PatchDesc> pc_pending;
   PinnedBuf<int8_t> pc_h_vals;                  // mapped staging of new imputed values, read by k_patch_columns
   // scratch of chain_get_cells (values of a few (SNP, individual) cells for the missing-genotype Gibbs step)
@@ -145,18 +152,22 @@ Chain* chain_create(Store* s);
 void chain_destroy(Chain* c);
 void chain_set_missing(Chain* c, int64_t snp, const int8_t* vals, int64_t count);
 void chain_set_missing_many(Chain* c, const int64_t* snps, int count, const int8_t* const* vals);
-int chain_overlay_columns(Chain* c, const int64_t* snps, int count, const uint32_t** out, const int8_t* const* host_vals = nullptr);
+int chain_overlay_columns(Chain* c, const int64_t* snps, int count, const uint32_t** out, const int8_t* const* host_vals = nullptr,
+                          const int32_t* types = nullptr);
 void chain_overlay_invalidate(Chain* c, const int64_t* keep, int k);
 void chain_set_missing_all(Chain* c, const int8_t* vals, int64_t count);
 void chain_impute_from_prior(Chain* c, const int64_t* loci, int k, uint64_t seed, uint64_t counter);
 void chain_get_cells(Chain* c, const int64_t* loci, int k, const int32_t* rows, int64_t q, int8_t* out);
-void chain_residual(Chain* c, const int64_t* loci, const double* beta_e, const double* beta_g, int k, double* stats9);
+void chain_residual(Chain* c, const int64_t* loci, const double* beta_e, const double* beta_g, int k, double* stats9,
+                    const int32_t* term_types = nullptr);
+void chain_scan_types(Chain* c, const int64_t* loci, const int32_t* loci_type, const double* beta2, const double* tau2, int k,
+                      const bmg_scan_types_params* prm, double* p_r_host, double* p_r_types_host);
 void chain_scan_dots(Chain* c);
 void chain_set_sharded(Chain* c, int world, int rank, int64_t stride, AllGatherFn fn, void* ctx);
 void chain_allgather(Chain* c, void* dev_buffer, int elem_bytes);
 void imma_prepare(Chain* c);
 void imma_quantize(Chain* c);
-void imma_launch(Chain* c);
+void imma_launch(Chain* c, bool het = false);
 void chain_scan(Chain* c, const int64_t* loci, const double* beta_g, const double* tau_g, int k,
                 const bmg_scan_params* prm, double* p_r_host);
 void chain_adapt(Chain* c, int update_rao, int64_t n_rao_mean, int update_prop, int64_t n_prop_mean, double q_add_min,

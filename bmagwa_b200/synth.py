@@ -107,7 +107,7 @@ basename = {outbase}
 seeds = {seeds}
 
 [model]
-types = A
+types = {types}
 
 [prior]
 use_individual_tau2 = {use_individual_tau2}
@@ -124,6 +124,10 @@ nu_tau2_A = 5
 s2_tau2_A = 0.05
 nu_tau2_H = 5
 s2_tau2_H = 0.05
+nu_tau2_D = 5
+s2_tau2_D = 0.05
+nu_tau2_R = 5
+s2_tau2_R = 0.05
 mu_alpha = 1
 inv_tau2_e_const_val = 0
 inv_tau2_e_val = 0.001
@@ -155,7 +159,7 @@ def write_dataset(directory, name, n, m_g, m_e=2, seed=20121101, miss_rate=0.0, 
     cfg = dict(base=base, recode=1, n=n, m_g=m_g, m_e=m_e, do_n_iter=1000, n_rao=500, n_rao_burnin=1000,
                verbosity=100000, thin=10, n_sample_tau2_and_missing=10, delay_rejection=10, max_move_size=20,
                save_beta=0, n_threads=1, outbase=os.path.join(directory, "chain"), seeds="1234",
-               use_individual_tau2=1, e_qg=min(20, max(1, m_g // 4)), var_qg=300 if m_g > 100 else 2)
+               use_individual_tau2=1, e_qg=min(20, max(1, m_g // 4)), var_qg=300 if m_g > 100 else 2, types="A")
     cfg.update(ini_overrides)
     ini_path = base + ".ini"
     with open(ini_path, "w") as fh:

@@ -154,6 +154,40 @@ typedef struct bmg_scan_params {
  * sampler.cpp:116-149.  p_r stays on the device; pass p_r_host != NULL to also copy it back. */
 int bmg_chain_scan(bmg_chain* c, const int64_t* loci, const double* beta_g, const double* tau_g, int k,
                    const bmg_scan_params* prm, double* p_r_host);
+/* ---- the scan with several effect types, or one type other than A (sampler.cpp:90-259) ------------------------------
+ * Effect types: 0 A, 1 H, 2 D, 3 R, 4 AH (data_model.hpp:41); AH is a SNP with two terms (additive + heterozygous).
+ * Fitted values of a model whose terms are typed columns: as bmg_chain_residual, with term_type[l] in 0..3 for every
+ * term (an AH SNP contributes two terms: its SNP index twice, types 0 and 1). */
+int bmg_chain_residual_types(bmg_chain* c, const int64_t* loci, const int32_t* term_type, const double* beta_e,
+                             const double* beta_g, int k, double* stats9);
+
+typedef struct bmg_scan_types_params {
+  double sigma2;
+  int32_t n_types;          /* effect types of the run ...                                      data_model.hpp:46-47 */
+  int32_t types[5];         /* ... in increasing code order (the reference sorts model.types, options.hpp:254)      */
+  double lmp_add[5];        /* by type code: log prior change of adding a SNP of that type      sampler.cpp:56-59    */
+  double lmp_rem[25];       /* [5 * type of the in-model SNP + type]: the same with that SNP removed  sampler.cpp:61-73 */
+  int32_t tau_mode;         /* 0: one value per TERM type (tau_shared); 1: per-SNP values drawn by the host in the
+                               reference's order -- per SNP one draw per allowed term, terms in increasing code
+                               (sampler.cpp:99-106)                                                                   */
+  double tau_shared[4];     /* by term type A, H, D, R                                          sampler.cpp:78-86    */
+  const double* tau_host;   /* tau_mode 1: m(local) x n_terms                                                          */
+  int32_t reference_offsets;/* 1: read the moment cache exactly as the reference does.  Its offset_type[t] counts TERMS
+                               although a term occupies two slots (precomputed_snp_covariances.hpp:73-83 vs :113-118), so
+                               with several term types every type but the first reads (sum, variance) one slot early;
+                               1 reproduces the reference's numbers, 0 uses the intended layout.                      */
+} bmg_scan_types_params;
+
+/* RaoBlackwellizer::p_raoblackwell for any configuration of effect types, over the local shard, using the residual left
+ * by bmg_chain_residual[_types].  Model SNP l has effect type loci_type[l] (0..4), coefficients beta2[2l], beta2[2l+1] and
+ * prior precisions tau2[2l], tau2[2l+1] (second entries used by AH only).  Both sums every type needs, sum_{x=1} r and
+ * sum_{x=2} r, come from two passes of the tensor-core scan kernel over the packed store (additive and heterozygote
+ * operands); p_r (m) always, p_r_types (m x n_types, the normalised type distribution of sampler.cpp:240-250) when
+ * n_types > 1.  Either host pointer may be NULL. */
+int bmg_chain_scan_types(bmg_chain* c, const int64_t* loci, const int32_t* loci_type, const double* beta2,
+                         const double* tau2, int k, const bmg_scan_types_params* prm, double* p_r_host,
+                         double* p_r_types_host);
+
 /* Only the x_j . r reductions of the scan (dot[local m]); the roofline kernel in isolation. */
 int bmg_chain_scan_dots(bmg_chain* c, double* dot_host);
 /* Kernel variant used by bmg_chain_scan/_dots: 0 = fp64, direct vectorised global loads;

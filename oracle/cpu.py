@@ -324,3 +324,144 @@ def probit_latent(mu, is_case, u):
     z = np.empty_like(mu)
     lib().orc_probit_latent(_p(mu), _u8(ic), _p(u), C.c_long(mu.size), _p(z))
     return z
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The all-SNP scan with several effect types (src/sampler.cpp:32-261 with n_types > 1, or one type other than A):
+# numpy restatement, pinned against the unmodified reference in tests/test_oracle_goldens.py.
+# ---------------------------------------------------------------------------------------------------------------
+TYPE_A, TYPE_H, TYPE_D, TYPE_R, TYPE_AH = 0, 1, 2, 3, 4
+
+
+def term_flags(types):
+    """DataModel::allow_types_ / allow_terms_ (data_model.hpp:61-73)."""
+    allow_types = [t in types for t in range(5)]
+    allow_terms = [False] * 4
+    for t in types:
+        if t == TYPE_AH:
+            allow_terms[TYPE_A] = allow_terms[TYPE_H] = True
+        else:
+            allow_terms[t] = True
+    return allow_types, allow_terms
+
+
+def typed(col, t):
+    """DataModel::get_genotypes[t] on an additive column (data_model.cpp:41-72)."""
+    if t == TYPE_A:
+        return col.copy()
+    if t == TYPE_H:
+        return (col == 1).astype(np.float64)
+    if t == TYPE_D:
+        return (col > 0).astype(np.float64)
+    return (col == 2).astype(np.float64)
+
+
+def scan_types(columns0, columns, n, types, y, y_hat, model, sigma2, lmp_add, lmp_rem, tau_shared=None, tau_snp=None,
+               reference_offsets=True):
+    """p_r (m) and p_r_types (m x n_types; None when n_types == 1).
+    columns0[j] / columns[j]: additive column of SNP j with missing cells = 0 / = the chain's imputed values.
+    model: dict snp -> (type code, [beta1, beta2], [tau1, tau2]) for the SNPs in the model.
+    tau_shared[4]: value per TERM type (shared-tau mode); tau_snp[m][n_terms]: per-SNP draws in increasing term code.
+    reference_offsets: index the moment cache as the reference does -- offset_type[t] counts TERMS although a term
+    occupies two slots (precomputed_snp_covariances.hpp:73-83 vs :113-118), so with several term types every non-first
+    type reads (s, v) one slot early.  False: the intended layout."""
+    m = len(columns)
+    n_types = len(types)
+    allow_types, allow_terms = term_flags(types)
+    terms = [t for t in range(4) if allow_terms[t]]
+    rank = {t: i for i, t in enumerate(terms)}
+    offset = 2 * len(terms) + (1 if allow_types[TYPE_AH] else 0)
+    r_cm = y - y_hat
+    mr_cm = r_cm.sum() / n
+    p_r = np.zeros(m)
+    prt = np.zeros((m, n_types))
+    for j in range(m):
+        x0, x1 = columns0[j], columns[j]
+        # PrecomputedSNPCovariances (missing = 0) then DataModel::update_prexx_cov (imputed values)
+        pre = np.zeros(offset)
+        for t in terms:
+            xt = typed(x0, t)
+            s0 = xt.sum()
+            pre[2 * rank[t]] = s0
+            pre[2 * rank[t] + 1] = xt @ xt - s0 * s0 / n
+        if allow_types[TYPE_AH]:
+            pre[offset - 1] = typed(x0, TYPE_A) @ typed(x0, TYPE_H) - typed(x0, TYPE_A).sum() * typed(x0, TYPE_H).sum() / n
+        miss = np.flatnonzero(x0 != x1)
+        # cells whose imputed value is 0 do not change anything either, so "x0 != x1" is enough
+        if miss.size:
+            sa_sh = pre[0] * pre[2] if allow_types[TYPE_AH] else 0.0
+            for t in terms:
+                vg = typed(x1, t)[miss]
+                sv, sv2 = vg.sum(), (vg * vg).sum()
+                old = pre[2 * rank[t]]
+                pre[2 * rank[t]] += sv
+                pre[2 * rank[t] + 1] += sv2 - sv * (old * 2.0 + sv) / n
+            if allow_types[TYPE_AH]:
+                pre[offset - 1] += (sa_sh - pre[0] * pre[2]) / n
+                pre[offset - 1] += float((x1[miss] == 1).sum())
+        # taus of this SNP
+        tau = np.zeros(4)
+        for t in terms:
+            tau[t] = tau_shared[t] if tau_snp is None else tau_snp[j][rank[t]]
+        if j in model:
+            mt, betas, mtaus = model[j]
+            if tau_snp is not None:
+                if mt == TYPE_AH:
+                    tau[TYPE_A], tau[TYPE_H] = mtaus[0], mtaus[1]
+                else:
+                    tau[mt] = mtaus[0]
+            if mt == TYPE_AH:
+                residual = r_cm + typed(x1, TYPE_A) * betas[0] + typed(x1, TYPE_H) * betas[1]
+            else:
+                residual = r_cm + typed(x1, mt) * betas[0]
+            mr = residual.sum() / n
+            lmp = lmp_rem[mt]
+        else:
+            residual, mr, lmp = r_cm, mr_cm, lmp_add
+        p = np.zeros(n_types)
+        for ti, t in enumerate(types):
+            if t == TYPE_AH:
+                sa, va = pre[0], pre[1] + tau[TYPE_A]
+                sh, vh = pre[2], pre[3] + tau[TYPE_H]
+                vah = pre[offset - 1]
+                sum_log_q = -np.log(tau[TYPE_A]) - np.log(tau[TYPE_H])
+                rxa = typed(x1, TYPE_A) @ residual - sa * mr
+                rxh = typed(x1, TYPE_H) @ residual - sh * mr
+                det = va * vh - vah * vah
+                exp_term = (rxa * rxa * vh - 2.0 * rxa * rxh * vah + rxh * rxh * va) / det
+            else:
+                o = rank[t] if reference_offsets else 2 * rank[t]
+                s = pre[o]
+                det = pre[o + 1] + tau[t]
+                sum_log_q = -np.log(tau[t])
+                rx = typed(x1, t) @ residual - s * mr
+                exp_term = rx * rx / det
+            with np.errstate(invalid="ignore", divide="ignore"):
+                p[ti] = exp_term / (2 * sigma2) - 0.5 * (np.log(det) + sum_log_q) + lmp[t]
+        if n_types == 1:
+            with np.errstate(over="ignore"):
+                e = np.exp(p[0])
+            p_r[j] = e / (1 + e) if np.isfinite(e) else 1.0
+            continue
+        mx = -np.inf
+        for v in p:   # "if (p > max_types)": a NaN never becomes the maximum
+            if v > mx:
+                mx = v
+        if not np.isfinite(mx):
+            if mx > 0:
+                w = np.array([1.0 if (not np.isfinite(v) and v > 0) else 0.0 for v in p])
+                prt[j] = w / w.sum()
+                p_r[j] = 1.0
+            else:
+                prt[j] = 1.0 / n_types
+                p_r[j] = 0.0
+            continue
+        w = np.exp(p - mx)
+        tot = 0.0
+        for v in w:
+            tot += v
+        prt[j] = w / tot
+        with np.errstate(over="ignore"):
+            st = np.exp(np.log(tot) + mx)
+        p_r[j] = st / (1 + st) if np.isfinite(st) else 1.0
+    return p_r, (prt if n_types > 1 else None)

@@ -145,6 +145,12 @@ class Ref:
                 "inv_tau2_alpha2_A", "e_g")
         return dict(zip(keys, out))
 
+    def prior_terms(self):
+        """(4, 3) array: per term type A,H,D,R the shared inv_tau2_alpha2 value, nu_tau2, s2_tau2 (NaN if not allowed)."""
+        out = np.zeros(12)
+        self.L.refd_prior_terms(self.h, _p(out))
+        return out.reshape(4, 3)
+
     def prior_set_alpha(self, a):
         self.L.refd_prior_set_alpha(self.h, C.c_double(a))
 

@@ -205,6 +205,13 @@ void refd_prior_params(void* h, double* out)
   out[8] = p->use_individual_tau2 ? NAN : p->inv_tau2_alpha2[0];
   out[9] = p->e_g();
 }
+/* per TERM type t = A,H,D,R: out[3t..] = {inv_tau2_alpha2[t] (shared-tau value), nu_tau2[t], s2_tau2[t]}; NaN where the
+   term is not allowed (prior.hpp:88-119) */
+void refd_prior_terms(void* h, double* out12)
+{
+  Prior* p = ((RefCtx*)h)->sampler->prior;
+  for (int t = 0; t < 4; ++t) { out12[3 * t] = p->inv_tau2_alpha2[t]; out12[3 * t + 1] = p->nu_tau2[t]; out12[3 * t + 2] = p->s2_tau2[t]; }
+}
 void refd_prior_set_alpha(void* h, double a) { RefCtx* c = (RefCtx*)h; c->sampler->prior->set_alpha(a, c->sampler->current_model); }
 
 /* ---- Model (model.hpp:199-312) on the sampler's current_model ---- */

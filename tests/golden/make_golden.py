@@ -405,7 +405,23 @@ def run_mcmcpos():
     print("wrote ref_mcmcpos.json")
 
 
+def run_typed_scan():
+    """The reference's scan for several effect-type configurations (tests/typed_scan_cases.py) -> ref_typed_scan.npz."""
+    from tests import typed_scan_cases as tc
+    out = {}
+    for tag, types, miss, indiv in tc.CASES:
+        c = tc.reference_case(ref, tempfile.mkdtemp(), types, miss, indiv)
+        for k in tc.GOLDEN_KEYS:
+            out["%s_%s" % (tag, k)] = np.asarray(c[k])
+    np.savez_compressed(os.path.join(HERE, "ref_typed_scan.npz"), **out)
+    print("wrote ref_typed_scan.npz:", len(out), "arrays;", os.path.getsize(os.path.join(HERE, "ref_typed_scan.npz")), "bytes")
+
+
 def main():
+    if "--typed-scan-only" in sys.argv:
+        assert ref.available(), "build oracle/_ref first (make -C oracle ref)"
+        run_typed_scan()
+        return
     if "--mcmcpos-only" in sys.argv:
         run_mcmcpos()
         return
@@ -438,6 +454,7 @@ def main():
     run_missing_chains(tmp, out2)
     np.savez_compressed(os.path.join(HERE, "ref_missing_chains.npz"), **out2)
     run_mcmcpos()
+    run_typed_scan()
     print("wrote", len(out), "arrays;", os.path.getsize(os.path.join(HERE, "ref_outputs.npz")), "bytes")
 
 

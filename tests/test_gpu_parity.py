@@ -411,6 +411,77 @@ def test_device_imputation_draws_follow_the_prior_and_skip_the_model(api):
     st.close()
 
 
+# ------------------------------------------------------------------------------ scan with effect types (f1)
+def test_typed_scan_matches_reference_goldens_and_oracle(api, tmp_path):
+    """the scan for every configuration of effect types (A, H, D, R, AH), models holding SNPs of those
+    types, shared and per-SNP prior precisions, with and without missing calls: p_r and the per-type distribution against
+    the unmodified reference's outputs (tests/golden/ref_typed_scan.npz) and against the numpy restatement, to 1e-9."""
+    from tests import typed_scan_cases as tc
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_typed_scan.npz"))
+    for tag, types, miss, indiv in tc.CASES:
+        c = tc.load_case(g, tag, str(tmp_path / tag))
+        st = api.GenotypeStore(c["payload"], tc.N, tc.M_G, recode_to_minor=True)
+        st.set_phenotype(c["y"], c["E"][:, 1:])
+        ch = api.Chain(st)
+        if c["miss_vals"].size:
+            ch.set_missing_all(c["miss_vals"])
+        loci, tt, bg = tc.model_terms(c)
+        ch.residual_types(loci, tt, c["beta_e"], bg)
+        loci_type = np.array([c["codes"][int(ti)] for ti in c["model_ti"]], dtype=np.int32)
+        p_r, prt = ch.scan_types(c["codes"], c["model_snp"], loci_type, c["model_beta"], c["model_tau"], c["sigma2"], c["lmp_add"],
+                                 c["lmp_rem"], tau_shared=c["tau_shared"], tau_snp=c["tau_snp"] if c["indiv"] else None)
+        assert np.allclose(p_r, c["p_r"], rtol=1e-9, atol=1e-12), tag
+        o_pr, o_prt = tc.oracle_scan(c)
+        assert np.allclose(p_r, o_pr, rtol=1e-9, atol=1e-12), tag
+        if len(c["codes"]) > 1:
+            assert np.allclose(prt, c["prt"], rtol=1e-9, atol=1e-12), tag
+            assert np.allclose(prt, o_prt, rtol=1e-9, atol=1e-12), tag
+        if tag == "A_H_D_R":   # the intended moment layout is available too, and differs from the reference's
+            p2, _ = ch.scan_types(c["codes"], c["model_snp"], loci_type, c["model_beta"], c["model_tau"], c["sigma2"], c["lmp_add"],
+                                  c["lmp_rem"], tau_shared=c["tau_shared"], tau_snp=c["tau_snp"] if c["indiv"] else None,
+                                  reference_offsets=False)
+            o2, _ = tc.oracle_scan(c, reference_offsets=False)
+            assert np.allclose(p2, o2, rtol=1e-9, atol=1e-12) and np.abs(p2 - p_r).max() > 1e-6
+        ch.close()
+        st.close()
+
+
+def test_typed_columns_feed_the_column_statistics(api):
+    """Typed columns (H, D, R) are materialised as 0/1 packed columns by the overlay cache, so the fitted values of a typed
+    model equal the oracle's: checked through the residual of bmg_chain_residual_types, with missing calls."""
+    n, m = 1203, 50
+    payload, y, E = make_data(n, m, seed=91, miss_rate=0.04)
+    bed, _ = oracle_store(payload, n, m, True)
+    st = api.GenotypeStore(payload, n, m, recode_to_minor=True)
+    st.set_phenotype(y, E)
+    ch = api.Chain(st)
+    off, idx, _ = cpu.missing_index(bed, n, m)
+    rs = np.random.default_rng(2)
+    val = rs.integers(0, 3, size=idx.size).astype(np.int8)
+    ch.set_missing_all(val)
+    loci = np.array([4, 4, 9, 17, 30, 41], dtype=np.int64)
+    tt = np.array([0, 1, 2, 3, 1, 0], dtype=np.int32)
+    bg = rs.normal(size=loci.size)
+    be = rs.normal(size=3)
+
+    def col(j):
+        return cpu.decode_column_overlay(bed, n, int(j), 0, idx[off[j]:off[j + 1]], val[off[j]:off[j + 1]])
+
+    X = np.column_stack([np.ones(n), E] + [cpu.typed(col(j), int(t)) for j, t in zip(loci, tt)])
+    for _ in range(2):   # second call: every typed column comes from the cache
+        ch.residual_types(loci, tt, be, bg)
+        assert np.allclose(ch.get_residual(), y - X @ np.concatenate([be, bg]), rtol=1e-12, atol=1e-10)
+    # new imputed values for SNP 4: its cached additive AND heterozygous columns must follow
+    j = 4
+    val[off[j]:off[j + 1]] = (val[off[j]:off[j + 1]] + 1) % 3
+    ch.set_missing(j, val[off[j]:off[j + 1]])
+    X = np.column_stack([np.ones(n), E] + [cpu.typed(col(jj), int(t)) for jj, t in zip(loci, tt)])
+    ch.residual_types(loci, tt, be, bg)
+    assert np.allclose(ch.get_residual(), y - X @ np.concatenate([be, bg]), rtol=1e-12, atol=1e-10)
+    ch.close()
+    st.close()
+
+
 # ------------------------------------------------------------------------------ column stats (a7)
 @pytest.mark.parametrize("n,m,miss", [(203, 300, 0.02), (5000, 200, 0.0), (40000, 50, 0.001)])
 def test_column_stats_match_oracle(api, n, m, miss):

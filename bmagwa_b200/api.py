@@ -203,7 +203,7 @@ class Chain:
         return stats
 
     def scan_types(self, types, loci, loci_type, beta2, tau2, sigma2, lmp_add, lmp_rem, tau_shared=None, tau_snp=None,
-                   reference_offsets=True):
+                   reference_offsets=True, fetch=True):
         """(p_r, p_r_types or None): bmg_chain_scan_types.  beta2 / tau2: (k, 2)."""
         from ._lib import ScanTypesParams
         prm = ScanTypesParams()
@@ -232,10 +232,10 @@ class Chain:
         b2 = _f64(np.asarray(beta2, dtype=np.float64).reshape(-1)) if loci.size else np.zeros(2)
         t2 = _f64(np.asarray(tau2, dtype=np.float64).reshape(-1)) if loci.size else np.zeros(2)
         m = self.store.m
-        p_r = np.zeros(m)
-        prt = np.zeros((m, len(types))) if len(types) > 1 else None
+        p_r = np.zeros(m) if fetch else None
+        prt = np.zeros((m, len(types))) if len(types) > 1 and fetch else None
         check(self.L.bmg_chain_scan_types(self.h, _pi(loci), lt.ctypes.data_as(i32p), _pf(b2), _pf(t2), loci.size, C.byref(prm),
-                                          _pf(p_r), _pf(prt) if prt is not None else None))
+                                          _pf(p_r) if p_r is not None else None, _pf(prt) if prt is not None else None))
         return p_r, prt
 
     def get_residual(self):

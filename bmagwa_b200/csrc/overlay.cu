@@ -66,12 +66,16 @@ static void overlay_prepare(Chain* c)
   c->pc_next = 0;
 }
 
+// Round-robin with a second chance: the model's SNPs take part in every request, so their slots always carry a recent
+// sequence number and survive; the slots of proposed SNPs that were not accepted go stale and are reused.
 static int overlay_take_slot(Chain* c)
 {
+  constexpr unsigned int kRecent = 128;   // requests
   for (int tries = 0; tries < 2 * c->pc_slots; ++tries) {
     const int slot = c->pc_next;
     c->pc_next = (slot + 1) % c->pc_slots;
     if (c->pc_use[slot] == c->pc_seq) continue;   // in use by the request being resolved
+    if (tries < c->pc_slots && c->pc_snp[slot] >= 0 && c->pc_seq - c->pc_use[slot] < kRecent) continue;
     if (c->pc_snp[slot] >= 0) c->pc_map.erase(c->pc_snp[slot]);
     return slot;
   }

@@ -130,45 +130,79 @@ def pin_rank_to_core(local_rank, world):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md).  nvidia-smi needs a few
+    hundred ms before its first line, more than a short timed region lasts, so it is started before the warm-up steps and
+    its time-stamped samples are cut to the timed region afterwards (begin() / end() bracket it)."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device_index):
         self.idx = device_index
         self.p = None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                       "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.p = None
+
+    def begin(self):
+        self.t0 = time.time()
+
+    def end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if self.p is None:
             return None
-        self.p.terminate()
+        if self.t1 is None:
+            self.end()
         try:
-            out, _ = self.p.communicate(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.p.kill()
-            out, _ = self.p.communicate()
-        sm, smax, reasons = [], [], set()
-        for line in out.splitlines():
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 9:
-                continue
+            self.p.terminate()
             try:
-                sm.append(float(f[1])); smax.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
+                out, _ = self.p.communicate(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.p.kill()
+                out, _ = self.p.communicate()
+            return parse_clock_samples(out, self.t0, self.t1)
+        except Exception:
             return None
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def parse_clock_samples(out, t0, t1):
+    """Samples of `nvidia-smi --query-gpu=timestamp,index,clocks.sm,... -lms` inside [t0, t1] (epoch seconds); when the
+    region is shorter than the sampling interval and holds none, the sample nearest to it is used and `window` says so."""
+    import datetime
+    rows = []
+    for line in out.splitlines():
+        f = [x.strip() for x in line.split(",")]
+        if len(f) < 10:
+            continue
+        try:
+            ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+            sm, smax = float(f[2]), float(f[3])
+        except ValueError:
+            continue
+        reasons = set(name for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[6:10])
+                      if v.lower().startswith("active"))
+        rows.append((ts, sm, smax, reasons))
+    if not rows:
+        return None
+    window = "timed region"
+    if t0 is not None and t1 is not None:
+        inside = [r for r in rows if t0 - 0.02 <= r[0] <= t1 + 0.02]
+        if not inside:
+            mid = 0.5 * (t0 + t1)
+            inside = [min(rows, key=lambda r: abs(r[0] - mid))]
+            window = "nearest sample, %.0f ms from the timed region (shorter than the sampling interval)" % (1e3 * abs(inside[0][0] - mid))
+        rows = inside
+    reasons = set()
+    for r in rows:
+        reasons |= r[3]
+    return {"sm_mhz": float(np.median([r[1] for r in rows])), "sm_max_mhz": float(max(r[2] for r in rows)),
+            "reasons": sorted(reasons), "samples": len(rows), "window": window}
 
 
 def measured_peak():
@@ -321,6 +355,8 @@ def ours_arm(args, rank, local_rank, world):
             flush.zero_()            # evict the 125 MB store from the 126 MB L2 before every step
         s.run(args.n_rao)
 
+    clocks = ClockSampler(dev)
+    clocks.start()   # streaming by the time the timed region begins; samples are cut to it afterwards
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
@@ -328,8 +364,7 @@ def ours_arm(args, rank, local_rank, world):
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
-    clocks = ClockSampler(dev)
-    clocks.start()
+    clocks.begin()
     launches0 = L.bmg_launch_count()
     h2d0, d2h0 = transfers()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -341,6 +376,7 @@ def ours_arm(args, rank, local_rank, world):
     e1.synchronize()
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
+    clocks.end()
     ev_ms = e0.elapsed_time(e1)
     clk = clocks.stop()
     launches = L.bmg_launch_count() - launches0
@@ -528,15 +564,16 @@ def sharded_arm(args, rank, local_rank, world):
             flush.zero_()
         s.run(args.n_rao)
 
+    clocks = ClockSampler(dev)
+    if rank == 0:
+        clocks.start()
     for _ in range(args.warmup):
         step()
     L.bmg_chain_scan_kernel_time(chain, 1, None, None, 1)
     st0 = s.stats()
     launches_a = int(L.bmg_launch_count())
-    clocks = ClockSampler(dev)
-    if rank == 0:
-        clocks.start()
     torch.cuda.synchronize(); dist.barrier()
+    clocks.begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record(stream)
@@ -545,6 +582,7 @@ def sharded_arm(args, rank, local_rank, world):
     e1.record(stream)
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
+    clocks.end()
     dist.barrier()
     clk = clocks.stop() if rank == 0 else None
     t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)

@@ -150,3 +150,25 @@ def test_multi_rank_launch_over_gloo(tmp_path):
                         "127.0.0.1", "--master-port", "29541", str(script)], capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stderr[-2000:]
     assert "gloo ok" in r.stdout
+
+
+def test_bench_clock_samples_are_cut_to_the_timed_region():
+    """bench.py starts nvidia-smi before the warm-up and keeps the time-stamped samples inside the timed region; a region
+    shorter than the sampling interval falls back to the nearest sample and says so."""
+    import datetime
+    import time
+    sys.path.insert(0, ROOT)
+    import bench
+    now = time.time()
+
+    def ts(t):
+        return datetime.datetime.fromtimestamp(t).strftime("%Y/%m/%d %H:%M:%S.%f")[:-3]
+
+    lines = "\n".join("%s, 0, %d, 1965, 400.1, 0x0000000000000000, Not Active, Not Active, Not Active, %s"
+                      % (ts(now + 0.05 * i), 1900 + i, "Active" if i == 3 else "Not Active") for i in range(10))
+    c = bench.parse_clock_samples(lines, now + 0.1, now + 0.3)
+    assert c["samples"] == 5 and c["sm_mhz"] == 1904.0 and c["sm_max_mhz"] == 1965.0
+    assert c["reasons"] == ["sw_power_cap"] and c["window"] == "timed region"
+    c = bench.parse_clock_samples(lines, now + 1.0, now + 1.01)
+    assert c["samples"] == 1 and c["sm_mhz"] == 1909.0 and c["window"].startswith("nearest sample")
+    assert bench.parse_clock_samples("garbage\n", now, now + 1) is None

@@ -73,19 +73,24 @@ inline void rows_missing_in_model(const MissingCells& mc, const std::vector<uint
   rows.erase(std::unique(rows.begin(), rows.end()), rows.end());
 }
 
+// Buffers of the Gibbs step, kept between calls (the step runs every n_sample_tau2_and_missing iterations)
+struct GibbsScratch {
+  std::vector<double> xold, xnew, y_hat, residual;
+  std::vector<int32_t> slot;      // individual -> position in rows; all -1 between calls
+  std::vector<uint8_t> changed;   // per row: did any of its cells get a new value
+};
+
 // Sampler::sample_missing (sampler.cpp:264-453), effect type A.
 //   cur    current model; xx and xy are patched in place (sampler.cpp:393-450), mu_beta_computed is cleared
 //   rows   rows_missing_in_model(...) (q of them); cells = k x q genotype values with the chain's imputed values
 //          applied, as they are BEFORE this update, bit 2 set where the cell is a missing call (bmg_chain_get_cells
 //          over cur.loci)
-//   slot   scratch of n entries, all -1 on entry and on return (individual -> position in rows)
 //   y, e   phenotype (n) and covariates (n x m_e, column-major, ones column included)
 //   yy     y'y.  The reference sums the squared residual over all n individuals; here r'r comes from the Gram
 //          matrix, r'r = y'y - 2 b'X'y + b'X'X b (it only enters through differences in which it cancels).
 // On return mc.val holds the new imputed values of the in-model SNPs.
 inline void gibbs_missing_in_model(Model& cur, MissingCells& mc, const std::vector<int32_t>& rows, const int8_t* cells,
-                                   const double* y, const double* e, size_t n, double yy, ChainRng& rng,
-                                   std::vector<int32_t>& slot)
+                                   const double* y, const double* e, size_t n, double yy, ChainRng& rng, GibbsScratch& ws)
 {
   const int m_e = cur.m_e, cols = cur.cols(), k = (int)cur.size();
   const size_t q = rows.size();
@@ -95,24 +100,41 @@ inline void gibbs_missing_in_model(Model& cur, MissingCells& mc, const std::vect
   const double sigma2_times_2 = cur.sigma2 * 2;
 
   // the touched rows of the design matrix, before (xold: the reference's new_model->x) and after (xnew) the update
-  std::vector<double> xold(q * (size_t)cols), y_hat(q), residual(q);
+  ws.xold.resize(q * (size_t)cols);
+  ws.xnew.resize(q * (size_t)cols);
+  ws.y_hat.resize(q);
+  ws.residual.resize(q);
+  ws.changed.assign(q, 0);
+  double* const xold = ws.xold.data();
+  double* const xnew = ws.xnew.data();
+  double* const y_hat = ws.y_hat.data();
+  double* const residual = ws.residual.data();
+  for (size_t u0 = 0; u0 < q; u0 += 128) {   // blocks of rows, column by column inside: e and cells are column-major
+    const size_t u1 = std::min(q, u0 + 128);
+    for (int c = 0; c < m_e; ++c) {
+      const double* ec = e + (size_t)c * n;
+      for (size_t u = u0; u < u1; ++u) xold[u * cols + c] = ec[rows[u]];
+    }
+    for (int l = 0; l < k; ++l) {
+      const int8_t* cl = cells + (size_t)l * q;
+      for (size_t u = u0; u < u1; ++u) xold[u * cols + m_e + l] = (double)(cl[u] & 3);
+    }
+  }
   for (size_t u = 0; u < q; ++u) {
-    double* row = &xold[u * cols];
-    for (int c = 0; c < m_e; ++c) row[c] = e[(size_t)c * n + rows[u]];
-    for (int l = 0; l < k; ++l) row[m_e + l] = (double)(cells[(size_t)l * q + u] & 3);
+    const double* row = xold + u * cols;
     double s = 0.0;   // y_hat = X beta, accumulated column by column like the dgemv of Vector::set_to_product
     for (int c = 0; c < cols; ++c) s += beta[c] * row[c];
     y_hat[u] = s;
     residual[u] = y[rows[u]] - s;
   }
-  std::vector<double> xnew(xold);
+  std::copy(xold, xold + q * (size_t)cols, xnew);
   double r2 = yy;
   for (int c = 0; c < cols; ++c) r2 -= 2.0 * beta[c] * cur.xy[c];
   r2 += cur.quad(0, cols);
 
-  if (slot.size() != n) slot.assign(n, -1);
+  if (ws.slot.size() != n) ws.slot.assign(n, -1);
+  int32_t* const slot = ws.slot.data();
   for (size_t u = 0; u < q; ++u) slot[rows[u]] = (int32_t)u;
-  auto slot_of = [&](int32_t individual) { return (size_t)slot[individual]; };
 
   double lprior[3], likelihood[3];
   for (int t = 0; t < k; ++t) {
@@ -124,8 +146,8 @@ inline void gibbs_missing_in_model(Model& cur, MissingCells& mc, const std::vect
     lprior[1] = std::log(p3[1] - p3[0]);
     lprior[2] = std::log(p3[2] - p3[1]);
     for (int64_t c = mc.off[snp]; c < mc.off[snp + 1]; ++c) {
-      const size_t u = slot_of(mc.idx[c]);
-      double* row = &xnew[u * cols];
+      const size_t u = (size_t)slot[mc.idx[c]];
+      double* row = xnew + u * cols;
       const double old_term2 = residual[u] * residual[u];
       for (int g = 0; g < 3; ++g) {
         const double new_term = residual[u] - beta[x_ind] * ((double)g - row[x_ind]);
@@ -138,6 +160,7 @@ inline void gibbs_missing_in_model(Model& cur, MissingCells& mc, const std::vect
       likelihood[2] = std::exp(likelihood[2]) + likelihood[1];
       const int g = MissingCells::draw3(likelihood, rng);
       mc.val[c] = (int8_t)g;
+      if ((double)g != row[x_ind]) ws.changed[u] = 1;
       y_hat[u] += beta[x_ind] * ((double)g - row[x_ind]);
       row[x_ind] = (double)g;
       residual[u] = y[mc.idx[c]] - y_hat[u];
@@ -145,21 +168,26 @@ inline void gibbs_missing_in_model(Model& cur, MissingCells& mc, const std::vect
     }
   }
 
-  // X'y and the upper triangle of X'X follow the changed cells (sampler.cpp:393-427)
+  // X'y and the upper triangle of X'X follow the changed cells (sampler.cpp:393-427).  A row in which no cell got a new
+  // value contributes x*x' - x*x' = 0 exactly to every entry, so it is skipped.
   for (int t = 0; t < k; ++t) {
     const size_t snp = cur.loci[t];
     if (mc.count(snp) == 0) continue;
     const int x_ind = m_e + t;
     for (int64_t c = mc.off[snp]; c < mc.off[snp + 1]; ++c) {
       const int32_t i_miss = mc.idx[c];
-      const size_t u = slot_of(i_miss);
-      const double* xn = &xnew[u * cols];
-      const double* xo = &xold[u * cols];
-      cur.xy[x_ind] += y[i_miss] * (xn[x_ind] - xo[x_ind]);
+      const size_t u = (size_t)slot[i_miss];
+      if (!ws.changed[u]) continue;
+      const double* xn = xnew + u * cols;
+      const double* xo = xold + u * cols;
+      const double xnx = xn[x_ind], xox = xo[x_ind];
+      cur.xy[x_ind] += y[i_miss] * (xnx - xox);
+      double* up = cur.xx.col(x_ind);   // xx(j, x_ind), j < x_ind
       int j = 0;
+      for (; j < m_e; ++j) up[j] += xnx * xn[j] - xox * xo[j];
       for (; j < x_ind; ++j)   // a column that is itself missing here is patched when its own cell comes up
-        if (j < m_e || !(cells[(size_t)(j - m_e) * q + u] & 4)) cur.xx(j, x_ind) += xn[x_ind] * xn[j] - xo[x_ind] * xo[j];
-      for (; j < cols; ++j) cur.xx(x_ind, j) += xn[x_ind] * xn[j] - xo[x_ind] * xo[j];
+        if (!(cells[(size_t)(j - m_e) * q + u] & 4)) up[j] += xnx * xn[j] - xox * xo[j];
+      for (; j < cols; ++j) cur.xx(x_ind, j) += xnx * xn[j] - xox * xo[j];
     }
   }
   for (size_t u = 0; u < q; ++u) slot[rows[u]] = -1;

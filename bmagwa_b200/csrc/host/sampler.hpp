@@ -134,7 +134,8 @@ class Sampler {
   int missing_on_device_ = -1;         // re-imputation before scans: 0 host stream (parity), 1 device, -1 follow tau_rng
   uint64_t impute_counter_ = 0;
   double yy_ = 0.0;                    // y'y of the working phenotype
-  std::vector<int32_t> gibbs_rows_, gibbs_slot_;
+  std::vector<int32_t> gibbs_rows_;
+  GibbsScratch gibbs_slot_;
   std::vector<int8_t> gibbs_cells_;
   std::vector<double> y_work_;         // probit mode: host copy of the latent phenotype for the Gibbs step
   void load_missing_index();

@@ -40,9 +40,9 @@ int harness_gibbs(int m_e, int k, const unsigned* loci, double* xx, double* xy, 
       cells[(size_t)l * q + u] = (int8_t)((int)xcols[(size_t)l * n + rows[u]] | (mc.is_missing(rows[u], loci[l]) ? 4 : 0));
   ChainRng rng(seed, nu);
   for (int i = 0; i < skip_draws; ++i) rng.u01();
-  std::vector<int32_t> slot;
-  gibbs_missing_in_model(cur, mc, rows, cells.data(), y, e, (size_t)n, yy, rng, slot);
-  for (int32_t v : slot) if (v != -1) return -1;   // the scratch must come back clean
+  GibbsScratch ws;
+  gibbs_missing_in_model(cur, mc, rows, cells.data(), y, e, (size_t)n, yy, rng, ws);
+  for (int32_t v : ws.slot) if (v != -1) return -1;   // the scratch must come back clean
   for (int c = 0; c < cols; ++c)
     for (int r = 0; r <= c; ++r) xx[(size_t)c * cols + r] = cur.xx(r, c);
   std::memcpy(xy, cur.xy.data(), sizeof(double) * cols);
@@ -65,3 +65,51 @@ void harness_draw_all_from_prior(long m_g, const long* off, signed char* val, co
 }
 
 }  // extern "C"
+
+#include <time.h>
+// Wall seconds per call of gibbs_missing_in_model over `reps` calls on the same starting state (development timing aid).
+extern "C" double harness_gibbs_seconds(int m_e, int k, const unsigned* loci, const double* xx, const double* xy, const double* beta,
+                                        double sigma2, long m_g, const long* off, const int* idx, const signed char* val,
+                                        const double* prior3, const double* xcols, const double* y, const double* e, long n,
+                                        double yy, int reps)
+{
+  Model base;
+  base.m_e = m_e;
+  base.loci.assign(loci, loci + k);
+  const int cols = m_e + k;
+  base.xx.resize(cols);
+  for (int c = 0; c < cols; ++c)
+    for (int r = 0; r <= c; ++r) base.xx(r, c) = xx[(size_t)c * cols + r];
+  base.xy.assign(xy, xy + cols);
+  base.beta.assign(beta, beta + cols);
+  base.sigma2 = sigma2;
+  MissingCells mc0;
+  mc0.off.assign(off, off + m_g + 1);
+  mc0.idx.assign(idx, idx + off[m_g]);
+  mc0.val.assign(val, val + off[m_g]);
+  mc0.prior3.assign(prior3, prior3 + 3 * m_g);
+  std::vector<int32_t> rows;
+  GibbsScratch slot;
+  ChainRng rng(1u, 1.0);
+  double total = 0.0;
+  for (int it = 0; it < reps; ++it) {
+    Model cur;
+    cur.assign(base);
+    MissingCells mc = mc0;
+    struct timespec a, b;
+    clock_gettime(CLOCK_MONOTONIC, &a);
+    rows_missing_in_model(mc, cur.loci, rows);
+    const size_t q = rows.size();
+    std::vector<int8_t> cells((size_t)k * q);
+    for (int l = 0; l < k; ++l)
+      for (size_t u = 0; u < q; ++u)
+        cells[(size_t)l * q + u] = (int8_t)((int)xcols[(size_t)l * n + rows[u]] | (mc.is_missing(rows[u], loci[l]) ? 4 : 0));
+    struct timespec a2;
+    clock_gettime(CLOCK_MONOTONIC, &a2);
+    gibbs_missing_in_model(cur, mc, rows, cells.data(), y, e, (size_t)n, yy, rng, slot);
+    clock_gettime(CLOCK_MONOTONIC, &b);
+    (void)a;
+    total += (b.tv_sec - a2.tv_sec) + 1e-9 * (b.tv_nsec - a2.tv_nsec);
+  }
+  return total / reps;
+}

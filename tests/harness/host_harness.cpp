@@ -113,3 +113,118 @@ extern "C" double harness_gibbs_seconds(int m_e, int k, const unsigned* loci, co
   }
   return total / reps;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// The other pure host pieces of the sampler (rng.hpp, model.hpp), for tests/test_cpu_host_model.py
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+// ChainRng (rand.hpp:36-191 re-stated): the draw pattern of tests/golden/make_golden.py::run_rng
+void harness_rng_sequence(unsigned seed, double nu, int rounds, double* out)
+{
+  ChainRng g(seed, nu);
+  for (int i = 0; i < rounds; ++i) {
+    *out++ = g.u01(); *out++ = g.normal(); *out++ = g.sinvchi2_fixed(0.7); *out++ = g.sinvchi2(5.0, 0.05);
+    *out++ = g.sinvchi2(0.6, 1.3); *out++ = g.u01(); *out++ = g.normal(); *out++ = g.sinvchi2(2.0, 1.0);
+  }
+}
+
+static Prior* make_prior(long n, long m_g, int m_e, double yy, double e_qg, double var_qg, double nu_sigma2, double s2_sigma2,
+                         double nu_tau2, double s2_tau2, double mu_alpha, int individual, double inv_tau2_e_const, double inv_tau2_e_val)
+{
+  const double types_prior[5] = {1, 1, 1, 1, 1};
+  std::vector<double> inv_tau2_e((size_t)m_e, inv_tau2_e_val);
+  inv_tau2_e[0] = inv_tau2_e_const;
+  return new Prior((size_t)n, (size_t)m_g, (size_t)m_e, yy, types_prior, e_qg, var_qg, inv_tau2_e, nu_sigma2, s2_sigma2, nu_tau2,
+                   s2_tau2, mu_alpha, individual != 0);
+}
+
+// Prior (prior.hpp:38-290): out = {n_plus_nu, nus2_plus_yy, alpha, shared inv_tau2_alpha2, e_g}, then for L = 0..L_max-1
+// log_change_on_add(L), log_change_on_rem(L + 1), log_model(L)
+void harness_prior(long n, long m_g, int m_e, double yy, double e_qg, double var_qg, double nu_sigma2, double s2_sigma2,
+                   double nu_tau2, double s2_tau2, double mu_alpha, int individual, int L_max, double* out5, double* add,
+                   double* rem, double* model)
+{
+  Prior* p = make_prior(n, m_g, m_e, yy, e_qg, var_qg, nu_sigma2, s2_sigma2, nu_tau2, s2_tau2, mu_alpha, individual, 0.0, 1.0);
+  out5[0] = p->n_plus_nu; out5[1] = p->nus2_plus_yy; out5[2] = p->alpha(); out5[3] = p->shared_inv_tau2_alpha2(); out5[4] = p->e_g();
+  for (int L = 0; L < L_max; ++L) { add[L] = p->log_change_on_add(L); rem[L] = p->log_change_on_rem(L + 1); model[L] = p->log_model(L); }
+  delete p;
+}
+
+// Model (model.hpp:199-312,432-556): a sequence of add_term / remove_term with the Gram entries taken from dense columns.
+// ops[3 i..] = {0 add | 1 remove, SNP | model index, inv_tau2_alpha2}; G = n x m_g additive columns, E = n x m_e (ones first).
+// trace[0] = log-likelihood of the covariate-only model, trace[i + 1] after op i; then the final xx / l (cols x cols,
+// upper), xy, v and the log-likelihood of a full recomputation.
+int harness_model_trace(long n, long m_g, int m_e, const double* G, const double* E, const double* y, double yy, double e_qg,
+                        double var_qg, double nu_sigma2, double s2_sigma2, double nu_tau2, double s2_tau2, int n_ops,
+                        const double* ops, double* trace, double* xx_out, double* l_out, double* xy_out, double* v_out,
+                        double* full_out, unsigned* loci_out)
+{
+  Prior* p = make_prior(n, m_g, m_e, yy, e_qg, var_qg, nu_sigma2, s2_sigma2, nu_tau2, s2_tau2, 1.0, 0, 0.0, 1.0);
+  auto dot = [&](const double* a, const double* b) { double s = 0.0; for (long i = 0; i < n; ++i) s += a[i] * b[i]; return s; };
+  UpperMat exx;
+  exx.resize(m_e);
+  std::vector<double> exy(m_e);
+  for (int c = 0; c < m_e; ++c) {
+    for (int r = 0; r <= c; ++r) exx(r, c) = dot(E + (size_t)r * n, E + (size_t)c * n);
+    exy[c] = dot(E + (size_t)c * n, y);
+  }
+  Model m;
+  m.init(m_e, exx, exy, p);
+  trace[0] = m.log_likelihood;
+  for (int i = 0; i < n_ops; ++i) {
+    if (ops[3 * i] == 0.0) {
+      const unsigned snp = (unsigned)ops[3 * i + 1];
+      const double* x = G + (size_t)snp * n;
+      std::vector<double> col(m.cols() + 1);
+      for (int c = 0; c < m_e; ++c) col[c] = dot(E + (size_t)c * n, x);
+      for (size_t t = 0; t < m.size(); ++t) col[m_e + t] = dot(G + (size_t)m.loci[t] * n, x);
+      col[m.cols()] = dot(x, x);
+      m.add_term(snp, dot(x, y), col.data(), ops[3 * i + 2]);
+    } else {
+      m.remove_term((int)ops[3 * i + 1]);
+    }
+    trace[i + 1] = m.log_likelihood;
+  }
+  const int cols = m.cols();
+  for (int c = 0; c < cols; ++c)
+    for (int r = 0; r < cols; ++r) {
+      xx_out[(size_t)c * cols + r] = r <= c ? m.xx(r, c) : 0.0;
+      l_out[(size_t)c * cols + r] = r <= c ? m.l(r, c) : 0.0;
+    }
+  for (int c = 0; c < cols; ++c) { xy_out[c] = m.xy[c]; v_out[c] = m.v[c]; }
+  for (size_t t = 0; t < m.size(); ++t) loci_out[t] = m.loci[t];
+  m.compute_log_likelihood();
+  *full_out = m.log_likelihood;
+  delete p;
+  return cols;
+}
+
+// ProposalCdf (discrete_distribution.hpp:64-330 semantics): a recorded sequence of zero / unzero / sample operations.
+// rec[4 i..] = {0 zero | 1 unzero | 2 sample, item, -, u}; got[i] = sampled item (or -1), total[i] = total weight afterwards.
+// order = the in-order permutation; weights are given by item and laid out in-order here, with per-block sums, as the
+// device does it.
+void harness_proposal_cdf(long m, const int* order, const double* w, int block, int n_rec, const double* rec, long* got,
+                          double* total)
+{
+  std::vector<int32_t> ord(order, order + m);
+  std::vector<double> w_io(m);
+  for (long p = 0; p < m; ++p) w_io[p] = w[ord[p]];
+  const long nb = (m + block - 1) / block;
+  std::vector<double> sums(nb, 0.0);
+  for (long p = 0; p < m; ++p) sums[p / block] += w_io[p];
+  ProposalCdf dd;
+  dd.init(&ord, block);
+  dd.update(w_io.data(), sums.data(), true, std::vector<uint32_t>());
+  for (int i = 0; i < n_rec; ++i) {
+    const int kind = (int)rec[4 * i];
+    const uint32_t item = (uint32_t)rec[4 * i + 1];
+    got[i] = -1;
+    if (kind == 0) dd.zero(item);
+    else if (kind == 1) dd.unzero(item);
+    else got[i] = (long)dd.sample(rec[4 * i + 3]);
+    total[i] = dd.total();
+  }
+}
+
+}  // extern "C"

@@ -1,0 +1,134 @@
+"""CPU tests of the product's pure host classes (bmagwa_b200/csrc/host/rng.hpp, model.hpp: ChainRng, Prior, Model,
+ProposalCdf) through tests/harness/host_harness.cpp, against the goldens the UNMODIFIED reference produced
+(tests/golden/ref_outputs.npz) and against the reference itself when oracle/_ref is built.  The GPU chain tests exercise the
+same classes end to end; these pin them without a device."""
+import ctypes as C
+import math
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import cpu
+from tests.helpers import SMALL_INI, load_small
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def harness(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("harness") / "libhost_harness.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-march=x86-64-v3", "-ffp-contract=off", "-fPIC", "-shared", "-I",
+                           os.path.join(ROOT, "bmagwa_b200", "csrc", "host"),
+                           os.path.join(ROOT, "tests", "harness", "host_harness.cpp"), "-o", out])
+    L = C.CDLL(out)
+    L.harness_model_trace.restype = C.c_int
+    return L
+
+
+def _p(a, t=C.c_double):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def test_chain_rng_reproduces_the_reference_stream(harness, golden):
+    """mt19937 + uniform / normal / scaled-inverse-chi2 draws of the product's ChainRng against the reference's Rand."""
+    out = np.zeros(64 * 8)
+    harness.harness_rng_sequence(C.c_uint(1234), C.c_double(1001.0), C.c_int(64), _p(out))
+    assert np.allclose(out, golden["rng_seed1234_nu1001"], rtol=1e-14, atol=0)
+
+
+# prior of SMALL_INI (tests/helpers.py): e_qg 2, var_qg 2, R2mode_sigma2 0.2, nu_sigma2 1, nu_tau2_A 3, s2_tau2_A 0.02
+def _small_prior_args(y, n=30, m_g=7):
+    var_y = float(np.var(y, ddof=1))
+    nu = 1.0
+    s2_sigma2 = var_y * (1 - 0.2) * (nu + 2) / nu   # sampler.hpp:173-177
+    return dict(n=n, m_g=m_g, m_e=1, yy=float(y @ y), e_qg=2.0, var_qg=2.0, nu_sigma2=nu, s2_sigma2=s2_sigma2, nu_tau2=3.0,
+                s2_tau2=0.02)
+
+
+def test_prior_matches_reference(harness, golden, golden_data_dir):
+    bed, y = load_small(golden_data_dir)
+    a = _small_prior_args(y)
+    out5, add, rem, model = np.zeros(5), np.zeros(7), np.zeros(7), np.zeros(7)
+    harness.harness_prior(C.c_long(a["n"]), C.c_long(a["m_g"]), C.c_int(1), C.c_double(a["yy"]), C.c_double(a["e_qg"]),
+                          C.c_double(a["var_qg"]), C.c_double(a["nu_sigma2"]), C.c_double(a["s2_sigma2"]), C.c_double(a["nu_tau2"]),
+                          C.c_double(a["s2_tau2"]), C.c_double(1.0), C.c_int(0), C.c_int(7), _p(out5), _p(add), _p(rem), _p(model))
+    g_a, g_b, n_plus_nu, nus2_plus_yy, alpha, s2_sigma2, nu_tau2, s2_tau2, shared, e_g = golden["small_prior"]
+    assert out5[0] == n_plus_nu and out5[1] == pytest.approx(nus2_plus_yy, rel=1e-13)
+    assert out5[2] == alpha and out5[3] == pytest.approx(shared, rel=1e-14) and out5[4] == pytest.approx(e_g, rel=1e-13)
+    # log ratios are differences of the full log model prior (prior.hpp:144-183), as the oracle's Prior
+    P = cpu.Prior.make(7, 2, 2)
+    for L in range(6):
+        assert add[L] == pytest.approx(P.log_add([L, 0, 0, 0, 0], L), rel=1e-12, abs=1e-12)
+        assert rem[L] == pytest.approx(P.log_rem([L + 1, 0, 0, 0, 0], L + 1), rel=1e-12, abs=1e-12)
+        assert add[L] == pytest.approx(model[L + 1] - model[L], rel=1e-10, abs=1e-10)
+        assert rem[L] == pytest.approx(model[L] - model[L + 1], rel=1e-10, abs=1e-10)
+
+
+def test_prior_log_ratios_against_live_reference(harness, ref_lib, tmp_path, golden_data_dir):
+    ini = tmp_path / "c.ini"
+    ini.write_text(SMALL_INI.format(d=golden_data_dir, out=str(tmp_path), recode=1, do_n_iter=10, n_rao=10, n_rao_burnin=1,
+                                    delay_rejection=7, thin=10, seed=1, indiv=0))
+    R = ref_lib.Ref(str(ini))
+    bed, y = load_small(golden_data_dir)
+    a = _small_prior_args(y)
+    out5, add, rem, model = np.zeros(5), np.zeros(7), np.zeros(7), np.zeros(7)
+    harness.harness_prior(C.c_long(a["n"]), C.c_long(a["m_g"]), C.c_int(1), C.c_double(a["yy"]), C.c_double(a["e_qg"]),
+                          C.c_double(a["var_qg"]), C.c_double(a["nu_sigma2"]), C.c_double(a["s2_sigma2"]), C.c_double(a["nu_tau2"]),
+                          C.c_double(a["s2_tau2"]), C.c_double(1.0), C.c_int(0), C.c_int(7), _p(out5), _p(add), _p(rem), _p(model))
+    for L in range(6):
+        Ns = np.array([L, 0, 0, 0, 0], dtype=np.int32)
+        assert add[L] == pytest.approx(R.prior_log_add(Ns, L, 0), rel=1e-12, abs=1e-12)
+        Ns1 = np.array([L + 1, 0, 0, 0, 0], dtype=np.int32)
+        assert rem[L] == pytest.approx(R.prior_log_rem(Ns1, L + 1, 0), rel=1e-12, abs=1e-12)
+        # log_model keeps the L-dependent terms only (what the sampler writes to _log_prior.dat)
+        assert model[L] == pytest.approx(R.prior_log_model(Ns), rel=1e-12, abs=1e-10)
+    R.close()
+
+
+def test_model_add_remove_trace_matches_reference(harness, golden, golden_data_dir):
+    """Model::add_term / remove_term (rank-1 Cholesky append, dchex-style delete, O(1) likelihood updates) against the
+    reference's own trace of the same operations, and its final Gram matrix, factor and v."""
+    bed, y = load_small(golden_data_dir)
+    n, m_g = 30, 7
+    a = _small_prior_args(y)
+    G = np.asfortranarray(np.stack([cpu.decode_column(bed, n, j, 0) for j in range(m_g)], axis=1))
+    E = np.asfortranarray(np.ones((n, 1)))
+    ops = np.ascontiguousarray(golden["ll_ops"], dtype=np.float64)
+    n_ops = ops.shape[0]
+    trace = np.zeros(n_ops + 1)
+    cols_max = 1 + m_g
+    xx, l = np.zeros(cols_max * cols_max), np.zeros(cols_max * cols_max)
+    xy, v, full = np.zeros(cols_max), np.zeros(cols_max), np.zeros(1)
+    loci = np.zeros(m_g, dtype=np.uint32)
+    cols = harness.harness_model_trace(C.c_long(n), C.c_long(m_g), C.c_int(1), _p(G), _p(E), _p(y), C.c_double(a["yy"]),
+                                       C.c_double(a["e_qg"]), C.c_double(a["var_qg"]), C.c_double(a["nu_sigma2"]),
+                                       C.c_double(a["s2_sigma2"]), C.c_double(a["nu_tau2"]), C.c_double(a["s2_tau2"]), C.c_int(n_ops),
+                                       _p(ops.reshape(-1)), _p(trace), _p(xx), _p(l), _p(xy), _p(v), _p(full), _p(loci, C.c_uint))
+    assert np.allclose(trace, golden["ll_trace"], rtol=0, atol=1e-10)
+    k = cols - 1
+    assert list(loci[:k]) == list(golden["ll_final_loci"])
+    assert np.allclose(xx[:cols * cols].reshape(cols, cols).T, golden["ll_final_xx"], rtol=0, atol=1e-12)
+    assert np.allclose(l[:cols * cols].reshape(cols, cols).T, golden["ll_final_l"], rtol=0, atol=1e-10)
+    assert np.allclose(xy[:cols], golden["ll_final_xy"], rtol=0, atol=1e-12)
+    assert np.allclose(v[:cols], golden["ll_final_v"], rtol=0, atol=1e-10)
+    assert full[0] == pytest.approx(golden["ll_final_full"][0], abs=1e-10)
+    assert trace[-1] == pytest.approx(full[0], abs=1e-10)   # incremental = full recomputation
+
+
+@pytest.mark.parametrize("m,block", [(1, 256), (2, 1), (5, 2), (10, 4), (31, 8), (257, 16), (257, 256)])
+def test_proposal_cdf_matches_reference_tree_draws(harness, golden, m, block):
+    """ProposalCdf (in-order layout + per-block partial CDFs + Fenwick tree) draws the items the reference's
+    DiscreteDistribution tree draws from the same uniforms, through zero / unzero updates."""
+    w = np.ascontiguousarray(golden["dd_w_%d" % m])
+    rec = np.ascontiguousarray(golden["dd_rec_%d" % m], dtype=np.float64)
+    order = np.ascontiguousarray(cpu.inorder_permutation(m), dtype=np.int32)
+    got = np.zeros(rec.shape[0], dtype=np.int64)
+    total = np.zeros(rec.shape[0])
+    harness.harness_proposal_cdf(C.c_long(m), _p(order, C.c_int), _p(w), C.c_int(block), C.c_int(rec.shape[0]), _p(rec.reshape(-1)),
+                                 _p(got, C.c_long), _p(total))
+    for i, (kind, item, tot, u) in enumerate(rec):
+        if kind == 2:
+            assert got[i] == int(item), "draw %d" % i
+        assert total[i] == pytest.approx(tot, rel=1e-12)

@@ -19,6 +19,7 @@
 #include <vector>
 #include "../store.cuh"
 #include "dataset.hpp"
+#include "exhaustive.hpp"
 #include "missing.hpp"
 #include "model.hpp"
 #include "options.hpp"
@@ -165,10 +166,5 @@ class Sampler {
   void adapt_p_move_size_acptrate(double t);
   void adapt_p_move_size_jd_mb();
 };
-
-void compute_exhaustive_modelset(size_t n_inds, ExhModel* exh, double* log_model_probabilities, double& max_log_model);
-void compute_proposal_probs_for_exh_modelset(int n_inds, const unsigned char* bit_to_normalized_order, const double* q_add,
-                                             const double* q_rem, double z_add, double z_rem, size_t const_loci, size_t m_g,
-                                             double* log_prop_probs);
 
 }  // namespace bmg

@@ -388,6 +388,16 @@ void refd_chol_swapadj(double* a, int k, int col, double* v)
   if (v) for (int i = 0; i < k; ++i) v[i] = vv(i);
 }
 
+/* ---- delayed rejection: proposal probabilities of the exhaustive model set (sampler.cpp:982-1049), one effect type ---- */
+void refd_dr_proposal_probs(int n_inds, const unsigned char* bit_to_normalized_order, const double* q_add, const double* q_rem,
+                            double z_add, double z_rem, long const_loci, long m_g, double* log_prop_probs)
+{
+  const bool use_types = false;
+  const size_t cl = (size_t)const_loci, mg = (size_t)m_g;
+  compute_proposal_probs_for_exh_modelset(use_types, n_inds, bit_to_normalized_order, q_add, q_rem, z_add, z_rem, cl, mg, NULL,
+                                          log_prop_probs);
+}
+
 /* ---- utils (utils.cpp:144-152) ---- */
 void refd_geometric_cdf(int maxsize, double p, double* out) { Utils::geometric_dist_cdf(maxsize, p, out); }
 double refd_gammaln(double x) { return Utils::gammaln(x); }

@@ -2,6 +2,7 @@
 // (bmagwa_b200/csrc/host/missing.hpp: no device dependency) so that they can be checked on the CPU against the
 // unmodified reference (oracle/_ref).  Compiled by tests/test_cpu_missing_gibbs.py with g++; not part of the product.
 #include <cstring>
+#include "exhaustive.hpp"
 #include "missing.hpp"
 
 using namespace bmg;
@@ -228,3 +229,56 @@ void harness_proposal_cdf(long m, const int* order, const double* w, int block, 
 }
 
 }  // extern "C"
+
+// Delayed rejection (sampler.cpp:882-980): log probabilities of all 2^ms sub-models of the last ms SNPs of a model, from
+// compute_exhaustive_modelset (adjacent Givens swaps, O(k) per sub-model) in P, and from a fresh Model per sub-model
+// (full incremental build) + the model prior in B.  Both are relative to the sub-model without any of the ms SNPs.
+extern "C" void harness_exhaustive(long n, long m_g, int m_e, const double* G, const double* E, const double* y, double yy,
+                                   double e_qg, double var_qg, double nu_sigma2, double s2_sigma2, double nu_tau2, double s2_tau2,
+                                   int const_loci, int ms, const unsigned* snps, const double* taus, double* P, double* B)
+{
+  Prior* p = make_prior(n, m_g, m_e, yy, e_qg, var_qg, nu_sigma2, s2_sigma2, nu_tau2, s2_tau2, 1.0, 0, 0.0, 1.0);
+  auto dot = [&](const double* a, const double* b) { double s = 0.0; for (long i = 0; i < n; ++i) s += a[i] * b[i]; return s; };
+  UpperMat exx;
+  exx.resize(m_e);
+  std::vector<double> exy(m_e);
+  for (int c = 0; c < m_e; ++c) {
+    for (int r = 0; r <= c; ++r) exx(r, c) = dot(E + (size_t)r * n, E + (size_t)c * n);
+    exy[c] = dot(E + (size_t)c * n, y);
+  }
+  auto add = [&](Model& m, int which) {
+    const double* x = G + (size_t)snps[which] * n;
+    std::vector<double> col(m.cols() + 1);
+    for (int c = 0; c < m_e; ++c) col[c] = dot(E + (size_t)c * n, x);
+    for (size_t t = 0; t < m.size(); ++t) col[m_e + t] = dot(G + (size_t)m.loci[t] * n, x);
+    col[m.cols()] = dot(x, x);
+    m.add_term(snps[which], dot(x, y), col.data(), taus[which]);
+  };
+  Model full;
+  full.init(m_e, exx, exy, p);
+  for (int i = 0; i < const_loci + ms; ++i) add(full, i);
+  ExhModel exh;
+  exh.update_to_model(full, const_loci);
+  double mx;
+  compute_exhaustive_modelset((size_t)ms, &exh, P, mx);
+  for (unsigned long mask = 0; mask < (1ul << ms); ++mask) {
+    Model m;
+    m.init(m_e, exx, exy, p);
+    for (int i = 0; i < const_loci; ++i) add(m, i);
+    for (int b = 0; b < ms; ++b)
+      if ((mask >> b) & 1) add(m, const_loci + b);
+    B[mask] = m.log_likelihood + p->log_model((int)m.size());
+  }
+  const double p0 = P[0], b0 = B[0];
+  for (unsigned long mask = 0; mask < (1ul << ms); ++mask) { P[mask] -= p0; B[mask] -= b0; }
+  delete p;
+}
+
+// Delayed rejection: proposal probabilities of the sub-models (sampler.cpp:982-1049), the product's restatement
+extern "C" void harness_dr_proposal_probs(int n_inds, const unsigned char* bit_to_normalized_order, const double* q_add,
+                                          const double* q_rem, double z_add, double z_rem, long const_loci, long m_g,
+                                          double* log_prop_probs)
+{
+  compute_proposal_probs_for_exh_modelset(n_inds, bit_to_normalized_order, q_add, q_rem, z_add, z_rem, (size_t)const_loci,
+                                          (size_t)m_g, log_prop_probs);
+}

@@ -282,3 +282,45 @@ extern "C" void harness_dr_proposal_probs(int n_inds, const unsigned char* bit_t
   compute_proposal_probs_for_exh_modelset(n_inds, bit_to_normalized_order, q_add, q_rem, z_add, z_rem, (size_t)const_loci,
                                           (size_t)m_g, log_prop_probs);
 }
+
+// One round of the model-level Gibbs updates on a model holding the given SNPs: Model::sample_beta_sigma2
+// (model.hpp:326-342), Prior::sample_alpha_and_tau2 (prior.cpp:30-141), a full likelihood recomputation and
+// Model::compute_pve (model.hpp:345-392), with the chain's random stream freshly seeded.
+//   out_beta / out_tau: cols entries; out3 = {sigma2, alpha, log likelihood}; pves: 3
+extern "C" void harness_model_gibbs(long n, long m_g, int m_e, const double* G, const double* E, const double* y, double yy,
+                                    double e_qg, double var_qg, double nu_sigma2, double s2_sigma2, double nu_tau2, double s2_tau2,
+                                    double mu_alpha, int individual, double inv_tau2_e_val, int k, const unsigned* snps,
+                                    const double* taus, unsigned seed, double* out_beta, double* out_tau, double* out3, double* pves)
+{
+  Prior* p = make_prior(n, m_g, m_e, yy, e_qg, var_qg, nu_sigma2, s2_sigma2, nu_tau2, s2_tau2, mu_alpha, individual, 0.0, inv_tau2_e_val);
+  auto dot = [&](const double* a, const double* b) { double s = 0.0; for (long i = 0; i < n; ++i) s += a[i] * b[i]; return s; };
+  UpperMat exx;
+  exx.resize(m_e);
+  std::vector<double> exy(m_e);
+  for (int c = 0; c < m_e; ++c) {
+    for (int r = 0; r <= c; ++r) exx(r, c) = dot(E + (size_t)r * n, E + (size_t)c * n);
+    exy[c] = dot(E + (size_t)c * n, y);
+  }
+  Model m;
+  m.init(m_e, exx, exy, p);
+  for (int i = 0; i < k; ++i) {
+    const double* x = G + (size_t)snps[i] * n;
+    std::vector<double> col(m.cols() + 1);
+    for (int c = 0; c < m_e; ++c) col[c] = dot(E + (size_t)c * n, x);
+    for (size_t t = 0; t < m.size(); ++t) col[m_e + t] = dot(G + (size_t)m.loci[t] * n, x);
+    col[m.cols()] = dot(x, x);
+    m.add_term(snps[i], dot(x, y), col.data(), taus[i]);
+  }
+  ChainRng rng(seed, (double)n + nu_sigma2);
+  m.sample_beta_sigma2(rng);
+  const int cols = m.cols();
+  for (int c = 0; c < cols; ++c) out_beta[c] = m.beta[c];
+  out3[0] = m.sigma2;
+  p->sample_alpha_and_tau2(&m, rng);
+  for (int c = 0; c < cols; ++c) out_tau[c] = m.inv_tau2_alpha2[c];
+  out3[1] = p->alpha();
+  m.compute_log_likelihood();
+  out3[2] = m.log_likelihood;
+  m.compute_pve((size_t)n, pves);
+  delete p;
+}

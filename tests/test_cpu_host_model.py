@@ -179,3 +179,47 @@ def test_dr_proposal_probabilities_match_reference_function(harness, ref_lib, n_
                                          C.c_double(z_rem), C.c_long(const_loci), C.c_long(m_g), _p(ref))
     assert np.isfinite(ref).all()
     assert np.allclose(ours, ref, rtol=1e-12, atol=1e-11)
+
+
+@pytest.mark.parametrize("indiv,k,seed", [(1, 4, 11), (0, 6, 12), (1, 0, 13)])
+def test_model_level_gibbs_updates_match_reference(harness, ref_lib, tmp_path, indiv, k, seed):
+    """sample_beta_sigma2, sample_alpha_and_tau2, compute_log_likelihood and compute_pve of the product (Gram-matrix
+    formulation, no n-vectors) against the reference's (n x k design matrix), same seed: the draws must coincide."""
+    from bmagwa_b200 import synth
+    n, m_g, m_e = 203, 120, 2
+    ds = synth.write_dataset(str(tmp_path), "syn", n=n, m_g=m_g, m_e=m_e, seed=seed, e_qg=5, var_qg=20, use_individual_tau2=indiv,
+                             do_n_iter=100, n_rao=50, n_rao_burnin=1, outbase=str(tmp_path / "chain"), seeds=str(700 + seed))
+    R = ref_lib.Ref(ds["ini"])
+    try:
+        rs = np.random.default_rng(seed)
+        snps = rs.choice(m_g, size=k, replace=False).astype(np.uint32) if k else np.zeros(0, dtype=np.uint32)
+        taus = 0.5 + rs.random(size=max(k, 1)) * 4
+        for j, t in zip(snps, taus):
+            R.model_add(int(j), float(t))
+        cols = R.model_cols()
+        pp, pt = R.prior_params(), R.prior_terms()
+        y, E = R.y(), np.asfortranarray(R.e())
+        G = np.asfortranarray(np.stack([R.get_column(j, 0) for j in range(m_g)], axis=1))
+        R.model_sample_beta_sigma2()
+        beta_ref = R.model_get("beta")[:cols].copy()
+        sigma2_ref = R.model_get("scalars")["sigma2"]
+        R.sample_alpha_and_tau2()
+        tau_ref = R.model_get("inv_tau2_alpha2")[:cols].copy()
+        alpha_ref = R.prior_params()["alpha"]
+        R.model_compute_loglik()
+        ll_ref = R.model_loglik()
+        pves_ref, _ = R.model_compute_pve()
+
+        beta, tau, out3, pves = np.zeros(cols), np.zeros(cols), np.zeros(3), np.zeros(3)
+        harness.harness_model_gibbs(C.c_long(n), C.c_long(m_g), C.c_int(m_e + 1), _p(G), _p(E), _p(y), C.c_double(float(y @ y)),
+                                    C.c_double(5.0), C.c_double(20.0), C.c_double(1.0), C.c_double(pp["s2_sigma2"]),
+                                    C.c_double(pt[0, 1]), C.c_double(pt[0, 2]), C.c_double(1.0), C.c_int(indiv), C.c_double(0.001),
+                                    C.c_int(k), _p(snps, C.c_uint), _p(taus), C.c_uint(700 + seed), _p(beta), _p(tau), _p(out3), _p(pves))
+        assert np.allclose(beta, beta_ref, rtol=1e-9, atol=1e-11)
+        assert out3[0] == pytest.approx(sigma2_ref, rel=1e-11)
+        assert out3[1] == pytest.approx(alpha_ref, rel=1e-9)
+        assert np.allclose(tau[m_e + 1:], tau_ref[m_e + 1:], rtol=1e-9)
+        assert out3[2] == pytest.approx(ll_ref, rel=1e-10)
+        assert np.allclose(pves, pves_ref, rtol=1e-8, atol=1e-12)
+    finally:
+        R.close()

@@ -74,25 +74,42 @@ inline void rows_missing_in_model(const MissingCells& mc, const std::vector<uint
 }
 
 // Buffers of the Gibbs step, kept between calls (the step runs every n_sample_tau2_and_missing iterations)
+// A SNP of the model as the Gibbs step sees it: effect type 0 A, 1 H, 2 D, 3 R, 4 AH (data_model.hpp:41) and the design-matrix
+// column(s) of its term(s); col2 is the heterozygous term of an AH SNP (model.hpp: x_ind1 / x_ind2)
+struct GibbsSnp {
+  uint32_t snp;
+  int type, col1, col2;
+};
+
 struct GibbsScratch {
   std::vector<double> xold, xnew, y_hat, residual;
   std::vector<int32_t> slot;      // individual -> position in rows; all -1 between calls
   std::vector<uint8_t> changed;   // per row: did any of its cells get a new value
+  std::vector<int32_t> col_snp;   // design-matrix column -> position of its SNP in the model
+  std::vector<GibbsSnp> snps;
 };
 
-// Sampler::sample_missing (sampler.cpp:264-453), effect type A.
+// value of a term of type t (0..3) on additive genotype g (DataModel::get_genotypes_*, data_model.cpp:41-72)
+inline double typed_genotype(int t, int g)
+{
+  return t == 0 ? (double)g : (t == 1 ? (double)(g == 1) : (t == 2 ? (double)(g > 0) : (double)(g == 2)));
+}
+
+// Sampler::sample_missing (sampler.cpp:264-453) for SNPs of any effect type.
 //   cur    current model; xx and xy are patched in place (sampler.cpp:393-450), mu_beta_computed is cleared
-//   rows   rows_missing_in_model(...) (q of them); cells = k x q genotype values with the chain's imputed values
-//          applied, as they are BEFORE this update, bit 2 set where the cell is a missing call (bmg_chain_get_cells
-//          over cur.loci)
+//   snps   the model's SNPs in model order with their types and columns
+//   rows   individuals (ascending, distinct) with a missing call in some SNP of the model (q of them);
+//          cells = n_snps x q ADDITIVE genotype values with the chain's imputed values applied, as they are BEFORE this
+//          update, bit 2 set where the cell is a missing call (bmg_chain_get_cells over the SNPs)
 //   y, e   phenotype (n) and covariates (n x m_e, column-major, ones column included)
 //   yy     y'y.  The reference sums the squared residual over all n individuals; here r'r comes from the Gram
 //          matrix, r'r = y'y - 2 b'X'y + b'X'X b (it only enters through differences in which it cancels).
-// On return mc.val holds the new imputed values of the in-model SNPs.
-inline void gibbs_missing_in_model(Model& cur, MissingCells& mc, const std::vector<int32_t>& rows, const int8_t* cells,
-                                   const double* y, const double* e, size_t n, double yy, ChainRng& rng, GibbsScratch& ws)
+// On return mc.val holds the new imputed values of the model's SNPs.
+inline void gibbs_missing_typed(Model& cur, const std::vector<GibbsSnp>& snps, MissingCells& mc, const std::vector<int32_t>& rows,
+                                const int8_t* cells, const double* y, const double* e, size_t n, double yy, ChainRng& rng,
+                                GibbsScratch& ws)
 {
-  const int m_e = cur.m_e, cols = cur.cols(), k = (int)cur.size();
+  const int m_e = cur.m_e, cols = cur.cols(), k = (int)snps.size();
   const size_t q = rows.size();
   cur.mu_beta_computed = false;   // sampler.cpp:452, unconditional
   if (q == 0) return;
@@ -105,10 +122,15 @@ inline void gibbs_missing_in_model(Model& cur, MissingCells& mc, const std::vect
   ws.y_hat.resize(q);
   ws.residual.resize(q);
   ws.changed.assign(q, 0);
+  ws.col_snp.assign(cols, -1);   // design-matrix column -> position of its SNP in snps (covariates: -1)
   double* const xold = ws.xold.data();
   double* const xnew = ws.xnew.data();
   double* const y_hat = ws.y_hat.data();
   double* const residual = ws.residual.data();
+  for (int l = 0; l < k; ++l) {
+    ws.col_snp[snps[l].col1] = l;
+    if (snps[l].type == 4) ws.col_snp[snps[l].col2] = l;
+  }
   for (size_t u0 = 0; u0 < q; u0 += 128) {   // blocks of rows, column by column inside: e and cells are column-major
     const size_t u1 = std::min(q, u0 + 128);
     for (int c = 0; c < m_e; ++c) {
@@ -117,7 +139,15 @@ inline void gibbs_missing_in_model(Model& cur, MissingCells& mc, const std::vect
     }
     for (int l = 0; l < k; ++l) {
       const int8_t* cl = cells + (size_t)l * q;
-      for (size_t u = u0; u < u1; ++u) xold[u * cols + m_e + l] = (double)(cl[u] & 3);
+      const int ty = snps[l].type, c1 = snps[l].col1, c2 = snps[l].col2;
+      if (ty == 0) {
+        for (size_t u = u0; u < u1; ++u) xold[u * cols + c1] = (double)(cl[u] & 3);
+      } else {
+        const int t1 = ty == 4 ? 0 : ty;
+        for (size_t u = u0; u < u1; ++u) xold[u * cols + c1] = typed_genotype(t1, cl[u] & 3);
+        if (ty == 4)
+          for (size_t u = u0; u < u1; ++u) xold[u * cols + c2] = typed_genotype(1, cl[u] & 3);
+      }
     }
   }
   for (size_t u = 0; u < q; ++u) {
@@ -137,10 +167,10 @@ inline void gibbs_missing_in_model(Model& cur, MissingCells& mc, const std::vect
   for (size_t u = 0; u < q; ++u) slot[rows[u]] = (int32_t)u;
 
   double lprior[3], likelihood[3];
-  for (int t = 0; t < k; ++t) {
-    const size_t snp = cur.loci[t];
+  for (int l = 0; l < k; ++l) {
+    const size_t snp = snps[l].snp;
     if (mc.count(snp) == 0) continue;
-    const int x_ind = m_e + t;
+    const int ty = snps[l].type, t1 = ty == 4 ? 0 : ty, x1 = snps[l].col1, x2 = snps[l].col2;
     const double* p3 = &mc.prior3[3 * snp];
     lprior[0] = std::log(p3[0]);
     lprior[1] = std::log(p3[1] - p3[0]);
@@ -150,7 +180,8 @@ inline void gibbs_missing_in_model(Model& cur, MissingCells& mc, const std::vect
       double* row = xnew + u * cols;
       const double old_term2 = residual[u] * residual[u];
       for (int g = 0; g < 3; ++g) {
-        const double new_term = residual[u] - beta[x_ind] * ((double)g - row[x_ind]);
+        double new_term = residual[u] - beta[x1] * (typed_genotype(t1, g) - row[x1]);
+        if (ty == 4) new_term -= beta[x2] * ((double)(g == 1) - row[x2]);
         likelihood[g] = lprior[g] - (r2 + new_term * new_term - old_term2) / sigma2_times_2;
       }
       likelihood[1] -= likelihood[0];
@@ -160,37 +191,56 @@ inline void gibbs_missing_in_model(Model& cur, MissingCells& mc, const std::vect
       likelihood[2] = std::exp(likelihood[2]) + likelihood[1];
       const int g = MissingCells::draw3(likelihood, rng);
       mc.val[c] = (int8_t)g;
-      if ((double)g != row[x_ind]) ws.changed[u] = 1;
-      y_hat[u] += beta[x_ind] * ((double)g - row[x_ind]);
-      row[x_ind] = (double)g;
+      const double v1 = typed_genotype(t1, g);
+      if (v1 != row[x1]) ws.changed[u] = 1;
+      y_hat[u] += beta[x1] * (v1 - row[x1]);
+      row[x1] = v1;
+      if (ty == 4) {
+        const double v2 = (double)(g == 1);
+        if (v2 != row[x2]) ws.changed[u] = 1;
+        y_hat[u] += beta[x2] * (v2 - row[x2]);
+        row[x2] = v2;
+      }
       residual[u] = y[mc.idx[c]] - y_hat[u];
       r2 += residual[u] * residual[u] - old_term2;
     }
   }
 
-  // X'y and the upper triangle of X'X follow the changed cells (sampler.cpp:393-427).  A row in which no cell got a new
-  // value contributes x*x' - x*x' = 0 exactly to every entry, so it is skipped.
-  for (int t = 0; t < k; ++t) {
-    const size_t snp = cur.loci[t];
+  // X'y and the upper triangle of X'X follow the changed cells (sampler.cpp:393-450): the term of a non-AH SNP or the
+  // first term of an AH SNP, then the second term of an AH SNP.  A row in which no cell got a new value contributes
+  // x*x' - x*x' = 0 exactly to every entry, so it is skipped.
+  for (int l = 0; l < k; ++l) {
+    const size_t snp = snps[l].snp;
     if (mc.count(snp) == 0) continue;
-    const int x_ind = m_e + t;
-    for (int64_t c = mc.off[snp]; c < mc.off[snp + 1]; ++c) {
-      const int32_t i_miss = mc.idx[c];
-      const size_t u = (size_t)slot[i_miss];
-      if (!ws.changed[u]) continue;
-      const double* xn = xnew + u * cols;
-      const double* xo = xold + u * cols;
-      const double xnx = xn[x_ind], xox = xo[x_ind];
-      cur.xy[x_ind] += y[i_miss] * (xnx - xox);
-      double* up = cur.xx.col(x_ind);   // xx(j, x_ind), j < x_ind
-      int j = 0;
-      for (; j < m_e; ++j) up[j] += xnx * xn[j] - xox * xo[j];
-      for (; j < x_ind; ++j)   // a column that is itself missing here is patched when its own cell comes up
-        if (!(cells[(size_t)(j - m_e) * q + u] & 4)) up[j] += xnx * xn[j] - xox * xo[j];
-      for (; j < cols; ++j) cur.xx(x_ind, j) += xnx * xn[j] - xox * xo[j];
+    for (int pass = 0; pass < (snps[l].type == 4 ? 2 : 1); ++pass) {
+      const int x_ind = pass == 0 ? snps[l].col1 : snps[l].col2;
+      for (int64_t c = mc.off[snp]; c < mc.off[snp + 1]; ++c) {
+        const int32_t i_miss = mc.idx[c];
+        const size_t u = (size_t)slot[i_miss];
+        if (!ws.changed[u]) continue;
+        const double* xn = xnew + u * cols;
+        const double* xo = xold + u * cols;
+        const double xnx = xn[x_ind], xox = xo[x_ind];
+        cur.xy[x_ind] += y[i_miss] * (xnx - xox);
+        double* up = cur.xx.col(x_ind);   // xx(j, x_ind), j < x_ind
+        int j = 0;
+        for (; j < m_e; ++j) up[j] += xnx * xn[j] - xox * xo[j];
+        for (; j < x_ind; ++j)   // a column whose SNP is itself missing here is patched when its own cell comes up
+          if (!(cells[(size_t)ws.col_snp[j] * q + u] & 4)) up[j] += xnx * xn[j] - xox * xo[j];
+        for (; j < cols; ++j) cur.xx(x_ind, j) += xnx * xn[j] - xox * xo[j];
+      }
     }
   }
   for (size_t u = 0; u < q; ++u) slot[rows[u]] = -1;
+}
+
+// The same for a model whose SNPs are all additive (model.types = A): SNP t of cur.loci owns column m_e + t
+inline void gibbs_missing_in_model(Model& cur, MissingCells& mc, const std::vector<int32_t>& rows, const int8_t* cells,
+                                   const double* y, const double* e, size_t n, double yy, ChainRng& rng, GibbsScratch& ws)
+{
+  ws.snps.resize(cur.size());
+  for (size_t t = 0; t < cur.size(); ++t) ws.snps[t] = GibbsSnp{cur.loci[t], 0, cur.m_e + (int)t, -1};
+  gibbs_missing_typed(cur, ws.snps, mc, rows, cells, y, e, n, yy, rng, ws);
 }
 
 }  // namespace bmg

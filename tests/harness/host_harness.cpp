@@ -324,3 +324,52 @@ extern "C" void harness_model_gibbs(long n, long m_g, int m_e, const double* G, 
   m.compute_pve((size_t)n, pves);
   delete p;
 }
+
+// The Gibbs update for a model whose SNPs have effect types (0 A, 1 H, 2 D, 3 R, 4 AH = two columns): as harness_gibbs, with
+// snp_type[l] per model SNP; columns are laid out in model order (AH: additive column, then heterozygous column).
+// xcols: n x k ADDITIVE columns (overlay applied, before the update).
+extern "C" int harness_gibbs_typed(int m_e, int k, const unsigned* loci, const int* snp_type, double* xx, double* xy,
+                                   const double* beta, double sigma2, long m_g, const long* off, const int* idx, signed char* val,
+                                   const double* prior3, const double* xcols, const double* y, const double* e, long n, double yy,
+                                   unsigned seed, double nu)
+{
+  std::vector<GibbsSnp> snps(k);
+  int cols = m_e;
+  Model cur;
+  cur.m_e = m_e;
+  for (int l = 0; l < k; ++l) {
+    snps[l].snp = loci[l];
+    snps[l].type = snp_type[l];
+    snps[l].col1 = cols++;
+    cur.loci.push_back(loci[l]);
+    snps[l].col2 = -1;
+    if (snp_type[l] == 4) { snps[l].col2 = cols++; cur.loci.push_back(loci[l]); }
+  }
+  cur.xx.resize(cols);
+  for (int c = 0; c < cols; ++c)
+    for (int r = 0; r <= c; ++r) cur.xx(r, c) = xx[(size_t)c * cols + r];
+  cur.xy.assign(xy, xy + cols);
+  cur.beta.assign(beta, beta + cols);
+  cur.sigma2 = sigma2;
+  MissingCells mc;
+  mc.off.assign(off, off + m_g + 1);
+  mc.idx.assign(idx, idx + off[m_g]);
+  mc.val.assign(val, val + off[m_g]);
+  mc.prior3.assign(prior3, prior3 + 3 * m_g);
+  std::vector<uint32_t> distinct(loci, loci + k);
+  std::vector<int32_t> rows;
+  rows_missing_in_model(mc, distinct, rows);
+  const size_t q = rows.size();
+  std::vector<int8_t> cells((size_t)k * q);
+  for (int l = 0; l < k; ++l)
+    for (size_t u = 0; u < q; ++u)
+      cells[(size_t)l * q + u] = (int8_t)((int)xcols[(size_t)l * n + rows[u]] | (mc.is_missing(rows[u], loci[l]) ? 4 : 0));
+  ChainRng rng(seed, nu);
+  GibbsScratch ws;
+  gibbs_missing_typed(cur, snps, mc, rows, cells.data(), y, e, (size_t)n, yy, rng, ws);
+  for (int c = 0; c < cols; ++c)
+    for (int r = 0; r <= c; ++r) xx[(size_t)c * cols + r] = cur.xx(r, c);
+  std::memcpy(xy, cur.xy.data(), sizeof(double) * cols);
+  std::memcpy(val, mc.val.data(), mc.val.size());
+  return cols;
+}

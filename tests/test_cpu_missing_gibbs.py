@@ -124,3 +124,63 @@ def test_prior_reimputation_matches_the_reference(ref_lib, harness, tmp_path):
         assert (val != val0).any()
     finally:
         R.close()
+
+
+@pytest.mark.parametrize("types,seed,miss_rate", [("H", 21, 0.1), ("D", 22, 0.1), ("R", 23, 0.15), ("A,H,D,R", 24, 0.1),
+                                                  ("AH", 25, 0.12), ("A,H,D,R,AH", 26, 0.2)])
+def test_gibbs_update_with_effect_types_matches_the_reference(ref_lib, harness, tmp_path, types, seed, miss_rate):
+    """The Gibbs step for models whose SNPs have effect types H, D, R and AH (two columns per SNP; sampler.cpp:318-385 and
+    :393-450): imputed values, X'X and X'y against the reference, same seed."""
+    from oracle import cpu, ref
+    names = {"A": 0, "H": 1, "D": 2, "R": 3, "AH": 4}
+    codes = sorted(names[t] for t in types.split(","))
+    n, m_g, m_e = 141, 50, 1
+    ds = synth.write_dataset(str(tmp_path), "syn", n=n, m_g=m_g, m_e=m_e, seed=seed, miss_rate=miss_rate, e_qg=5, var_qg=20,
+                             use_individual_tau2=1, do_n_iter=100, n_rao=50, n_rao_burnin=1, types=types,
+                             outbase=str(tmp_path / "chain"), seeds=str(800 + seed))
+    R = ref.Ref(ds["ini"])
+    try:
+        rng = np.random.default_rng(seed)
+        k = 6
+        loci = rng.choice(m_g, size=k, replace=False)
+        tis = [i % len(codes) for i in range(k)]
+        for j in loci:
+            for q in range(R.missing(int(j))[0].size):
+                R.set_miss_val(int(j), q, int(rng.integers(0, 3)))
+        for j, ti in zip(loci, tis):
+            R.model_add(int(j), [0.7 + 0.1 * float(rng.random()), 0.9], ti)
+        cols = R.model_cols()
+        snp_type = np.array([codes[ti] for ti in tis], dtype=np.int32)
+        assert cols == m_e + 1 + k + int((snp_type == 4).sum())
+        beta = rng.normal(size=cols) * 0.4
+        sigma2 = 0.8
+        R.model_set_beta_sigma2(beta, sigma2)
+        xx0, xy0 = R.model_get("xx"), R.model_get("xy")
+        off, idx, val0, prior3 = _reference_state(R)
+        xcols = np.asfortranarray(np.stack([R.get_column(int(j), 0, overlay=True) for j in loci], axis=1))
+        y, e = R.y(), np.asfortranarray(R.e())
+        R.sample_missing()
+        xx_ref, xy_ref = R.model_get("xx"), R.model_get("xy")
+        _, _, val_ref, _ = _reference_state(R)
+
+        xx, xy, val = np.asfortranarray(xx0.copy()), xy0.copy(), val0.copy()
+        got_cols = harness.harness_gibbs_typed(C.c_int(m_e + 1), C.c_int(k), _p(loci.astype(np.uint32), C.c_uint),
+                                               _p(snp_type, C.c_int), _p(xx, C.c_double), _p(xy, C.c_double), _p(beta, C.c_double),
+                                               C.c_double(sigma2), C.c_long(m_g), _p(off, C.c_long), _p(idx, C.c_int),
+                                               _p(val, C.c_byte), _p(np.ascontiguousarray(prior3), C.c_double), _p(xcols, C.c_double),
+                                               _p(y, C.c_double), _p(e, C.c_double), C.c_long(n), C.c_double(float(y @ y)),
+                                               C.c_uint(800 + seed), C.c_double(n + 1.0))
+        assert got_cols == cols
+        assert np.array_equal(val, val_ref), "imputed values differ from the reference's Gibbs draw"
+        assert (val != val0).any()
+        assert np.allclose(np.triu(xx), np.triu(xx_ref), rtol=1e-12, atol=1e-9)
+        assert np.allclose(xy, xy_ref, rtol=1e-12, atol=1e-9)
+        # and the patched Gram matrix is the Gram matrix of the updated typed columns
+        X = [e]
+        for j, t in zip(loci, snp_type):
+            a = R.get_column(int(j), 0, overlay=True)
+            X += [a, cpu.typed(a, 1)] if t == 4 else [cpu.typed(a, int(t))]
+        X = np.column_stack(X)
+        assert np.allclose(np.triu(xx), np.triu(X.T @ X), rtol=1e-12, atol=1e-9)
+    finally:
+        R.close()

@@ -373,3 +373,58 @@ extern "C" int harness_gibbs_typed(int m_e, int k, const unsigned* loci, const i
   std::memcpy(val, mc.val.data(), mc.val.size());
   return cols;
 }
+
+// Scratch reuse: the sampler keeps one GibbsScratch for the whole chain while the model grows and shrinks.  Runs the update
+// for the first k1 SNPs, then (same scratch) for all k SNPs, and compares the second result with a run on a fresh scratch.
+// Returns 1 when both runs give identical values, X'X and X'y; 0 otherwise.
+extern "C" int harness_gibbs_scratch_reuse(int m_e, int k1, int k, const unsigned* loci, const double* xx_k1, const double* xy_k1,
+                                           const double* xx, const double* xy, const double* beta, double sigma2, long m_g,
+                                           const long* off, const int* idx, const signed char* val, const double* prior3,
+                                           const double* xcols, const double* y, const double* e, long n, double yy)
+{
+  auto make_model = [&](int kk, const double* gx, const double* gy) {
+    Model m;
+    m.m_e = m_e;
+    m.loci.assign(loci, loci + kk);
+    const int cols = m_e + kk;
+    m.xx.resize(cols);
+    for (int c = 0; c < cols; ++c)
+      for (int r = 0; r <= c; ++r) m.xx(r, c) = gx[(size_t)c * cols + r];
+    m.xy.assign(gy, gy + cols);
+    m.beta.assign(beta, beta + cols);
+    m.sigma2 = sigma2;
+    return m;
+  };
+  auto run = [&](Model& m, MissingCells& mc, GibbsScratch& ws, unsigned seed) {
+    std::vector<int32_t> rows;
+    rows_missing_in_model(mc, m.loci, rows);
+    const size_t q = rows.size();
+    const int kk = (int)m.size();
+    std::vector<int8_t> cells((size_t)kk * q);
+    for (int l = 0; l < kk; ++l)
+      for (size_t u = 0; u < q; ++u)
+        cells[(size_t)l * q + u] = (int8_t)((int)xcols[(size_t)l * n + rows[u]] | (mc.is_missing(rows[u], loci[l]) ? 4 : 0));
+    ChainRng rng(seed, 1.0);
+    gibbs_missing_in_model(m, mc, rows, cells.data(), y, e, (size_t)n, yy, rng, ws);
+  };
+  MissingCells base;
+  base.off.assign(off, off + m_g + 1);
+  base.idx.assign(idx, idx + off[m_g]);
+  base.val.assign(val, val + off[m_g]);
+  base.prior3.assign(prior3, prior3 + 3 * m_g);
+
+  GibbsScratch shared;
+  { Model small = make_model(k1, xx_k1, xy_k1); MissingCells mc = base; run(small, mc, shared, 5u); }
+  Model a = make_model(k, xx, xy);
+  MissingCells mca = base;
+  run(a, mca, shared, 9u);
+  GibbsScratch fresh;
+  Model b = make_model(k, xx, xy);
+  MissingCells mcb = base;
+  run(b, mcb, fresh, 9u);
+  if (mca.val != mcb.val || a.xy != b.xy) return 0;
+  for (int c = 0; c < a.cols(); ++c)
+    for (int r = 0; r <= c; ++r)
+      if (a.xx(r, c) != b.xx(r, c)) return 0;
+  return 1;
+}

@@ -184,3 +184,36 @@ def test_gibbs_update_with_effect_types_matches_the_reference(ref_lib, harness, 
         assert np.allclose(np.triu(xx), np.triu(X.T @ X), rtol=1e-12, atol=1e-9)
     finally:
         R.close()
+
+
+def test_gibbs_scratch_is_reusable_across_model_sizes(harness):
+    """The sampler keeps one scratch for the whole chain: an update for a larger model after one for a smaller model must
+    equal the same update on a fresh scratch, bit for bit."""
+    from oracle import cpu
+    n, m, k1, k, m_e = 400, 60, 5, 13, 2
+    payload, f = synth.make_genotypes(n, m, seed=17, miss_rate=0.08)
+    bed = payload.copy()
+    cpu.recode_minor(bed, n, m)
+    off, idx, prior3 = cpu.missing_index(bed, n, m)
+    rs = np.random.default_rng(1)
+    val = rs.integers(0, 3, size=idx.size).astype(np.int8)
+    loci = rs.choice(m, size=k, replace=False).astype(np.uint32)
+    cols = [cpu.decode_column_overlay(bed, n, int(j), 0, idx[off[j]:off[j + 1]], val[off[j]:off[j + 1]]) for j in loci]
+    E = np.asfortranarray(np.column_stack([np.ones(n), rs.uniform(size=n)]))
+    y = rs.normal(size=n)
+    beta = rs.normal(size=m_e + k) * 0.2
+
+    def gram(kk):
+        X = np.column_stack([E] + cols[:kk])
+        return np.asfortranarray(X.T @ X), X.T @ y
+
+    xx1, xy1 = gram(k1)
+    xx, xy = gram(k)
+    xcols = np.asfortranarray(np.stack(cols, axis=1))
+    ok = harness.harness_gibbs_scratch_reuse(C.c_int(m_e), C.c_int(k1), C.c_int(k), _p(loci, C.c_uint), _p(xx1, C.c_double),
+                                             _p(xy1, C.c_double), _p(xx, C.c_double), _p(xy, C.c_double), _p(beta, C.c_double),
+                                             C.c_double(0.9), C.c_long(m), _p(off.astype(np.int64), C.c_long),
+                                             _p(idx.astype(np.int32), C.c_int), _p(val, C.c_byte),
+                                             _p(np.ascontiguousarray(prior3, dtype=np.float64), C.c_double), _p(xcols, C.c_double),
+                                             _p(y, C.c_double), _p(E, C.c_double), C.c_long(n), C.c_double(float(y @ y)))
+    assert ok == 1

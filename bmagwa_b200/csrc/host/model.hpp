@@ -124,6 +124,70 @@ class Prior {
   void sample_alpha_and_tau2(Model* model, ChainRng& rng);  // prior.hpp:201-210
   void set_alpha(double val, Model* model);                 // prior.cpp:116-141
 
+  // ---- several effect types (prior.hpp:60-183, prior.cpp:71-141).  Effect types 0 A, 1 H, 2 D, 3 R, 4 AH; an AH SNP has
+  // two TERMS (A and H), so per-term hyper-parameters exist for 0..3 only.  configure_types() is called once, before the
+  // chain starts; the type-A members above are left as they are (a model.types = A run never gets here).
+  void configure_types(const std::vector<int>& types, const double* types_prior5, const double* nu_tau2_4, const double* s2_tau2_4)
+  {
+    typed_ = true;
+    tp_sum_t_ = 0.0;
+    for (int t = 0; t < 5; ++t) { allow_type_t_[t] = false; tp_t_[t] = NAN; }
+    for (int t = 0; t < 4; ++t) { allow_term_t_[t] = false; nu_t_[t] = s2_t_[t] = nus2_t_[t] = inv_tau2_alpha2_t_[t] = NAN; }
+    for (int t : types) {
+      if (t < 0 || t > 4) throw std::runtime_error("Prior::configure_types: effect type out of range");
+      allow_type_t_[t] = true;
+      if (t == 4) allow_term_t_[0] = allow_term_t_[1] = true; else allow_term_t_[t] = true;
+    }
+    for (int t = 0; t < 5; ++t)
+      if (allow_type_t_[t]) { tp_t_[t] = types_prior5[t]; tp_sum_t_ += types_prior5[t]; }
+    static const char* names[4] = {"A", "H", "D", "R"};
+    for (int t = 0; t < 4; ++t) {
+      if (!allow_term_t_[t]) continue;
+      nu_t_[t] = nu_tau2_4[t];
+      s2_t_[t] = s2_tau2_4[t];
+      if (s2_t_[t] <= 0) throw std::runtime_error(std::string("Prior specification error: s2_tau2 for ") + names[t] + " is not positive.");
+      if (nu_t_[t] <= 0) throw std::runtime_error(std::string("Prior specification error: nu_tau2 for ") + names[t] + " is not positive.");
+      nus2_t_[t] = nu_t_[t] * s2_t_[t];
+      const double tau2_init = nus2_t_[t] / std::max(0.1, nu_t_[t] - 2);
+      inv_tau2_alpha2_t_[t] = 1.0 / (alpha2_ * tau2_init);
+    }
+  }
+  bool typed() const { return typed_; }
+  bool allow_term(int t) const { return allow_term_t_[t]; }
+  double shared_inv_tau2_alpha2(int term_type) const { return inv_tau2_alpha2_t_[term_type]; }
+  // prior.hpp:144-167
+  double log_change_on_add(const int* Ns, int L, int type) const
+  {
+    return (std::log(g_a_ + L) - std::log(g_b_ + (double)m_g_ - L - 1)) + (std::log(tp_t_[type] + Ns[type]) - std::log(tp_sum_t_ + L));
+  }
+  double log_change_on_rem(const int* Ns, int L, int type) const
+  {
+    return (std::log(g_b_ + (double)m_g_ - L) - std::log(g_a_ + L - 1)) + (std::log(tp_sum_t_ + L - 1) - std::log(tp_t_[type] + Ns[type] - 1));
+  }
+  // prior.hpp:160-167: the type of a SNP of the model changes
+  double log_change_on_swi(const int* Ns, int type_add, int type_rem) const
+  {
+    return type_add == type_rem ? 0.0 : std::log(tp_t_[type_add] + Ns[type_add]) - std::log(tp_t_[type_rem] + Ns[type_rem] - 1);
+  }
+  // prior.hpp:169-183
+  double log_model(const int* Ns) const
+  {
+    double lp = 0.0;
+    int n_g = 0;
+    for (int t = 0; t < 5; ++t)
+      if (allow_type_t_[t]) { lp += std::lgamma(tp_t_[t] + (double)Ns[t]); n_g += Ns[t]; }
+    lp += std::lgamma(g_a_ + (double)n_g) + std::lgamma(g_b_ + (double)m_g_ - (double)n_g) - std::lgamma(tp_sum_t_ + (double)n_g);
+    return lp;
+  }
+  // prior.hpp:192-199 for a term of the given type
+  double draw_inv_tau2_alpha2(int term_type, ChainRng& rng) const
+  {
+    if (use_individual_tau2) return 1.0 / (alpha2_ * rng.sinvchi2(nu_t_[term_type], s2_t_[term_type]));
+    return inv_tau2_alpha2_t_[term_type];
+  }
+  // sample_alpha_and_tau2 for a model whose columns carry term types (Model::term_type)
+  void sample_alpha_and_tau2_typed(Model* model, ChainRng& rng);
+
   void print(const std::string& filename) const
   {
     std::ofstream f(filename.c_str());
@@ -153,6 +217,12 @@ class Prior {
   double types_prior_[5];
   double types_prior_sum_;
   mutable std::vector<double> add_tab_, rem_tab_;
+  // several effect types (configure_types)
+  bool typed_ = false;
+  bool allow_type_t_[5] = {false, false, false, false, false}, allow_term_t_[4] = {false, false, false, false};
+  double tp_t_[5] = {NAN, NAN, NAN, NAN, NAN}, tp_sum_t_ = 0.0;
+  double nu_t_[4] = {NAN, NAN, NAN, NAN}, s2_t_[4] = {NAN, NAN, NAN, NAN}, nus2_t_[4] = {NAN, NAN, NAN, NAN};
+  double inv_tau2_alpha2_t_[4] = {NAN, NAN, NAN, NAN};
 
   double sample_alpha(Model* model, ChainRng& rng);  // prior.cpp:30-69
   void sample_tau2(Model* model, ChainRng& rng);     // prior.cpp:71-114
@@ -195,6 +265,7 @@ struct MoveGram {
 struct Model {
   int m_e = 0;
   std::vector<uint32_t> loci;     // SNP of term i (column m_e + i)
+  std::vector<uint8_t> term_type; // per column (covariates included) when effect types are in use: 0 A, 1 H, 2 D, 3 R; empty otherwise
   UpperMat xx, l;                 // X'X (upper) and the Cholesky factor of X'X + diag(inv_tau2_alpha2)
   std::vector<double> xy, v, inv_tau2_alpha2, beta, mu_beta;
   double sigma2 = 0.0, syx_plus_vs2 = 0.0, log_det_invQ = 0.0, log_det_invQ_plus_xx = 0.0;
@@ -213,6 +284,7 @@ struct Model {
   {
     m_e = o.m_e;
     loci = o.loci;
+    term_type = o.term_type;
     xx.copy_upper_from(o.xx);
     l.copy_upper_from(o.l);
     xy = o.xy; v = o.v; inv_tau2_alpha2 = o.inv_tau2_alpha2; beta = o.beta; mu_beta = o.mu_beta;
@@ -267,10 +339,15 @@ struct Model {
 
   // Model::add_term + update_likelihood_on_add (model.hpp:239-268,432-506).  newcol has cols()+1 entries:
   // X'x_new for the existing columns, then x_new'x_new.
-  void add_term(uint32_t snp, double xy_new, const double* newcol, double inv_tau2_alpha2_val)
+  // term_type_val >= 0: the column's term type (0 A, 1 H, 2 D, 3 R) is recorded in term_type (runs with effect types)
+  void add_term(uint32_t snp, double xy_new, const double* newcol, double inv_tau2_alpha2_val, int term_type_val = -1)
   {
     const int col = cols();
     if (col + 1 > kMaxModelColumns) throw std::runtime_error("Not enough memory for adding term.");
+    if (term_type_val >= 0) {
+      term_type.resize(col, 0);
+      term_type.push_back((uint8_t)term_type_val);
+    }
     loci.push_back(snp);
     mu_beta_computed = false;
     xy.push_back(xy_new);
@@ -299,6 +376,7 @@ struct Model {
   {
     const int x_ind = m_e + model_ind;
     loci.erase(loci.begin() + model_ind);
+    if (!term_type.empty()) term_type.erase(term_type.begin() + x_ind);
     xy.erase(xy.begin() + x_ind);
     xx.remove_colrow(x_ind);
     const double inv_val = inv_tau2_alpha2[x_ind];
@@ -449,6 +527,45 @@ inline void Prior::sample_alpha_and_tau2(Model* model, ChainRng& rng)
 {
   sample_tau2(model, rng);
   set_alpha(sample_alpha(model, rng), model);
+}
+
+// prior.cpp:71-141 with x_types: tau2 per term (individual) or per term TYPE (shared), then alpha and the rescaling
+inline void Prior::sample_alpha_and_tau2_typed(Model* model, ChainRng& rng)
+{
+  const int k = (int)model->beta.size();
+  const std::vector<uint8_t>& tt = model->term_type;
+  if ((int)tt.size() != k) throw std::logic_error("sample_alpha_and_tau2_typed: the model carries no term types");
+  const double alpha2_sigma2 = alpha2_ * model->sigma2;
+  if (use_individual_tau2) {
+    for (int i = (int)m_e_; i < k; ++i) {
+      const double nu = nu_t_[tt[i]] + 1.0;
+      const double s2 = (nus2_t_[tt[i]] + model->beta[i] * model->beta[i] / alpha2_sigma2) / nu;
+      model->inv_tau2_alpha2[i] = 1.0 / (alpha2_ * rng.sinvchi2(nu, s2));
+    }
+  } else {
+    double beta2sum[4] = {0.0, 0.0, 0.0, 0.0};
+    size_t m_types[4] = {0, 0, 0, 0};
+    for (int i = (int)m_e_; i < k; ++i) { beta2sum[tt[i]] += model->beta[i] * model->beta[i]; ++m_types[tt[i]]; }
+    for (int t = 0; t < 4; ++t) {
+      if (!allow_term_t_[t]) continue;
+      const double nu = nu_t_[t] + (double)m_types[t];
+      const double s2 = (nus2_t_[t] + beta2sum[t] / alpha2_sigma2) / nu;
+      inv_tau2_alpha2_t_[t] = 1.0 / (alpha2_ * rng.sinvchi2(nu, s2));
+    }
+    for (int i = (int)m_e_; i < k; ++i) model->inv_tau2_alpha2[i] = inv_tau2_alpha2_t_[tt[i]];
+  }
+  model->mu_beta_computed = false;
+  const double val = sample_alpha(model, rng);
+  const double old_alpha2 = alpha2_;
+  alpha_ = val;
+  alpha2_ = alpha_ * alpha_;
+  if (use_individual_tau2) {
+    for (int i = (int)m_e_; i < k; ++i) model->inv_tau2_alpha2[i] = model->inv_tau2_alpha2[i] * old_alpha2 / alpha2_;
+  } else {
+    for (int t = 0; t < 4; ++t)
+      if (allow_term_t_[t]) inv_tau2_alpha2_t_[t] = inv_tau2_alpha2_t_[t] * old_alpha2 / alpha2_;
+    for (int i = (int)m_e_; i < k; ++i) model->inv_tau2_alpha2[i] = inv_tau2_alpha2_t_[tt[i]];
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -34,7 +34,7 @@ def lib():
         L.refd_last_error.restype = C.c_char_p
         L.refd_open.restype = C.c_void_p
         L.refd_open.argtypes = [C.c_char_p, C.c_int]
-        for f in ("refd_get_genotype", "refd_prior_log_add", "refd_prior_log_rem", "refd_prior_log_model",
+        for f in ("refd_get_genotype", "refd_prior_log_add", "refd_prior_log_rem", "refd_prior_log_model", "refd_prior_log_swi",
                   "refd_model_loglik", "refd_scan_time", "refd_run_chain", "refd_continue_chain", "refd_rng_u01", "refd_rng_normal",
                   "refd_rng_sinvchi2_1", "refd_rng_sinvchi2_2", "refd_dd_total", "refd_gammaln"):
             getattr(L, f).restype = C.c_double
@@ -133,6 +133,10 @@ class Ref:
     def prior_log_rem(self, Ns, L, type_=0):
         Ns = np.asarray(Ns, dtype=np.int32)
         return self.L.refd_prior_log_rem(self.h, _p(Ns, C.c_int), C.c_int(L), C.c_int(type_))
+
+    def prior_log_swi(self, Ns, type_add, type_rem):
+        Ns = np.ascontiguousarray(Ns, dtype=np.int32)
+        return self.L.refd_prior_log_swi(self.h, _p(Ns, C.c_int), C.c_int(type_add), C.c_int(type_rem))
 
     def prior_log_model(self, Ns):
         Ns = np.asarray(Ns, dtype=np.int32)

@@ -196,6 +196,7 @@ void refd_update_prexx_cov(void* h, long snp, double* inout) { ((RefCtx*)h)->sam
 /* ---- Prior (prior.hpp:144-183) ---- */
 double refd_prior_log_add(void* h, const int* Ns, int n_loci, int type) { return ((RefCtx*)h)->sampler->prior->compute_log_change_on_add(Ns, n_loci, (DataModel::ef_t)type); }
 double refd_prior_log_rem(void* h, const int* Ns, int n_loci, int type) { return ((RefCtx*)h)->sampler->prior->compute_log_change_on_rem(Ns, n_loci, (DataModel::ef_t)type); }
+double refd_prior_log_swi(void* h, const int* Ns, int type_add, int type_rem) { return ((RefCtx*)h)->sampler->prior->compute_log_change_on_swi(Ns, (DataModel::ef_t)type_add, (DataModel::ef_t)type_rem); }
 double refd_prior_log_model(void* h, const int* Ns) { return ((RefCtx*)h)->sampler->prior->compute_log_model(Ns); }
 void refd_prior_params(void* h, double* out)
 {

@@ -428,3 +428,78 @@ extern "C" int harness_gibbs_scratch_reuse(int m_e, int k1, int k, const unsigne
       if (a.xx(r, c) != b.xx(r, c)) return 0;
   return 1;
 }
+
+// ---- several effect types: the typed side of Prior (prior.hpp:60-183, prior.cpp:71-141) ----------------------------------
+static void configure(Prior* p, int n_types, const int* types, double nu_tau2, double s2_tau2)
+{
+  const double tp[5] = {1, 1, 1, 1, 1}, nu[4] = {nu_tau2, nu_tau2, nu_tau2, nu_tau2}, s2[4] = {s2_tau2, s2_tau2, s2_tau2, s2_tau2};
+  p->configure_types(std::vector<int>(types, types + n_types), tp, nu, s2);
+}
+
+// queries[7 i..] = {Ns[0..4], L, type}: add[i] = log_change_on_add, rem[i] = log_change_on_rem (Ns, L are the OLD state),
+// model[i] = log_model(Ns); swi[i] = log_change_on_swi(Ns, type, swi_rem[i])
+extern "C" void harness_prior_typed(long n, long m_g, int m_e, double yy, double e_qg, double var_qg, double s2_sigma2,
+                                    int n_types, const int* types, int n_q, const int* queries, const int* swi_rem, double* add,
+                                    double* rem, double* model, double* swi, double* shared4)
+{
+  Prior* p = make_prior(n, m_g, m_e, yy, e_qg, var_qg, 1.0, s2_sigma2, 5.0, 0.05, 1.0, 0, 0.0, 0.001);
+  configure(p, n_types, types, 5.0, 0.05);
+  for (int i = 0; i < n_q; ++i) {
+    const int* Ns = queries + 7 * i;
+    const int L = queries[7 * i + 5], t = queries[7 * i + 6];
+    add[i] = p->log_change_on_add(Ns, L, t);
+    rem[i] = Ns[t] > 0 ? p->log_change_on_rem(Ns, L, t) : 0.0;
+    model[i] = p->log_model(Ns);
+    swi[i] = Ns[swi_rem[i]] > 0 ? p->log_change_on_swi(Ns, t, swi_rem[i]) : 0.0;
+  }
+  for (int t = 0; t < 4; ++t) shared4[t] = p->allow_term(t) ? p->shared_inv_tau2_alpha2(t) : -1.0;
+  delete p;
+}
+
+// harness_model_gibbs for a model whose SNPs have effect types (snp_type 0..4; AH = additive + heterozygous column):
+// sample_beta_sigma2, then Prior::sample_alpha_and_tau2_typed
+extern "C" int harness_model_gibbs_typed(long n, long m_g, int m_e, const double* G, const double* E, const double* y, double yy,
+                                         double e_qg, double var_qg, double s2_sigma2, int individual, int n_types, const int* types,
+                                         int k, const unsigned* snps, const int* snp_type, const double* taus2, unsigned seed,
+                                         double* out_beta, double* out_tau, double* out3)
+{
+  Prior* p = make_prior(n, m_g, m_e, yy, e_qg, var_qg, 1.0, s2_sigma2, 5.0, 0.05, 1.0, individual, 0.0, 0.001);
+  configure(p, n_types, types, 5.0, 0.05);
+  auto dot = [&](const double* a, const double* b) { double s = 0.0; for (long i = 0; i < n; ++i) s += a[i] * b[i]; return s; };
+  UpperMat exx;
+  exx.resize(m_e);
+  std::vector<double> exy(m_e);
+  for (int c = 0; c < m_e; ++c) {
+    for (int r = 0; r <= c; ++r) exx(r, c) = dot(E + (size_t)r * n, E + (size_t)c * n);
+    exy[c] = dot(E + (size_t)c * n, y);
+  }
+  Model m;
+  m.init(m_e, exx, exy, p);
+  std::vector<std::vector<double>> colsx;   // typed dense columns of the model, in column order
+  auto add_col = [&](unsigned snp, int tt, double tau) {
+    std::vector<double> x(n);
+    for (long i = 0; i < n; ++i) x[i] = typed_genotype(tt, (int)G[(size_t)snp * n + i]);
+    std::vector<double> col(m.cols() + 1);
+    for (int c = 0; c < m_e; ++c) col[c] = dot(E + (size_t)c * n, x.data());
+    for (size_t t = 0; t < colsx.size(); ++t) col[m_e + t] = dot(colsx[t].data(), x.data());
+    col[m.cols()] = dot(x.data(), x.data());
+    m.add_term(snp, dot(x.data(), y), col.data(), tau, tt);
+    colsx.push_back(x);
+  };
+  for (int l = 0; l < k; ++l) {
+    if (snp_type[l] == 4) { add_col(snps[l], 0, taus2[2 * l]); add_col(snps[l], 1, taus2[2 * l + 1]); }
+    else add_col(snps[l], snp_type[l], taus2[2 * l]);
+  }
+  ChainRng rng(seed, (double)n + 1.0);
+  m.sample_beta_sigma2(rng);
+  const int cols = m.cols();
+  for (int c = 0; c < cols; ++c) out_beta[c] = m.beta[c];
+  out3[0] = m.sigma2;
+  p->sample_alpha_and_tau2_typed(&m, rng);
+  for (int c = 0; c < cols; ++c) out_tau[c] = m.inv_tau2_alpha2[c];
+  out3[1] = p->alpha();
+  m.compute_log_likelihood();
+  out3[2] = m.log_likelihood;
+  delete p;
+  return cols;
+}

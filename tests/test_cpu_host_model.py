@@ -223,3 +223,104 @@ def test_model_level_gibbs_updates_match_reference(harness, ref_lib, tmp_path, i
         assert np.allclose(pves, pves_ref, rtol=1e-8, atol=1e-12)
     finally:
         R.close()
+
+
+# ------------------------------------------------------------------------------- several effect types
+NAMES = {"A": 0, "H": 1, "D": 2, "R": 3, "AH": 4}
+
+
+@pytest.mark.parametrize("types,seed", [("A,H", 31), ("A,H,D,R", 32), ("AH", 33), ("A,H,D,R,AH", 34), ("D", 35)])
+def test_typed_prior_matches_reference(harness, ref_lib, tmp_path, types, seed):
+    """Prior::log_change_on_add / _rem / _swi / log_model with per-type counts Ns, and the shared per-term precisions, against
+    the reference's Prior (prior.hpp:60-183) for several model.types settings."""
+    from bmagwa_b200 import synth
+    n, m_g, m_e = 101, 40, 1
+    ds = synth.write_dataset(str(tmp_path), "syn", n=n, m_g=m_g, m_e=m_e, seed=seed, e_qg=5, var_qg=20, use_individual_tau2=0,
+                             do_n_iter=100, n_rao=50, n_rao_burnin=1, types=types, outbase=str(tmp_path / "chain"), seeds="1")
+    R = ref_lib.Ref(ds["ini"])
+    try:
+        codes = sorted(NAMES[t] for t in types.split(","))
+        rs = np.random.default_rng(seed)
+        pp, pt = R.prior_params(), R.prior_terms()
+        queries, swi_rem = [], []
+        for _ in range(25):
+            Ns = np.zeros(5, dtype=np.int32)
+            for t in codes:
+                Ns[t] = rs.integers(0, 5)
+            queries.append(list(Ns) + [int(Ns.sum()), int(rs.choice(codes))])
+            swi_rem.append(int(rs.choice(codes)))
+        q = np.ascontiguousarray(queries, dtype=np.int32)
+        sr = np.ascontiguousarray(swi_rem, dtype=np.int32)
+        add, rem, model, swi = (np.zeros(len(queries)) for _ in range(4))
+        shared4 = np.zeros(4)
+        y = R.y()
+        harness.harness_prior_typed(C.c_long(n), C.c_long(m_g), C.c_int(m_e + 1), C.c_double(float(y @ y)), C.c_double(5.0),
+                                    C.c_double(20.0), C.c_double(pp["s2_sigma2"]), C.c_int(len(codes)),
+                                    _p(np.asarray(codes, dtype=np.int32), C.c_int), C.c_int(len(queries)), _p(q.reshape(-1), C.c_int),
+                                    _p(sr, C.c_int), _p(add), _p(rem), _p(model), _p(swi), _p(shared4))
+        for i, row in enumerate(queries):
+            Ns, L, t = np.asarray(row[:5], dtype=np.int32), row[5], row[6]
+            assert add[i] == pytest.approx(R.prior_log_add(Ns, L, t), rel=1e-13, abs=1e-13)
+            if Ns[t] > 0:
+                assert rem[i] == pytest.approx(R.prior_log_rem(Ns, L, t), rel=1e-13, abs=1e-13)
+            assert model[i] == pytest.approx(R.prior_log_model(Ns), rel=1e-13, abs=1e-12)
+            if Ns[swi_rem[i]] > 0:
+                assert swi[i] == pytest.approx(R.prior_log_swi(Ns, t, swi_rem[i]), rel=1e-13, abs=1e-13)
+        for t in range(4):
+            if np.isnan(pt[t, 0]):
+                assert shared4[t] == -1.0
+            else:
+                assert shared4[t] == pytest.approx(pt[t, 0], rel=1e-14)
+    finally:
+        R.close()
+
+
+@pytest.mark.parametrize("types,indiv,seed", [("A,H,D,R", 1, 41), ("A,H,D,R", 0, 42), ("AH", 0, 43), ("A,H,D,R,AH", 1, 44),
+                                              ("H,R", 0, 45)])
+def test_typed_model_gibbs_updates_match_reference(harness, ref_lib, tmp_path, types, indiv, seed):
+    """A model whose SNPs have effect types (AH = two columns): sample_beta_sigma2 and the typed tau2 / alpha update
+    (prior.cpp:71-141 with x_types; one tau2 per term type in the shared mode) against the reference, same seed."""
+    from bmagwa_b200 import synth
+    n, m_g, m_e = 151, 60, 1
+    ds = synth.write_dataset(str(tmp_path), "syn", n=n, m_g=m_g, m_e=m_e, seed=seed, e_qg=5, var_qg=20, use_individual_tau2=indiv,
+                             do_n_iter=100, n_rao=50, n_rao_burnin=1, types=types, outbase=str(tmp_path / "chain"),
+                             seeds=str(600 + seed))
+    R = ref_lib.Ref(ds["ini"])
+    try:
+        codes = sorted(NAMES[t] for t in types.split(","))
+        rs = np.random.default_rng(seed)
+        k = 6
+        snps = rs.choice(m_g, size=k, replace=False).astype(np.uint32)
+        tis = [i % len(codes) for i in range(k)]
+        snp_type = np.array([codes[ti] for ti in tis], dtype=np.int32)
+        taus2 = 0.5 + rs.random(size=(k, 2)) * 3
+        for j, ti, t2 in zip(snps, tis, taus2):
+            R.model_add(int(j), list(t2), ti)
+        cols = R.model_cols()
+        pp = R.prior_params()
+        y, E = R.y(), np.asfortranarray(R.e())
+        G = np.asfortranarray(np.stack([R.get_column(j, 0) for j in range(m_g)], axis=1))
+        R.model_sample_beta_sigma2()
+        beta_ref = R.model_get("beta")[:cols].copy()
+        sigma2_ref = R.model_get("scalars")["sigma2"]
+        R.sample_alpha_and_tau2()
+        tau_ref = R.model_get("inv_tau2_alpha2")[:cols].copy()
+        alpha_ref = R.prior_params()["alpha"]
+        R.model_compute_loglik()
+        ll_ref = R.model_loglik()
+
+        beta, tau, out3 = np.zeros(cols), np.zeros(cols), np.zeros(3)
+        got = harness.harness_model_gibbs_typed(C.c_long(n), C.c_long(m_g), C.c_int(m_e + 1), _p(G), _p(E), _p(y),
+                                                C.c_double(float(y @ y)), C.c_double(5.0), C.c_double(20.0),
+                                                C.c_double(pp["s2_sigma2"]), C.c_int(indiv), C.c_int(len(codes)),
+                                                _p(np.asarray(codes, dtype=np.int32), C.c_int), C.c_int(k), _p(snps, C.c_uint),
+                                                _p(snp_type, C.c_int), _p(np.ascontiguousarray(taus2).reshape(-1)),
+                                                C.c_uint(600 + seed), _p(beta), _p(tau), _p(out3))
+        assert got == cols
+        assert np.allclose(beta, beta_ref, rtol=1e-9, atol=1e-11)
+        assert out3[0] == pytest.approx(sigma2_ref, rel=1e-11)
+        assert out3[1] == pytest.approx(alpha_ref, rel=1e-9)
+        assert np.allclose(tau[m_e + 1:], tau_ref[m_e + 1:], rtol=1e-9)
+        assert out3[2] == pytest.approx(ll_ref, rel=1e-10)
+    finally:
+        R.close()

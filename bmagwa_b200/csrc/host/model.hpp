@@ -459,6 +459,48 @@ struct Model {
   }
 };
 
+// ------------------------------------------------------------------------------------------------
+// SNP-level view of a model whose SNPs have effect types (the reference's loci / type_inds / x_ind1 / x_ind2 / Ns,
+// src/model.hpp:239-312): which columns of the Model belong to which SNP.  An AH SNP owns two consecutive columns (additive,
+// then heterozygous); removing it drops the larger column first, as the reference does, so the Cholesky downdates run in the
+// same order.  The Gram entries of the typed columns come from the caller (typed columns of the overlay cache).
+// ------------------------------------------------------------------------------------------------
+struct TypedTerms {
+  std::vector<uint32_t> snp;       // SNPs in model order
+  std::vector<uint8_t> type;       // effect type 0 A, 1 H, 2 D, 3 R, 4 AH
+  std::vector<int> col1, col2;     // design-matrix columns of the SNP's term(s); col2 = -1 unless AH
+  int Ns[5] = {0, 0, 0, 0, 0};     // SNPs per effect type
+
+  size_t size() const { return snp.size(); }
+  static int n_columns(int type_code) { return type_code == 4 ? 2 : 1; }
+  // term type of the c-th column (0 or 1) of a SNP of this effect type
+  static int term_type(int type_code, int c) { return type_code == 4 ? c : type_code; }
+  // a SNP whose term(s) were appended to the Model at columns first_col (and first_col + 1 for AH)
+  void add(uint32_t s, int type_code, int first_col)
+  {
+    snp.push_back(s);
+    type.push_back((uint8_t)type_code);
+    col1.push_back(first_col);
+    col2.push_back(type_code == 4 ? first_col + 1 : -1);
+    ++Ns[type_code];
+  }
+  // forgets SNP model_ind; cols_out receives the Model columns to remove, in the order to remove them; returns how many
+  int remove(int model_ind, int cols_out[2])
+  {
+    const int t = type[model_ind], c1 = col1[model_ind], c2 = col2[model_ind];
+    --Ns[t];
+    snp.erase(snp.begin() + model_ind);
+    type.erase(type.begin() + model_ind);
+    col1.erase(col1.begin() + model_ind);
+    col2.erase(col2.begin() + model_ind);
+    const int xmove = t == 4 ? 2 : 1;
+    for (size_t i = model_ind; i < snp.size(); ++i) { col1[i] -= xmove; if (col2[i] >= 0) col2[i] -= xmove; }
+    if (t == 4) { cols_out[0] = std::max(c1, c2); cols_out[1] = std::min(c1, c2); return 2; }
+    cols_out[0] = c1;
+    return 1;
+  }
+};
+
 inline void Prior::sample_tau2(Model* model, ChainRng& rng)
 {
   const int k = (int)model->beta.size();

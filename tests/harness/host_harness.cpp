@@ -503,3 +503,59 @@ extern "C" int harness_model_gibbs_typed(long n, long m_g, int m_e, const double
   delete p;
   return cols;
 }
+
+// Add / remove trace of a model whose SNPs have effect types, through TypedTerms + Model (AH: two add_term calls; removal
+// drops the larger column first).  ops[5 i..] = {0 add | 1 remove, SNP | model index, effect type, tau1, tau2}.
+// trace[i] = log-likelihood after op i; the final upper triangle of X'X goes to xx_out (cols x cols); returns cols.
+extern "C" int harness_typed_model_trace(long n, long m_g, int m_e, const double* G, const double* E, const double* y, double yy,
+                                         double s2_sigma2, int n_types, const int* types, int n_ops, const double* ops,
+                                         double* trace, double* xx_out, int* Ns_out)
+{
+  Prior* p = make_prior(n, m_g, m_e, yy, 5.0, 20.0, 1.0, s2_sigma2, 5.0, 0.05, 1.0, 1, 0.0, 0.001);
+  configure(p, n_types, types, 5.0, 0.05);
+  auto dot = [&](const double* a, const double* b) { double s = 0.0; for (long i = 0; i < n; ++i) s += a[i] * b[i]; return s; };
+  UpperMat exx;
+  exx.resize(m_e);
+  std::vector<double> exy(m_e);
+  for (int c = 0; c < m_e; ++c) {
+    for (int r = 0; r <= c; ++r) exx(r, c) = dot(E + (size_t)r * n, E + (size_t)c * n);
+    exy[c] = dot(E + (size_t)c * n, y);
+  }
+  Model m;
+  m.init(m_e, exx, exy, p);
+  TypedTerms terms;
+  std::vector<std::vector<double>> colsx;   // typed dense columns in column order
+  for (int i = 0; i < n_ops; ++i) {
+    const double* op = ops + 5 * i;
+    if (op[0] == 0.0) {
+      const unsigned snp = (unsigned)op[1];
+      const int ty = (int)op[2];
+      terms.add(snp, ty, m.cols());
+      for (int c = 0; c < TypedTerms::n_columns(ty); ++c) {
+        const int tt = TypedTerms::term_type(ty, c);
+        std::vector<double> x(n);
+        for (long r = 0; r < n; ++r) x[r] = typed_genotype(tt, (int)G[(size_t)snp * n + r]);
+        std::vector<double> col(m.cols() + 1);
+        for (int e2 = 0; e2 < m_e; ++e2) col[e2] = dot(E + (size_t)e2 * n, x.data());
+        for (size_t t = 0; t < colsx.size(); ++t) col[m_e + t] = dot(colsx[t].data(), x.data());
+        col[m.cols()] = dot(x.data(), x.data());
+        m.add_term(snp, dot(x.data(), y), col.data(), op[3 + c], tt);
+        colsx.push_back(x);
+      }
+    } else {
+      int rem[2];
+      const int cnt = terms.remove((int)op[1], rem);
+      for (int c = 0; c < cnt; ++c) {
+        m.remove_term(rem[c] - m_e);
+        colsx.erase(colsx.begin() + (rem[c] - m_e));
+      }
+    }
+    trace[i] = m.log_likelihood;
+  }
+  const int cols = m.cols();
+  for (int c = 0; c < cols; ++c)
+    for (int r = 0; r < cols; ++r) xx_out[(size_t)c * cols + r] = r <= c ? m.xx(r, c) : 0.0;
+  for (int t = 0; t < 5; ++t) Ns_out[t] = terms.Ns[t];
+  delete p;
+  return cols;
+}

@@ -324,3 +324,51 @@ def test_typed_model_gibbs_updates_match_reference(harness, ref_lib, tmp_path, t
         assert out3[2] == pytest.approx(ll_ref, rel=1e-10)
     finally:
         R.close()
+
+
+@pytest.mark.parametrize("types,seed", [("A,H,D,R,AH", 51), ("AH", 52), ("A,AH", 53)])
+def test_typed_model_add_remove_trace_matches_reference(harness, ref_lib, tmp_path, types, seed):
+    """Adding and removing SNPs of several effect types (AH = two columns, removed larger column first) through TypedTerms +
+    Model: the log-likelihood after every operation and the final X'X against the reference's Model (model.hpp:239-312)."""
+    from bmagwa_b200 import synth
+    n, m_g, m_e = 131, 40, 1
+    ds = synth.write_dataset(str(tmp_path), "syn", n=n, m_g=m_g, m_e=m_e, seed=seed, e_qg=5, var_qg=20, use_individual_tau2=1,
+                             do_n_iter=100, n_rao=50, n_rao_burnin=1, types=types, outbase=str(tmp_path / "chain"), seeds="3")
+    R = ref_lib.Ref(ds["ini"])
+    try:
+        codes = sorted(NAMES[t] for t in types.split(","))
+        rs = np.random.default_rng(seed)
+        in_model, ops, trace_ref = [], [], []
+        free = list(rs.permutation(m_g))
+        for step in range(24):
+            if in_model and (rs.random() < 0.4 or len(in_model) > 8):
+                mi = int(rs.integers(0, len(in_model)))
+                R.model_remove(mi)
+                in_model.pop(mi)
+                ops.append([1, mi, 0, 0, 0])
+            else:
+                snp, ti = int(free.pop()), int(rs.integers(0, len(codes)))
+                t1, t2 = 0.5 + 3 * rs.random(), 0.5 + 3 * rs.random()
+                R.model_add(snp, [t1, t2], ti)
+                in_model.append(snp)
+                ops.append([0, snp, codes[ti], t1, t2])
+            trace_ref.append(R.model_loglik())
+        cols = R.model_cols()
+        xx_ref = R.model_get("xx")
+        pp = R.prior_params()
+        y, E = R.y(), np.asfortranarray(R.e())
+        G = np.asfortranarray(np.stack([R.get_column(j, 0) for j in range(m_g)], axis=1))
+        ops_a = np.ascontiguousarray(ops, dtype=np.float64)
+        trace = np.zeros(len(ops))
+        xx = np.zeros(64 * 64)
+        Ns = np.zeros(5, dtype=np.int32)
+        got = harness.harness_typed_model_trace(C.c_long(n), C.c_long(m_g), C.c_int(m_e + 1), _p(G), _p(E), _p(y), C.c_double(float(y @ y)),
+                                                C.c_double(pp["s2_sigma2"]), C.c_int(len(codes)),
+                                                _p(np.asarray(codes, dtype=np.int32), C.c_int), C.c_int(len(ops)), _p(ops_a.reshape(-1)),
+                                                _p(trace), _p(xx), _p(Ns, C.c_int))
+        assert got == cols
+        assert np.allclose(trace, trace_ref, rtol=0, atol=1e-9)
+        assert np.allclose(xx[:cols * cols].reshape(cols, cols).T, xx_ref, rtol=0, atol=1e-10)
+        assert Ns.sum() == len(in_model)
+    finally:
+        R.close()

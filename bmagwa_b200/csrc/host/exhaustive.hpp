@@ -17,7 +17,9 @@ const double kLogHalf = -0.69314718055994528622676398299518041312694549560546875
 // ------------------------------------------------------------------------------------------------
 // exhaustive enumeration helpers (sampler.cpp:882-1049)
 // ------------------------------------------------------------------------------------------------
-inline void compute_exhaustive_modelset(size_t n_inds, ExhModel* exh, double* logp, double& max_log_model)
+// Exh: ExhModel (model.types = A) or TypedExhModel (several effect types) -- the walk over the sub-models is the same
+template <class Exh>
+inline void compute_exhaustive_modelset(size_t n_inds, Exh* exh, double* logp, double& max_log_model)
 {
   std::vector<size_t> inds(n_inds);
   for (size_t i = 0; i < n_inds; ++i) inds[i] = i;

@@ -559,3 +559,56 @@ extern "C" int harness_typed_model_trace(long n, long m_g, int m_e, const double
   delete p;
   return cols;
 }
+
+// Delayed-rejection enumeration for SNPs with effect types: TypedExhModel + compute_exhaustive_modelset against a model built
+// from scratch per sub-model (as harness_exhaustive, with snp_type per SNP; AH = two columns).
+extern "C" void harness_exhaustive_typed(long n, long m_g, int m_e, const double* G, const double* E, const double* y, double yy,
+                                         double s2_sigma2, int n_types, const int* types, int const_loci, int ms,
+                                         const unsigned* snps, const int* snp_type, const double* taus2, double* P, double* B)
+{
+  Prior* p = make_prior(n, m_g, m_e, yy, 5.0, 20.0, 1.0, s2_sigma2, 5.0, 0.05, 1.0, 1, 0.0, 0.001);
+  configure(p, n_types, types, 5.0, 0.05);
+  auto dot = [&](const double* a, const double* b) { double s = 0.0; for (long i = 0; i < n; ++i) s += a[i] * b[i]; return s; };
+  UpperMat exx;
+  exx.resize(m_e);
+  std::vector<double> exy(m_e);
+  for (int c = 0; c < m_e; ++c) {
+    for (int r = 0; r <= c; ++r) exx(r, c) = dot(E + (size_t)r * n, E + (size_t)c * n);
+    exy[c] = dot(E + (size_t)c * n, y);
+  }
+  struct Built { Model m; TypedTerms terms; std::vector<std::vector<double>> colsx; };
+  auto add = [&](Built& b, int which) {
+    const unsigned snp = snps[which];
+    const int ty = snp_type[which];
+    b.terms.add(snp, ty, b.m.cols());
+    for (int c = 0; c < TypedTerms::n_columns(ty); ++c) {
+      const int tt = TypedTerms::term_type(ty, c);
+      std::vector<double> x(n);
+      for (long r = 0; r < n; ++r) x[r] = typed_genotype(tt, (int)G[(size_t)snp * n + r]);
+      std::vector<double> col(b.m.cols() + 1);
+      for (int e2 = 0; e2 < m_e; ++e2) col[e2] = dot(E + (size_t)e2 * n, x.data());
+      for (size_t t = 0; t < b.colsx.size(); ++t) col[m_e + t] = dot(b.colsx[t].data(), x.data());
+      col[b.m.cols()] = dot(x.data(), x.data());
+      b.m.add_term(snp, dot(x.data(), y), col.data(), taus2[2 * which + c], tt);
+      b.colsx.push_back(x);
+    }
+  };
+  Built full;
+  full.m.init(m_e, exx, exy, p);
+  for (int i = 0; i < const_loci + ms; ++i) add(full, i);
+  TypedExhModel exh;
+  exh.update_to_model(full.m, full.terms, const_loci);
+  double mx;
+  compute_exhaustive_modelset((size_t)ms, &exh, P, mx);
+  for (unsigned long mask = 0; mask < (1ul << ms); ++mask) {
+    Built b;
+    b.m.init(m_e, exx, exy, p);
+    for (int i = 0; i < const_loci; ++i) add(b, i);
+    for (int bit = 0; bit < ms; ++bit)
+      if ((mask >> bit) & 1) add(b, const_loci + bit);
+    B[mask] = b.m.log_likelihood + p->log_model(b.terms.Ns);
+  }
+  const double p0 = P[0], b0 = B[0];
+  for (unsigned long mask = 0; mask < (1ul << ms); ++mask) { P[mask] -= p0; B[mask] -= b0; }
+  delete p;
+}

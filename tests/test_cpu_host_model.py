@@ -372,3 +372,38 @@ def test_typed_model_add_remove_trace_matches_reference(harness, ref_lib, tmp_pa
         assert Ns.sum() == len(in_model)
     finally:
         R.close()
+
+
+@pytest.mark.parametrize("types,const_loci,ms,seed", [("A,H,D,R", 2, 4, 61), ("AH", 1, 3, 62), ("A,AH", 2, 5, 63),
+                                                       ("A,H,D,R,AH", 3, 6, 64), ("A,H,D,R,AH", 0, 7, 65)])
+def test_typed_exhaustive_modelset_equals_brute_force(harness, types, const_loci, ms, seed):
+    """TypedExhModel walks the 2^ms sub-models of SNPs with effect types (an AH SNP moves as a pair of columns: one, two or
+    four adjacent Givens swaps per step, model.hpp:706-829): every log probability -- likelihood plus the per-type model
+    prior -- must equal the one of a model built from scratch."""
+    from bmagwa_b200 import synth
+    n, m_g = 150, 40
+    payload, f = synth.make_genotypes(n, m_g, seed=seed)
+    bed = payload.copy()
+    cpu.recode_minor(bed, n, m_g)
+    rs = np.random.default_rng(seed)
+    codes = sorted(NAMES[t] for t in types.split(","))
+    G = np.asfortranarray(np.stack([cpu.decode_column(bed, n, j, 0) for j in range(m_g)], axis=1))
+    E = np.asfortranarray(np.column_stack([np.ones(n), rs.uniform(size=n)]))
+    y = rs.normal(size=n) + 0.5 * G[:, 3]
+    k = const_loci + ms
+    snps = rs.choice(m_g, size=k, replace=False).astype(np.uint32)
+    snp_type = np.array([codes[int(rs.integers(0, len(codes)))] for _ in range(k)], dtype=np.int32)
+    if 4 in codes:
+        snp_type[const_loci] = 4          # at least one pair among the moving SNPs ...
+        if ms > 1:
+            snp_type[const_loci + 1] = 4  # ... and two pairs next to each other
+    taus2 = 0.5 + rs.random(size=(k, 2)) * 5
+    P, B = np.zeros(1 << ms), np.zeros(1 << ms)
+    var_y = float(np.var(y, ddof=1))
+    harness.harness_exhaustive_typed(C.c_long(n), C.c_long(m_g), C.c_int(2), _p(G), _p(E), _p(y), C.c_double(float(y @ y)),
+                                     C.c_double(var_y * 0.8 * 3.0), C.c_int(len(codes)), _p(np.asarray(codes, dtype=np.int32), C.c_int),
+                                     C.c_int(const_loci), C.c_int(ms), _p(snps, C.c_uint), _p(snp_type, C.c_int),
+                                     _p(np.ascontiguousarray(taus2).reshape(-1)), _p(P), _p(B))
+    assert np.isfinite(P).all() and np.isfinite(B).all()
+    assert np.allclose(P, B, rtol=0, atol=1e-9)
+    assert np.abs(B).max() > 1e-3

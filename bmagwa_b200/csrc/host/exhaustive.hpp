@@ -69,7 +69,7 @@ inline void compute_exhaustive_modelset(size_t n_inds, Exh* exh, double* logp, d
 
 inline void compute_proposal_probs_for_exh_modelset(int n_inds, const unsigned char* bit_to_normalized_order, const double* q_add,
                                              const double* q_rem, double z_add, double z_rem, size_t const_loci, size_t m_g,
-                                             double* log_prop_probs)
+                                             double* log_prop_probs, const double* log_q_add_types = nullptr)
 {
   // sampler.cpp:982-1049.  Same sequence of factors as the reference; the logs of the ms weights are taken once
   // and the normalising totals are multiplied up and logged once per sub-model instead of once per step.
@@ -99,6 +99,7 @@ inline void compute_proposal_probs_for_exh_modelset(int n_inds, const unsigned c
       if (isadd[j]) {
         --max_adds;
         sum_log_q += lq_add[j];
+        if (log_q_add_types) sum_log_q += log_q_add_types[j];   // several effect types: the type proposal of the addition
         prod_z *= z_a;
         z_a -= q_add[j];
       } else {

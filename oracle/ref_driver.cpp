@@ -391,12 +391,13 @@ void refd_chol_swapadj(double* a, int k, int col, double* v)
 
 /* ---- delayed rejection: proposal probabilities of the exhaustive model set (sampler.cpp:982-1049), one effect type ---- */
 void refd_dr_proposal_probs(int n_inds, const unsigned char* bit_to_normalized_order, const double* q_add, const double* q_rem,
-                            double z_add, double z_rem, long const_loci, long m_g, double* log_prop_probs)
+                            double z_add, double z_rem, long const_loci, long m_g, const double* log_q_add_types,
+                            double* log_prop_probs)
 {
-  const bool use_types = false;
+  const bool use_types = log_q_add_types != NULL;   /* several effect types: the type proposal of each addition */
   const size_t cl = (size_t)const_loci, mg = (size_t)m_g;
-  compute_proposal_probs_for_exh_modelset(use_types, n_inds, bit_to_normalized_order, q_add, q_rem, z_add, z_rem, cl, mg, NULL,
-                                          log_prop_probs);
+  compute_proposal_probs_for_exh_modelset(use_types, n_inds, bit_to_normalized_order, q_add, q_rem, z_add, z_rem, cl, mg,
+                                          log_q_add_types, log_prop_probs);
 }
 
 /* ---- utils (utils.cpp:144-152) ---- */

@@ -277,10 +277,10 @@ extern "C" void harness_exhaustive(long n, long m_g, int m_e, const double* G, c
 // Delayed rejection: proposal probabilities of the sub-models (sampler.cpp:982-1049), the product's restatement
 extern "C" void harness_dr_proposal_probs(int n_inds, const unsigned char* bit_to_normalized_order, const double* q_add,
                                           const double* q_rem, double z_add, double z_rem, long const_loci, long m_g,
-                                          double* log_prop_probs)
+                                          const double* log_q_add_types, double* log_prop_probs)
 {
   compute_proposal_probs_for_exh_modelset(n_inds, bit_to_normalized_order, q_add, q_rem, z_add, z_rem, (size_t)const_loci,
-                                          (size_t)m_g, log_prop_probs);
+                                          (size_t)m_g, log_prop_probs, log_q_add_types);
 }
 
 // One round of the model-level Gibbs updates on a model holding the given SNPs: Model::sample_beta_sigma2

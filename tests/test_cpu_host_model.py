@@ -159,8 +159,9 @@ def test_exhaustive_modelset_equals_brute_force(harness, const_loci, ms, seed):
     assert np.abs(B).max() > 1e-3
 
 
+@pytest.mark.parametrize("with_types", [False, True])
 @pytest.mark.parametrize("n_inds,const_loci,m_g,seed", [(2, 0, 50, 1), (3, 4, 50, 2), (6, 1, 30, 3), (8, 10, 200, 4), (4, 0, 4, 5)])
-def test_dr_proposal_probabilities_match_reference_function(harness, ref_lib, n_inds, const_loci, m_g, seed):
+def test_dr_proposal_probabilities_match_reference_function(harness, ref_lib, n_inds, const_loci, m_g, seed, with_types):
     """compute_proposal_probs_for_exh_modelset: the product's restatement (logs of the weights taken once, normalising totals
     multiplied up and logged once per sub-model) against the reference's own function (sampler.cpp:982-1049)."""
     rs = np.random.default_rng(seed)
@@ -173,10 +174,12 @@ def test_dr_proposal_probabilities_match_reference_function(harness, ref_lib, n_
         z_rem = 0.0
     start = rs.normal(size=1 << n_inds)
     ours, ref = start.copy(), start.copy()
+    lqt = np.log(rs.uniform(0.1, 1.0, size=n_inds)) if with_types else None   # type proposals of the additions (several types)
     harness.harness_dr_proposal_probs(C.c_int(n_inds), _p(order, C.c_ubyte), _p(q_add), _p(q_rem), C.c_double(z_add), C.c_double(z_rem),
-                                      C.c_long(const_loci), C.c_long(m_g), _p(ours))
+                                      C.c_long(const_loci), C.c_long(m_g), _p(lqt) if with_types else None, _p(ours))
     ref_lib.lib().refd_dr_proposal_probs(C.c_int(n_inds), _p(order, C.c_ubyte), _p(q_add), _p(q_rem), C.c_double(z_add),
-                                         C.c_double(z_rem), C.c_long(const_loci), C.c_long(m_g), _p(ref))
+                                         C.c_double(z_rem), C.c_long(const_loci), C.c_long(m_g), _p(lqt) if with_types else None,
+                                         _p(ref))
     assert np.isfinite(ref).all()
     assert np.allclose(ours, ref, rtol=1e-12, atol=1e-11)
 

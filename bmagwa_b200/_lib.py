@@ -79,6 +79,7 @@ SIGNATURES = {
     "bmg_sampler_run": (C.c_int, [vp, i64]),
     "bmg_sampler_end": (C.c_int, [vp]),
     "bmg_sampler_stats": (C.c_int, [vp, f64p]),
+    "bmg_sampler_counters": (C.c_int, [vp, f64p, C.c_int]),
     "bmg_sampler_inclusion_counts": (C.c_int, [vp, C.POINTER(C.c_uint32), i64p]),
     "bmg_sampler_store": (vp, [vp]),
     "bmg_sampler_chain": (vp, [vp]),

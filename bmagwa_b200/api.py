@@ -364,6 +364,13 @@ class Sampler:
         keys = ("iterations", "accepted", "model_size", "log_likelihood", "move_seconds", "scan_seconds", "scans", "column_stats_seconds")
         return dict(zip(keys, out))
 
+    def counters(self):
+        out = np.zeros(12)
+        check(self.L.bmg_sampler_counters(self.h, _pf(out), 12))
+        keys = ("moves_with_additions", "served_from_memo", "partly_from_memo", "device_requests", "memo_pairs", "server_fallbacks",
+                "delayed_rejection_seconds", "delayed_rejection_events", "epilogue_seconds", "gibbs_seconds", "probit_sweeps")
+        return dict(zip(keys, out))
+
     def inclusion_counts(self, m_g):
         """(counts[m_g] uint32, number of thinned samples counted): running MCMC inclusion counts of the chain."""
         counts = np.zeros(m_g, dtype=np.uint32)

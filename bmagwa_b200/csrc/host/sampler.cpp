@@ -290,6 +290,7 @@ void Sampler::probit_sweep()
   }
   prior_->set_yy(st[1]);
   yy_ = st[1];
+  cache_.bump_phenotype();   // every memoised x'z is stale
   ++n_probit_sweeps_;
 }
 
@@ -319,6 +320,8 @@ void Sampler::set_option(const std::string& key, const std::string& value)
   } else if (key == "probit") {
     if (value != "0") enable_probit();
     else if (probit_) throw std::runtime_error("probit mode cannot be switched off once enabled");
+  } else if (key == "gram_cache") {
+    cache_.enabled = value != "0";
   } else if (key == "colstats_server") {
     chain_->server_enabled = value != "0";
   } else if (key == "scan_variant") {
@@ -363,24 +366,91 @@ void Sampler::begin_gram(const std::vector<uint32_t>& cand)
   gram_.k_cur = (int)current_.loci.size();
   gram_.m_c = (int)cand.size();
   gram_.cand = cand;
+  gram_req_.clear();
   if (cand.empty()) return;
-  gram_c64_.assign(cand.begin(), cand.end());
+  const size_t m_c = cand.size(), k = current_.loci.size();
+  gram_.xy.assign(m_c, 0.0);
+  gram_.xe.assign(m_c * m_e_, 0.0);
+  gram_.xm.assign(m_c * std::max<size_t>(1, k), 0.0);
+  gram_.xc.assign(m_c * m_c, 0.0);
+  // What the memo (gramcache.hpp) already holds is copied straight into gram_; a candidate with anything missing is
+  // asked of the device, together with the other incomplete candidates, in one request.
+  const bool memo = cache_.enabled;
+  if (memo) {
+    if (!cache_.ready()) cache_.init(m_g_, m_e_);
+    ++cache_.requests;
+    for (size_t c = 0; c < m_c; ++c) {
+      const uint32_t snp = cand[c];
+      bool complete = cacheable(snp) && cache_.have_snp(snp);
+      if (complete) {
+        gram_.xy[c] = cache_.xy(snp);
+        const double* xe = cache_.xe(snp);
+        for (size_t j = 0; j < m_e_; ++j) gram_.xe[c * m_e_ + j] = xe[j];
+        gram_.xc[c * m_c + c] = cache_.xx(snp);
+        for (size_t l = 0; l < k && complete; ++l)
+          complete = cacheable(current_.loci[l]) && cache_.get_pair(snp, current_.loci[l], &gram_.xm[c * k + l]);
+        for (size_t d = 0; d < m_c && complete; ++d)
+          if (d != c) complete = cacheable(cand[d]) && cache_.get_pair(snp, cand[d], &gram_.xc[c * m_c + d]);
+      }
+      if (!complete) gram_req_.push_back((int)c);
+    }
+    if (gram_req_.empty()) { ++cache_.served; return; }
+    if (gram_req_.size() < m_c) ++cache_.partial;
+  } else {
+    for (size_t c = 0; c < m_c; ++c) gram_req_.push_back((int)c);
+  }
+  const size_t m_r = gram_req_.size();
+  gram_c64_.resize(m_r);
+  for (size_t i = 0; i < m_r; ++i) gram_c64_[i] = (int64_t)cand[gram_req_[i]];
   gram_l64_.assign(current_.loci.begin(), current_.loci.end());
-  gram_.xy.assign(cand.size(), 0.0);
-  gram_.xe.assign(cand.size() * m_e_, 0.0);
-  gram_.xm.assign(cand.size() * std::max<size_t>(1, gram_l64_.size()), 0.0);
-  gram_.xc.assign(cand.size() * cand.size(), 0.0);
+  req_xy_.assign(m_r, 0.0);
+  req_xe_.assign(m_r * m_e_, 0.0);
+  req_xm_.assign(m_r * std::max<size_t>(1, k), 0.0);
+  req_xc_.assign(m_r * m_r, 0.0);
   const double t0 = wall_seconds();
-  chain_column_stats_launch(chain_, gram_c64_.data(), (int)gram_c64_.size(), gram_l64_.data(), (int)gram_l64_.size(),
-                            gram_.xy.data(), gram_.xe.data(), gram_.xm.data(), gram_.xc.data(), true);
+  chain_column_stats_launch(chain_, gram_c64_.data(), (int)m_r, gram_l64_.data(), (int)k, req_xy_.data(), req_xe_.data(),
+                            req_xm_.data(), req_xc_.data(), true);
   device_wait_seconds_ += wall_seconds() - t0;
+  ++n_gram_requests_;
 }
 void Sampler::finish_gram()
 {
-  if (gram_.m_c == 0) return;
+  if (gram_req_.empty()) return;
   const double t0 = wall_seconds();
-  chain_column_stats_wait(chain_, gram_.xy.data(), gram_.xe.data(), gram_.xm.data(), gram_.xc.data());
+  chain_column_stats_wait(chain_, req_xy_.data(), req_xe_.data(), req_xm_.data(), req_xc_.data());
   device_wait_seconds_ += wall_seconds() - t0;
+  const size_t m_c = gram_.cand.size(), k = (size_t)gram_.k_cur, m_r = gram_req_.size();
+  const bool memo = cache_.enabled;
+  for (size_t i = 0; i < m_r; ++i) {
+    const size_t c = (size_t)gram_req_[i];
+    const uint32_t snp = gram_.cand[c];
+    gram_.xy[c] = req_xy_[i];
+    for (size_t j = 0; j < m_e_; ++j) gram_.xe[c * m_e_ + j] = req_xe_[i * m_e_ + j];
+    for (size_t l = 0; l < k; ++l) gram_.xm[c * k + l] = req_xm_[i * k + l];
+    for (size_t j = 0; j < m_r; ++j) gram_.xc[c * m_c + (size_t)gram_req_[j]] = req_xc_[i * m_r + j];
+    if (!memo) continue;
+    const bool keep = cacheable(snp) && cache_.repeat_visitor(snp);
+    if (keep) cache_.put_snp(snp, req_xy_[i], &req_xe_[i * m_e_], req_xc_[i * m_r + i]);
+    for (size_t l = 0; l < k; ++l)
+      if (keep && cacheable(current_.loci[l])) cache_.put_pair(snp, current_.loci[l], req_xm_[i * k + l]);
+    for (size_t j = i + 1; j < m_r; ++j)
+      if (keep && cacheable(gram_.cand[(size_t)gram_req_[j]])) cache_.put_pair(snp, gram_.cand[(size_t)gram_req_[j]], req_xc_[i * m_r + j]);
+  }
+  if (memo && m_r < m_c) {
+    // products of a requested candidate with a candidate served from the memo: the latter was complete, i.e. it held
+    // its product with every other candidate of the move
+    for (size_t i = 0; i < m_r; ++i) {
+      const size_t c = (size_t)gram_req_[i];
+      for (size_t d = 0; d < m_c; ++d) {
+        bool requested = false;
+        for (size_t j = 0; j < m_r; ++j) requested = requested || (size_t)gram_req_[j] == d;
+        if (requested) continue;
+        if (!cache_.get_pair(gram_.cand[c], gram_.cand[d], &gram_.xc[c * m_c + d]))
+          throw std::logic_error("finish_gram: a memoised candidate lacks a product of the move");
+      }
+    }
+  }
+  gram_req_.clear();
 }
 void Sampler::fetch_gram(const std::vector<uint32_t>& cand)
 {
@@ -584,6 +654,8 @@ void Sampler::run(int64_t do_n_iter)
     }
   }
   n_iter_ = end_iter;
+  // the caller may now stay away for longer than the server's idle time-out; the next request restarts it
+  chain_server_stop(chain_);
 }
 
 // y_hat as Model::compute_pve leaves it (model.hpp:345-392), kept as coefficients (see sampler.hpp)
@@ -698,7 +770,9 @@ void Sampler::end()
     std::cerr << "[bmg timing] iterations " << n_iter_ << " moves " << move_seconds_ << " s, of which column-stats wait "
               << device_wait_seconds_ << " s, move-0 delayed rejection " << dr_seconds_ << " s (" << n_dr_ << " events); scans "
               << scan_seconds_ << " s, scan epilogue (adapt + weights to the host, waits for the scan) " << epilogue_seconds_ << " s; missing-genotype Gibbs step "
-              << gibbs_seconds_ << " s" << std::endl;
+              << gibbs_seconds_ << " s; column-statistics memo: " << cache_.requests << " moves asked, " << cache_.served
+              << " needed no device trip, " << cache_.partial << " a subset, " << n_gram_requests_ << " device requests, "
+              << cache_.pairs() << " pairs held; server fall-backs " << chain_->server_fallbacks << std::endl;
   // _rao.dat (sampler.cpp:847-849): the running mean kept on the device
   p_rao_.assign(m_g_, 0.0);
   BMG_CUDA(cudaSetDevice(store_->device));
@@ -724,6 +798,14 @@ void Sampler::stats(double* out8) const
 {
   out8[0] = (double)n_iter_; out8[1] = (double)n_accepted_; out8[2] = (double)current_.size(); out8[3] = current_.log_likelihood;
   out8[4] = move_seconds_; out8[5] = scan_seconds_; out8[6] = (double)n_scans_; out8[7] = device_wait_seconds_;
+}
+
+void Sampler::counters(double* out12) const
+{
+  out12[0] = (double)cache_.requests; out12[1] = (double)cache_.served; out12[2] = (double)cache_.partial;
+  out12[3] = (double)n_gram_requests_; out12[4] = (double)cache_.pairs(); out12[5] = (double)chain_->server_fallbacks;
+  out12[6] = dr_seconds_; out12[7] = (double)n_dr_; out12[8] = epilogue_seconds_; out12[9] = gibbs_seconds_;
+  out12[10] = (double)n_probit_sweeps_; out12[11] = 0.0;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -20,6 +20,7 @@
 #include "../store.cuh"
 #include "dataset.hpp"
 #include "exhaustive.hpp"
+#include "gramcache.hpp"
 #include "missing.hpp"
 #include "model.hpp"
 #include "options.hpp"
@@ -43,6 +44,7 @@ class Sampler {
   void run(int64_t n_iter);            // sampler.cpp:625-834
   void end();                          // sampler.cpp:836-879
   void stats(double* out8) const;
+  void counters(double* out12) const;
   // inclusion counts over the thinned samples after pip_burnin (what bmagwa_postprocess.py mcmcpos recomputes offline
   // from _loci.dat / _modelsize.dat, bmagwa_postprocess.py:79-123)
   int64_t inclusion_counts(uint32_t* counts) const;
@@ -123,6 +125,12 @@ class Sampler {
   void begin_gram(const std::vector<uint32_t>& cand);
   void finish_gram();
   std::vector<int64_t> gram_c64_, gram_l64_;
+  // memo of the device's column statistics (gramcache.hpp): most moves after burn-in need no device round trip
+  GramCache cache_;
+  std::vector<int> gram_req_;                       // candidates of the pending move the device was asked for
+  std::vector<double> req_xy_, req_xe_, req_xm_, req_xc_;
+  uint64_t n_gram_requests_ = 0;
+  bool cacheable(uint32_t snp) const { return !have_missing_ || miss_.count(snp) == 0; }
   void add_to_proposal(uint32_t snp, double inv_tau2_alpha2);
   void readd_to_proposal(uint32_t snp);
   void remove_from_proposal(int model_ind);

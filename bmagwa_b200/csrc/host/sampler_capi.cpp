@@ -202,6 +202,15 @@ BMG_API int bmg_sampler_stats(bmg_sampler* sp, double* out8)
   H(sp)->sampler->stats(out8);
   BMG_CATCH
 }
+BMG_API int bmg_sampler_counters(bmg_sampler* sp, double* out, int n)
+{
+  BMG_TRY
+  BMG_REQUIRE(out != nullptr && n >= 0, "bmg_sampler_counters: invalid argument");
+  double v[12];
+  H(sp)->sampler->counters(v);
+  for (int i = 0; i < n && i < 12; ++i) out[i] = v[i];
+  BMG_CATCH
+}
 BMG_API int bmg_sampler_inclusion_counts(bmg_sampler* sp, uint32_t* counts, int64_t* n_samples)
 {
   BMG_TRY

@@ -144,6 +144,9 @@ struct Chain {
   const double* server_base_y = nullptr;
   const void* server_base_out = nullptr;
   int64_t server_requests = 0;
+  int server_failures = 0;                      // consecutive requests a server instance left unserved (see chain_column_stats_wait)
+  int64_t server_fallbacks = 0;                 // requests repeated as an ordinary launch
+  std::vector<unsigned char> cs_last_req;       // the pending request (a ColStatInline), kept for that repeat
   int cs_p_mc = 0, cs_p_k = 0, cs_p_nseg = 0;
   unsigned int cs_p_seq = 0;
 };

@@ -277,7 +277,9 @@ int bmg_sampler_create_sharded(const char* ini_path, int chain_index, bmg_store*
  * "verbosity"; "reference_quirks" = 1 | 0 (keep the reference's stale-y_hat behaviour, model.hpp:345-392);
  * "scan_variant" = 2 | 1 | 0; "probit" = 1 (0/1 phenotype, Albert-Chib latent updates on the device; no reference
  * counterpart); "colstats_server" = 1 | 0 (serve the per-move column statistics from one persistent kernel fed through
- * a host mailbox instead of one launch per move).  Unknown keys are an error. */
+ * a host mailbox instead of one launch per move); "gram_cache" = 1 | 0 (keep the device's x_j'y, x_j'E, x_j'x_l results on
+ * the host so that a move whose SNPs were all seen before needs no device request; replaces the recomputation of
+ * src/model.hpp:453-470, chain files are byte-identical either way).  Unknown keys are an error. */
 int bmg_sampler_set_option(bmg_sampler* sp, const char* key, const char* value);
 /* Opens output files, initialises the chain (sampler.cpp:592-620). */
 int bmg_sampler_begin(bmg_sampler* sp);
@@ -288,6 +290,13 @@ int bmg_sampler_end(bmg_sampler* sp);
 /* stats: {iterations done, accepted, model size, log likelihood, seconds in moves,
  * seconds in scans, scans done, seconds of the move time spent waiting for per-proposal column statistics}. */
 int bmg_sampler_stats(bmg_sampler* sp, double* out8);
+/* More counters of the same run (the reference's SamplerStats has no counterpart for these, src/samplerstats.hpp:33-128):
+ * out[0..11] = {moves that needed column statistics, of which served from the host memo without a device request,
+ * of which asked the device for a subset of their SNPs, device requests, SNP pairs held by the memo, requests the
+ * persistent server left unserved and an ordinary launch repeated, seconds in move-0 delayed rejection, delayed-rejection
+ * events, seconds in the scan epilogue (adaptation + weights to the host), seconds in the missing-genotype Gibbs step,
+ * probit sweeps, reserved}.  n = number of doubles `out` holds (the first min(n, 12) are written). */
+int bmg_sampler_counters(bmg_sampler* sp, double* out, int n);
 /* Running MCMC inclusion counts: counts[j] (m_g entries, may be NULL) = number of thinned samples, after the first
  * "pip_burnin" of them, whose model contains SNP j; n_samples = how many samples were counted.  counts / n_samples is what
  * `bmagwa_postprocess.py mcmcpos basename m_g burnin 1` recomputes offline from _loci.dat and _modelsize.dat

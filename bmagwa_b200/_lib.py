@@ -80,6 +80,12 @@ SIGNATURES = {
     "bmg_sampler_end": (C.c_int, [vp]),
     "bmg_sampler_stats": (C.c_int, [vp, f64p]),
     "bmg_sampler_counters": (C.c_int, [vp, f64p, C.c_int]),
+    "bmg_group_create": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, i64, C.c_char_p, C.POINTER(vp)]),
+    "bmg_sampler_create_grouped": (C.c_int, [C.c_char_p, C.c_int, vp, vp, C.POINTER(vp)]),
+    "bmg_group_serve": (C.c_int, [vp, i64]),
+    "bmg_group_scan_chain": (vp, [vp]),
+    "bmg_group_stats": (C.c_int, [vp, f64p]),
+    "bmg_group_destroy": (C.c_int, [vp]),
     "bmg_sampler_inclusion_counts": (C.c_int, [vp, C.POINTER(C.c_uint32), i64p]),
     "bmg_sampler_store": (vp, [vp]),
     "bmg_sampler_chain": (vp, [vp]),

@@ -332,11 +332,14 @@ class Chain:
 class Sampler:
     """The MH driver (src/sampler.cpp:551-880) behind bmg_sampler_*; reads the reference's INI file."""
 
-    def __init__(self, ini_path, chain_index=0, device=0, store=None, comm=None, **options):
+    def __init__(self, ini_path, chain_index=0, device=0, store=None, comm=None, group=None, **options):
         self.L = _lib.lib()
         h = vp()
         self._comm = comm   # keeps the callback object alive as long as the sampler
-        if comm is not None:
+        self._group = group
+        if group is not None and comm is None:   # one of several chains over the sharded store (bmg_group_create)
+            check(self.L.bmg_sampler_create_grouped(str(ini_path).encode(), chain_index, store.h, group.h, C.byref(h)))
+        elif comm is not None:
             check(self.L.bmg_sampler_create_sharded(str(ini_path).encode(), chain_index, store.h, C.byref(comm.struct), C.byref(h)))
         elif store is None:
             check(self.L.bmg_sampler_create(str(ini_path).encode(), chain_index, device, C.byref(h)))

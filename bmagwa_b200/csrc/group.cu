@@ -1,0 +1,304 @@
+// group.cu -- several chains over ONE SNP-sharded store (BASELINE.json configs[4]: "sharded over 8xB200, 4 parallel
+// chains").  The reference's chains are threads of one process sharing one Data (src/main.cpp:54-85);
+// here a "shard group" is one process per GPU: rank r holds the packed SNPs [r stride, (r+1) stride) and -- for
+// r < n_chains -- the host sampler of chain r.  Nothing of a chain is replicated on other ranks:
+//
+//   per iteration   chain r asks ITS GPU for the column statistics of the SNPs it proposes; columns of other shards are
+//                   read over NVLink through CUDA-IPC peer mappings (store.cu).  No collective, no other rank involved.
+//   per scan        (every n_rao iterations, all chains at the same cadence)
+//     1. chain r quantises its residual into the tensor-core scan's limb format (scan_imma.cu) inside its exchange
+//        buffer, which every peer has mapped;
+//     2. barrier (host, POSIX shared memory: the ranks of a group live on one box);
+//     3. every rank runs the scan kernel over ITS shard once per chain (the chain's limbs are pulled over NVLink,
+//        n x 8 bytes) and a small kernel adds the per-chunk partial sums and stores the shard's dot products
+//        STRAIGHT INTO THE OWNING CHAIN'S GPU (peer stores, 8 bytes per SNP) -- compute and exchange in one pass,
+//        no NCCL call and no Python on the data path;
+//     4. barrier; chain r finishes the scan on its own GPU (per-SNP algebra over all m_g SNPs with its own tau draws)
+//        and carries on.  Integer accumulation makes the dot products independent of the sharding, so every chain
+//        writes the bytes its single-GPU run writes (tests/test_gpu_sharded.py).
+//
+// Ranks without a chain (n_chains < world, e.g. 4 chains over 8 GPUs) only serve step 3 (bmg_group_serve).
+#include <fcntl.h>
+#include <immintrin.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <time.h>
+#include <unistd.h>
+#include <atomic>
+#include <cstring>
+#include "common.cuh"
+#include "store.cuh"
+#include "group.cuh"
+
+namespace bmg {
+
+namespace {
+constexpr uint32_t kShmMagic = 0x424D4731u;   // "BMG1"
+constexpr double kBarrierTimeout = 300.0;     // seconds; a missing peer must not hang the box
+
+struct GroupShm {
+  std::atomic<uint32_t> magic;
+  std::atomic<uint32_t> attached;
+  std::atomic<uint32_t> bar_count, bar_gen;
+  std::atomic<uint32_t> failed;
+  uint32_t pad[11];
+  unsigned char handle[kGroupMaxRanks][64];
+  int64_t lo[kGroupMaxRanks], hi[kGroupMaxRanks];
+};
+
+double now_seconds()
+{
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+__global__ void k_group_combine(const double* __restrict__ partial, int n_chunks, int64_t m, double* __restrict__ out)
+{
+  const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  double d = 0.0;   // the order k_scan_finalize adds the chunks in: same bits as the single-GPU scan
+  for (int c = 0; c < n_chunks; ++c) d += partial[(int64_t)c * m + j];
+  out[j] = d;       // `out` is the owning chain's buffer: a peer store over NVLink unless the chain is local
+}
+}  // namespace
+
+struct Group {
+  int world = 1, rank = 0, n_chains = 1;
+  int64_t stride = 0;
+  Store* store = nullptr;
+  Chain* scan_chain = nullptr;   // geometry, partial sums and stream of this rank's share of every scan
+  GroupShm* shm = nullptr;
+  std::string shm_name;
+  DevBuf<unsigned char> xbuf;    // | limbs of this rank's chain | exponent | dots of this rank's chain over all SNPs |
+  size_t q_bytes = 0, off_exp = 0, off_dots = 0, xbuf_bytes = 0;
+  unsigned char* peer[kGroupMaxRanks] = {nullptr};
+  bool peer_opened[kGroupMaxRanks] = {false};
+  DevBuf<unsigned char> q_stage[2];   // a peer chain's limbs + exponent, double-buffered
+  DevBuf<int32_t> n1_all, n2_all;
+  int64_t rounds = 0;
+  double barrier_seconds = 0.0;
+};
+
+static void group_fail(Group* g)
+{
+  if (g && g->shm) g->shm->failed.store(1u, std::memory_order_release);
+}
+
+void group_barrier(Group* g)
+{
+  if (g->world <= 1) return;
+  GroupShm* s = g->shm;
+  const double t0 = now_seconds();
+  const uint32_t gen = s->bar_gen.load(std::memory_order_acquire);
+  if (s->bar_count.fetch_add(1u, std::memory_order_acq_rel) + 1u == (uint32_t)g->world) {
+    s->bar_count.store(0u, std::memory_order_relaxed);
+    s->bar_gen.fetch_add(1u, std::memory_order_release);
+  } else {
+    unsigned long spins = 0;
+    while (s->bar_gen.load(std::memory_order_acquire) == gen) {
+      if (s->failed.load(std::memory_order_acquire)) throw Error("shard group: a peer rank failed");
+      _mm_pause();
+      if ((++spins & 0x3FF) == 0) {
+        if (spins > 200000) usleep(20);   // a rank without a chain waits for a whole Rao-Blackwell period: leave the core
+        if (now_seconds() - t0 > kBarrierTimeout) {
+          group_fail(g);
+          throw Error("shard group: barrier timed out (a peer rank is missing)");
+        }
+      }
+    }
+  }
+  g->barrier_seconds += now_seconds() - t0;
+}
+
+// In-place all-gather over the group: every rank owns elements [rank per, (rank+1) per) of dev_buffer (world x per
+// elements).  Same contract as the host-supplied bmg_allgather_fn, served natively through the peer mappings.
+int group_allgather(void* ctx, void* dev_buffer, int64_t elems_per_rank, int elem_bytes, void* cuda_stream)
+{
+  Group* g = reinterpret_cast<Group*>(ctx);
+  try {
+    if (g->world <= 1) return 0;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+    const size_t per = (size_t)elems_per_rank * (size_t)elem_bytes;
+    BMG_REQUIRE(per <= g->xbuf_bytes - g->off_dots, "shard group: all-gather block larger than the exchange buffer");
+    unsigned char* buf = reinterpret_cast<unsigned char*>(dev_buffer);
+    BMG_CUDA(cudaMemcpyAsync(g->xbuf.p + g->off_dots, buf + (size_t)g->rank * per, per, cudaMemcpyDeviceToDevice, st));
+    BMG_CUDA(cudaStreamSynchronize(st));
+    group_barrier(g);
+    for (int i = 1; i < g->world; ++i) {
+      const int r = (g->rank + i) % g->world;
+      BMG_CUDA(cudaMemcpyAsync(buf + (size_t)r * per, g->peer[r] + g->off_dots, per, cudaMemcpyDefault, st));
+    }
+    BMG_CUDA(cudaStreamSynchronize(st));
+    group_barrier(g);   // nobody overwrites its staging area before everyone has read it
+    return 0;
+  } catch (const std::exception& e) {
+    group_fail(g);
+    set_last_error(e.what());
+    return 1;
+  }
+}
+
+Group* group_create(Store* s, int world, int rank, int n_chains, int64_t stride, const char* shm_name)
+{
+  BMG_REQUIRE(world >= 1 && world <= kGroupMaxRanks && rank >= 0 && rank < world, "shard group: invalid world / rank");
+  BMG_REQUIRE(n_chains >= 1 && n_chains <= world, "shard group: 1 <= n_chains <= world (one chain per rank at most)");
+  BMG_REQUIRE(stride > 0 && (int64_t)world * stride >= s->m_g, "shard group: world x stride does not cover m_g");
+  BMG_REQUIRE(s->lo == std::min(s->m_g, (int64_t)rank * stride) && s->hi == std::min(s->m_g, (int64_t)(rank + 1) * stride),
+              "shard group: the store's SNP range is not this rank's shard");
+  BMG_REQUIRE(s->m_e >= 1, "shard group: call bmg_store_set_phenotype on the shard first");
+  BMG_REQUIRE(world == 1 || (shm_name != nullptr && shm_name[0] == '/'), "shard group: a POSIX shared-memory name (\"/...\") is required");
+  BMG_CUDA(cudaSetDevice(s->device));
+  std::unique_ptr<Group> g(new Group());
+  g->world = world; g->rank = rank; g->n_chains = n_chains; g->stride = stride; g->store = s;
+  g->scan_chain = chain_create(s);
+  imma_prepare(g->scan_chain);
+  const int64_t n_pad = 16 * (int64_t)g->scan_chain->imma_chunks * g->scan_chain->imma_chunk_words;
+  g->q_bytes = (size_t)n_pad * 8;
+  g->off_exp = g->q_bytes;
+  g->off_dots = g->q_bytes + 256;
+  g->xbuf_bytes = g->off_dots + (size_t)world * (size_t)stride * sizeof(double);
+  g->xbuf.alloc(g->xbuf_bytes);
+  BMG_CUDA(cudaMemset(g->xbuf.p, 0, g->xbuf_bytes));
+  g->q_stage[0].alloc(g->q_bytes + 256);
+  g->q_stage[1].alloc(g->q_bytes + 256);
+  BMG_CUDA(cudaDeviceSynchronize());   // the memset ran on the null stream; everything below uses non-blocking streams
+  g->peer[rank] = g->xbuf.p;
+  if (world > 1) {
+    g->shm_name = shm_name;
+    int fd = -1;
+    if (rank == 0) {
+      fd = shm_open(shm_name, O_CREAT | O_EXCL | O_RDWR, 0600);
+      BMG_REQUIRE(fd >= 0, std::string("shard group: shm_open(create) failed for ") + shm_name);
+      BMG_REQUIRE(ftruncate(fd, sizeof(GroupShm)) == 0, "shard group: ftruncate failed");
+    } else {
+      const double t0 = now_seconds();
+      while ((fd = shm_open(shm_name, O_RDWR, 0600)) < 0) {
+        BMG_REQUIRE(now_seconds() - t0 < 120.0, std::string("shard group: rank 0 never created ") + shm_name);
+        usleep(1000);
+      }
+      struct stat sb;
+      while (fstat(fd, &sb) == 0 && (size_t)sb.st_size < sizeof(GroupShm)) {
+        BMG_REQUIRE(now_seconds() - t0 < 120.0, "shard group: shared segment never sized");
+        usleep(1000);
+      }
+    }
+    void* p = mmap(nullptr, sizeof(GroupShm), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    BMG_REQUIRE(p != MAP_FAILED, "shard group: mmap failed");
+    g->shm = reinterpret_cast<GroupShm*>(p);
+    if (rank == 0) g->shm->magic.store(kShmMagic, std::memory_order_release);   // a fresh segment is zero-filled
+    else {
+      const double t0 = now_seconds();
+      while (g->shm->magic.load(std::memory_order_acquire) != kShmMagic) {
+        BMG_REQUIRE(now_seconds() - t0 < 120.0, "shard group: shared segment never initialised");
+        usleep(100);
+      }
+    }
+    cudaIpcMemHandle_t h;
+    BMG_CUDA(cudaIpcGetMemHandle(&h, g->xbuf.p));
+    std::memcpy(g->shm->handle[rank], &h, 64);
+    g->shm->lo[rank] = s->lo; g->shm->hi[rank] = s->hi;
+    g->shm->attached.fetch_add(1u, std::memory_order_acq_rel);
+    group_barrier(g.get());
+    if (rank == 0) shm_unlink(shm_name);   // everyone has it mapped: nothing is left behind whatever happens next
+    for (int r = 0; r < world; ++r) {
+      if (r == rank) continue;
+      cudaIpcMemHandle_t hr;
+      std::memcpy(&hr, g->shm->handle[r], 64);
+      void* ptr = nullptr;
+      BMG_CUDA(cudaIpcOpenMemHandle(&ptr, hr, cudaIpcMemLazyEnablePeerAccess));
+      g->peer[r] = reinterpret_cast<unsigned char*>(ptr);
+      g->peer_opened[r] = true;
+    }
+    group_barrier(g.get());
+  }
+  // genotype counts of every SNP on every rank: the per-SNP algebra of a chain's scan runs on the chain's own GPU
+  const int64_t total = (int64_t)world * stride;
+  g->n1_all.alloc(total); g->n2_all.alloc(total);
+  cudaStream_t st = g->scan_chain->stream;
+  BMG_CUDA(cudaMemsetAsync(g->n1_all.p, 0, total * sizeof(int32_t), st));
+  BMG_CUDA(cudaMemsetAsync(g->n2_all.p, 0, total * sizeof(int32_t), st));
+  BMG_CUDA(cudaMemcpyAsync(g->n1_all.p + (int64_t)rank * stride, s->n1.p, s->m * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  BMG_CUDA(cudaMemcpyAsync(g->n2_all.p + (int64_t)rank * stride, s->n2.p, s->m * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  BMG_REQUIRE(group_allgather(g.get(), g->n1_all.p, stride, (int)sizeof(int32_t), (void*)st) == 0, "shard group: exchange of the genotype counts failed");
+  BMG_REQUIRE(group_allgather(g.get(), g->n2_all.p, stride, (int)sizeof(int32_t), (void*)st) == 0, "shard group: exchange of the genotype counts failed");
+  BMG_CUDA(cudaStreamSynchronize(st));
+  return g.release();
+}
+
+void group_destroy(Group* g)
+{
+  if (!g) return;
+  cudaSetDevice(g->store->device);
+  if (g->scan_chain) { cudaStreamSynchronize(g->scan_chain->stream); }
+  for (int r = 0; r < g->world; ++r)
+    if (g->peer_opened[r]) cudaIpcCloseMemHandle(g->peer[r]);
+  chain_destroy(g->scan_chain);
+  if (g->shm) munmap(g->shm, sizeof(GroupShm));
+  delete g;
+}
+
+int group_world(const Group* g) { return g->world; }
+int group_rank(const Group* g) { return g->rank; }
+int group_chains(const Group* g) { return g->n_chains; }
+int64_t group_stride(const Group* g) { return g->stride; }
+const int32_t* group_n1(const Group* g) { return g->n1_all.p; }
+const int32_t* group_n2(const Group* g) { return g->n2_all.p; }
+Chain* group_scan_chain(Group* g) { return g->scan_chain; }
+void group_stats(const Group* g, double* out4)
+{
+  out4[0] = (double)g->rounds; out4[1] = g->barrier_seconds; out4[2] = 0.0; out4[3] = 0.0;
+}
+
+// One scan round (see the header of this file).  mine: this rank's chain with its residual ready, or nullptr on a rank
+// without a chain.  Returns the chain's dot products over all m_g SNPs (device pointer on this GPU), complete when the
+// call returns.
+const double* group_scan_round(Group* g, Chain* mine)
+{
+  Store* s = g->store;
+  try {
+    BMG_CUDA(cudaSetDevice(s->device));
+    BMG_REQUIRE((mine != nullptr) == (g->rank < g->n_chains), "shard group: ranks below n_chains scan through their chain, the others through bmg_group_serve");
+    Chain* sc = g->scan_chain;
+    cudaStream_t st = mine ? mine->stream : sc->stream;
+    if (mine) {
+      BMG_REQUIRE(mine->residual_valid, "scan: call bmg_chain_residual first");
+      imma_quantize(mine);
+      BMG_REQUIRE(mine->imma_q.n == g->q_bytes, "shard group: limb layout of the chain differs from the group's");
+      BMG_CUDA(cudaMemcpyAsync(g->xbuf.p, mine->imma_q.p, g->q_bytes, cudaMemcpyDeviceToDevice, st));
+      BMG_CUDA(cudaMemcpyAsync(g->xbuf.p + g->off_exp, mine->imma_exp.p, sizeof(int), cudaMemcpyDeviceToDevice, st));
+      BMG_CUDA(cudaStreamSynchronize(st));
+    }
+    group_barrier(g);   // every chain's limbs are in place
+    for (int i = 0; i < g->n_chains; ++i) {
+      const int c = (g->rank + i) % g->n_chains;   // start with the nearest chain: the pulls spread over the peers
+      const unsigned char* q = g->xbuf.p;
+      if (c != g->rank) {
+        DevBuf<unsigned char>& stage = g->q_stage[i & 1];
+        BMG_CUDA(cudaMemcpyAsync(stage.p, g->peer[c], g->q_bytes + 256, cudaMemcpyDefault, st));
+        q = stage.p;
+      }
+      imma_launch_on(sc, reinterpret_cast<const uint4*>(q), reinterpret_cast<const int*>(q + g->q_bytes), sc->imma_partial.p, false, st,
+                     mine ? mine : sc);
+      double* out = reinterpret_cast<double*>(g->peer[c] + g->off_dots) + s->lo;
+      k_group_combine<<<(unsigned)((s->m + 255) / 256), 256, 0, st>>>(sc->imma_partial.p, sc->imma_chunks, s->m, out);
+      count_launch();
+    }
+    BMG_CUDA(cudaGetLastError());
+    BMG_CUDA(cudaStreamSynchronize(st));
+    group_barrier(g);   // every shard's dot products have landed on every chain's GPU
+    ++g->rounds;
+    return mine ? reinterpret_cast<const double*>(g->xbuf.p + g->off_dots) : nullptr;
+  } catch (...) {
+    group_fail(g);
+    throw;
+  }
+}
+
+void group_serve(Group* g, int64_t n_rounds)
+{
+  for (int64_t i = 0; i < n_rounds; ++i) group_scan_round(g, nullptr);
+}
+
+}  // namespace bmg

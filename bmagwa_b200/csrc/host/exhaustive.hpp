@@ -1,9 +1,24 @@
-// exhaustive.hpp -- delayed rejection: log probabilities of all 2^ms sub-models of the SNPs a rejected move touched, and the
-// proposal probabilities of reaching each of them (src/sampler.cpp:882-1049).  Plain host code over ExhModel (model.hpp);
-// kept apart from sampler.cpp so that it is unit-tested on the CPU (tests/test_cpu_host_model.py).
+// exhaustive.hpp -- delayed rejection: the log posterior of all 2^ms sub-models of the SNPs a rejected move touched, and
+// the probabilities with which the move would propose flipping all of them from each sub-model.  Written from the
+// specification ("Delayed rejection"); the reference obtains the same numbers by walking a Gray-like
+// sequence of adjacent column swaps of the whole factor (src/model.hpp:602-839, src/sampler.cpp:882-1049).  Plain host
+// code, unit-tested on the CPU against from-scratch models and against the reference's own function
+// (tests/test_cpu_host_model.py).
+//
+// Sub-model enumeration (SubmodelEnumerator).  The move's ms SNPs are the LAST terms of the model handed in.  With U the
+// upper Cholesky factor of X'X + diag(tau) in that order and v = U^-T X'y, the trailing block T of U and the tail z of v
+// describe the ms SNPs conditionally on the rest of the model, and only those (ms x ms numbers) are ever touched:
+//   * INCLUDING the first remaining SNP is free: it contributes log T_00, z_0^2 and its prior terms, and the SNPs after
+//     it are described, conditionally on it, by T[1:,1:] and z[1:] -- a pointer offset;
+//   * EXCLUDING it deletes T's first column: T[:,1:] is upper Hessenberg and r-1 Givens rotations (applied to z as well)
+//     make it triangular again, written into a scratch block of its own.
+// A depth-first walk over "include / exclude the next SNP" therefore visits every sub-model exactly once at the price of
+// about one rotation and two logarithms per sub-model, on data that stays in L1.  A SNP with two columns (effect type AH)
+// is included / deleted as a pair.
 #pragma once
 #include <cmath>
 #include <cstddef>
+#include <cstring>
 #include <utility>
 #include <vector>
 #include "model.hpp"
@@ -11,68 +26,162 @@
 namespace bmg {
 
 namespace exhaustive_detail {
-const double kLogHalf = -0.69314718055994528622676398299518041312694549560546875;  // sampler.hpp:39
-}
+const double kLogHalf = -0.69314718055994528622676398299518041312694549560546875;  // log 1/2
 
-// ------------------------------------------------------------------------------------------------
-// exhaustive enumeration helpers (sampler.cpp:882-1049)
-// ------------------------------------------------------------------------------------------------
-// Exh: ExhModel (model.types = A) or TypedExhModel (several effect types) -- the walk over the sub-models is the same
-template <class Exh>
-inline void compute_exhaustive_modelset(size_t n_inds, Exh* exh, double* logp, double& max_log_model)
-{
-  std::vector<size_t> inds(n_inds);
-  for (size_t i = 0; i < n_inds; ++i) inds[i] = i;
-  size_t binary = 0;
-  int model_size = 0;
-  auto note = [&](double v) { logp[binary] = v; if (v > max_log_model) max_log_model = v; };
-  logp[binary] = exh->log_prob();
-  max_log_model = logp[binary];
-  for (size_t i = 0; i < n_inds; ++i) {
-    ++model_size;
-    if (i > 1) { ++model_size; exh->update_on_add(); }
-    binary = ((size_t)1 << model_size) - 1;
-    note(exh->update_on_add());
-    for (size_t j = 0; j < i; ++j) {   // walk the new variable to the left-most place
-      --model_size;
-      std::swap(inds[model_size - 1], inds[model_size]);
-      binary &= ~((size_t)1 << inds[model_size]);
-      note(exh->update_on_moveleft());
+// model prior along a path of inclusions (src/prior.hpp:144-167): one effect type / several
+struct PriorWalkA {
+  const Prior* p; int L; double acc;
+  void add(int) { acc += p->log_change_on_add(L); ++L; }
+};
+struct PriorWalkTyped {
+  const Prior* p; int Ns[5]; int L; double acc;
+  void add(int t) { acc += p->log_change_on_add(Ns, L, t); ++Ns[t]; ++L; }
+};
+}  // namespace exhaustive_detail
+
+class SubmodelEnumerator {
+ public:
+  // logp[b], b in [0, 2^ms): log marginal likelihood + log model prior of the sub-model holding the first const_loci SNPs
+  // of `src` and those of its last ms SNPs whose bit is set in b (bit i = the i-th of them, in model order), relative to
+  // the model prior of the sub-model b = 0.  max_log_model = the largest entry.
+  void run(const Model& src, int const_loci, int ms, double* logp, double& max_log_model)
+  {
+    width_.assign(ms, 1);
+    type_.assign(ms, 0);
+    exhaustive_detail::PriorWalkA pw{src.prior, const_loci, 0.0};
+    start(src, src.m_e + const_loci, ms, logp);
+    walk(0, t_.data(), ncols_, z_.data(), ncols_, 0ul, half_logtau0_, sum_logdiag0_, s0_, pw);
+    max_log_model = max_;
+  }
+  // the same for SNPs with effect types: an AH SNP (type 4) owns two adjacent columns
+  void run_typed(const Model& src, const TypedTerms& terms, int const_loci, int ms, double* logp, double& max_log_model)
+  {
+    width_.resize(ms);
+    type_.resize(ms);
+    exhaustive_detail::PriorWalkTyped pw{src.prior, {0, 0, 0, 0, 0}, const_loci, 0.0};
+    for (int i = 0; i < const_loci; ++i) ++pw.Ns[terms.type[i]];
+    for (int i = 0; i < ms; ++i) { type_[i] = terms.type[const_loci + i]; width_[i] = TypedTerms::n_columns(type_[i]); }
+    const int base = ms > 0 ? terms.col1[const_loci] : src.cols();
+    start(src, base, ms, logp);
+    walk(0, t_.data(), ncols_, z_.data(), ncols_, 0ul, half_logtau0_, sum_logdiag0_, s0_, pw);
+    max_log_model = max_;
+  }
+
+ private:
+  const Prior* prior_ = nullptr;
+  int ms_ = 0, ncols_ = 0;
+  double* logp_ = nullptr;
+  double max_ = 0.0, half_logtau0_ = 0.0, sum_logdiag0_ = 0.0, s0_ = 0.0;
+  std::vector<int> width_, type_, col0_;
+  std::vector<double> t_, z_, half_logtau_;     // trailing block (column-major, ld = ncols_), tail of v, 0.5 log tau per column
+  std::vector<std::vector<double>> scratch_;    // per depth: the block after a deletion, then its z
+
+  void start(const Model& src, int base, int ms, double* logp)
+  {
+    prior_ = src.prior;
+    ms_ = ms;
+    logp_ = logp;
+    col0_.resize(ms + 1);
+    int c = 0;
+    for (int i = 0; i < ms; ++i) { col0_[i] = c; c += width_[i]; }
+    col0_[ms] = c;
+    ncols_ = c;
+    // the part of the model every sub-model shares
+    double vv = 0.0, sld = 0.0, slt = prior_->log_det_invQ_e();
+    for (int i = 0; i < base; ++i) { vv += src.v[i] * src.v[i]; sld += std::log(src.l(i, i)); }
+    for (int i = src.m_e; i < base; ++i) slt += std::log(src.inv_tau2_alpha2[i]);
+    s0_ = prior_->nus2_plus_yy - vv;
+    sum_logdiag0_ = sld;
+    half_logtau0_ = 0.5 * slt;
+    // the move's SNPs given that part
+    t_.assign((size_t)ncols_ * ncols_, 0.0);
+    z_.resize(ncols_);
+    half_logtau_.resize(ncols_);
+    for (int q = 0; q < ncols_; ++q) {
+      const double* col = src.l.col(base + q) + base;
+      for (int r = 0; r <= q; ++r) t_[(size_t)q * ncols_ + r] = col[r];
+      z_[q] = src.v[base + q];
+      half_logtau_[q] = 0.5 * std::log(src.inv_tau2_alpha2[base + q]);
     }
-    const size_t nmodels = ((size_t)1 << i) - i - 1;
-    size_t j = 0, nK = 0;
-    char do_lefts = 0;
-    while (j < nmodels) {
-      if (do_lefts < 2) {
-        ++model_size;
-        std::swap(inds[model_size], inds[model_size - 1]);
-        binary |= ((size_t)1 << inds[model_size - 1]);
-        note(exh->update_on_twonewswap());
-        ++j;
-        ++do_lefts;
-      } else {
-        ++nK;
-        size_t K = 0;
-        while (((nK >> K) & 1) == 0) ++K;   // 0,1,0,2,0,1,0,3,...
-        for (size_t k = 0; k <= K; ++k) {
-          --model_size;
-          std::swap(inds[model_size - 1], inds[model_size]);
-          binary &= ~((size_t)1 << inds[model_size]);
-          note(exh->update_on_moveleft());
-          ++j;
-        }
-        do_lefts = 0;
+    if ((int)scratch_.size() < ms + 1) scratch_.resize(ms + 1);
+    max_ = half_logtau0_ - sum_logdiag0_ + prior_->residual_term(s0_);
+    logp_[0] = max_;
+  }
+
+  // first column of the r x r upper-triangular block at (a, ld) removed in place; z likewise (its last entry is then void)
+  static void delete_first_column(double* a, int ld, double* z, int r)
+  {
+    for (int q = 0; q + 1 < r; ++q) std::memcpy(a + (size_t)q * ld, a + (size_t)(q + 1) * ld, sizeof(double) * (size_t)(q + 2));
+    for (int j = 0; j + 1 < r; ++j) {   // upper Hessenberg -> upper triangular, positive diagonal
+      double* cj = a + (size_t)j * ld;
+      const double x = cj[j], y = cj[j + 1];
+      const double h = std::sqrt(x * x + y * y);
+      const double c = x / h, s = y / h;
+      cj[j] = h;
+      for (int q = j + 1; q + 1 < r; ++q) {
+        double* cq = a + (size_t)q * ld;
+        const double u = cq[j], w = cq[j + 1];
+        cq[j] = c * u + s * w;
+        cq[j + 1] = c * w - s * u;
       }
+      const double u = z[j], w = z[j + 1];
+      z[j] = c * u + s * w;
+      z[j + 1] = c * w - s * u;
     }
   }
-}
 
+  // SNPs d.. of the move are undecided; (a, ld, z) describe their r columns given everything included so far
+  template <class PriorWalk>
+  void walk(int d, const double* a, int ld, const double* z, int r, unsigned long mask, double half_logtau, double sum_logdiag,
+            double s, PriorWalk pw)
+  {
+    if (d == ms_) return;
+    const int w = width_[d];
+    {   // with SNP d
+      double hl = half_logtau, sl = sum_logdiag, s1 = s;
+      for (int c = 0; c < w; ++c) {
+        hl += half_logtau_[col0_[d] + c];
+        sl += std::log(a[(size_t)c * ld + c]);
+        s1 -= z[c] * z[c];
+      }
+      PriorWalk pw1 = pw;
+      pw1.add(type_[d]);
+      const unsigned long m1 = mask | (1ul << d);
+      const double val = hl - sl + prior_->residual_term(s1) + pw1.acc;
+      logp_[m1] = val;
+      if (val > max_) max_ = val;
+      walk(d + 1, a + (size_t)w * ld + w, ld, z + w, r - w, m1, hl, sl, s1, pw1);
+    }
+    if (d + 1 < ms_) {   // without it
+      std::vector<double>& buf = scratch_[d + 1];
+      if (buf.size() < (size_t)r * r + r) buf.resize((size_t)r * r + r);
+      double* b = buf.data();
+      double* bz = b + (size_t)r * r;
+      for (int q = 0; q < r; ++q) std::memcpy(b + (size_t)q * r, a + (size_t)q * ld, sizeof(double) * (size_t)(q + 1));
+      std::memcpy(bz, z, sizeof(double) * (size_t)r);
+      for (int c = 0; c < w; ++c) delete_first_column(b, r, bz, r - c);
+      walk(d + 1, b, r, bz, r - w, mask, half_logtau, sum_logdiag, s, pw);
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// log_prop_probs[b] += log q(b -> complement of b): the probability that move 0 proposes to flip ALL ms SNPs when the
+// chain is at the sub-model b (src/sampler.cpp:982-1049 gives the reference's numbers).
+//   bit j of b      SNP j of the move is in the model (the move would remove it); bit_to_normalized_order[j] = the
+//                   position of that SNP in the order move 0 would handle the ms steps in
+//   q_add / q_rem   proposal weights by normalised position; z_add / z_rem the totals of the sub-model b = 0
+// Move 0 handles position p = 0, 1, ...: an addition is drawn with probability q_add[p] / (total add weight left), a
+// removal step draws the removable SNPs in reverse position order, and a fair coin precedes every step at which both kinds
+// are still possible.
+// ------------------------------------------------------------------------------------------------
+// One pass over the ms steps per sub-model; the logarithms of the ms weights are taken once and the normalising totals
+// are multiplied up and logged once per sub-model.  (A table-driven O(1)-per-sub-model variant was tried and measured
+// slower for ms <= 10: tools/dr_bench.cpp, profiles/round2_notes.md.)
 inline void compute_proposal_probs_for_exh_modelset(int n_inds, const unsigned char* bit_to_normalized_order, const double* q_add,
-                                             const double* q_rem, double z_add, double z_rem, size_t const_loci, size_t m_g,
-                                             double* log_prop_probs, const double* log_q_add_types = nullptr)
+                                            const double* q_rem, double z_add, double z_rem, size_t const_loci, size_t m_g,
+                                            double* log_prop_probs, const double* log_q_add_types = nullptr)
 {
-  // sampler.cpp:982-1049.  Same sequence of factors as the reference; the logs of the ms weights are taken once
-  // and the normalising totals are multiplied up and logged once per sub-model instead of once per step.
   char isadd[256];
   double lq_add[256], lq_rem[256];
   for (int j = 0; j < n_inds; ++j) { lq_add[j] = std::log(q_add[j]); lq_rem[j] = std::log(q_rem[j]); }

@@ -610,227 +610,7 @@ inline void Prior::sample_alpha_and_tau2_typed(Model* model, ChainRng& rng)
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// ExhModel (src/model.hpp:585-844), type A only: walks all 2^ms sub-models of the last ms terms
-// ------------------------------------------------------------------------------------------------
-struct ExhModel {
-  const Prior* prior = nullptr;
-  int m_e = 0;
-  UpperMat l;
-  std::vector<double> xy, v, inv_tau2_alpha2;
-  std::vector<double> log_diag, log_tau;   // log l(i,i) and log inv_tau2_alpha2[i], kept in step with the swaps
-  double syx_plus_vs2 = 0, log_det_invQ = 0, log_det_invQ_plus_xx = 0, log_likelihood = 0, log_model_prior = 0;
-  int model_size = 0, v_size = 0, n_terms = 0;
-
-  double log_prob() const { return log_likelihood + log_model_prior; }
-  void refresh() { log_likelihood = log_det_invQ - log_det_invQ_plus_xx + prior->residual_term(syx_plus_vs2); }
-
-  double update_to_model(const Model& src, int const_loci)  // model.hpp:602-671
-  {
-    prior = src.prior;
-    m_e = src.m_e;
-    l.copy_upper_from(src.l);
-    xy = src.xy;
-    v = src.v;
-    inv_tau2_alpha2 = src.inv_tau2_alpha2;
-    const int k = src.cols();
-    log_diag.resize(k);
-    log_tau.resize(k);
-    for (int i = 0; i < k; ++i) log_diag[i] = std::log(l(i, i));
-    for (int i = m_e; i < k; ++i) log_tau[i] = std::log(inv_tau2_alpha2[i]);
-    model_size = const_loci;
-    v_size = m_e + const_loci;
-    double vv = 0.0;
-    for (int i = 0; i < v_size; ++i) vv += v[i] * v[i];
-    syx_plus_vs2 = prior->nus2_plus_yy - vv;
-    log_det_invQ_plus_xx = 0.0;
-    for (int i = 0; i < v_size; ++i) log_det_invQ_plus_xx += log_diag[i];
-    log_det_invQ = prior->log_det_invQ_e();
-    for (int i = m_e; i < v_size; ++i) log_det_invQ += log_tau[i];
-    log_det_invQ *= 0.5;
-    refresh();
-    log_model_prior = 0.0;
-    n_terms = model_size;
-    return log_prob();
-  }
-  double update_on_add()  // model.hpp:673-704
-  {
-    syx_plus_vs2 -= v[v_size] * v[v_size];
-    log_det_invQ += 0.5 * log_tau[v_size];
-    log_det_invQ_plus_xx += log_diag[v_size];
-    ++v_size;
-    refresh();
-    log_model_prior += prior->log_change_on_add(model_size);
-    ++n_terms;
-    ++model_size;
-    return log_prob();
-  }
-  double update_on_moveleft()  // model.hpp:706-829
-  {
-    --model_size;
-    --v_size;  // the kept variable
-    syx_plus_vs2 += v[v_size] * v[v_size];
-    log_det_invQ_plus_xx -= log_diag[v_size];
-    --v_size;  // the removed variable
-    syx_plus_vs2 += v[v_size] * v[v_size];
-    log_det_invQ -= 0.5 * log_tau[v_size];
-    log_det_invQ_plus_xx -= log_diag[v_size];
-    const int ind_keep = m_e + model_size, ind_rem = m_e + model_size - 1;
-    l.swap_adjacent(ind_rem, v.data());
-    log_diag[ind_rem] = std::log(l(ind_rem, ind_rem));
-    log_diag[ind_keep] = std::log(l(ind_keep, ind_keep));
-    std::swap(xy[ind_keep], xy[ind_rem]);
-    std::swap(inv_tau2_alpha2[ind_keep], inv_tau2_alpha2[ind_rem]);
-    std::swap(log_tau[ind_keep], log_tau[ind_rem]);
-    syx_plus_vs2 -= v[v_size] * v[v_size];
-    log_det_invQ_plus_xx += log_diag[v_size];
-    ++v_size;
-    refresh();
-    log_model_prior += prior->log_change_on_rem(model_size + 1);
-    --n_terms;
-    return log_prob();
-  }
-  double update_on_twonewswap()
-  {
-    update_on_add();
-    update_on_add();
-    return update_on_moveleft();
-  }
-};
-
-// ------------------------------------------------------------------------------------------------
-// ExhModel for SNPs with effect types (src/model.hpp:585-844 in full): an AH SNP moves as a pair of adjacent columns, so
-// walking a SNP one place to the left is one, two or four adjacent Givens swaps depending on the two SNPs' types.
-// Used by the delayed-rejection enumeration of runs with several effect types; the type-A ExhModel above is the same
-// walk with every SNP one column wide.
-// ------------------------------------------------------------------------------------------------
-struct TypedExhModel {
-  const Prior* prior = nullptr;
-  int m_e = 0;
-  UpperMat l;
-  std::vector<double> xy, v, inv_tau2_alpha2;
-  std::vector<uint8_t> type;       // effect type per SNP (0..4), in model order
-  std::vector<int> x_ind1, x_ind2; // columns per SNP
-  int Ns[5] = {0, 0, 0, 0, 0};
-  double syx_plus_vs2 = 0, log_det_invQ = 0, log_det_invQ_plus_xx = 0, log_likelihood = 0, log_model_prior = 0;
-  int model_size = 0, v_size = 0;
-
-  double log_prob() const { return log_likelihood + log_model_prior; }
-  void refresh() { log_likelihood = log_det_invQ - log_det_invQ_plus_xx + prior->residual_term(syx_plus_vs2); }
-  void take(int col) { syx_plus_vs2 -= v[col] * v[col]; }
-
-  double update_to_model(const Model& src, const TypedTerms& terms, int const_loci)  // model.hpp:602-671
-  {
-    prior = src.prior;
-    m_e = src.m_e;
-    l.copy_upper_from(src.l);
-    xy = src.xy;
-    v = src.v;
-    inv_tau2_alpha2 = src.inv_tau2_alpha2;
-    type = terms.type;
-    x_ind1 = terms.col1;
-    x_ind2 = terms.col2;
-    model_size = const_loci;
-    if (model_size > 0) v_size = (type[model_size - 1] == 4 ? x_ind2[model_size - 1] : x_ind1[model_size - 1]) + 1;
-    else v_size = m_e;
-    double vv = 0.0;
-    for (int i = 0; i < v_size; ++i) vv += v[i] * v[i];
-    syx_plus_vs2 = prior->nus2_plus_yy - vv;
-    log_det_invQ_plus_xx = 0.0;
-    for (int i = 0; i < v_size; ++i) log_det_invQ_plus_xx += std::log(l(i, i));
-    log_det_invQ = prior->log_det_invQ_e();
-    for (int i = m_e; i < v_size; ++i) log_det_invQ += std::log(inv_tau2_alpha2[i]);
-    log_det_invQ *= 0.5;
-    refresh();
-    log_model_prior = 0.0;
-    for (int t = 0; t < 5; ++t) Ns[t] = 0;
-    for (int i = 0; i < model_size; ++i) ++Ns[type[i]];
-    return log_prob();
-  }
-  double update_on_add()  // model.hpp:673-704
-  {
-    const int ty = type[model_size];
-    for (int c = 0; c < (ty == 4 ? 2 : 1); ++c) {
-      syx_plus_vs2 -= v[v_size] * v[v_size];
-      log_det_invQ += 0.5 * std::log(inv_tau2_alpha2[v_size]);
-      log_det_invQ_plus_xx += std::log(l(v_size, v_size));
-      ++v_size;
-    }
-    refresh();
-    log_model_prior += prior->log_change_on_add(Ns, model_size, ty);
-    ++Ns[ty];
-    ++model_size;
-    return log_prob();
-  }
-  double update_on_moveleft()  // model.hpp:706-829
-  {
-    --model_size;
-    const int ind_keep = model_size, ind_rem = model_size - 1;
-    const int type_keep = type[ind_keep], type_rem = type[ind_rem];
-    for (int c = 0; c < (type_keep == 4 ? 2 : 1); ++c) {   // the kept SNP leaves its old place
-      --v_size;
-      syx_plus_vs2 += v[v_size] * v[v_size];
-      log_det_invQ_plus_xx -= std::log(l(v_size, v_size));
-    }
-    for (int c = 0; c < (type_rem == 4 ? 2 : 1); ++c) {    // the removed SNP leaves the model
-      --v_size;
-      syx_plus_vs2 += v[v_size] * v[v_size];
-      log_det_invQ -= 0.5 * std::log(inv_tau2_alpha2[v_size]);
-      log_det_invQ_plus_xx -= std::log(l(v_size, v_size));
-    }
-    std::swap(type[ind_keep], type[ind_rem]);
-    auto sw = [&](int a, int b) { std::swap(xy[a], xy[b]); std::swap(inv_tau2_alpha2[a], inv_tau2_alpha2[b]); };
-    if (type_rem == 4) {
-      if (type_keep == 4) {          // two pairs change places: four adjacent swaps
-        int s = x_ind2[ind_rem];
-        l.swap_adjacent(s, v.data());
-        ++s; l.swap_adjacent(s, v.data());
-        s -= 2; l.swap_adjacent(s, v.data());
-        ++s; l.swap_adjacent(s, v.data());
-        sw(x_ind1[ind_keep], x_ind2[ind_rem]);
-        sw(x_ind1[ind_keep], x_ind2[ind_keep]);
-        sw(x_ind1[ind_rem], x_ind2[ind_rem]);
-        sw(x_ind1[ind_keep], x_ind2[ind_rem]);
-      } else {                       // a single column moves left past a pair
-        int s = x_ind2[ind_rem];
-        l.swap_adjacent(s, v.data());
-        --s; l.swap_adjacent(s, v.data());
-        sw(x_ind2[ind_rem], x_ind1[ind_keep]);
-        sw(x_ind1[ind_rem], x_ind2[ind_rem]);
-        x_ind2[ind_keep] = x_ind1[ind_keep];
-        --x_ind1[ind_keep];
-      }
-    } else {
-      if (type_keep == 4) {          // a pair moves left past a single column
-        int s = x_ind1[ind_rem];
-        l.swap_adjacent(s, v.data());
-        ++s; l.swap_adjacent(s, v.data());
-        sw(x_ind1[ind_rem], x_ind1[ind_keep]);
-        sw(x_ind1[ind_keep], x_ind2[ind_keep]);
-        x_ind2[ind_rem] = x_ind1[ind_keep];
-        x_ind1[ind_keep] = x_ind2[ind_keep];
-      } else {
-        l.swap_adjacent(x_ind1[ind_rem], v.data());
-        sw(x_ind1[ind_keep], x_ind1[ind_rem]);
-      }
-    }
-    for (int c = 0; c < (type_keep == 4 ? 2 : 1); ++c) {   // the kept SNP at its new place
-      syx_plus_vs2 -= v[v_size] * v[v_size];
-      log_det_invQ_plus_xx += std::log(l(v_size, v_size));
-      ++v_size;
-    }
-    refresh();
-    log_model_prior += prior->log_change_on_rem(Ns, model_size + 1, type_rem);
-    --Ns[type_rem];
-    return log_prob();
-  }
-  double update_on_twonewswap()
-  {
-    update_on_add();
-    update_on_add();
-    return update_on_moveleft();
-  }
-};
+// The delayed-rejection enumeration of sub-models lives in exhaustive.hpp (SubmodelEnumerator).
 
 // ------------------------------------------------------------------------------------------------
 // Proposal weights with in-order CDF semantics (src/discrete_distribution.hpp:64-330)

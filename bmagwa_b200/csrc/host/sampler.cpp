@@ -128,7 +128,8 @@ Sampler::Sampler(const Options& opts, int chain_index, Store* store, const std::
   pip_burnin_ = (int64_t)opts.pip_burnin;
 
   chain_ = chain_create(store_);
-  if (comm != nullptr) chain_set_sharded(chain_, comm->world, comm->rank, comm->stride, comm->allgather, comm->ctx);
+  if (comm != nullptr && comm->group != nullptr) chain_set_group(chain_, comm->group);
+  else if (comm != nullptr) chain_set_sharded(chain_, comm->world, comm->rank, comm->stride, comm->allgather, comm->ctx);
   dd_add_.init(&chain_->inorder_host(), (int)chain_->cdf_block);
   dd_rem_.init(&chain_->inorder_host(), (int)chain_->cdf_block);
   h_w_.alloc(m_g_);
@@ -966,10 +967,9 @@ unsigned char Sampler::delayed_rejection_move0(unsigned char ms_rem, double, dou
     dr_q_add_[i] = q_add(ind);
     dr_q_rem_[i] = q_rem(ind);
   }
-  exh_.update_to_model(proposal_, (int)const_loci);
   double max_log_model;
   double* P = dr_model_probabilities_.data();
-  compute_exhaustive_modelset(ms, &exh_, P, max_log_model);
+  exh_.run(proposal_, (int)const_loci, (int)ms, P, max_log_model);
   compute_proposal_probs_for_exh_modelset(ms, dr_bit_to_normalized_order_.data(), dr_q_add_.data(), dr_q_rem_.data(), z_add, z_rem,
                                           const_loci, m_g_, P);
   const unsigned long nmodels = 1ul << ms, mask = nmodels - 1;
@@ -1165,10 +1165,9 @@ unsigned char Sampler::do_statechange_of_nearby_snps()
   size_t const_loci = current_.size() - ms_rem;
   const unsigned long newmodel_binary = (1ul << ms_add) - 1;
   for (unsigned char i = 0; i < ms_rem; ++i) readd_to_proposal((uint32_t)move_inds_rem_[i]);
-  exh_.update_to_model(proposal_, (int)const_loci);
   double max_log_model;
   double* P = dr_model_probabilities_.data();
-  compute_exhaustive_modelset(ms, &exh_, P, max_log_model);
+  exh_.run(proposal_, (int)const_loci, (int)ms, P, max_log_model);
   const unsigned long nmodels = 1ul << ms, mask = nmodels - 1;
   for (unsigned long i = 0; i < nmodels; ++i) P[i] -= std::log((double)(const_loci + (size_t)__builtin_popcountl(i)));
   double sum = 0.0;

@@ -32,7 +32,8 @@ class Sampler {
  public:
   // Takes ownership of nothing: store and dataset summaries must outlive the sampler.
   // SNP-sharded chain: `store` holds rank's SNP block (peers attached), the same sampler runs in lockstep on every rank
-  struct ShardComm { int world = 1, rank = 0; int64_t stride = 0; AllGatherFn allgather = nullptr; void* ctx = nullptr; };
+  // group != nullptr: one of several chains over the sharded store (group.cu) -- this chain lives on this rank only
+  struct ShardComm { int world = 1, rank = 0; int64_t stride = 0; AllGatherFn allgather = nullptr; void* ctx = nullptr; Group* group = nullptr; };
   Sampler(const Options& opts, int chain_index, Store* store, const std::vector<double>& y, const std::vector<double>& e,
           double var_y, double yy, double var_x, double mean_x, const ShardComm* comm = nullptr);
   ~Sampler();
@@ -66,7 +67,7 @@ class Sampler {
   ChainRng rng_;
   std::unique_ptr<Prior> prior_;
   Model current_, proposal_;   // the reference's current_model / new_model
-  ExhModel exh_;
+  SubmodelEnumerator exh_;   // delayed rejection: all sub-models of a rejected move's SNPs (exhaustive.hpp)
   std::vector<int32_t> pos_in_proposal_;   // model_inds of the proposal model: SNP -> term index or -1
   std::vector<int32_t> pos_in_current_;
   std::vector<double> p_rao_;              // fetched at the end only

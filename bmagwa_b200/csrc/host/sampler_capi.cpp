@@ -8,6 +8,7 @@
 #include <memory>
 #include "../common.cuh"
 #include "../store.cuh"
+#include "../group.cuh"
 #include "../../../include/bmagwa_b200.h"
 #include "dataset.hpp"
 #include "options.hpp"
@@ -18,6 +19,15 @@ using namespace bmg;
 #define BMG_API extern "C" __attribute__((visibility("default")))
 
 namespace {
+// a shard group with the data-set summaries every chain of it needs (computed collectively at creation, because ranks
+// without a chain never construct a sampler)
+struct GroupHandle {
+  Group* g = nullptr;
+  double summaries[6] = {0, 0, 0, 0, 0, 0};
+  int64_t missing_cells = 0;
+  ~GroupHandle() { group_destroy(g); }
+};
+
 struct SamplerHandle {
   std::unique_ptr<Options> opt;
   std::unique_ptr<Dataset> data;
@@ -82,7 +92,8 @@ static int64_t global_summaries(Store* st, const Sampler::ShardComm& cm, double*
   return missing;   // over all shards: the same number on every rank
 }
 
-SamplerHandle* make(const char* ini, int chain_index, int device, Store* existing, const Sampler::ShardComm* comm = nullptr)
+SamplerHandle* make(const char* ini, int chain_index, int device, Store* existing, const Sampler::ShardComm* comm = nullptr,
+                    const GroupHandle* group = nullptr)
 {
   BMG_REQUIRE(ini != nullptr, "bmg_sampler_create: null ini path");
   const bool timing = getenv("BMG_TIMING") != nullptr;
@@ -111,7 +122,13 @@ SamplerHandle* make(const char* ini, int chain_index, int device, Store* existin
   if (comm != nullptr) {
     BMG_REQUIRE(existing != nullptr, "bmg_sampler_create_sharded: a shard store is required");
     BMG_REQUIRE(existing->m_e >= 1, "bmg_sampler_create_sharded: call bmg_store_set_phenotype on the shard first");
-    const int64_t missing_cells = global_summaries(h->store, *comm, sm);
+    int64_t missing_cells;
+    if (group != nullptr) {
+      for (int i = 0; i < 4; ++i) sm[i] = group->summaries[i];
+      missing_cells = group->missing_cells;
+    } else {
+      missing_cells = global_summaries(h->store, *comm, sm);
+    }
     // every rank sees the same total, so every rank refuses together (no rank is left waiting in a collective)
     BMG_REQUIRE(missing_cells == 0, "bmg_sampler_create_sharded: genotype data contains missing calls; the SNP-sharded chain keeps the "
                                     "imputed values of a shard on its owner only (use a single-GPU chain for such data)");
@@ -152,11 +169,75 @@ BMG_API int bmg_sampler_create_sharded(const char* ini_path, int chain_index, bm
 {
   BMG_TRY
   BMG_REQUIRE(out != nullptr && shard != nullptr && comm != nullptr, "bmg_sampler_create_sharded: null argument");
-  BMG_REQUIRE(comm->allgather != nullptr && comm->world >= 1 && comm->rank >= 0 && comm->rank < comm->world && comm->snp_stride > 0,
+  BMG_REQUIRE(comm->world >= 1 && comm->rank >= 0 && comm->rank < comm->world && comm->snp_stride > 0,
               "bmg_sampler_create_sharded: invalid communicator");
+  BMG_REQUIRE(comm->allgather != nullptr || comm->ctx != nullptr, "bmg_sampler_create_sharded: an all-gather callback or a shard group is required");
   Sampler::ShardComm cm;
   cm.world = comm->world; cm.rank = comm->rank; cm.stride = comm->snp_stride; cm.allgather = comm->allgather; cm.ctx = comm->ctx;
-  *out = reinterpret_cast<bmg_sampler*>(make(ini_path, chain_index, -1, reinterpret_cast<Store*>(shard), &cm));
+  const GroupHandle* gh = nullptr;
+  if (comm->allgather == nullptr) {   // the lockstep chain over the group's native all-gather (peer memory, no host callback)
+    gh = reinterpret_cast<const GroupHandle*>(comm->ctx);
+    BMG_REQUIRE(group_world(gh->g) == comm->world && group_rank(gh->g) == comm->rank && group_stride(gh->g) == comm->snp_stride,
+                "bmg_sampler_create_sharded: communicator and shard group disagree");
+    cm.allgather = group_allgather;
+    cm.ctx = gh->g;
+  }
+  *out = reinterpret_cast<bmg_sampler*>(make(ini_path, chain_index, -1, reinterpret_cast<Store*>(shard), &cm, gh));
+  BMG_CATCH
+}
+BMG_API int bmg_group_create(bmg_store* shard, int world, int rank, int n_chains, int64_t snp_stride, const char* shm_name, bmg_group** out)
+{
+  BMG_TRY
+  BMG_REQUIRE(out != nullptr && shard != nullptr, "bmg_group_create: null argument");
+  Store* st = reinterpret_cast<Store*>(shard);
+  std::unique_ptr<GroupHandle> gh(new GroupHandle());
+  gh->g = group_create(st, world, rank, n_chains, snp_stride, shm_name);
+  for (int i = 0; i < 6; ++i) gh->summaries[i] = st->summaries[i];
+  if (world > 1) {
+    Sampler::ShardComm cm;
+    cm.world = world; cm.rank = rank; cm.stride = snp_stride; cm.allgather = group_allgather; cm.ctx = gh->g;
+    gh->missing_cells = global_summaries(st, cm, gh->summaries);
+  } else {
+    gh->missing_cells = st->n_missing;
+  }
+  *out = reinterpret_cast<bmg_group*>(gh.release());
+  BMG_CATCH
+}
+BMG_API int bmg_sampler_create_grouped(const char* ini_path, int chain_index, bmg_store* shard, bmg_group* g, bmg_sampler** out)
+{
+  BMG_TRY
+  BMG_REQUIRE(out != nullptr && shard != nullptr && g != nullptr, "bmg_sampler_create_grouped: null argument");
+  const GroupHandle* gh = reinterpret_cast<const GroupHandle*>(g);
+  BMG_REQUIRE(chain_index == group_rank(gh->g) && chain_index < group_chains(gh->g),
+              "bmg_sampler_create_grouped: chain c of a shard group lives on rank c (chain_index == rank < n_chains)");
+  Sampler::ShardComm cm;
+  cm.world = group_world(gh->g); cm.rank = group_rank(gh->g); cm.stride = group_stride(gh->g);
+  cm.allgather = group_allgather; cm.ctx = gh->g; cm.group = gh->g;
+  *out = reinterpret_cast<bmg_sampler*>(make(ini_path, chain_index, -1, reinterpret_cast<Store*>(shard), &cm, gh));
+  BMG_CATCH
+}
+BMG_API int bmg_group_serve(bmg_group* g, int64_t n_rounds)
+{
+  BMG_TRY
+  BMG_REQUIRE(g != nullptr && n_rounds >= 0, "bmg_group_serve: invalid argument");
+  group_serve(reinterpret_cast<GroupHandle*>(g)->g, n_rounds);
+  BMG_CATCH
+}
+BMG_API bmg_chain* bmg_group_scan_chain(bmg_group* g)
+{
+  return g ? reinterpret_cast<bmg_chain*>(group_scan_chain(reinterpret_cast<GroupHandle*>(g)->g)) : nullptr;
+}
+BMG_API int bmg_group_stats(bmg_group* g, double* out4)
+{
+  BMG_TRY
+  BMG_REQUIRE(g != nullptr && out4 != nullptr, "bmg_group_stats: null argument");
+  group_stats(reinterpret_cast<GroupHandle*>(g)->g, out4);
+  BMG_CATCH
+}
+BMG_API int bmg_group_destroy(bmg_group* g)
+{
+  BMG_TRY
+  delete reinterpret_cast<GroupHandle*>(g);
   BMG_CATCH
 }
 BMG_API int bmg_sampler_create_on_store(const char* ini_path, int chain_index, bmg_store* s, bmg_sampler** out)

@@ -23,6 +23,7 @@
 #include <algorithm>
 #include "common.cuh"
 #include "store.cuh"
+#include "group.cuh"
 #include "philox.cuh"
 
 namespace bmg {
@@ -575,6 +576,23 @@ void chain_set_sharded(Chain* c, int world, int rank, int64_t stride, AllGatherF
   BMG_CUDA(cudaDeviceSynchronize());
 }
 
+// One of several chains over a SNP-sharded store (group.cu): the chain's per-SNP arrays cover all m_g SNPs with the
+// GLOBAL in-order permutation, as for chain_set_sharded, but nothing is replicated -- the chain exists on this rank only.
+void chain_set_group(Chain* c, Group* g)
+{
+  Store* s = c->store;
+  BMG_REQUIRE(g != nullptr && c->group == nullptr && c->world == 1, "shard group: chain already attached");
+  BMG_CUDA(cudaSetDevice(s->device));
+  c->group = g;
+  c->mw = s->m_g; c->w_off = s->lo; c->mw_alloc = (int64_t)group_world(g) * group_stride(g);
+  alloc_weight_arrays(c);
+  c->dot.alloc(c->mw_alloc);
+  build_inorder_permutation(c->mw, c->h_inorder_own);
+  c->inorder_own.alloc(c->mw);
+  bmg::copy_h2d_sync(c->inorder_own.p, c->h_inorder_own.data(), c->mw * sizeof(int32_t));
+  BMG_CUDA(cudaDeviceSynchronize());
+}
+
 // every rank contributes elems [rank stride, (rank+1) stride) of dev_buffer (world x stride elements) in place
 void chain_allgather(Chain* c, void* dev_buffer, int elem_bytes)
 {
@@ -847,6 +865,34 @@ void chain_residual(Chain* c, const int64_t* loci, const double* beta_e, const d
   if (stats9) for (int q = 0; q < kRed; ++q) stats9[q] = c->h_red.p[q];
 }
 
+// optional CUDA-event pair around the scan's reduction kernel (bmg_chain_scan_kernel_time; bench.py roofline)
+void scan_timer_begin(Chain* c, cudaStream_t st)
+{
+  if (!c->time_scan) return;
+  if (c->scan_ev_used >= 4096) {   // fold finished pairs into the running total
+    BMG_CUDA(cudaStreamSynchronize(st));
+    for (size_t i = 0; i < c->scan_ev_used; ++i) {
+      float ms = 0.f;
+      BMG_CUDA(cudaEventElapsedTime(&ms, c->scan_ev[2 * i], c->scan_ev[2 * i + 1]));
+      c->scan_ms_done += ms;
+    }
+    c->scan_launches_done += (int64_t)c->scan_ev_used;
+    c->scan_ev_used = 0;
+  }
+  while (c->scan_ev.size() < 2 * (c->scan_ev_used + 1)) {
+    cudaEvent_t e;
+    BMG_CUDA(cudaEventCreate(&e));
+    c->scan_ev.push_back(e);
+  }
+  BMG_CUDA(cudaEventRecord(c->scan_ev[2 * c->scan_ev_used], st));
+}
+void scan_timer_end(Chain* c, cudaStream_t st)
+{
+  if (!c->time_scan) return;
+  BMG_CUDA(cudaEventRecord(c->scan_ev[2 * c->scan_ev_used + 1], st));
+  ++c->scan_ev_used;
+}
+
 void chain_scan_dots(Chain* c)
 {
   Store* s = c->store;
@@ -858,27 +904,7 @@ void chain_scan_dots(Chain* c)
   a.tiles = (s->m + kTileSnps - 1) / kTileSnps; a.slices = c->scan_ctas_per_chunk; a.out = c->dot_partial.p;
   const unsigned grid = (unsigned)(c->scan_chunks * c->scan_ctas_per_chunk);
   if (c->scan_variant == 2) imma_quantize(c);   // residual -> fixed-point limbs, outside the timed pair
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  if (c->time_scan) {
-    if (c->scan_ev_used >= 4096) {   // fold finished pairs into the running total
-      BMG_CUDA(cudaStreamSynchronize(c->stream));
-      for (size_t i = 0; i < c->scan_ev_used; ++i) {
-        float ms = 0.f;
-        BMG_CUDA(cudaEventElapsedTime(&ms, c->scan_ev[2 * i], c->scan_ev[2 * i + 1]));
-        c->scan_ms_done += ms;
-      }
-      c->scan_launches_done += (int64_t)c->scan_ev_used;
-      c->scan_ev_used = 0;
-    }
-    while (c->scan_ev.size() < 2 * (c->scan_ev_used + 1)) {
-      cudaEvent_t e;
-      BMG_CUDA(cudaEventCreate(&e));
-      c->scan_ev.push_back(e);
-    }
-    ev0 = c->scan_ev[2 * c->scan_ev_used];
-    ev1 = c->scan_ev[2 * c->scan_ev_used + 1];
-    BMG_CUDA(cudaEventRecord(ev0, c->stream));
-  }
+  scan_timer_begin(c, c->stream);
   if (c->scan_variant == 2) {
     imma_launch(c);
   } else {
@@ -890,10 +916,7 @@ void chain_scan_dots(Chain* c)
     c->last_partial = c->dot_partial.p;
     c->last_chunks = c->scan_chunks;
   }
-  if (ev1) {
-    BMG_CUDA(cudaEventRecord(ev1, c->stream));
-    ++c->scan_ev_used;
-  }
+  scan_timer_end(c, c->stream);
   BMG_CUDA(cudaGetLastError());
 }
 
@@ -910,8 +933,32 @@ void chain_scan(Chain* c, const int64_t* loci, const double* beta_g, const doubl
   upload_model(c, loci, beta_g, tau_g, k);
   if (prm->tau_mode == 1) {
     BMG_REQUIRE(prm->tau_host != nullptr, "bmg_chain_scan: tau_host required for tau_mode 1");
-    if (c->tau_dev.n < (size_t)s->m) c->tau_dev.alloc(s->m);
-    bmg::copy_h2d(c->tau_dev.p, prm->tau_host + c->w_off, s->m * sizeof(double), st);   // tau_host covers [0, mw)
+    const size_t need = c->group ? (size_t)c->mw : (size_t)s->m;
+    if (c->tau_dev.n < need) { BMG_CUDA(cudaStreamSynchronize(st)); c->tau_dev.alloc(need); }
+    if (!c->group) bmg::copy_h2d(c->tau_dev.p, prm->tau_host + c->w_off, s->m * sizeof(double), st);   // tau_host covers [0, mw)
+  }
+  if (c->group) {
+    // several chains over the sharded store: every rank of the group scans its shard for this chain's residual and stores
+    // the dot products into this GPU's memory (group.cu); the per-SNP algebra then runs here over all m_g SNPs
+    BMG_REQUIRE(c->scan_variant == 2 && s->n_missing == 0, "shard group: tensor-core scan on data without missing calls only");
+    if (prm->tau_mode == 1) bmg::copy_h2d(c->tau_dev.p, prm->tau_host, c->mw * sizeof(double), st);
+    const double* dots = group_scan_round(c->group, c);
+    FinalizeArgs f;
+    f.dot_partial = dots; f.n_chunks = 1; f.m = c->mw; f.lo = 0; f.n = s->n;
+    f.n1 = group_n1(c->group); f.n2 = group_n2(c->group); f.miss_corr = nullptr;
+    f.loci = c->loci_dev.p; f.beta_g = c->beta_dev.p; f.tau_g = c->taug_dev.p; f.k = k;
+    f.sum_r = c->sum_r; f.sigma2 = prm->sigma2; f.lmp_add = prm->lmp_add; f.lmp_rem = prm->lmp_rem;
+    f.tau_mode = prm->tau_mode; f.tau_shared = prm->tau_shared; f.tau_snp = c->tau_dev.p;
+    f.seed = prm->tau_seed; f.counter = prm->tau_counter; f.nu_tau2 = prm->nu_tau2; f.s2_tau2 = prm->s2_tau2; f.alpha2 = prm->alpha2;
+    f.dot = c->dot.p; f.p_r = c->p_r.p;
+    k_scan_finalize<<<(unsigned)((c->mw + 255) / 256), 256, 0, st>>>(f);
+    count_launch();
+    BMG_CUDA(cudaGetLastError());
+    if (p_r_host) {
+      bmg::copy_d2h(p_r_host, c->p_r.p, c->mw * sizeof(double), st);
+      BMG_CUDA(cudaStreamSynchronize(st));
+    }
+    return;
   }
   chain_scan_dots(c);
   if (s->n_missing > 0) {

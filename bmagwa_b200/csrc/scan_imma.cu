@@ -334,28 +334,38 @@ void imma_quantize(Chain* c)
   c->imma_q_valid = true;
 }
 
-// the tensor-core scan into imma_partial ([chunks][m] doubles); het: the heterozygote-indicator pass into imma_partial_h
+// the tensor-core scan of this store's SNPs against ONE quantised right-hand side (q, scale_exp: the layout k_quantize
+// writes; they may belong to another chain, group.cu) into out ([chunks][m] doubles), with the geometry of `geom`
+void imma_launch_on(Chain* geom, const uint4* q, const int* scale_exp, double* out, bool het, cudaStream_t st, Chain* timed)
+{
+  Store* s = geom->store;
+  if (!geom->imma_ready) imma_prepare(geom);
+  ImmaArgs a;
+  a.codes = s->codes.p; a.Wp = s->Wp; a.m = s->m; a.q = q; a.scale_exp = scale_exp;
+  a.chunk_words = (int)geom->imma_chunk_words; a.n_chunks = geom->imma_chunks; a.tiles = (s->m + kImmaTile - 1) / kImmaTile;
+  a.slices = geom->imma_slices; a.row_stride = (int)geom->imma_chunk_words + 16;
+  a.out = out;
+  const unsigned grid = (unsigned)(geom->imma_chunks * geom->imma_slices);
+  if (timed) scan_timer_begin(timed, st);
+  if (het) k_scan_dots_imma<true><<<grid, 32 * (geom->imma_warps + 1), imma_smem_bytes(geom), st>>>(a);
+  else k_scan_dots_imma<false><<<grid, 32 * (geom->imma_warps + 1), imma_smem_bytes(geom), st>>>(a);
+  if (timed) scan_timer_end(timed, st);
+  count_launch();
+}
+
+// the chain's own scan into imma_partial; het: the heterozygote-indicator pass into imma_partial_h
 void imma_launch(Chain* c, bool het)
 {
   Store* s = c->store;
-  ImmaArgs a;
-  a.codes = s->codes.p; a.Wp = s->Wp; a.m = s->m; a.q = reinterpret_cast<const uint4*>(c->imma_q.p); a.scale_exp = c->imma_exp.p;
-  a.chunk_words = (int)c->imma_chunk_words; a.n_chunks = c->imma_chunks; a.tiles = (s->m + kImmaTile - 1) / kImmaTile;
-  a.slices = c->imma_slices; a.row_stride = (int)c->imma_chunk_words + 16;
-  const unsigned grid = (unsigned)(c->imma_chunks * c->imma_slices);
   if (het) {
     if ((int64_t)c->imma_partial_h.n < (int64_t)c->imma_chunks * s->m) {
       BMG_CUDA(cudaStreamSynchronize(c->stream));
       c->imma_partial_h.alloc((size_t)c->imma_chunks * s->m);
     }
-    a.out = c->imma_partial_h.p;
-    k_scan_dots_imma<true><<<grid, 32 * (c->imma_warps + 1), imma_smem_bytes(c), c->stream>>>(a);
-    count_launch();
+    imma_launch_on(c, reinterpret_cast<const uint4*>(c->imma_q.p), c->imma_exp.p, c->imma_partial_h.p, true, c->stream, nullptr);
     return;
   }
-  a.out = c->imma_partial.p;
-  k_scan_dots_imma<false><<<grid, 32 * (c->imma_warps + 1), imma_smem_bytes(c), c->stream>>>(a);
-  count_launch();
+  imma_launch_on(c, reinterpret_cast<const uint4*>(c->imma_q.p), c->imma_exp.p, c->imma_partial.p, false, c->stream, nullptr);
   c->last_partial = c->imma_partial.p;
   c->last_chunks = c->imma_chunks;
 }

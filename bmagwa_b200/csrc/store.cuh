@@ -31,8 +31,13 @@ struct PatchDesc {
   int type;              // 0 additive values; 1 H [x == 1], 2 D [x > 0], 3 R [x == 2] written as 0/1 fields
 };
 
+struct Group;   // group.cuh
+
 struct Chain {
   Store* store = nullptr;
+  // several chains over one SNP-sharded store (group.cu): this chain lives on its rank only, its weight arrays cover all
+  // m_g SNPs, and its scan is served by every rank of the group
+  Group* group = nullptr;
   cudaStream_t stream = nullptr;
   // Range of the per-SNP proposal / Rao-Blackwell arrays (p_r, p_rao, p_proposal, q_add, q_rem, zero flags, CDF
   // blocks).  Unsharded: mw = store->m, w_off = 0.  SNP-sharded chain: every rank keeps them for ALL m_g SNPs
@@ -167,6 +172,10 @@ void chain_scan_types(Chain* c, const int64_t* loci, const int32_t* loci_type, c
                       const bmg_scan_types_params* prm, double* p_r_host, double* p_r_types_host);
 void chain_scan_dots(Chain* c);
 void chain_set_sharded(Chain* c, int world, int rank, int64_t stride, AllGatherFn fn, void* ctx);
+void chain_set_group(Chain* c, Group* g);
+void scan_timer_begin(Chain* c, cudaStream_t st);
+void scan_timer_end(Chain* c, cudaStream_t st);
+void imma_launch_on(Chain* geom, const uint4* q, const int* scale_exp, double* out, bool het, cudaStream_t st, Chain* timed);
 void chain_allgather(Chain* c, void* dev_buffer, int elem_bytes);
 void imma_prepare(Chain* c);
 void imma_quantize(Chain* c);

@@ -1,4 +1,5 @@
-"""One chain over a SNP-sharded store: host-side plumbing for bmg_sampler_create_sharded.
+"""Chains over a SNP-sharded store: host-side plumbing for bmg_sampler_create_sharded (one lockstep chain) and
+bmg_group_create / bmg_sampler_create_grouped (several chains, one per rank; SURVEY.md 8e, BASELINE configs[4]).
 
 One process per GPU (torchrun).  Rank r builds the store of SNPs [r*stride, (r+1)*stride), exports its packed shard
 over CUDA IPC, attaches every peer's shard (column statistics read remote columns over NVLink), and runs the same
@@ -98,3 +99,66 @@ def create_sharded_sampler(dist, ini_path, n, m_g, bed_path, device, y, covariat
                                                recode_to_minor=recode_to_minor)
     sampler, comm = finish_sharded_sampler(dist, ini_path, store, stride, lo, hi, device, y, covariates, **options)
     return sampler, store, comm
+
+
+class ShardGroup:
+    """bmg_group of this rank: several chains over one SNP-sharded store, chain c on rank c.  Collective constructor.
+    torch.distributed only carries the name of the POSIX shared-memory segment the ranks synchronise through; scans
+    exchange their data through CUDA-IPC peer memory inside the library."""
+
+    def __init__(self, dist, store, stride, n_chains):
+        self.L = _lib.lib()
+        self.world, self.rank, self.n_chains, self.stride = dist.get_world_size(), dist.get_rank(), n_chains, stride
+        name = [None]
+        if self.rank == 0:
+            import os
+            import uuid
+            name[0] = "/bmg_%d_%s" % (os.getpid(), uuid.uuid4().hex[:12])
+        if self.world > 1:
+            dist.broadcast_object_list(name, src=0)
+        self.name = name[0]
+        h = api.vp()
+        api.check(self.L.bmg_group_create(store.h, self.world, self.rank, n_chains, stride, self.name.encode(), C.byref(h)))
+        self.h = h
+        self._store = store
+
+    @property
+    def has_chain(self):
+        return self.rank < self.n_chains
+
+    def serve(self, n_rounds):
+        api.check(self.L.bmg_group_serve(self.h, n_rounds))
+
+    def scan_chain(self):
+        return self.L.bmg_group_scan_chain(self.h)
+
+    def stats(self):
+        out = np.zeros(4)
+        api.check(self.L.bmg_group_stats(self.h, out.ctypes.data_as(api.f64p)))
+        return {"rounds": int(out[0]), "barrier_seconds": float(out[1])}
+
+    def native_comm(self):
+        """bmg_shard_comm for the lockstep single chain over this group's all-gather (no host callback)."""
+        class _Native:
+            pass
+        nc = _Native()
+        nc.struct = _lib.ShardCommStruct(self.world, self.rank, self.stride, _lib.ALLGATHER_FN(), C.cast(self.h, C.c_void_p))
+        nc.calls = nc.bytes = 0
+        return nc
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.bmg_group_destroy(self.h)
+            self.h = None
+
+
+def create_group(dist, n, m_g, device, y, covariates=None, n_chains=None, bed_path=None, payload_device_ptr=None,
+                 recode_to_minor=True):
+    """Shard store of this rank (phenotype set, peers attached) and the shard group.  Returns (store, group)."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    store, stride, lo, hi = create_shard_store(dist, n, m_g, device, bed_path=bed_path, payload_device_ptr=payload_device_ptr,
+                                               recode_to_minor=recode_to_minor)
+    store.set_phenotype(y, covariates)
+    attach_all_peers(dist, store, world, rank, lo, hi)
+    group = ShardGroup(dist, store, stride, world if n_chains is None else n_chains)
+    return store, group

@@ -270,6 +270,27 @@ struct bmg_shard_comm {
 };
 int bmg_sampler_create_sharded(const char* ini_path, int chain_index, bmg_store* shard, const struct bmg_shard_comm* comm,
                                bmg_sampler** out);
+/* SEVERAL chains over ONE SNP-sharded store (BASELINE configs[4]; the reference's chains are threads sharing one
+ * `const Data*`, main.cpp:54-85).  A shard group is one process per GPU of a box: rank r holds the shard of
+ * bmg_sampler_create_sharded (phenotype set, peers attached) and, for r < n_chains, the host sampler of chain r -- nothing
+ * of a chain is replicated.  Per iteration a chain only talks to its own GPU (remote columns over the peer mappings).
+ * At every scan all ranks meet: each scans its shard once per chain and stores the shard's dot products straight into the
+ * owning chain's GPU through CUDA-IPC peer memory; the ranks synchronise through a POSIX shared-memory segment `shm_name`
+ * ("/name", unique per job; created by rank 0 and unlinked as soon as every rank has mapped it).  No host callback and no
+ * NCCL on the data path.  Every chain writes the bytes of its single-GPU run.
+ * bmg_group_create is collective (every rank calls it); chain_index of bmg_sampler_create_grouped must equal the rank.
+ * Ranks without a chain (n_chains <= rank) call bmg_group_serve(g, n) to take part in the next n scans; all chains must
+ * run the same schedule (n_rao, iteration counts).  Passing comm->allgather == NULL and comm->ctx = a bmg_group* to
+ * bmg_sampler_create_sharded runs the lockstep single chain over the group's native all-gather instead of a host one. */
+typedef struct bmg_group bmg_group;
+int bmg_group_create(bmg_store* shard, int world, int rank, int n_chains, int64_t snp_stride, const char* shm_name, bmg_group** out);
+int bmg_sampler_create_grouped(const char* ini_path, int chain_index, bmg_store* shard, bmg_group* g, bmg_sampler** out);
+int bmg_group_serve(bmg_group* g, int64_t n_rounds);
+/* the chain-like handle this rank's share of the scans runs on (bmg_chain_scan_kernel_time, bmg_chain_stream) */
+bmg_chain* bmg_group_scan_chain(bmg_group* g);
+/* out[0..3] = {scan rounds served, seconds spent waiting in the group's barriers, 0, 0} */
+int bmg_group_stats(bmg_group* g, double* out4);
+int bmg_group_destroy(bmg_group* g);
 /* Overrides applied after the INI file, before bmg_sampler_begin.  Keys: "tau_rng" = host | device (per-SNP tau2 draws
  * of the scan from the chain's stream in reference order, or Philox on the device); "missing_rng" = host | device (the
  * re-imputation of missing calls before each scan likewise; defaults to tau_rng); "pip_burnin" = thinned samples to drop

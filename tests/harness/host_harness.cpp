@@ -231,7 +231,7 @@ void harness_proposal_cdf(long m, const int* order, const double* w, int block, 
 }  // extern "C"
 
 // Delayed rejection (sampler.cpp:882-980): log probabilities of all 2^ms sub-models of the last ms SNPs of a model, from
-// compute_exhaustive_modelset (adjacent Givens swaps, O(k) per sub-model) in P, and from a fresh Model per sub-model
+// SubmodelEnumerator (include / delete-first-column walk over the trailing block of the factor) in P, and from a fresh Model per sub-model
 // (full incremental build) + the model prior in B.  Both are relative to the sub-model without any of the ms SNPs.
 extern "C" void harness_exhaustive(long n, long m_g, int m_e, const double* G, const double* E, const double* y, double yy,
                                    double e_qg, double var_qg, double nu_sigma2, double s2_sigma2, double nu_tau2, double s2_tau2,
@@ -257,10 +257,9 @@ extern "C" void harness_exhaustive(long n, long m_g, int m_e, const double* G, c
   Model full;
   full.init(m_e, exx, exy, p);
   for (int i = 0; i < const_loci + ms; ++i) add(full, i);
-  ExhModel exh;
-  exh.update_to_model(full, const_loci);
+  SubmodelEnumerator exh;
   double mx;
-  compute_exhaustive_modelset((size_t)ms, &exh, P, mx);
+  exh.run(full, const_loci, ms, P, mx);
   for (unsigned long mask = 0; mask < (1ul << ms); ++mask) {
     Model m;
     m.init(m_e, exx, exy, p);
@@ -560,7 +559,7 @@ extern "C" int harness_typed_model_trace(long n, long m_g, int m_e, const double
   return cols;
 }
 
-// Delayed-rejection enumeration for SNPs with effect types: TypedExhModel + compute_exhaustive_modelset against a model built
+// Delayed-rejection enumeration for SNPs with effect types: SubmodelEnumerator::run_typed against a model built
 // from scratch per sub-model (as harness_exhaustive, with snp_type per SNP; AH = two columns).
 extern "C" void harness_exhaustive_typed(long n, long m_g, int m_e, const double* G, const double* E, const double* y, double yy,
                                          double s2_sigma2, int n_types, const int* types, int const_loci, int ms,
@@ -596,10 +595,9 @@ extern "C" void harness_exhaustive_typed(long n, long m_g, int m_e, const double
   Built full;
   full.m.init(m_e, exx, exy, p);
   for (int i = 0; i < const_loci + ms; ++i) add(full, i);
-  TypedExhModel exh;
-  exh.update_to_model(full.m, full.terms, const_loci);
+  SubmodelEnumerator exh;
   double mx;
-  compute_exhaustive_modelset((size_t)ms, &exh, P, mx);
+  exh.run_typed(full.m, full.terms, const_loci, ms, P, mx);
   for (unsigned long mask = 0; mask < (1ul << ms); ++mask) {
     Built b;
     b.m.init(m_e, exx, exy, p);

@@ -11,9 +11,12 @@ its epilogue (reference: Sampler::sample loop, src/sampler.cpp:626-834).  value 
 summed over the chains of the job.  Sampler/prior settings are those of the reference's bundled
 testdata/testdata.ini; data are seeded synthetic genotypes (bmagwa_b200/synth.py).
 
-Workload at N=1: BASELINE.json configs[1] ("C2": n=5,000 x p=100,000, linear, single chain).
-N>1: one chain per rank (the reference's own multi-core mode, thread.n_threads = N, src/main.cpp:70-95),
-every rank holding the whole C2 store; no data-path collective, scaling "weak".
+N = 1: BASELINE.json configs[1] ("C2": n=5,000 x p=100,000, linear, single chain) is the headline line; the
+       same JSON line carries sub-records for configs[2] (C3, probit) and configs[3] (C4, n=50,000 x p=1,000,000) on the
+       one GPU under "workloads" (value, roofline, clocks, e2e; C4 with a CPU baseline).
+N > 1: the split the north star names -- C4 SNP-SHARDED over the N GPUs, N chains over the one sharded store (chain c on
+       rank c; every scan served by all ranks through peer memory, bmagwa_b200/csrc/group.cu); scaling "weak" in chains.
+       The earlier chain-per-GPU figure on replicated C2 stores is carried as the extra key "replicas_c2".
 """
 import argparse
 import json
@@ -224,7 +227,7 @@ def scan_traffic(workload):
 # ------------------------------------------------------------------------------------------------
 # reference arm: the unmodified reference sampler on the host cores (oracle/_ref)
 # ------------------------------------------------------------------------------------------------
-def run_reference_chains(ini, n_chains, n_rao, warmup, steps):
+def run_reference_chains(ini, n_chains, n_rao, warmup, steps, scan_probe=None):
     """Returns (seconds of the K timed steps, per-chain wall times).  One host thread per chain over one shared
     Data, as main.cpp does.  The reference's Sampler::sample() cannot be re-entered on a non-empty model (it rebuilds
     its removal distribution as if the model were empty, sampler.cpp:599-606), so "W warm-up steps, then K timed"
@@ -264,6 +267,8 @@ def run_reference_chains(ini, n_chains, n_rao, warmup, steps):
     if warmup > 0:
         t_w, _ = phase(fresh_set(), warmup * n_rao)
     t_wk, per = phase(fresh_set(), (warmup + steps) * n_rao)
+    if scan_probe is not None:   # the all-SNP scan alone on one thread (p_raoblackwell, src/sampler.cpp:32-261), same Data
+        scan_probe.append(parent.scan_time(1))
     for c in reversed(opened):
         c.close()
     return t_wk - t_w, per
@@ -273,8 +278,22 @@ def reference_arm(args, rank, world):
     if rank != 0:
         return None
     from oracle import ref
-    spec = WORKLOADS[args.workload]
     n_chains = max(1, args.gpus)
+    if args.workload is None:
+        args.workload = "C2" if args.gpus <= 1 else "C4"
+    spec = WORKLOADS[args.workload]
+    if args.workload in ("C4", "C5", "C3") and ref.available():
+        # our arm's config at N > 1: n_chains chains on the big workload; the reference gets one host thread per chain
+        res = sliced_reference(args, args.workload, n_chains, min(args.warmup, 2), min(args.steps, 4))
+        return {"metric": "mcmc_iterations_per_sec", "unit": "iterations/s", "impl": "reference", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "value": res["value"], "ms_per_step": 1e3 * res["step_seconds_full"],
+                "config": {"workload": "%s: %s; %d chain(s), one host thread each (the reference's only parallelism, thread.n_threads)"
+                           % (args.workload, spec["desc"], n_chains), "n": spec["n"], "m_g": spec["m_g"], "n_rao": args.n_rao, "chains": n_chains,
+                           "step": "%d MCMC iterations per chain incl. one all-SNP scan per chain" % args.n_rao},
+                "cpu_baseline": {"value": res["value"], "unit": "iterations/s", "cores": n_chains, "kind": "reference", "sample": res["sample"]},
+                "e2e": {"value": res["value"], "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
     out = {"metric": "mcmc_iterations_per_sec", "unit": "iterations/s", "impl": "reference", "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic"}
@@ -296,7 +315,7 @@ def reference_arm(args, rank, world):
                    "step": "%d MCMC iterations incl. one all-SNP scan" % args.n_rao},
         "cpu_baseline": {"value": value, "unit": "iterations/s", "cores": n_chains, "kind": "reference",
                          "sample": "%d timed iterations per chain after %d warm-up (T(W+K) - T(W) of the same seeded chain), "
-                                   "unmodified reference sources built against oracle/shim (OpenBLAS 1 thread per chain), "
+                                   "unmodified reference sources built -O3 -march=x86-64-v3 -ffp-contract=off against oracle/shim (OpenBLAS 1 thread per chain), "
                                    "host has %s cores"
                                    % (args.steps * args.n_rao, args.warmup * args.n_rao, cores)},
         "e2e": {"value": value, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -308,33 +327,24 @@ def reference_arm(args, rank, world):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-def ours_arm(args, rank, local_rank, world):
+def ours_arm(args, rank, local_rank, world, dist=None, workload=None, with_cpu_baseline=True):
+    """One chain per rank, every rank holding the whole store (host files -> bmg_sampler_create)."""
     import torch
     from bmagwa_b200 import _lib, api
     import ctypes as C
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
-    dist = None
-    if world > 1:
-        import torch.distributed as dist_mod
-        dist = dist_mod
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    workload = workload or args.workload
     dev = local_rank
     torch.cuda.set_device(dev)
-    pinned = pin_rank_to_core(local_rank, world) if world > 1 else None
-    if pinned is not None:
-        log("[bench] rank %d pinned to CPUs %s" % (rank, pinned))
     L = _lib.lib()
-    spec = WORKLOADS[args.workload]
+    spec = WORKLOADS[workload]
     n, m = spec["n"], spec["m_g"]
     tmp = tempfile.mkdtemp(prefix="bmagwa_bench_r%d_" % rank)
     if rank == 0:
-        prepare_dataset(args.workload, args.n_rao, world, tmp, args.n_rao)
+        prepare_dataset(workload, args.n_rao, world, tmp, args.n_rao)
     if dist is not None:
         dist.barrier()
-    ini, _ = prepare_dataset(args.workload, args.n_rao, world, tmp, args.n_rao)
+    ini, _ = prepare_dataset(workload, args.n_rao, world, tmp, args.n_rao)
 
     def transfers():
         a, b = C.c_uint64(), C.c_uint64()
@@ -384,6 +394,7 @@ def ours_arm(args, rank, local_rank, world):
     ms_tot, n_l = C.c_double(), C.c_int64()
     L.bmg_chain_scan_kernel_time(chain, 1, C.byref(ms_tot), C.byref(n_l), 0)
     st = s.stats()
+    cnt = s.counters()
     s.end()
     s.close()
     elapsed_ms = max(ev_ms, 0.0)
@@ -419,8 +430,6 @@ def ours_arm(args, rank, local_rank, world):
         e2e_secs = float(t.item())
 
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
         return None
     iters = world * args.steps * args.n_rao
     value = iters / (elapsed_ms * 1e-3)
@@ -433,7 +442,7 @@ def ours_arm(args, rank, local_rank, world):
         "metric": "mcmc_iterations_per_sec", "value": value, "unit": "iterations/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "%s: %s%s" % (args.workload, spec["desc"], "" if world == 1 else "; %d independent chains, one per GPU" % world),
+        "config": {"workload": "%s: %s%s" % (workload, spec["desc"], "" if world == 1 else "; %d independent chains, one per GPU, every GPU holding the whole store" % world),
                    "n": n, "m_g": m, "n_rao": args.n_rao, "step": "%d MCMC iterations incl. one all-SNP scan" % args.n_rao,
                    "sampler": "testdata/testdata.ini settings (PMV, thin 10, DR 10, individual tau2)",
                    "tau_rng": args.tau_rng, "miss_rate": args.miss_rate,
@@ -448,16 +457,18 @@ def ours_arm(args, rank, local_rank, world):
                         % args.steps},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "k_scan_dots (genotype scan reduction, variant %s)" % os.environ.get("BMG_SCAN_VARIANT", "default"),
-                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": scan_traffic(args.workload),
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": scan_traffic(workload),
                      "bytes_per_launch": bytes_scan, "avg_launch_ms": scan_ms, "launches_timed": int(n_l.value), "peak_source": peak_src},
         "clocks": clk,
         "breakdown": {"move_seconds": st["move_seconds"], "scan_seconds": st["scan_seconds"], "scans": st["scans"], "column_stats_seconds": st["column_stats_seconds"],
+                      "delayed_rejection_seconds": cnt["delayed_rejection_seconds"], "delayed_rejection_events": cnt["delayed_rejection_events"],
+                      "moves_with_additions": cnt["moves_with_additions"], "served_from_memo": cnt["served_from_memo"],
+                      "device_requests": cnt["device_requests"], "server_fallbacks": cnt["server_fallbacks"],
+                      "note": "seconds are those of the whole resident chain (warm-up included), counts likewise",
                       "h2d_bytes_per_step_resident": (h2d1 - h2d0) / args.steps, "d2h_bytes_per_step_resident": (d2h1 - d2h0) / args.steps},
     }
-    if world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline(args, spec)
-    if dist is not None:
-        dist.destroy_process_group()
+    if world == 1 and with_cpu_baseline and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(args, spec, workload)
     return out
 
 
@@ -488,13 +499,12 @@ def device_payload(n, snp_lo, snp_hi, seed, device, block=2048):
 
 
 def sharded_arm(args, rank, local_rank, world):
+    """--lockstep: ONE chain replicated in lockstep over a SNP-sharded store (round 1's mode; strong scaling of the scan only)."""
     import torch
     import torch.distributed as dist
     from bmagwa_b200 import _lib, sharded, synth
     import ctypes as C
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = local_rank
     if not dist.is_initialized():
@@ -628,30 +638,359 @@ def sharded_arm(args, rank, local_rank, world):
             "breakdown": {"move_seconds": st1["move_seconds"] - st0["move_seconds"], "scan_seconds": st1["scan_seconds"] - st0["scan_seconds"],
                           "column_stats_seconds": st1["column_stats_seconds"] - st0["column_stats_seconds"],
                           "allgather_calls": comm.calls, "allgather_bytes_received": comm.bytes, "model_size": st1["model_size"], "model_size_trace": ms_trace},
-            "cpu_baseline": {"value": None, "unit": "iterations/s", "cores": 0, "kind": "reference",
-                             "sample": "not run: the reference needs n x m_g doubles (%.0f GB) in host memory for this workload"
-                                       % (8.0 * n * m / 1e9)},
         }
     dist.barrier()
-    dist.destroy_process_group()
     return out
 
 
-def cpu_baseline(args, spec):
+# ------------------------------------------------------------------------------------------------
+# chains over a SNP-sharded store (bmagwa_b200/csrc/group.cu): the north star's multi-GPU split
+# ------------------------------------------------------------------------------------------------
+class LocalDist:
+    """Stand-in for torch.distributed in a one-rank job (no process group needed)."""
+
+    def get_world_size(self):
+        return 1
+
+    def get_rank(self):
+        return 0
+
+    def get_backend(self):
+        return "local"
+
+    def barrier(self):
+        pass
+
+    def all_gather_object(self, out, obj):
+        out[0] = obj
+
+    def broadcast_object_list(self, objs, src=0):
+        pass
+
+
+def sharded_phenotype(store, lo, hi, n, m, m_e, dist, world, probit):
+    """20 causal SNPs spread over the genome, 0.14 s.d. each on the file's allele coding; each owner adds its columns."""
+    import torch
+    rs = np.random.default_rng(GEN_SEED)
+    causal = np.linspace(0, m - 1, 20).astype(np.int64)
+    contrib = np.zeros(n)
+    swapped = store.counts()[3]
+    for j in causal:
+        if lo <= j < hi:
+            x = store.get_column(int(j), 0)
+            if swapped[j - lo]:
+                x = 2.0 - x   # effects are positive on the file's allele coding, as in synth.make_phenotype (mixed signs on
+                              # the minor-allele coding; same-sign effects make the reference's model grow to > 100 SNPs)
+            contrib += 0.14 * (x - x.mean()) / max(x.std(), 1e-9)
+    if world > 1:
+        t = torch.from_numpy(contrib).cuda()
+        dist.all_reduce(t)
+        contrib = t.cpu().numpy()
+    y = contrib + rs.normal(size=n) * np.sqrt(0.6)
+    if probit:
+        y = (y > 0).astype(np.float64)   # case-control labels from the liability
+    E = rs.uniform(0.0, 1.0, size=(n, m_e))
+    return y, E
+
+
+def write_group_files(shared, n, m, m_e, y, E, n_rao, n_chains):
+    from bmagwa_b200 import synth
+    os.makedirs(shared, exist_ok=True)
+    base = os.path.join(shared, "syn")
+    ids = ["per%d per%d" % (i, i) for i in range(n)]
+    with open(base + ".fam", "w") as fh:
+        fh.write("".join("%s 0 0 1 %.10g\n" % (ident, v) for ident, v in zip(ids, y)))
+    with open(base + ".y", "w") as fh:
+        fh.write("".join("%s %.17g\n" % (ident, v) for ident, v in zip(ids, y)))
+    with open(base + ".e", "w") as fh:
+        fh.write("".join("%s %s\n" % (ident, " ".join("%.17g" % v for v in row)) for ident, row in zip(ids, E)))
+    open(base + ".bed", "wb").write(bytes([0x6C, 0x1B, 0x01]))   # never read: the shards come from memory
+    cfg = dict(base=base, recode=1, n=n, m_g=m, m_e=m_e, save_beta=0, types="A", do_n_iter=n_rao, n_rao=n_rao, n_rao_burnin=1000,
+               thin=10, n_sample_tau2_and_missing=10, delay_rejection=10, max_move_size=20, use_individual_tau2=1, e_qg=20,
+               var_qg=300, n_threads=n_chains, seeds=",".join(str(v) for v in CHAIN_SEEDS[:n_chains]),
+               outbase=os.path.join(shared, "chain"), verbosity=0)
+    with open(os.path.join(shared, "bench.ini"), "w") as fh:
+        fh.write(synth.INI_TEMPLATE.format(**cfg))
+    return os.path.join(shared, "bench.ini")
+
+
+def group_arm(args, workload, rank, local_rank, world, dist, n_chains, probit=False, with_e2e=True):
+    """n_chains chains over ONE store sharded by SNP over the `world` GPUs (chain c on rank c)."""
+    import torch
+    from bmagwa_b200 import _lib, api, sharded
+    import ctypes as C
+
+    dev = local_rank
+    torch.cuda.set_device(dev)
+    L = _lib.lib()
+    spec = WORKLOADS[workload]
+    n, m, m_e = spec["n"], spec["m_g"], spec["m_e"]
+    if dist is None:
+        dist = LocalDist()
+    stride, lo, hi = sharded.shard_range(m, world, rank)
+    t0 = time.perf_counter()
+    payload = device_payload(n, lo, hi, GEN_SEED, torch.device("cuda", dev))
+    host_payload = payload.cpu().numpy() if with_e2e else None   # the shard as a host buffer, for the end-to-end run
+    t_gen = time.perf_counter() - t0
+
+    def build(from_host):
+        if from_host:
+            return api.GenotypeStore(host_payload, n, m, recode_to_minor=True, device=dev, snp_lo=lo, snp_hi=hi)
+        return api.GenotypeStore(None, n, m, recode_to_minor=True, device=dev, snp_lo=lo, snp_hi=hi, payload_device_ptr=payload.data_ptr())
+
+    store = build(False)
+    del payload
+    torch.cuda.empty_cache()
+    y, E = sharded_phenotype(store, lo, hi, n, m, m_e, dist, world, probit)
+    tmp = tempfile.mkdtemp(prefix="bmagwa_group_r%d_" % rank)
+    shared = os.path.join(tempfile.gettempdir(), "bmagwa_group_job_%s_%d" % (workload, world))
+    if rank == 0:
+        write_group_files(shared, n, m, m_e, y, E, args.n_rao, n_chains)
+    dist.barrier()
+    ini = os.path.join(shared, "bench.ini")
+
+    def open_group(store, tag):
+        store.set_phenotype(y, E)
+        sharded.attach_all_peers(dist, store, world, rank, lo, hi)
+        group = sharded.ShardGroup(dist, store, stride, n_chains)
+        smp = None
+        if group.has_chain:
+            smp = api.Sampler(ini, rank, dev, store=store, group=group, tau_rng=args.tau_rng)
+            smp.set_option("basename", os.path.join(tmp, "%s%d" % (tag, rank)))
+            if probit:
+                smp.set_option("probit", "1")
+        return group, smp
+
+    group, smp = open_group(store, "bench")
+    log("[bench] %s rank %d: shard [%d, %d) generated in %.1f s, ready after %.1f s" % (workload, rank, lo, hi, t_gen, time.perf_counter() - t0))
+    if smp is not None:
+        smp.begin()
+    chain = L.bmg_sampler_chain(smp.h) if smp is not None else group.scan_chain()
+    stream = torch.cuda.ExternalStream(L.bmg_chain_stream(chain), device=torch.device("cuda", dev))
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+
+    def step(sampler, grp):
+        with torch.cuda.stream(stream):
+            flush.zero_()
+        if sampler is not None:
+            sampler.run(args.n_rao)
+        else:
+            grp.serve(1)
+
+    def transfers():
+        a, b = C.c_uint64(), C.c_uint64()
+        L.bmg_transfer_bytes(C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    clocks = ClockSampler(dev)
+    if rank == 0:
+        clocks.start()
+    for _ in range(args.warmup):
+        step(smp, group)
+    L.bmg_chain_scan_kernel_time(chain, 1, None, None, 1)
+    st0 = smp.stats() if smp is not None else None
+    g0 = group.stats()
+    launches_a = int(L.bmg_launch_count())
+    torch.cuda.synchronize(); dist.barrier()
+    clocks.begin()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t1 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step(smp, group)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t1
+    clocks.end()
+    dist.barrier()
+    clk = clocks.stop() if rank == 0 else None
+    elapsed_ms = max_over_ranks(e0.elapsed_time(e1))
+    launches_b = int(L.bmg_launch_count())
+    st1 = smp.stats() if smp is not None else None
+    cnt = smp.counters() if smp is not None else None
+    g1 = group.stats()
+    ms_total, n_l = C.c_double(), C.c_int64()
+    L.bmg_chain_scan_kernel_time(chain, 0, C.byref(ms_total), C.byref(n_l), 0)
+    if smp is not None:
+        smp.end(); smp.close()
+    group.close(); store.close()
+    try:
+        ms_trace = np.fromfile(os.path.join(tmp, "bench%d_modelsize.dat" % rank), dtype=np.uint32)
+        ms_trace = [int(v) for v in ms_trace[::max(1, len(ms_trace) // 12)]]
+    except Exception:
+        ms_trace = None
+
+    # ---- end to end: the shard as a HOST buffer -> store (H2D + device re-coding) -> group -> sampler -> K steps -> end
+    e2e = None
+    if with_e2e:
+        torch.cuda.synchronize(); dist.barrier()
+        h2d_a, d2h_a = transfers()
+        t2 = time.perf_counter()
+        store2 = build(True)
+        t3 = time.perf_counter()
+        group2, smp2 = open_group(store2, "e2e")
+        if smp2 is not None:
+            smp2.begin()
+        t4 = time.perf_counter()
+        for _ in range(args.steps):
+            if smp2 is not None:
+                smp2.run(args.n_rao)
+            else:
+                group2.serve(1)
+        if smp2 is not None:
+            smp2.end()
+        torch.cuda.synchronize()
+        e2e_secs = max_over_ranks(time.perf_counter() - t2)
+        h2d_b, d2h_b = transfers()
+        log("[bench] %s rank %d e2e phases: store from host buffer %.3f s, group + sampler + begin %.3f s, %d steps + end %.3f s"
+            % (workload, rank, t3 - t2, t4 - t3, args.steps, time.perf_counter() - t4))
+        if smp2 is not None:
+            smp2.close()
+        group2.close(); store2.close()
+        e2e = {"value": n_chains * args.steps * args.n_rao / e2e_secs, "unit": "iterations/s",
+               "h2d_bytes_per_step": (h2d_b - h2d_a) / args.steps, "d2h_bytes_per_step": (d2h_b - d2h_a) / args.steps,
+               "what": "per rank: bmg_store_create from the shard's packed bytes in HOST memory (H2D + device re-coding) + peers + "
+                       "bmg_group_create + bmg_sampler_create_grouped + begin + %d steps + end, wall clock, max over ranks; bytes are rank 0's"
+                       % args.steps}
+    dist.barrier()
+    if rank != 0:
+        return None
+    peak, peak_src = measured_peak()
+    B = (n + 3) // 4
+    bytes_scan = (hi - lo) * B + 8 * (hi - lo) + 8 * n      # rank 0's shard, one chain's residual
+    avg_ms = ms_total.value / max(1, n_l.value)
+    iters = n_chains * args.steps * args.n_rao
+    out = {
+        "metric": "mcmc_iterations_per_sec", "value": iters / (elapsed_ms / 1e3), "unit": "iterations/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "%s: %s; %d chain(s) over ONE store SNP-sharded over %d GPU(s) (%d SNPs per shard), chain c on rank c"
+                   % (workload, spec["desc"], n_chains, world, stride), "n": n, "m_g": m, "n_rao": args.n_rao, "chains": n_chains,
+                   "step": "%d MCMC iterations per chain incl. one all-SNP scan per chain" % args.n_rao, "tau_rng": args.tau_rng,
+                   "likelihood": "probit: latent phenotype redrawn on the device every 10 iterations, sigma2 = 1" if probit else "linear",
+                   "sampler": "testdata/testdata.ini settings (PMV, thin 10, DR 10, individual tau2)",
+                   "l2": "256 MiB write on the chain's stream before every step, inside the timed region",
+                   "exchange": "per scan: every rank scans its shard once per chain (limbs pulled over NVLink, n x 8 B) and stores the dot "
+                               "products into the owning chain's GPU through CUDA-IPC peer memory (8 B per SNP); two host barriers in POSIX "
+                               "shared memory; no NCCL and no host callback on the data path; column statistics read remote shards over the "
+                               "peer mappings",
+                   "timing": "CUDA events on the chain's stream, max over ranks; wall %.3f ms/step" % (1e3 * wall / args.steps)},
+        "gpu_launches": launches_b - launches_a,
+        "roofline": {"bound": "hbm", "kernel": "k_scan_dots_imma on rank 0's shard (one launch per chain and scan)",
+                     "achieved": bytes_scan / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0, "peak": peak, "unit": "GB/s",
+                     "frac": (bytes_scan / (avg_ms * 1e-3) / 1e9 / peak) if avg_ms > 0 else 0.0, "traffic": scan_traffic(workload),
+                     "bytes_per_launch": bytes_scan, "avg_launch_ms": avg_ms, "launches_timed": int(n_l.value), "peak_source": peak_src},
+        "clocks": clk,
+        "breakdown": {"move_seconds": st1["move_seconds"] - st0["move_seconds"], "scan_seconds": st1["scan_seconds"] - st0["scan_seconds"],
+                      "column_stats_seconds": st1["column_stats_seconds"] - st0["column_stats_seconds"],
+                      "barrier_wait_seconds": g1["barrier_seconds"] - g0["barrier_seconds"], "scan_rounds": g1["rounds"] - g0["rounds"],
+                      "delayed_rejection_seconds": cnt["delayed_rejection_seconds"], "served_from_memo": cnt["served_from_memo"],
+                      "moves_with_additions": cnt["moves_with_additions"], "model_size": st1["model_size"], "model_size_trace": ms_trace,
+                      "note": "rank 0's chain; seconds between the first and the last timed step"},
+    }
+    if e2e is not None:
+        out["e2e"] = e2e
+    return out
+
+
+def sliced_reference(args, workload, n_chains, warmup, steps, m_slice=10000):
+    """The unmodified reference sampler on a workload whose start-up passes alone take a quarter of an hour on the host
+    (C4: 5e10 genotypes at ~20 ns each): timed on a SLICE of the SNP axis (same n, m_slice SNPs, same
+    generator and sampler settings), then the scan's share of a step is scaled to the full SNP count -- the scan is a
+    loop over SNPs (src/sampler.cpp:90-259), everything else in a step costs O(n k) or O(m_g) host passes."""
+    import torch
+    from oracle import ref
+    from bmagwa_b200 import synth
+    spec = WORKLOADS[workload]
+    n, m, m_e = spec["n"], spec["m_g"], spec["m_e"]
+    m_slice = min(m_slice, m)
+    d = os.path.join(os.environ.get("BMAGWA_BENCH_DIR", os.path.join(tempfile.gettempdir(), "bmagwa_bench")), "%s_slice_n%d_m%d" % (workload, n, m_slice))
+    os.makedirs(d, exist_ok=True)
+    base = os.path.join(d, "syn")
+    t0 = time.time()
+    if not os.path.exists(os.path.join(d, "done")):
+        dev = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
+        payload = device_payload(n, 0, m_slice, GEN_SEED, dev).cpu().numpy()
+        with open(base + ".bed", "wb") as fh:
+            fh.write(bytes([0x6C, 0x1B, 0x01]))
+            fh.write(payload.tobytes())
+        B = (n + 3) // 4
+        rs = np.random.default_rng(GEN_SEED)
+        causal = np.linspace(0, m_slice - 1, 20).astype(np.int64)
+        contrib = np.zeros(n)
+        for j in causal:
+            x = synth.unpack_payload(payload[j * B:(j + 1) * B], n, 1).astype(np.float64).reshape(-1)
+            x[x < 0] = 0.0
+            contrib += 0.14 * (x - x.mean()) / max(x.std(), 1e-9)
+        y = contrib + rs.normal(size=n) * np.sqrt(0.6)
+        E = rs.uniform(0.0, 1.0, size=(n, m_e))
+        ids = ["per%d per%d" % (i, i) for i in range(n)]
+        with open(base + ".fam", "w") as fh:
+            fh.write("".join("%s 0 0 1 %.10g\n" % (ident, v) for ident, v in zip(ids, y)))
+        with open(base + ".y", "w") as fh:
+            fh.write("".join("%s %.17g\n" % (ident, v) for ident, v in zip(ids, y)))
+        with open(base + ".e", "w") as fh:
+            fh.write("".join("%s %s\n" % (ident, " ".join("%.17g" % v for v in row)) for ident, row in zip(ids, E)))
+        del payload
+        open(os.path.join(d, "done"), "w").write("ok")
+    out_dir = tempfile.mkdtemp(prefix="bmagwa_refslice_")
+    cfg = dict(base=base, recode=1, n=n, m_g=m_slice, m_e=m_e, save_beta=0, types="A", do_n_iter=args.n_rao, n_rao=args.n_rao,
+               n_rao_burnin=1000, thin=10, n_sample_tau2_and_missing=10, delay_rejection=10, max_move_size=20, use_individual_tau2=1,
+               e_qg=20, var_qg=300, n_threads=n_chains, seeds=",".join(str(v) for v in CHAIN_SEEDS[:n_chains]),
+               outbase=os.path.join(out_dir, "chain"), verbosity=0)
+    ini = os.path.join(out_dir, "bench.ini")
+    with open(ini, "w") as fh:
+        fh.write(synth.INI_TEMPLATE.format(**cfg))
+    t_data = time.time() - t0
+    probe = []
+    secs, _ = run_reference_chains(ini, n_chains, args.n_rao, warmup, steps, scan_probe=probe)
+    t_scan = probe[0]
+    step_slice = secs / steps
+    step_full = max(step_slice - t_scan, 0.0) + t_scan * (m / float(m_slice))
+    log("[bench] sliced reference %s: data %.1f s, %d chain(s): %.3f s per step on the slice of which scan %.3f s -> %.3f s per step at m_g = %d"
+        % (workload, t_data, n_chains, step_slice, t_scan, step_full, m))
+    return {"value": n_chains * args.n_rao / step_full, "step_seconds_slice": step_slice, "scan_seconds_slice": t_scan,
+            "step_seconds_full": step_full, "m_slice": m_slice,
+            "sample": "EXTRAPOLATED from a slice: the unmodified reference sampler (oracle/_ref, -O3 -march=x86-64-v3 -ffp-contract=off, "
+                      "OpenBLAS 1 thread per chain) run on n = %d x the first %d SNPs of the same generator, %d chain(s) x %d timed iterations "
+                      "after %d warm-up; measured %.3f s per %d-iteration step of which %.3f s is the all-SNP scan (timed alone, "
+                      "src/sampler.cpp:32-261); the scan's share is scaled by m_g / m_slice = %.0f to %.3f s per step.  The full workload's "
+                      "start-up passes alone (5e10 genotypes at ~20 ns, src/data.cpp:324-434) take ~17 min on one core and are not timed; "
+                      "host has %s cores" % (n, m_slice, n_chains, steps * args.n_rao, warmup * args.n_rao, step_slice, args.n_rao, t_scan,
+                                             m / float(m_slice), step_full, os.cpu_count())}
+
+
+def cpu_baseline(args, spec, workload=None):
     """The reference sampler (oracle/_ref) on this box's host cores, bounded sample of the same workload."""
+    workload = workload or args.workload
     from oracle import ref
     if not ref.available():
         return {"value": None, "unit": "iterations/s", "cores": 0, "kind": "port",
                 "sample": "oracle/_ref not present on this box; no sampler-level CPU number (the C oracle restates kernels only)"}
     with tempfile.TemporaryDirectory() as tmp:
-        ini, _ = prepare_dataset(args.workload, args.n_rao, 1, tmp, args.n_rao)
+        ini, _ = prepare_dataset(workload, args.n_rao, 1, tmp, args.n_rao)
         t0 = time.time()
         secs, _ = run_reference_chains(ini, 1, args.n_rao, 1, 2)   # T(3 steps) - T(1 step)
         log("[bench] cpu_baseline total %.1f s (timed %.2f s)" % (time.time() - t0, secs))
     return {"value": 2 * args.n_rao / secs, "unit": "iterations/s", "cores": 1, "kind": "reference",
             "sample": "%d timed iterations (2 steps) after one warm-up step of one chain of the unmodified reference sampler "
-                      "(oracle/_ref, OpenBLAS 1 thread); the reference is single-threaded per chain; host has %s cores"
+                      "(oracle/_ref: reference sources unmodified, built -O3 -march=x86-64-v3 -ffp-contract=off against oracle/shim, "
+                      "OpenBLAS 1 thread); the reference is single-threaded per chain; host has %s cores"
                       % (2 * args.n_rao, os.cpu_count())}
+
+
+def compact(rec):
+    """Sub-record of another workload inside the headline JSON line."""
+    keep = ("value", "unit", "ms_per_step", "steps", "warmup", "n_gpus", "config", "e2e", "roofline", "clocks", "gpu_launches", "breakdown",
+            "cpu_baseline")
+    return {k: rec[k] for k in keep if k in rec}
 
 
 def main():
@@ -660,15 +999,19 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS),
+                    help="default: C2 (+ C3, C4 sub-records) on one GPU, C4 sharded with one chain per GPU on several")
     ap.add_argument("--n-rao", type=int, default=500, dest="n_rao")
     ap.add_argument("--tau-rng", default="device", choices=["device", "host"], dest="tau_rng")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sub", action="store_true", help="headline workload only (no C3 / C4 / replica sub-records)")
+    ap.add_argument("--chains", type=int, default=0, help="chains over the sharded store (default: one per GPU; e.g. 4 on 8 GPUs for C5)")
+    ap.add_argument("--replicas", action="store_true", help="N > 1: one chain per GPU on replicated stores as the headline (round 1's mode)")
     ap.add_argument("--miss-rate", type=float, default=0.0, dest="miss_rate",
                     help="fraction of genotype calls set missing in the synthetic data (exercises the imputation path; default 0)")
-    ap.add_argument("--probit", action="store_true", help="case-control labels + latent-variable updates (with --sharded; e.g. --workload C3)")
-    ap.add_argument("--sharded", action="store_true",
-                    help="ONE chain over a SNP-sharded store (strong scaling) instead of one chain per GPU")
+    ap.add_argument("--probit", action="store_true", help="case-control labels + latent-variable updates (sharded workloads; C3 implies it)")
+    ap.add_argument("--sharded", "--lockstep", action="store_true", dest="sharded",
+                    help="ONE chain replicated in lockstep over a SNP-sharded store (strong scaling of the scan only)")
     args = ap.parse_args()
     global MISS_RATE
     MISS_RATE = args.miss_rate
@@ -682,10 +1025,60 @@ def main():
     with stdout_to_stderr():
         if args.impl == "reference":
             line = reference_arm(args, rank, world)
-        elif args.sharded:
-            line = sharded_arm(args, rank, local_rank, world)
         else:
-            line = ours_arm(args, rank, local_rank, world)
+            import torch
+            if not torch.cuda.is_available():
+                raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+            torch.cuda.set_device(local_rank)
+            dist = None
+            if world > 1:
+                import torch.distributed as dist_mod
+                dist = dist_mod
+                dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+                pinned = pin_rank_to_core(local_rank, world)
+                if pinned is not None:
+                    log("[bench] rank %d pinned to CPUs %s" % (rank, pinned))
+            if args.sharded:
+                args.workload = args.workload or "C4"
+                line = sharded_arm(args, rank, local_rank, world)
+            elif world == 1:
+                wl = args.workload or "C2"
+                if wl in ("C3", "C4", "C4s", "C5"):
+                    line = group_arm(args, wl, rank, local_rank, 1, None, 1, probit=args.probit or wl == "C3")
+                else:
+                    args.workload = wl
+                    line = ours_arm(args, rank, local_rank, world)
+                    if not args.no_sub and wl == "C2" and args.miss_rate == 0.0:
+                        subs = {}
+                        for sub, probit in (("C3", True), ("C4", False)):
+                            try:
+                                rec = group_arm(args, sub, rank, local_rank, 1, None, 1, probit=probit)
+                                if sub == "C4" and not args.no_cpu_baseline:
+                                    from oracle import ref
+                                    if ref.available():
+                                        res = sliced_reference(args, "C4", 1, 1, 2)
+                                        rec["cpu_baseline"] = {"value": res["value"], "unit": "iterations/s", "cores": 1, "kind": "reference",
+                                                               "sample": res["sample"]}
+                                subs[sub] = compact(rec)
+                            except Exception as e:   # a sub-record must not cost the headline
+                                subs[sub] = {"error": repr(e)}
+                                log("[bench] sub-record %s failed: %r" % (sub, e))
+                        line["workloads"] = subs
+            else:
+                wl = args.workload or "C4"
+                n_chains = args.chains if args.chains > 0 else world
+                if args.replicas:
+                    args.workload = args.workload or "C2"
+                    line = ours_arm(args, rank, local_rank, world, dist)
+                else:
+                    line = group_arm(args, wl, rank, local_rank, world, dist, n_chains, probit=args.probit or wl == "C3")
+                    if not args.no_sub:
+                        rep = ours_arm(args, rank, local_rank, world, dist, workload="C2", with_cpu_baseline=False)
+                        if line is not None and rep is not None:
+                            line["replicas_c2"] = compact(rep)
+            if dist is not None:
+                dist.barrier()
+                dist.destroy_process_group()
     if line is not None:
         print(json.dumps(line), flush=True)
 

@@ -175,10 +175,11 @@ class SubmodelEnumerator {
 // removal step draws the removable SNPs in reverse position order, and a fair coin precedes every step at which both kinds
 // are still possible.
 // ------------------------------------------------------------------------------------------------
-// One pass over the ms steps per sub-model; the logarithms of the ms weights are taken once and the normalising totals
-// are multiplied up and logged once per sub-model.  (A table-driven O(1)-per-sub-model variant was tried and measured
-// slower for ms <= 10: tools/dr_bench.cpp, profiles/round2_notes.md.)
-inline void compute_proposal_probs_for_exh_modelset(int n_inds, const unsigned char* bit_to_normalized_order, const double* q_add,
+// The direct statement: one pass over the ms steps per sub-model; the logarithms of the ms weights are taken once and the
+// normalising totals are multiplied up and logged once per sub-model.  Its 2 ms data-dependent branches per sub-model
+// mispredict on the sub-model bits (about 100 ns per sub-model inside a chain, 20 % of a C2 chain's host time); it serves the
+// corner the recurrences below leave out.
+inline void compute_proposal_probs_stepwise(int n_inds, const unsigned char* bit_to_normalized_order, const double* q_add,
                                             const double* q_rem, double z_add, double z_rem, size_t const_loci, size_t m_g,
                                             double* log_prop_probs, const double* log_q_add_types = nullptr)
 {
@@ -221,6 +222,62 @@ inline void compute_proposal_probs_for_exh_modelset(int n_inds, const unsigned c
       }
     }
     log_prop_probs[i] += (double)n_half * exhaustive_detail::kLogHalf + sum_log_q - std::log(prod_z);
+  }
+}
+
+
+// The usual case (more SNPs outside the model than the move could add, so an addition is always possible): the add steps
+// and the removal steps normalise independently of each other.  With the in-model positions of a sub-model as a bit set u
+// and the positions to add as its complement c,
+//     the removal of the SNP at position p draws from    z_rem + (removal weights of u at positions <= p)
+//     the addition at position p draws from              (z_add - all ms add weights) + (add weights of c at positions >= p)
+// so the product over u's removals follows from the product for u without its HIGHEST position, and the product over c's
+// additions from the product for c without its LOWEST position: two branch-free recurrences over 2^ms table entries and
+// one logarithm per sub-model.
+inline void compute_proposal_probs_for_exh_modelset(int n_inds, const unsigned char* bit_to_normalized_order, const double* q_add,
+                                                    const double* q_rem, double z_add, double z_rem, size_t const_loci, size_t m_g,
+                                                    double* log_prop_probs, const double* log_q_add_types = nullptr)
+{
+  if (n_inds > 20 || m_g < const_loci + (size_t)n_inds + 1) {
+    compute_proposal_probs_stepwise(n_inds, bit_to_normalized_order, q_add, q_rem, z_add, z_rem, const_loci, m_g, log_prop_probs,
+                                    log_q_add_types);
+    return;
+  }
+  const unsigned long nmodels = 1ul << n_inds;
+  struct Entry { double sum_r, prod_r, slq_r, sum_a, prod_a, slq_a; unsigned long index; };
+  static thread_local std::vector<Entry> table;
+  if (table.size() < nmodels) table.resize(nmodels);
+  Entry* t = table.data();
+  unsigned long bit_at[32];   // normalised position -> bit of the caller's sub-model index
+  double lq_add[32], lq_rem[32], q_add_all = 0.0;
+  for (int j = 0; j < n_inds; ++j) bit_at[bit_to_normalized_order[j]] = 1ul << j;
+  for (int p = 0; p < n_inds; ++p) {
+    lq_add[p] = std::log(q_add[p]) + (log_q_add_types ? log_q_add_types[p] : 0.0);
+    lq_rem[p] = std::log(q_rem[p]);
+    q_add_all += q_add[p];
+  }
+  const double z0 = z_add - q_add_all;
+  t[0].sum_r = 0.0; t[0].prod_r = 1.0; t[0].slq_r = 0.0; t[0].sum_a = 0.0; t[0].prod_a = 1.0; t[0].slq_a = 0.0; t[0].index = 0;
+  for (unsigned long u = 1; u < nmodels; ++u) {
+    const int hi = 63 - __builtin_clzl(u), lo = __builtin_ctzl(u);
+    const Entry& a = t[u ^ (1ul << hi)];   // u without its highest position
+    const Entry& b = t[u & (u - 1)];       // u without its lowest position
+    Entry& e = t[u];
+    e.sum_r = a.sum_r + q_rem[hi];
+    e.prod_r = a.prod_r * (z_rem + e.sum_r);
+    e.slq_r = a.slq_r + lq_rem[hi];
+    e.index = a.index | bit_at[hi];
+    e.sum_a = b.sum_a + q_add[lo];
+    e.prod_a = b.prod_a * (z0 + e.sum_a);
+    e.slq_a = b.slq_a + lq_add[lo];
+  }
+  // a fair coin precedes every step at which a removal is still possible: all ms steps when the rest of the model holds
+  // SNPs, otherwise the steps up to the sub-model's last in-model position
+  for (unsigned long u = 0; u < nmodels; ++u) {
+    const Entry& r = t[u];
+    const Entry& a = t[(nmodels - 1) ^ u];
+    const int n_half = const_loci > 0 ? n_inds : (u ? 64 - __builtin_clzl(u) : 0);
+    log_prop_probs[r.index] += (double)n_half * exhaustive_detail::kLogHalf + (r.slq_r + a.slq_a) - std::log(r.prod_r * a.prod_a);
   }
 }
 

@@ -28,32 +28,21 @@ static void* run_chain(void* arg)
   return NULL;
 }
 
-// minimal lookup of "key = value" in a section of the INI file (only for n_threads / do_n_iter here;
-// the library parses the file in full)
-static std::string ini_lookup(const char* path, const char* section, const char* key, const char* dflt)
+// n_threads / do_n_iter as the library reads them (same parser as the samplers: bmg_ini_lookup)
+static long ini_long(const char* path, const char* section, const char* key, const char* dflt)
 {
-  FILE* f = fopen(path, "r");
-  if (!f) return dflt;
-  char line[256];
-  std::string cur, out = dflt;
-  while (fgets(line, sizeof line, f)) {
-    char* s = line;
-    while (*s == ' ' || *s == '\t') ++s;
-    if (*s == '[') { char* e = strchr(s, ']'); if (e) cur.assign(s + 1, e - s - 1); continue; }
-    if (*s == ';' || *s == '#' || cur != section) continue;
-    char* eq = strchr(s, '=');
-    if (!eq) continue;
-    std::string name(s, eq - s);
-    while (!name.empty() && (name.back() == ' ' || name.back() == '\t')) name.pop_back();
-    if (name != key) continue;
-    std::string v(eq + 1);
-    size_t c = v.find(" ;");
-    if (c != std::string::npos) v.resize(c);
-    size_t a = v.find_first_not_of(" \t\r\n"), b = v.find_last_not_of(" \t\r\n");
-    out = a == std::string::npos ? "" : v.substr(a, b - a + 1);
+  char buf[256];
+  if (bmg_ini_lookup(path, section, key, dflt, buf, (int)sizeof buf)) {
+    fprintf(stderr, "terminate called after throwing an instance of 'std::runtime_error'\n  what():  %s\n", bmg_last_error());
+    exit(134);
   }
-  fclose(f);
-  return out;
+  char* end = NULL;
+  const long v = strtol(buf, &end, 10);
+  if (end == buf) {
+    fprintf(stderr, "terminate called after throwing an instance of 'std::runtime_error'\n  what():  Config error: invalid value for %s.%s\n", section, key);
+    exit(134);
+  }
+  return v;
 }
 
 int main(int argc, char* argv[])
@@ -66,19 +55,26 @@ int main(int argc, char* argv[])
     return 0;
   }
   const char* ini = argv[1];
-  const int n_threads = atoi(ini_lookup(ini, "thread", "n_threads", "1").c_str());
-  const long do_n_iter = atol(ini_lookup(ini, "sampler", "do_n_iter", "0").c_str());
-  std::vector<Job> jobs(n_threads > 0 ? n_threads : 1);
+  const long n_threads = ini_long(ini, "thread", "n_threads", "1");
+  const long do_n_iter = ini_long(ini, "sampler", "do_n_iter", "0");
+  std::vector<Job> jobs(n_threads > 0 ? (size_t)n_threads : 1);
   bmg_sampler* first = NULL;
   for (size_t t = 0; t < jobs.size(); ++t) {
-    printf("Initializing sampler %zu\n", t);
+    // chain 0 loads the data and builds the device store (the reference's Data + PrecomputedSNPCovariances,
+    // src/main.cpp:54-68); its summaries are printed where the reference prints them
     int rc = t == 0 ? bmg_sampler_create(ini, 0, -1, &jobs[t].sampler)
                     : bmg_sampler_create_on_store(ini, (int)t, bmg_sampler_store(first), &jobs[t].sampler);
     if (rc) {
       fprintf(stderr, "terminate called after throwing an instance of 'std::runtime_error'\n  what():  %s\n", bmg_last_error());
       return 134;
     }
-    if (t == 0) first = jobs[t].sampler;
+    if (t == 0) {
+      first = jobs[t].sampler;
+      double sm[6];
+      if (bmg_store_summaries(bmg_sampler_store(first), sm) == 0)   // src/main.cpp:60-62 (iostream default precision: %g)
+        printf("var y = %g\nvar x = %g\nmean x = %g\nPrecomputing SNP covariances\n", sm[4], sm[2] / sm[3], sm[0] / sm[1]);
+    }
+    printf("Initializing sampler %zu\n", t);
     jobs[t].n_iter = do_n_iter;
     jobs[t].status = 0;
   }

@@ -592,14 +592,17 @@ void Sampler::run(int64_t do_n_iter)
 {
   if (!begun_) throw std::runtime_error("bmg_sampler_run: call bmg_sampler_begin first");
   Files& f = *files_;
+  sec_last_ = __builtin_ia32_rdtsc();
   const size_t end_iter = n_iter_ + (size_t)do_n_iter;
   for (size_t iter = n_iter_; iter < end_iter; ++iter) {
+    mark(kSecOther);
     if ((iter + 1) % n_sample_tau2_and_missing_ == 0) {   // sampler.cpp:628-635
       sample_missing();
       if (probit_) probit_sweep();   // the latent phenotype moves with the same cadence as tau2 / missing genotypes
       prior_->sample_alpha_and_tau2(&current_, rng_);
       current_.compute_log_likelihood();
       copy_current_to_proposal();
+      mark(kSecTauAlpha);
     }
     const unsigned char move = (unsigned char)sample_discrete_naive(p_moves_cumsum_, 7, rng_);
     unsigned char jumpdistance = 0;
@@ -615,11 +618,13 @@ void Sampler::run(int64_t do_n_iter)
       default: throw std::logic_error("Move is not in 0...2 for the PMV sampler with one effect type");
     }
     move_seconds_ += wall_seconds() - t0;
+    if (move == 1) mark(kSecMove1);
+    else if (move == 2) mark(kSecMove2);
     ++n_moves_[move];
     n_acpt_moves_[move] += jumpdistance > 0;
     n_accepted_ += jumpdistance > 0;
 
-    if ((iter + 1) % thin_ == 0 || (iter + 2) % n_sample_tau2_and_missing_ == 0) current_.sample_beta_sigma2(rng_);
+    if ((iter + 1) % thin_ == 0 || (iter + 2) % n_sample_tau2_and_missing_ == 0) { mark(kSecOther); current_.sample_beta_sigma2(rng_); mark(kSecBetaSigma); }
 
     f.jumpdistance.write(reinterpret_cast<const char*>(&jumpdistance), 1);
     f.move_type.write(reinterpret_cast<const char*>(&move), 1);
@@ -643,7 +648,8 @@ void Sampler::run(int64_t do_n_iter)
       const double a = prior_->alpha();
       f.alpha.write(reinterpret_cast<const char*>(&a), sizeof(double));
     }
-    if ((iter + 1) % n_rao_ == 0) rao_block();
+    mark(kSecOutput);
+    if ((iter + 1) % n_rao_ == 0) { rao_block(); mark(kSecRao); }
     if (verbosity_ > 0 && (iter + 1) % verbosity_ == 0) {   // sampler.cpp:813-833
       f.log << "(" << (iter + 1) << ")"
             << " acc.rate " << (double)n_accepted_ / (iter + 1) << " acc.rate2 " << (double)n_acpt_moves_[1] / n_moves_[1]
@@ -774,6 +780,20 @@ void Sampler::end()
               << gibbs_seconds_ << " s; column-statistics memo: " << cache_.requests << " moves asked, " << cache_.served
               << " needed no device trip, " << cache_.partial << " a subset, " << n_gram_requests_ << " device requests, "
               << cache_.pairs() << " pairs held; server fall-backs " << chain_->server_fallbacks << std::endl;
+  if (getenv("BMG_TIMING")) {
+    static const char* names[kSecCount] = {"propose", "request", "removals", "wait", "additions", "backward", "accept-copy", "reject-copy",
+                                           "dr-readd", "dr-enumerate", "dr-proposal-probs", "dr-sample", "dr-apply", "move1", "move2",
+                                           "beta/sigma2", "tau2/alpha", "output", "rao-block", "other"};
+    uint64_t total = 0;
+    for (int i = 0; i < kSecCount; ++i) total += sec_ticks_[i];
+    std::cerr << "[bmg timing] host time by section (% of " << total << " ticks, " << n_iter_ << " iterations):";
+    char num[32];
+    for (int i = 0; i < kSecCount; ++i) {
+      std::snprintf(num, sizeof num, " %.1f", 100.0 * (double)sec_ticks_[i] / (double)std::max<uint64_t>(1, total));
+      std::cerr << " " << names[i] << num;
+    }
+    std::cerr << std::endl;
+  }
   // _rao.dat (sampler.cpp:847-849): the running mean kept on the device
   p_rao_.assign(m_g_, 0.0);
   BMG_CUDA(cudaSetDevice(store_->device));
@@ -882,6 +902,7 @@ void Sampler::do_addrem(double& log_q_forward, double& log_q_backward, double& l
   std::vector<double> taus;
   if (have_missing_) taus = draw_for_additions(cand);   // removals draw nothing, so the stream order is the reference's
   begin_gram(cand);
+  mark(kSecRequest);
   for (unsigned char i = 0; i < ms; ++i) {   // removals first
     if (move_isadd_[i]) continue;
     const size_t ind = move_inds_[i];
@@ -892,7 +913,9 @@ void Sampler::do_addrem(double& log_q_forward, double& log_q_backward, double& l
     log_mpc += prior_->log_change_on_rem((int)proposal_.size());
     remove_from_proposal(model_ind);
   }
+  mark(kSecRemovals);
   finish_gram();
+  mark(kSecWait);
   size_t n_added = 0;
   for (unsigned char i = 0; i < ms; ++i) {   // then additions
     if (!move_isadd_[i]) continue;
@@ -903,6 +926,7 @@ void Sampler::do_addrem(double& log_q_forward, double& log_q_backward, double& l
     ++n_added;
     add_to_proposal((uint32_t)ind, tau);
   }
+  mark(kSecAdditions);
 }
 
 void Sampler::undo_move0_flags()
@@ -919,9 +943,12 @@ unsigned char Sampler::do_multistep_additions_and_removals()
   movesize_ = (unsigned char)(sample_discrete_naive(q_p_move_size_.data(), max_move_size_, rng_) + 1);
   double log_q_forward = 0.0, log_q_backward = 0.0, log_mpc = 0.0;
   unsigned char ms_rem = 0;
+  mark(kSecOther);
   prepare_addrem(log_q_forward, ms_rem, movesize_);
+  mark(kSecPropose);
   do_addrem(log_q_forward, log_q_backward, log_mpc, movesize_);
   backward_prepare_addrem(log_q_backward, movesize_);
+  mark(kSecBackward);
   double log_r = log_q_backward - log_q_forward;
   log_r += log_mpc + proposal_.log_likelihood - current_.log_likelihood;
   if (delay_rejection_ == 0) r_move_size_sum_[movesize_ - 1] += (log_r >= 0 ? 1.0 : std::exp(log_r));
@@ -929,6 +956,7 @@ unsigned char Sampler::do_multistep_additions_and_removals()
   if (log_r >= 0 || std::log(rng_.u01()) <= log_r) {
     copy_proposal_to_current();
     if (delay_rejection_ != 0) r_move_size_sum_[movesize_ - 1] += 1.0;
+    mark(kSecAcceptCopy);
     return movesize_;
   }
   if (movesize_ <= delay_rejection_ && movesize_ > 1) {
@@ -940,6 +968,7 @@ unsigned char Sampler::do_multistep_additions_and_removals()
   }
   copy_current_to_proposal();
   undo_move0_flags();
+  mark(kSecRejectCopy);
   return 0;
 }
 
@@ -967,11 +996,14 @@ unsigned char Sampler::delayed_rejection_move0(unsigned char ms_rem, double, dou
     dr_q_add_[i] = q_add(ind);
     dr_q_rem_[i] = q_rem(ind);
   }
+  mark(kSecDrReadd);
   double max_log_model;
   double* P = dr_model_probabilities_.data();
   exh_.run(proposal_, (int)const_loci, (int)ms, P, max_log_model);
+  mark(kSecDrEnumerate);
   compute_proposal_probs_for_exh_modelset(ms, dr_bit_to_normalized_order_.data(), dr_q_add_.data(), dr_q_rem_.data(), z_add, z_rem,
                                           const_loci, m_g_, P);
+  mark(kSecDrProposal);
   const unsigned long nmodels = 1ul << ms, mask = nmodels - 1;
   double sum = 0.0;
   for (unsigned long i = 0; i < nmodels / 2; ++i) {
@@ -984,10 +1016,12 @@ unsigned char Sampler::delayed_rejection_move0(unsigned char ms_rem, double, dou
   }
   unsigned long sampled = (unsigned long)sample_discrete(P, nmodels / 2, (int)ms / 2 - 3, rng_);
   if (P[(~sampled) & mask] < 0) sampled = (~sampled) & mask;
+  mark(kSecDrSample);
   unsigned char moved = 0;
   if (sampled == ((~newmodel_binary) & mask)) {   // the current model: stay
     copy_current_to_proposal();
     undo_move0_flags();
+    mark(kSecDrApply);
     return 0;
   }
   for (unsigned char b = 0; b < ms; ++b) {
@@ -1011,6 +1045,7 @@ unsigned char Sampler::delayed_rejection_move0(unsigned char ms_rem, double, dou
   }
   r_move_size_sum_[ms - 1] += (double)moved / (double)ms;
   copy_proposal_to_current();
+  mark(kSecDrApply);
   return moved;
 }
 

@@ -112,6 +112,17 @@ class Sampler {
   struct FittedState { std::vector<int64_t> loci; std::vector<double> beta_g, beta_e; } fitted_;
   bool reference_quirks_ = true;
   void track_fitted_values();
+  // ---- where the host time of an iteration goes (BMG_TIMING prints it): time-stamp-counter ticks per section
+  enum Section { kSecPropose = 0, kSecRequest, kSecRemovals, kSecWait, kSecAdditions, kSecBackward, kSecAcceptCopy, kSecRejectCopy,
+                 kSecDrReadd, kSecDrEnumerate, kSecDrProposal, kSecDrSample, kSecDrApply, kSecMove1, kSecMove2, kSecBetaSigma,
+                 kSecTauAlpha, kSecOutput, kSecRao, kSecOther, kSecCount };
+  uint64_t sec_ticks_[kSecCount] = {0}, sec_last_ = 0;
+  void mark(Section s)
+  {
+    const uint64_t now = __builtin_ia32_rdtsc();
+    sec_ticks_[s] += now - sec_last_;
+    sec_last_ = now;
+  }
   // ---- output files
   struct Files;
   std::unique_ptr<Files> files_;

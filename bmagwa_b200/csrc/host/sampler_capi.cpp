@@ -247,6 +247,16 @@ BMG_API int bmg_sampler_create_on_store(const char* ini_path, int chain_index, b
   *out = reinterpret_cast<bmg_sampler*>(make(ini_path, chain_index, -1, reinterpret_cast<Store*>(s)));
   BMG_CATCH
 }
+BMG_API int bmg_ini_lookup(const char* ini_path, const char* section, const char* key, const char* dflt, char* out, int out_len)
+{
+  BMG_TRY
+  BMG_REQUIRE(ini_path && section && key && out && out_len > 0, "bmg_ini_lookup: invalid argument");
+  IniFile ini(ini_path);
+  BMG_REQUIRE(ini.parse_error() >= 0, std::string("Can't load ") + ini_path);
+  const std::string v = ini.get(section, key, dflt ? dflt : "");
+  std::snprintf(out, (size_t)out_len, "%s", v.c_str());
+  BMG_CATCH
+}
 BMG_API int bmg_sampler_set_option(bmg_sampler* sp, const char* key, const char* value)
 {
   BMG_TRY

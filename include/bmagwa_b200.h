@@ -291,6 +291,11 @@ bmg_chain* bmg_group_scan_chain(bmg_group* g);
 /* out[0..3] = {scan rounds served, seconds spent waiting in the group's barriers, 0, 0} */
 int bmg_group_stats(bmg_group* g, double* out4);
 int bmg_group_destroy(bmg_group* g);
+/* Value of `key` in [section] of an INI file, read with the library's own parser (the inih rules the reference follows,
+ * src/inih/ini.c:60-140: case-insensitive names, '=' or ':' separators, continuation lines, " ;" comments, 199-character
+ * lines); `dflt` when absent.  Copies at most out_len - 1 characters.  For hosts that need n_threads / do_n_iter
+ * before constructing samplers (src/main.cpp:47-52). */
+int bmg_ini_lookup(const char* ini_path, const char* section, const char* key, const char* dflt, char* out, int out_len);
 /* Overrides applied after the INI file, before bmg_sampler_begin.  Keys: "tau_rng" = host | device (per-SNP tau2 draws
  * of the scan from the chain's stream in reference order, or Philox on the device); "missing_rng" = host | device (the
  * re-imputation of missing calls before each scan likewise; defaults to tau_rng); "pip_burnin" = thinned samples to drop

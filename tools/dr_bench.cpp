@@ -47,7 +47,7 @@ int main()
     auto t2 = std::chrono::steady_clock::now();
     for (int r = 0; r < reps; ++r) { std::fill(P.begin(), P.end(), 0.0); compute_proposal_probs_for_exh_modelset(ms, order.data(), qa.data(), qr.data(), 30.0, 18.0, k0, 100000, P.data()); sink += P[1]; }
     auto t3b = std::chrono::steady_clock::now();
-    for (int r = 0; r < reps; ++r) { std::fill(P.begin(), P.end(), 0.0); compute_proposal_probs_for_exh_modelset(ms, order.data(), qa.data(), qr.data(), 30.0, 18.0, k0, 100000, P.data()); sink += P[1]; }
+    for (int r = 0; r < reps; ++r) { std::fill(P.begin(), P.end(), 0.0); compute_proposal_probs_stepwise(ms, order.data(), qa.data(), qr.data(), 30.0, 18.0, k0, 100000, P.data()); sink += P[1]; }
     auto t4 = std::chrono::steady_clock::now();
     auto t3 = std::chrono::steady_clock::now();
     auto us = [&](auto a, auto b) { return std::chrono::duration<double, std::micro>(b - a).count() / reps; };

@@ -44,6 +44,9 @@ WORKLOADS = {
 }
 GEN_SEED = 20121101
 CHAIN_SEEDS = [1234, 2345, 3456, 4567, 5678, 6789, 7890, 8901]
+if os.environ.get("BMG_BENCH_SEED_SHIFT"):   # development: which seed the first chain gets
+    _k = int(os.environ["BMG_BENCH_SEED_SHIFT"]) % len(CHAIN_SEEDS)
+    CHAIN_SEEDS = CHAIN_SEEDS[_k:] + CHAIN_SEEDS[:_k]
 
 
 def log(*a):
@@ -766,6 +769,7 @@ def group_arm(args, workload, rank, local_rank, world, dist, n_chains, probit=Fa
     if smp is not None:
         smp.begin()
     chain = L.bmg_sampler_chain(smp.h) if smp is not None else group.scan_chain()
+    timer_chain = group.scan_chain()   # the scan kernels of every chain over this rank's shard run on the service's stream
     stream = torch.cuda.ExternalStream(L.bmg_chain_stream(chain), device=torch.device("cuda", dev))
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
 
@@ -794,7 +798,7 @@ def group_arm(args, workload, rank, local_rank, world, dist, n_chains, probit=Fa
         clocks.start()
     for _ in range(args.warmup):
         step(smp, group)
-    L.bmg_chain_scan_kernel_time(chain, 1, None, None, 1)
+    L.bmg_chain_scan_kernel_time(timer_chain, 1, None, None, 1)
     st0 = smp.stats() if smp is not None else None
     g0 = group.stats()
     launches_a = int(L.bmg_launch_count())
@@ -817,7 +821,7 @@ def group_arm(args, workload, rank, local_rank, world, dist, n_chains, probit=Fa
     cnt = smp.counters() if smp is not None else None
     g1 = group.stats()
     ms_total, n_l = C.c_double(), C.c_int64()
-    L.bmg_chain_scan_kernel_time(chain, 0, C.byref(ms_total), C.byref(n_l), 0)
+    L.bmg_chain_scan_kernel_time(timer_chain, 0, C.byref(ms_total), C.byref(n_l), 0)
     if smp is not None:
         smp.end(); smp.close()
     group.close(); store.close()
@@ -826,6 +830,9 @@ def group_arm(args, workload, rank, local_rank, world, dist, n_chains, probit=Fa
         ms_trace = [int(v) for v in ms_trace[::max(1, len(ms_trace) // 12)]]
     except Exception:
         ms_trace = None
+    if smp is not None:
+        log("[bench] %s rank %d: chain %d model size trace %s, %.1f us per iteration in moves" %
+            (workload, rank, rank, ms_trace, 1e6 * (st1["move_seconds"] - st0["move_seconds"]) / (args.steps * args.n_rao)))
 
     # ---- end to end: the shard as a HOST buffer -> store (H2D + device re-coding) -> group -> sampler -> K steps -> end
     e2e = None
@@ -890,7 +897,7 @@ def group_arm(args, workload, rank, local_rank, world, dist, n_chains, probit=Fa
         "clocks": clk,
         "breakdown": {"move_seconds": st1["move_seconds"] - st0["move_seconds"], "scan_seconds": st1["scan_seconds"] - st0["scan_seconds"],
                       "column_stats_seconds": st1["column_stats_seconds"] - st0["column_stats_seconds"],
-                      "barrier_wait_seconds": g1["barrier_seconds"] - g0["barrier_seconds"], "scan_rounds": g1["rounds"] - g0["rounds"],
+                      "scan_wait_seconds": g1["scan_wait_seconds"] - g0["scan_wait_seconds"], "scans_served_by_rank0": g1["served"] - g0["served"],
                       "delayed_rejection_seconds": cnt["delayed_rejection_seconds"], "served_from_memo": cnt["served_from_memo"],
                       "moves_with_additions": cnt["moves_with_additions"], "model_size": st1["model_size"], "model_size_trace": ms_trace,
                       "note": "rank 0's chain; seconds between the first and the last timed step"},

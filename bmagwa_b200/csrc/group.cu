@@ -1,23 +1,26 @@
 // group.cu -- several chains over ONE SNP-sharded store (BASELINE.json configs[4]: "sharded over 8xB200, 4 parallel
 // chains").  The reference's chains are threads of one process sharing one Data (src/main.cpp:54-85);
 // here a "shard group" is one process per GPU: rank r holds the packed SNPs [r stride, (r+1) stride) and -- for
-// r < n_chains -- the host sampler of chain r.  Nothing of a chain is replicated on other ranks:
+// r < n_chains -- the host sampler of chain r.  Nothing of a chain is replicated on other ranks, and chains never wait
+// for each other:
 //
-//   per iteration   chain r asks ITS GPU for the column statistics of the SNPs it proposes; columns of other shards are
+//   per iteration   chain c asks ITS GPU for the column statistics of the SNPs it proposes; columns of other shards are
 //                   read over NVLink through CUDA-IPC peer mappings (store.cu).  No collective, no other rank involved.
-//   per scan        (every n_rao iterations, all chains at the same cadence)
-//     1. chain r quantises its residual into the tensor-core scan's limb format (scan_imma.cu) inside its exchange
-//        buffer, which every peer has mapped;
-//     2. barrier (host, POSIX shared memory: the ranks of a group live on one box);
-//     3. every rank runs the scan kernel over ITS shard once per chain (the chain's limbs are pulled over NVLink,
-//        n x 8 bytes) and a small kernel adds the per-chunk partial sums and stores the shard's dot products
-//        STRAIGHT INTO THE OWNING CHAIN'S GPU (peer stores, 8 bytes per SNP) -- compute and exchange in one pass,
-//        no NCCL call and no Python on the data path;
-//     4. barrier; chain r finishes the scan on its own GPU (per-SNP algebra over all m_g SNPs with its own tau draws)
-//        and carries on.  Integer accumulation makes the dot products independent of the sharding, so every chain
-//        writes the bytes its single-GPU run writes (tests/test_gpu_sharded.py).
+//   per scan        (chain c, every n_rao iterations of ITS OWN clock)
+//     1. chain c quantises its residual into the tensor-core scan's limb format (scan_imma.cu) inside its exchange
+//        buffer, which every peer has mapped, and posts a request number in a POSIX shared-memory segment;
+//     2. every rank runs a SCAN SERVICE thread with its own CUDA stream: it picks the request up, pulls the chain's limbs
+//        over NVLink (n x 8 bytes), runs the scan kernel over ITS shard, and a small kernel adds the per-chunk partial sums
+//        and stores the shard's dot products STRAIGHT INTO THE OWNING CHAIN'S GPU (peer stores, 8 bytes per SNP) --
+//        compute and exchange in one pass, no NCCL call, no barrier and no Python on the data path -- then acknowledges;
+//     3. with every rank's acknowledgement chain c finishes the scan on its own GPU (per-SNP algebra over all m_g SNPs
+//        with its own tau draws) and carries on.  Integer accumulation makes the dot products independent of the
+//        sharding, so every chain writes the bytes its single-GPU run writes (tests/test_gpu_sharded.py).
 //
-// Ranks without a chain (n_chains < world, e.g. 4 chains over 8 GPUs) only serve step 3 (bmg_group_serve).
+// A chain's scan therefore costs it one pass over 1/world of the store per rank, all ranks in parallel, whatever the other
+// chains are doing; a slow chain (large model) delays nobody.  Ranks without a chain (n_chains < world, e.g. 4 chains over
+// 8 GPUs) only run the service.  Collective operations (creation, the start-up exchanges, destruction) use a
+// shared-memory barrier.
 #include <fcntl.h>
 #include <immintrin.h>
 #include <sys/mman.h>
@@ -26,6 +29,7 @@
 #include <unistd.h>
 #include <atomic>
 #include <cstring>
+#include <thread>
 #include "common.cuh"
 #include "store.cuh"
 #include "group.cuh"
@@ -44,6 +48,10 @@ struct GroupShm {
   uint32_t pad[11];
   unsigned char handle[kGroupMaxRanks][64];
   int64_t lo[kGroupMaxRanks], hi[kGroupMaxRanks];
+  // scan service: request[c] = number of the latest scan chain c asked for; done[c][r] = the latest rank r has served
+  struct alignas(64) Flag { std::atomic<uint64_t> v; };
+  Flag request[kGroupMaxRanks];
+  Flag done[kGroupMaxRanks][kGroupMaxRanks];
 };
 
 double now_seconds()
@@ -76,8 +84,18 @@ struct Group {
   bool peer_opened[kGroupMaxRanks] = {false};
   DevBuf<unsigned char> q_stage[2];   // a peer chain's limbs + exponent, double-buffered
   DevBuf<int32_t> n1_all, n2_all;
-  int64_t rounds = 0;
   double barrier_seconds = 0.0;
+  // scan service
+  GroupShm local_shm;                  // world == 1: the flags live here
+  std::thread service;
+  std::atomic<bool> stop{false};
+  std::atomic<int64_t> served{0};      // requests this rank's service has completed
+  uint64_t served_seq[kGroupMaxRanks] = {0};
+  std::string service_error;
+  // this rank's chain
+  uint64_t my_seq = 0;
+  int64_t my_scans = 0;
+  double scan_wait_seconds = 0.0;
 };
 
 static void group_fail(Group* g)
@@ -138,6 +156,8 @@ int group_allgather(void* ctx, void* dev_buffer, int64_t elems_per_rank, int ele
     return 1;
   }
 }
+
+static void group_service_loop(Group* g);
 
 Group* group_create(Store* s, int world, int rank, int n_chains, int64_t stride, const char* shm_name)
 {
@@ -224,18 +244,28 @@ Group* group_create(Store* s, int world, int rank, int n_chains, int64_t stride,
   BMG_REQUIRE(group_allgather(g.get(), g->n1_all.p, stride, (int)sizeof(int32_t), (void*)st) == 0, "shard group: exchange of the genotype counts failed");
   BMG_REQUIRE(group_allgather(g.get(), g->n2_all.p, stride, (int)sizeof(int32_t), (void*)st) == 0, "shard group: exchange of the genotype counts failed");
   BMG_CUDA(cudaStreamSynchronize(st));
+  if (g->shm == nullptr) {   // one rank: no segment to share
+    std::memset(static_cast<void*>(&g->local_shm), 0, sizeof(GroupShm));
+    g->shm = &g->local_shm;
+  }
+  Group* raw = g.get();
+  g->service = std::thread([raw] { group_service_loop(raw); });
   return g.release();
 }
 
+// collective: every rank's service must stay up until every chain of the group has ended
 void group_destroy(Group* g)
 {
   if (!g) return;
   cudaSetDevice(g->store->device);
+  try { group_barrier(g); } catch (...) {}
+  g->stop.store(true, std::memory_order_release);
+  if (g->service.joinable()) g->service.join();
   if (g->scan_chain) { cudaStreamSynchronize(g->scan_chain->stream); }
   for (int r = 0; r < g->world; ++r)
     if (g->peer_opened[r]) cudaIpcCloseMemHandle(g->peer[r]);
   chain_destroy(g->scan_chain);
-  if (g->shm) munmap(g->shm, sizeof(GroupShm));
+  if (g->shm && g->shm != &g->local_shm) munmap(g->shm, sizeof(GroupShm));
   delete g;
 }
 
@@ -248,57 +278,107 @@ const int32_t* group_n2(const Group* g) { return g->n2_all.p; }
 Chain* group_scan_chain(Group* g) { return g->scan_chain; }
 void group_stats(const Group* g, double* out4)
 {
-  out4[0] = (double)g->rounds; out4[1] = g->barrier_seconds; out4[2] = 0.0; out4[3] = 0.0;
+  out4[0] = (double)g->served.load(std::memory_order_acquire); out4[1] = g->scan_wait_seconds; out4[2] = (double)g->my_scans;
+  out4[3] = g->barrier_seconds;
 }
 
-// One scan round (see the header of this file).  mine: this rank's chain with its residual ready, or nullptr on a rank
-// without a chain.  Returns the chain's dot products over all m_g SNPs (device pointer on this GPU), complete when the
-// call returns.
+// ---- the scan service of this rank: serves every chain's requests over this rank's shard ----------------------------
+static void group_serve_one(Group* g, int c)
+{
+  Store* s = g->store;
+  Chain* sc = g->scan_chain;
+  cudaStream_t st = sc->stream;
+  const unsigned char* q = g->xbuf.p;
+  if (c != g->rank) {
+    BMG_CUDA(cudaMemcpyAsync(g->q_stage[0].p, g->peer[c], g->q_bytes + 256, cudaMemcpyDefault, st));
+    q = g->q_stage[0].p;
+  }
+  imma_launch_on(sc, reinterpret_cast<const uint4*>(q), reinterpret_cast<const int*>(q + g->q_bytes), sc->imma_partial.p, false, st, sc);
+  double* out = reinterpret_cast<double*>(g->peer[c] + g->off_dots) + s->lo;
+  k_group_combine<<<(unsigned)((s->m + 255) / 256), 256, 0, st>>>(sc->imma_partial.p, sc->imma_chunks, s->m, out);
+  count_launch();
+  BMG_CUDA(cudaGetLastError());
+  BMG_CUDA(cudaStreamSynchronize(st));   // the peer stores have landed before the acknowledgement is visible
+}
+
+static void group_service_loop(Group* g)
+{
+  try {
+    BMG_CUDA(cudaSetDevice(g->store->device));
+    GroupShm* shm = g->shm;
+    unsigned idle = 0;
+    while (!g->stop.load(std::memory_order_acquire)) {
+      bool found = false;
+      for (int i = 0; i < g->n_chains; ++i) {
+        const int c = (g->rank + i) % g->n_chains;   // the local chain first
+        const uint64_t req = shm->request[c].v.load(std::memory_order_acquire);
+        if (req == g->served_seq[c]) continue;
+        group_serve_one(g, c);
+        g->served_seq[c] = req;
+        shm->done[c][g->rank].v.store(req, std::memory_order_release);
+        g->served.fetch_add(1, std::memory_order_acq_rel);
+        found = true;
+      }
+      if (found) { idle = 0; continue; }
+      if (shm->failed.load(std::memory_order_acquire)) break;
+      if (++idle < 2000) _mm_pause();
+      else usleep(20);   // a request comes once per Rao-Blackwell period and chain: do not burn a core on the wait
+    }
+  } catch (const std::exception& e) {
+    g->service_error = e.what();
+    group_fail(g);
+  }
+}
+
+// Chain `mine` (residual ready) asks every rank for its scan and waits for the dot products over all m_g SNPs
+// (device pointer on this GPU, complete when the call returns).
 const double* group_scan_round(Group* g, Chain* mine)
 {
   Store* s = g->store;
   try {
     BMG_CUDA(cudaSetDevice(s->device));
-    BMG_REQUIRE((mine != nullptr) == (g->rank < g->n_chains), "shard group: ranks below n_chains scan through their chain, the others through bmg_group_serve");
-    Chain* sc = g->scan_chain;
-    cudaStream_t st = mine ? mine->stream : sc->stream;
-    if (mine) {
-      BMG_REQUIRE(mine->residual_valid, "scan: call bmg_chain_residual first");
-      imma_quantize(mine);
-      BMG_REQUIRE(mine->imma_q.n == g->q_bytes, "shard group: limb layout of the chain differs from the group's");
-      BMG_CUDA(cudaMemcpyAsync(g->xbuf.p, mine->imma_q.p, g->q_bytes, cudaMemcpyDeviceToDevice, st));
-      BMG_CUDA(cudaMemcpyAsync(g->xbuf.p + g->off_exp, mine->imma_exp.p, sizeof(int), cudaMemcpyDeviceToDevice, st));
-      BMG_CUDA(cudaStreamSynchronize(st));
-    }
-    group_barrier(g);   // every chain's limbs are in place
-    for (int i = 0; i < g->n_chains; ++i) {
-      const int c = (g->rank + i) % g->n_chains;   // start with the nearest chain: the pulls spread over the peers
-      const unsigned char* q = g->xbuf.p;
-      if (c != g->rank) {
-        DevBuf<unsigned char>& stage = g->q_stage[i & 1];
-        BMG_CUDA(cudaMemcpyAsync(stage.p, g->peer[c], g->q_bytes + 256, cudaMemcpyDefault, st));
-        q = stage.p;
+    BMG_REQUIRE(mine != nullptr && g->rank < g->n_chains, "shard group: only ranks below n_chains hold a chain");
+    BMG_REQUIRE(mine->residual_valid, "scan: call bmg_chain_residual first");
+    cudaStream_t st = mine->stream;
+    imma_quantize(mine);
+    BMG_REQUIRE(mine->imma_q.n == g->q_bytes, "shard group: limb layout of the chain differs from the group's");
+    BMG_CUDA(cudaMemcpyAsync(g->xbuf.p, mine->imma_q.p, g->q_bytes, cudaMemcpyDeviceToDevice, st));
+    BMG_CUDA(cudaMemcpyAsync(g->xbuf.p + g->off_exp, mine->imma_exp.p, sizeof(int), cudaMemcpyDeviceToDevice, st));
+    BMG_CUDA(cudaStreamSynchronize(st));   // also: the previous scan's per-SNP algebra has finished reading the dot products
+    GroupShm* shm = g->shm;
+    const uint64_t seq = ++g->my_seq;
+    const double t0 = now_seconds();
+    shm->request[g->rank].v.store(seq, std::memory_order_release);
+    unsigned long spins = 0;
+    for (int r = 0; r < g->world; ++r) {
+      while (shm->done[g->rank][r].v.load(std::memory_order_acquire) != seq) {
+        _mm_pause();
+        if ((++spins & 0xFFF) == 0) {
+          if (shm->failed.load(std::memory_order_acquire))
+            throw Error("shard group: a rank's scan service failed" + (g->service_error.empty() ? std::string() : ": " + g->service_error));
+          if (now_seconds() - t0 > kBarrierTimeout) throw Error("shard group: a rank's scan service does not answer");
+        }
       }
-      imma_launch_on(sc, reinterpret_cast<const uint4*>(q), reinterpret_cast<const int*>(q + g->q_bytes), sc->imma_partial.p, false, st,
-                     mine ? mine : sc);
-      double* out = reinterpret_cast<double*>(g->peer[c] + g->off_dots) + s->lo;
-      k_group_combine<<<(unsigned)((s->m + 255) / 256), 256, 0, st>>>(sc->imma_partial.p, sc->imma_chunks, s->m, out);
-      count_launch();
     }
-    BMG_CUDA(cudaGetLastError());
-    BMG_CUDA(cudaStreamSynchronize(st));
-    group_barrier(g);   // every shard's dot products have landed on every chain's GPU
-    ++g->rounds;
-    return mine ? reinterpret_cast<const double*>(g->xbuf.p + g->off_dots) : nullptr;
+    g->scan_wait_seconds += now_seconds() - t0;
+    ++g->my_scans;
+    return reinterpret_cast<const double*>(g->xbuf.p + g->off_dots);
   } catch (...) {
     group_fail(g);
     throw;
   }
 }
 
+// a rank without a chain: returns once its service has completed n_rounds more requests of every chain
 void group_serve(Group* g, int64_t n_rounds)
 {
-  for (int64_t i = 0; i < n_rounds; ++i) group_scan_round(g, nullptr);
+  const int64_t target = g->served.load(std::memory_order_acquire) + n_rounds * g->n_chains;
+  const double t0 = now_seconds();
+  while (g->served.load(std::memory_order_acquire) < target) {
+    if (g->shm->failed.load(std::memory_order_acquire)) throw Error("shard group: a peer rank failed" + (g->service_error.empty() ? std::string() : ": " + g->service_error));
+    if (now_seconds() - t0 > 20 * kBarrierTimeout) throw Error("shard group: no scan request arrives");
+    usleep(200);
+  }
 }
 
 }  // namespace bmg

@@ -135,7 +135,7 @@ class ShardGroup:
     def stats(self):
         out = np.zeros(4)
         api.check(self.L.bmg_group_stats(self.h, out.ctypes.data_as(api.f64p)))
-        return {"rounds": int(out[0]), "barrier_seconds": float(out[1])}
+        return {"served": int(out[0]), "scan_wait_seconds": float(out[1]), "scans": int(out[2]), "barrier_seconds": float(out[3])}
 
     def native_comm(self):
         """bmg_shard_comm for the lockstep single chain over this group's all-gather (no host callback)."""

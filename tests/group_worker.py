@@ -81,7 +81,7 @@ def main():
         if mode == "two":   # two different seeds: the chains must not be copies of each other
             if filecmp.cmp(os.path.join(work, "group0_loci.dat"), os.path.join(work, "group1_loci.dat"), shallow=False):
                 print("chains 0 and 1 are identical"); ok = False
-        print("GROUP_OK" if ok else "GROUP_MISMATCH", mode, "rounds", gst["rounds"], "barrier wait %.3f s" % gst["barrier_seconds"])
+        print("GROUP_OK" if ok else "GROUP_MISMATCH", mode, "served", gst["served"], "scan wait %.3f s" % gst["scan_wait_seconds"])
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
 

@@ -643,3 +643,64 @@ def test_scan_full_size_linearity_and_checksum(api):
     tot = vals.sum(dim=0).cpu().numpy()
     assert d1.sum() == pytest.approx(tot @ y, rel=1e-11)
     ch.close(); ch2.close(); st.close(); st2.close()
+
+
+# ------------------------------------------------------- BASELINE's own shapes against the oracle (not only properties)
+def _oracle_scan_case(api, n, m, n_model, seed):
+    """Seeded Binomial(2, f_j) genotypes of a BASELINE shape generated on the device (bench.device_payload), the same bytes
+    handed to the C oracle on the host: counts, moment cache, scan dot products and p_r for a model of n_model SNPs with
+    per-SNP tau, and the column statistics of a few candidate SNPs."""
+    import torch
+    import bench
+    from oracle import cpu
+    payload_dev = bench.device_payload(n, 0, m, seed, torch.device("cuda", 0))
+    payload = payload_dev.cpu().numpy()
+    st = api.GenotypeStore(None, n, m, recode_to_minor=True, payload_device_ptr=payload_dev.data_ptr())
+    del payload_dev
+    rs = np.random.default_rng(seed)
+    y = rs.normal(size=n)
+    E = rs.uniform(size=(n, 2))
+    st.set_phenotype(y, E)
+    bed = payload.copy()
+    cpu.recode_minor(bed, n, m)
+    xx = cpu.moments(bed, n, m)
+    assert np.array_equal(st.moments(), xx)
+    loci = np.sort(rs.choice(m, size=n_model, replace=False)).astype(np.int64)
+    beta_e = rs.normal(size=3) * 0.1
+    beta_g = rs.normal(size=n_model) * 0.2
+    tau_g = rs.uniform(0.5, 5.0, size=n_model)
+    tau = rs.uniform(0.5, 5.0, size=m)
+    ch = api.Chain(st)
+    ch.residual(loci, beta_e, beta_g)
+    yhat = beta_e[0] + E @ beta_e[1:]
+    for l, b in zip(loci, beta_g):
+        yhat = yhat + b * cpu.decode_column(bed, n, int(l), 0)
+    model_ind = -np.ones(m, dtype=np.int32)
+    model_ind[loci] = np.arange(n_model)
+    want_p, want_dot, _ = cpu.scan_A(bed, n, m, xx, y, yhat, model_ind, beta_g, tau_g, tau, 1, 0.8, -8.5, -8.0, want_dot=True)
+    got_p = ch.scan(loci, beta_g, tau_g, 0.8, -8.5, -8.0, tau=tau)
+    got_dot = ch.scan_dots()
+    scale = np.sqrt(n) * 2.0 * np.linalg.norm(y - yhat)   # >= ||x_j|| ||r||
+    assert np.abs(got_dot - want_dot).max() <= 1e-12 * scale
+    assert np.abs(got_p - want_p).max() <= 1e-9
+    cand = rs.choice(m, size=3, replace=False).astype(np.int64)
+    xy, xe, xm, xc = ch.column_stats(cand, loci)
+    for i, c in enumerate(cand):
+        x = cpu.decode_column(bed, n, int(c), 0)
+        assert abs(xy[i] - x @ y) <= 1e-12 * np.linalg.norm(x) * np.linalg.norm(y) + 1e-9
+        assert np.allclose(xe[i], np.concatenate([[x.sum()], x @ E]), rtol=1e-12, atol=1e-9)
+        for q, l in enumerate(loci[:5]):
+            assert xm[i, q] == x @ cpu.decode_column(bed, n, int(l), 0)
+    ch.close()
+    st.close()
+
+
+def test_scan_and_column_stats_at_the_c2_shape_against_the_oracle(api):
+    """BASELINE configs[1]: n = 5,000 x p = 100,000 in full ("full C2 p_r vs oracle.c, not just checksums")."""
+    _oracle_scan_case(api, 5000, 100000, 20, 11)
+
+
+def test_scan_and_column_stats_at_the_c4_shape_against_the_oracle(api):
+    """BASELINE configs[3] shape: n = 50,000 individuals (3,125 packed words per column, 17 chunks of the tensor-core scan),
+    10,000 SNPs of it -- what the oracle finishes in seconds."""
+    _oracle_scan_case(api, 50000, 10000, 24, 12)

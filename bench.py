@@ -796,6 +796,13 @@ def group_arm(args, workload, rank, local_rank, world, dist, n_chains, probit=Fa
     clocks = ClockSampler(dev)
     if rank == 0:
         clocks.start()
+    burn_steps = max(0, args.burnin // args.n_rao)
+    t_b = time.perf_counter()
+    for _ in range(burn_steps):
+        step(smp, group)
+    if smp is not None and burn_steps:
+        log("[bench] %s rank %d: %d burn-in iterations in %.1f s, model size %d" % (workload, rank, burn_steps * args.n_rao,
+                                                                                   time.perf_counter() - t_b, int(smp.stats()["model_size"])))
     for _ in range(args.warmup):
         step(smp, group)
     L.bmg_chain_scan_kernel_time(timer_chain, 1, None, None, 1)
@@ -883,11 +890,13 @@ def group_arm(args, workload, rank, local_rank, world, dist, n_chains, probit=Fa
                    "step": "%d MCMC iterations per chain incl. one all-SNP scan per chain" % args.n_rao, "tau_rng": args.tau_rng,
                    "likelihood": "probit: latent phenotype redrawn on the device every 10 iterations, sigma2 = 1" if probit else "linear",
                    "sampler": "testdata/testdata.ini settings (PMV, thin 10, DR 10, individual tau2)",
+                   "burnin": "%d iterations per chain before the warm-up steps, untimed (start-up transient of the chains: models of up to "
+                             "~200 SNPs for some seeds, which cost 10x per iteration)" % (burn_steps * args.n_rao),
                    "l2": "256 MiB write on the chain's stream before every step, inside the timed region",
-                   "exchange": "per scan: every rank scans its shard once per chain (limbs pulled over NVLink, n x 8 B) and stores the dot "
-                               "products into the owning chain's GPU through CUDA-IPC peer memory (8 B per SNP); two host barriers in POSIX "
-                               "shared memory; no NCCL and no host callback on the data path; column statistics read remote shards over the "
-                               "peer mappings",
+                   "exchange": "per scan of a chain: every rank's scan-service thread scans its shard for that chain (limbs pulled over NVLink, "
+                               "n x 8 B) and stores the dot products into the chain's GPU through CUDA-IPC peer memory (8 B per SNP); request / "
+                               "acknowledgement flags in POSIX shared memory; no NCCL, no barrier and no host callback on the data path; column "
+                               "statistics read remote shards over the peer mappings",
                    "timing": "CUDA events on the chain's stream, max over ranks; wall %.3f ms/step" % (1e3 * wall / args.steps)},
         "gpu_launches": launches_b - launches_a,
         "roofline": {"bound": "hbm", "kernel": "k_scan_dots_imma on rank 0's shard (one launch per chain and scan)",
@@ -1012,6 +1021,9 @@ def main():
     ap.add_argument("--tau-rng", default="device", choices=["device", "host"], dest="tau_rng")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sub", action="store_true", help="headline workload only (no C3 / C4 / replica sub-records)")
+    ap.add_argument("--burnin", type=int, default=20000,
+                    help="sharded workloads (C3/C4/C5): MCMC iterations every chain is advanced before the warm-up steps, untimed, so that "
+                         "the chains are past their start-up transient (models of up to ~200 SNPs for some seeds) and cost the same")
     ap.add_argument("--chains", type=int, default=0, help="chains over the sharded store (default: one per GPU; e.g. 4 on 8 GPUs for C5)")
     ap.add_argument("--replicas", action="store_true", help="N > 1: one chain per GPU on replicated stores as the headline (round 1's mode)")
     ap.add_argument("--miss-rate", type=float, default=0.0, dest="miss_rate",

@@ -88,9 +88,17 @@ struct ColStatInline {
   int n_seg, seg_words;
   const double* y;
   const double* e;
-  ulonglong2* out_host;      // [m_c][n_seg][n_tasks] tagged results in mapped host memory
+  ulonglong2* out_host;      // tagged results in mapped host memory: [m_c][n_seg][n_tasks], or [m_c][n_tasks] with `part`
   unsigned int seq;          // launch sequence number = the tag
+  // Many slices per column (n_seg > kHostReduceSegs, i.e. n > 8,192): the per-slice results stay in device memory
+  // (part, [m_c][n_seg][n_tasks]) and the LAST work item to finish (ticket) adds them in slice order -- the order the host
+  // uses otherwise, so the numbers are the same -- and publishes only the sums: the host then reads 16 (1 + m_e + k + m_c)
+  // bytes per candidate instead of n_seg times as much (at n = 50,000: 0.4 kB instead of 22 kB of freshly written lines).
+  double* part;              // nullptr: the host adds the slices
+  unsigned int* ticket;      // [4], slot seq & 3; left at 0 by the last item
 };
+constexpr int kHostReduceSegs = 8;
+constexpr int kReduceTile = 4096;   // doubles of shared memory for the last item's reduction (32 kB)
 
 // A result travels to the host as two 8-byte words, each carrying half of the double and the launch's sequence
 // number in its upper half, written by ONE 16-byte store.  Every word validates itself, so the kernel needs no
@@ -118,6 +126,7 @@ __device__ __forceinline__ void colstat_item(const ColStatInline& a, const int c
   const int n_fp = a.m_e + 1;
   const int n_tasks = n_fp + a.k + a.m_c;
   ulonglong2* out = a.out_host + ((int64_t)c * a.n_seg + seg) * n_tasks;
+  double* part = a.part ? a.part + ((int64_t)c * a.n_seg + seg) * n_tasks : nullptr;
   const int64_t i_lo = 16 * w0, i_hi = min(a.n, i_lo + 16 * (int64_t)nwords);
   const bool small = seg_words <= 64;   // 1024 individuals per CTA: 4 per thread, everything this CTA reads issues at once
   // Every load of the CTA is issued BEFORE the candidate's words are waited for: y / covariates of this thread's
@@ -206,7 +215,10 @@ __device__ __forceinline__ void colstat_item(const ColStatInline& a, const int c
         for (int j = 0; j < 2; ++j)
           if (lane + 32 * j < nwords) acc += packed_dot(cw[lane + 32 * j], ow[u][j]);
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0 && task < n_tasks) publish_tagged(out + task, (double)acc, a.seq);
+        if (lane == 0 && task < n_tasks) {
+          if (part) part[task] = (double)acc;
+          else publish_tagged(out + task, (double)acc, a.seq);
+        }
       }
     }
   } else {
@@ -221,14 +233,61 @@ __device__ __forceinline__ void colstat_item(const ColStatInline& a, const int c
       for (int j = 0; j < kFastSegMax / 32; ++j)
         if (lane + 32 * j < nwords) acc += packed_dot(cw[lane + 32 * j], ow[j]);
       for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (lane == 0) publish_tagged(out + task, (double)acc, a.seq);
+      if (lane == 0) {
+        if (part) part[task] = (double)acc;
+        else publish_tagged(out + task, (double)acc, a.seq);
+      }
     }
   }
   __syncthreads();
   if (t < n_fp) {
     double v = 0.0;
     for (int wv = 0; wv < nw; ++wv) v += fpart[wv][t];
-    publish_tagged(out + t, v, a.seq);
+    if (part) part[t] = v;
+    else publish_tagged(out + t, v, a.seq);
+  }
+  if (part == nullptr) return;
+  // ---- the last item of the request adds the slices (in slice order) and publishes the sums
+  __shared__ int is_last;
+  __threadfence();   // this thread's slice results are visible device-wide ...
+  __syncthreads();
+  if (t == 0) {      // ... before the item is counted
+    const unsigned int total = (unsigned int)(a.m_c * a.n_seg);
+    unsigned int* tk = a.ticket + (a.seq & 3u);
+    const unsigned int got = atomicAdd(tk, 1u);
+    is_last = got == total - 1u;
+    if (is_last) *tk = 0u;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  // All slice results of a tile of outputs are fetched from L2 at once (every thread a few independent loads), then one
+  // thread per output adds its n_seg values in slice order from shared memory.
+  __shared__ double red[kReduceTile];
+  const int n_out = a.m_c * n_tasks;                       // outputs (candidate, task), task fastest
+  const int tile_out = max(1, kReduceTile / a.n_seg);      // outputs per tile
+  for (int o0 = 0; o0 < n_out; o0 += tile_out) {
+    const int cnt = min(tile_out, n_out - o0);
+    if (a.n_seg <= kReduceTile) {
+      for (int e = t; e < cnt * a.n_seg; e += blockDim.x) {
+        const int g = e / cnt, o = o0 + (e - g * cnt);     // consecutive threads read consecutive tasks of one slice
+        const int ci = o / n_tasks, task = o - ci * n_tasks;
+        red[(e - g * cnt) * a.n_seg + g] = __ldcg(a.part + ((int64_t)ci * a.n_seg + g) * n_tasks + task);
+      }
+      __syncthreads();
+      for (int o = t; o < cnt; o += blockDim.x) {
+        const double* r = red + o * a.n_seg;
+        double v = 0.0;
+        for (int g = 0; g < a.n_seg; ++g) v += r[g];
+        publish_tagged(a.out_host + o0 + o, v, a.seq);
+      }
+      __syncthreads();
+    } else if (t == 0) {                                    // more slices than the tile holds (n > 4 M): plain loop
+      const int ci = o0 / n_tasks, task = o0 - ci * n_tasks;
+      double v = 0.0;
+      for (int g = 0; g < a.n_seg; ++g) v += __ldcg(a.part + ((int64_t)ci * a.n_seg + g) * n_tasks + task);
+      publish_tagged(a.out_host + o0, v, a.seq);
+    }
   }
 }
 
@@ -377,7 +436,7 @@ static void server_start(Chain* c, const ColStatInline& base, unsigned int last_
     c->server_req.alloc(2 * kMailChunks);
     c->server_flag.alloc(1);
     memset(c->server_mail.p, 0, kMailChunks * sizeof(uint4));
-    c->server_ctas = std::min(64, std::max(8, s->sm_count / 2));
+    c->server_ctas = std::max(8, s->sm_count);   // one CTA per SM: a request of up to sm_count (candidate, slice) items is one wave
   }
   // nothing is "fresh" until the next post: mailbox head and device flag both carry the last served sequence number
   volatile uint32_t* head = reinterpret_cast<volatile uint32_t*>(c->server_mail.p);
@@ -449,6 +508,7 @@ static void server_fallback_inline(Chain* c)
   BMG_REQUIRE(c->cs_last_req.size() == sizeof(ColStatInline), "column statistics: no request to repeat");
   ColStatInline a;
   memcpy(&a, c->cs_last_req.data(), sizeof(a));
+  if (a.ticket) BMG_CUDA(cudaMemsetAsync(a.ticket, 0, 4 * sizeof(unsigned int), c->stream));   // the dead instance may have counted some items
   k_column_stats_inline<<<dim3(a.m_c, a.n_seg), 256, 0, c->stream>>>(a);
   count_launch();
   const cudaError_t le = cudaGetLastError();
@@ -472,11 +532,13 @@ void chain_column_stats_wait(Chain* c, double* xy, double* xe, double* xx_model,
   const unsigned long long tag = (unsigned long long)c->cs_p_seq << 32;
   const volatile unsigned long long* words = reinterpret_cast<const volatile unsigned long long*>(c->cs_map.p);
   unsigned long spins = 0;
+  const bool device_reduced = c->cs_p_reduced;
+  const int n_host_seg = device_reduced ? 1 : n_seg;
   for (int ci = 0; ci < m_c; ++ci) {
     for (int task = 0; task < n_tasks; ++task) {
       double v = 0.0;
-      for (int g = 0; g < n_seg; ++g) {
-        const size_t slot = ((size_t)ci * n_seg + g) * n_tasks + task;
+      for (int g = 0; g < n_host_seg; ++g) {
+        const size_t slot = ((size_t)ci * n_host_seg + g) * n_tasks + task;
         unsigned long long w0, w1;
         for (;;) {
           w0 = words[2 * slot];
@@ -568,6 +630,18 @@ void chain_column_stats_launch(Chain* c, const int64_t* cand, int m_c, const int
     a.m_c = m_c; a.k = k; a.m_e = s->m_e; a.n = s->n; a.W = s->W; a.n_seg = n_seg; a.seg_words = seg_words; a.y = c->y.p; a.e = s->e.p;
     a.out_host = reinterpret_cast<ulonglong2*>(c->cs_map.p);
     a.seq = ++c->cs_seq;
+    a.part = nullptr; a.ticket = nullptr;
+    static const bool host_reduce_forced = getenv("BMG_COLSTATS_HOSTREDUCE") != nullptr;   // development: A/B of the two ways
+    if (n_seg > kHostReduceSegs && !host_reduce_forced) {
+      if (c->cs_part.n < need_fast || c->cs_ticket.n == 0) {
+        chain_server_stop(c);
+        BMG_CUDA(cudaStreamSynchronize(st));
+        if (c->cs_part.n < need_fast) c->cs_part.alloc(need_fast * 2);
+        if (c->cs_ticket.n == 0) { c->cs_ticket.alloc(4); BMG_CUDA(cudaMemset(c->cs_ticket.p, 0, 4 * sizeof(unsigned int))); BMG_CUDA(cudaDeviceSynchronize()); }
+      }
+      a.part = c->cs_part.p; a.ticket = c->cs_ticket.p;
+    }
+    c->cs_p_reduced = a.part != nullptr;
     if (c->server_enabled) {
       if (patched > 0) BMG_CUDA(cudaStreamSynchronize(st));   // the server runs on its own stream: columns must be complete
       c->cs_last_req.resize(sizeof(ColStatInline));            // kept so that the wait can repeat it with a plain launch
@@ -580,7 +654,7 @@ void chain_column_stats_launch(Chain* c, const int64_t* cand, int m_c, const int
       const cudaError_t le = cudaGetLastError();
       if (le != cudaSuccess) throw Error(std::string("k_column_stats_inline launch: ") + cudaGetErrorString(le));
     }
-    g_d2h_bytes.fetch_add(need_fast * 2 * sizeof(double), std::memory_order_relaxed);
+    g_d2h_bytes.fetch_add((a.part ? (size_t)m_c * n_tasks : need_fast) * 2 * sizeof(double), std::memory_order_relaxed);
     g_h2d_bytes.fetch_add(sizeof(ColStatInline), std::memory_order_relaxed);
     c->cs_pending = true;
     c->cs_p_mc = m_c; c->cs_p_k = k; c->cs_p_nseg = n_seg; c->cs_p_seq = a.seq;

@@ -152,6 +152,9 @@ struct Chain {
   int server_failures = 0;                      // consecutive requests a server instance left unserved (see chain_column_stats_wait)
   int64_t server_fallbacks = 0;                 // requests repeated as an ordinary launch
   std::vector<unsigned char> cs_last_req;       // the pending request (a ColStatInline), kept for that repeat
+  DevBuf<double> cs_part;                       // per-slice results kept on the device (many slices: summed by the last work item)
+  DevBuf<unsigned int> cs_ticket;
+  bool cs_p_reduced = false;
   int cs_p_mc = 0, cs_p_k = 0, cs_p_nseg = 0;
   unsigned int cs_p_seq = 0;
 };

@@ -28,6 +28,8 @@
 #include <time.h>
 #include <unistd.h>
 #include <atomic>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 #include "common.cuh"
@@ -52,6 +54,7 @@ struct GroupShm {
   struct alignas(64) Flag { std::atomic<uint64_t> v; };
   Flag request[kGroupMaxRanks];
   Flag done[kGroupMaxRanks][kGroupMaxRanks];
+  double request_time[kGroupMaxRanks];   // CLOCK_MONOTONIC of the latest request (diagnostics only)
 };
 
 double now_seconds()
@@ -92,6 +95,7 @@ struct Group {
   std::atomic<int64_t> served{0};      // requests this rank's service has completed
   uint64_t served_seq[kGroupMaxRanks] = {0};
   std::string service_error;
+  double pickup_seconds = 0.0, serve_seconds = 0.0, pickup_max = 0.0, serve_max = 0.0;   // request -> pick-up, pick-up -> acknowledged
   // this rank's chain
   uint64_t my_seq = 0;
   int64_t my_scans = 0;
@@ -261,6 +265,11 @@ void group_destroy(Group* g)
   try { group_barrier(g); } catch (...) {}
   g->stop.store(true, std::memory_order_release);
   if (g->service.joinable()) g->service.join();
+  if (getenv("BMG_TIMING") && g->served.load() > 0)
+    fprintf(stderr, "[bmg timing] shard group rank %d: scan service served %lld requests; request -> pick-up mean %.0f us (max %.0f), pick-up -> acknowledged "
+                    "mean %.0f us (max %.0f); own chain waited %.3f s for %lld scans\n", g->rank, (long long)g->served.load(),
+            1e6 * g->pickup_seconds / (double)g->served.load(), 1e6 * g->pickup_max, 1e6 * g->serve_seconds / (double)g->served.load(),
+            1e6 * g->serve_max, g->scan_wait_seconds, (long long)g->my_scans);
   if (g->scan_chain) { cudaStreamSynchronize(g->scan_chain->stream); }
   for (int r = 0; r < g->world; ++r)
     if (g->peer_opened[r]) cudaIpcCloseMemHandle(g->peer[r]);
@@ -313,9 +322,15 @@ static void group_service_loop(Group* g)
         const int c = (g->rank + i) % g->n_chains;   // the local chain first
         const uint64_t req = shm->request[c].v.load(std::memory_order_acquire);
         if (req == g->served_seq[c]) continue;
+        const double t_pick = now_seconds();
+        const double waited = t_pick - shm->request_time[c];
         group_serve_one(g, c);
         g->served_seq[c] = req;
         shm->done[c][g->rank].v.store(req, std::memory_order_release);
+        const double took = now_seconds() - t_pick;
+        g->pickup_seconds += waited; g->serve_seconds += took;
+        if (waited > g->pickup_max) g->pickup_max = waited;
+        if (took > g->serve_max) g->serve_max = took;
         g->served.fetch_add(1, std::memory_order_acq_rel);
         found = true;
       }
@@ -348,6 +363,7 @@ const double* group_scan_round(Group* g, Chain* mine)
     GroupShm* shm = g->shm;
     const uint64_t seq = ++g->my_seq;
     const double t0 = now_seconds();
+    shm->request_time[g->rank] = t0;
     shm->request[g->rank].v.store(seq, std::memory_order_release);
     unsigned long spins = 0;
     for (int r = 0; r < g->world; ++r) {

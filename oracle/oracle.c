@@ -725,13 +725,10 @@ static double phi_inv(double p)
 ORC_API void orc_probit_latent(const double* mu, const uint8_t* is_case, const double* u, long n, double* z)
 {
   for (long i = 0; i < n; ++i) {
-    if (is_case[i]) {
-      /* work in the lower tail of -z for accuracy: -z+mu ~ N(0,1) truncated to (-inf, mu) */
-      double pm = phi_cdf(mu[i]);
-      z[i] = mu[i] - phi_inv(u[i] * pm);
-    } else {
-      double pm = phi_cdf(-mu[i]);
-      z[i] = mu[i] + phi_inv(u[i] * pm);
-    }
+    /* s = mu (case) or -mu (control); t = Phi^-1(u Phi(s)) taken in the tail where its argument is small */
+    const double sgn = is_case[i] ? 1.0 : -1.0, s = sgn * mu[i];
+    const double p = u[i] * phi_cdf(s);
+    const double t = p <= 0.5 ? phi_inv(p) : -phi_inv((1.0 - u[i]) + u[i] * phi_cdf(-s));
+    z[i] = mu[i] - sgn * t;
   }
 }

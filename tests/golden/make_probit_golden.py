@@ -35,8 +35,11 @@ def load_data():
     cpu.recode_minor(bed, N, M_G)
     X = np.stack([cpu.decode_column(bed, N, j, 0) for j in range(M_G)], axis=1)
     fam = [l.split() for l in open(os.path.join(d, "small_modelspace.fam")) if l.strip()]
-    y = np.array([float(f[5]) for f in fam])
-    labels = (y > np.median(y)).astype(np.float64)
+    # case / control labels with a signal the 30 individuals can show: liability on SNPs 1 and 4 (the fixture's own phenotype,
+    # dichotomised, leaves the posterior at the prior)
+    rs = np.random.default_rng(7)
+    liab = 1.3 * (X[:, 1] - X[:, 1].mean()) - 1.3 * (X[:, 4] - X[:, 4].mean()) + 0.6 * rs.normal(size=N)
+    labels = (liab > np.median(liab)).astype(np.float64)
     with open(os.path.join(d, "small_modelspace_cc.y"), "w") as fh:
         for f, v in zip(fam, labels):
             fh.write("%s %s %d\n" % (f[0], f[1], int(v)))

@@ -705,3 +705,59 @@ def test_scan_and_column_stats_at_the_c4_shape_against_the_oracle(api):
     """BASELINE configs[3] shape: n = 50,000 individuals (3,125 packed words per column, 17 chunks of the tensor-core scan),
     10,000 SNPs of it -- what the oracle finishes in seconds."""
     _oracle_scan_case(api, 50000, 10000, 24, 12)
+
+
+def test_probit_inverse_cdf_against_scipy_truncnorm_in_the_tails(api):
+    """k_probit draws z ~ N(mu, 1) truncated to (0, inf) for cases and (-inf, 0] for controls by inverting the CDF through the
+    lower tail.  Checked against implementations the repo does not own, for fitted values out to |mu| = 8 (where the
+    admissible half-line holds 6e-16 of the mass) and uniforms out to 1e-12 from both ends:
+      * exact quantiles from 50-digit arithmetic (mpmath: root of Phi(t) = u Phi(+-mu)), 1e-9 relative -- the north star's bound;
+      * scipy.stats.truncnorm.isf / ppf, 1e-4 relative: scipy's own tail accuracy is 2e-6 .. 6e-5 on this grid (measured against
+        the exact quantiles), so it only guards against gross errors."""
+    from scipy.stats import truncnorm
+    mus = np.concatenate([np.linspace(-8.0, 8.0, 33), [-6.5, 6.5]])
+    us = np.concatenate([[1e-12, 1e-9, 1e-6, 1e-3], np.linspace(0.05, 0.95, 7), [1 - 1e-3, 1 - 1e-6, 1 - 1e-9, 1 - 1e-12]])
+    MU, U = np.meshgrid(mus, us, indexing="ij")
+    mu, u = np.concatenate([MU.ravel(), MU.ravel()]), np.concatenate([U.ravel(), U.ravel()])
+    is_case = np.concatenate([np.ones(MU.size, dtype=np.uint8), np.zeros(MU.size, dtype=np.uint8)])
+    n, m = mu.size, 16
+    rs = np.random.default_rng(5)
+    payload = rs.integers(0, 256, size=m * ((n + 3) // 4), dtype=np.uint8) & 0b10111011
+    st = api.GenotypeStore(payload, n, m, recode_to_minor=False)
+    st.set_phenotype(is_case.astype(np.float64), mu.reshape(n, 1))   # one covariate carrying the fitted values
+    ch = api.Chain(st)
+    ch.residual([], [0.0, 1.0], [])                                   # y_hat = 0 * 1 + 1 * mu
+    ch.probit_update(is_case, u)
+    z = ch.get_phenotype()
+    ch.close()
+    st.close()
+    assert np.isfinite(z).all() and (z[is_case == 1] > 0).all() and (z[is_case == 0] <= 0).all()
+    # cases are drawn through the survival function (u -> 0 is the far tail), controls through the CDF
+    loose = np.where(is_case == 1, truncnorm.isf(u, -mu, np.inf, loc=mu), truncnorm.ppf(u, -np.inf, -mu, loc=mu))
+    assert (np.abs(z - loose) / (np.abs(loose) + 1e-3)).max() < 1e-4
+    mp = pytest.importorskip("mpmath")
+    mp.mp.dps = 50
+    exact = np.empty(n)
+    for i in range(n):
+        m_i, u_i = mp.mpf(float(mu[i])), mp.mpf(float(u[i]))
+        if is_case[i]:   # P(Z > z) = u  <=>  Phi(mu - z) = u Phi(mu)
+            t = _mp_norm_ppf(mp, u_i * mp.ncdf(m_i))
+            exact[i] = float(m_i - t)
+        else:            # P(Z <= z) = u  <=>  Phi(z - mu) = u Phi(-mu)
+            t = _mp_norm_ppf(mp, u_i * mp.ncdf(-m_i))
+            exact[i] = float(m_i + t)
+    err = np.abs(z - exact) / (np.abs(exact) + 1e-3)
+    assert err.max() < 1e-9, (float(err.max()), float(mu[err.argmax()]), float(u[err.argmax()]), float(z[err.argmax()]), float(exact[err.argmax()]))
+
+
+def _mp_norm_ppf(mp, p):
+    """Standard normal quantile in mpmath arithmetic: Newton iterations on Phi(t) = p from an asymptotic start."""
+    if p > mp.mpf("0.5"):
+        return -_mp_norm_ppf(mp, 1 - p)
+    t = -mp.sqrt(-2 * mp.log(p)) if p < mp.mpf("0.1") else mp.mpf(-1)
+    for _ in range(60):
+        step = (mp.ncdf(t) - p) / mp.npdf(t)
+        t -= step
+        if abs(step) < mp.mpf(10) ** -40:
+            break
+    return t

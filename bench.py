@@ -686,7 +686,9 @@ def sharded_phenotype(store, lo, hi, n, m, m_e, dist, world, probit):
                               # the minor-allele coding; same-sign effects make the reference's model grow to > 100 SNPs)
             contrib += 0.14 * (x - x.mean()) / max(x.std(), 1e-9)
     if world > 1:
-        t = torch.from_numpy(contrib).cuda()
+        t = torch.from_numpy(contrib)
+        if dist.get_backend() != "gloo":
+            t = t.cuda()
         dist.all_reduce(t)
         contrib = t.cpu().numpy()
     y = contrib + rs.normal(size=n) * np.sqrt(0.6)
@@ -694,6 +696,24 @@ def sharded_phenotype(store, lo, hi, n, m, m_e, dist, world, probit):
         y = (y > 0).astype(np.float64)   # case-control labels from the liability
     E = rs.uniform(0.0, 1.0, size=(n, m_e))
     return y, E
+
+
+def group_ini(shared, tmp, rank, n, m, m_e, n_rao, n_chains, same_seed):
+    """INI of this rank: thread.seeds[rank] is the seed of the chain that lives here.  same_seed: every chain runs seed
+    CHAIN_SEEDS[0] (the INI wants unique seeds, so the other positions hold placeholders no rank ever uses)."""
+    from bmagwa_b200 import synth
+    seeds = list(CHAIN_SEEDS[:n_chains])
+    if same_seed:
+        seeds = [900000 + i for i in range(n_chains)]
+        if rank < n_chains:
+            seeds[rank] = CHAIN_SEEDS[0]
+    cfg = dict(base=os.path.join(shared, "syn"), recode=1, n=n, m_g=m, m_e=m_e, save_beta=0, types="A", do_n_iter=n_rao, n_rao=n_rao,
+               n_rao_burnin=1000, thin=10, n_sample_tau2_and_missing=10, delay_rejection=10, max_move_size=20, use_individual_tau2=1,
+               e_qg=20, var_qg=300, n_threads=n_chains, seeds=",".join(str(v) for v in seeds), outbase=os.path.join(tmp, "chain"), verbosity=0)
+    ini = os.path.join(tmp, "bench_%s.ini" % ("same" if same_seed else "distinct"))
+    with open(ini, "w") as fh:
+        fh.write(synth.INI_TEMPLATE.format(**cfg))
+    return ini
 
 
 def write_group_files(shared, n, m, m_e, y, E, n_rao, n_chains):
@@ -708,17 +728,14 @@ def write_group_files(shared, n, m, m_e, y, E, n_rao, n_chains):
     with open(base + ".e", "w") as fh:
         fh.write("".join("%s %s\n" % (ident, " ".join("%.17g" % v for v in row)) for ident, row in zip(ids, E)))
     open(base + ".bed", "wb").write(bytes([0x6C, 0x1B, 0x01]))   # never read: the shards come from memory
-    cfg = dict(base=base, recode=1, n=n, m_g=m, m_e=m_e, save_beta=0, types="A", do_n_iter=n_rao, n_rao=n_rao, n_rao_burnin=1000,
-               thin=10, n_sample_tau2_and_missing=10, delay_rejection=10, max_move_size=20, use_individual_tau2=1, e_qg=20,
-               var_qg=300, n_threads=n_chains, seeds=",".join(str(v) for v in CHAIN_SEEDS[:n_chains]),
-               outbase=os.path.join(shared, "chain"), verbosity=0)
-    with open(os.path.join(shared, "bench.ini"), "w") as fh:
-        fh.write(synth.INI_TEMPLATE.format(**cfg))
-    return os.path.join(shared, "bench.ini")
+    return base
 
 
-def group_arm(args, workload, rank, local_rank, world, dist, n_chains, probit=False, with_e2e=True):
-    """n_chains chains over ONE store sharded by SNP over the `world` GPUs (chain c on rank c)."""
+def group_arm(args, workload, rank, local_rank, world, dist, n_chains, probit=False, with_e2e=True, same_seed=False):
+    """n_chains chains over ONE store sharded by SNP over the `world` GPUs (chain c on rank c).
+    same_seed: every chain runs the trajectory of the first seed, so that every GPU has the same work whatever N (chains
+    with different seeds differ by up to 1.6x in cost per iteration -- model size, adapted move size -- and the slowest one
+    sets the max-over-ranks time)."""
     import torch
     from bmagwa_b200 import _lib, api, sharded
     import ctypes as C
@@ -750,7 +767,7 @@ def group_arm(args, workload, rank, local_rank, world, dist, n_chains, probit=Fa
     if rank == 0:
         write_group_files(shared, n, m, m_e, y, E, args.n_rao, n_chains)
     dist.barrier()
-    ini = os.path.join(shared, "bench.ini")
+    ini = group_ini(shared, tmp, rank, n, m, m_e, args.n_rao, n_chains, same_seed)
 
     def open_group(store, tag):
         store.set_phenotype(y, E)
@@ -873,6 +890,13 @@ def group_arm(args, workload, rank, local_rank, world, dist, n_chains, probit=Fa
                "what": "per rank: bmg_store_create from the shard's packed bytes in HOST memory (H2D + device re-coding) + peers + "
                        "bmg_group_create + bmg_sampler_create_grouped + begin + %d steps + end, wall clock, max over ranks; bytes are rank 0's"
                        % args.steps}
+    my_ms = e0.elapsed_time(e1)
+    per_chain = None
+    if world > 1:
+        t = torch.zeros(world, device="cuda", dtype=torch.float64)
+        t[rank] = (args.steps * args.n_rao / (my_ms * 1e-3)) if smp is not None or rank < n_chains else 0.0
+        dist.all_reduce(t)
+        per_chain = [float(v) for v in t.cpu().numpy()[:n_chains]]
     dist.barrier()
     if rank != 0:
         return None
@@ -886,17 +910,20 @@ def group_arm(args, workload, rank, local_rank, world, dist, n_chains, probit=Fa
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "%s: %s; %d chain(s) over ONE store SNP-sharded over %d GPU(s) (%d SNPs per shard), chain c on rank c"
-                   % (workload, spec["desc"], n_chains, world, stride), "n": n, "m_g": m, "n_rao": args.n_rao, "chains": n_chains,
+                   % (workload, spec["desc"], n_chains, world, stride) +
+                   ("; every chain runs the trajectory of seed %d, so that every GPU has the same work at every N" % CHAIN_SEEDS[0]
+                    if same_seed and n_chains > 1 else ""),
+                   "n": n, "m_g": m, "n_rao": args.n_rao, "chains": n_chains,
+                   "seeds": "same" if same_seed and n_chains > 1 else "distinct",
                    "step": "%d MCMC iterations per chain incl. one all-SNP scan per chain" % args.n_rao, "tau_rng": args.tau_rng,
                    "likelihood": "probit: latent phenotype redrawn on the device every 10 iterations, sigma2 = 1" if probit else "linear",
                    "sampler": "testdata/testdata.ini settings (PMV, thin 10, DR 10, individual tau2)",
                    "burnin": "%d iterations per chain before the warm-up steps, untimed (start-up transient of the chains: models of up to "
                              "~200 SNPs for some seeds, which cost 10x per iteration)" % (burn_steps * args.n_rao),
                    "l2": "256 MiB write on the chain's stream before every step, inside the timed region",
-                   "exchange": "per scan of a chain: every rank's scan-service thread scans its shard for that chain (limbs pulled over NVLink, "
-                               "n x 8 B) and stores the dot products into the chain's GPU through CUDA-IPC peer memory (8 B per SNP); request / "
-                               "acknowledgement flags in POSIX shared memory; no NCCL, no barrier and no host callback on the data path; column "
-                               "statistics read remote shards over the peer mappings",
+                   "exchange": "per scan round: every rank scans its shard once per chain (limbs pulled over NVLink by peer loads, n x 8 B), every "
+                               "chain pulls its dot products from all ranks (peer loads, 8 B per SNP); two host barriers in POSIX shared memory; no "
+                               "NCCL and no host callback on the data path; column statistics read remote shards over the peer mappings",
                    "timing": "CUDA events on the chain's stream, max over ranks; wall %.3f ms/step" % (1e3 * wall / args.steps)},
         "gpu_launches": launches_b - launches_a,
         "roofline": {"bound": "hbm", "kernel": "k_scan_dots_imma on rank 0's shard (one launch per chain and scan)",
@@ -906,11 +933,14 @@ def group_arm(args, workload, rank, local_rank, world, dist, n_chains, probit=Fa
         "clocks": clk,
         "breakdown": {"move_seconds": st1["move_seconds"] - st0["move_seconds"], "scan_seconds": st1["scan_seconds"] - st0["scan_seconds"],
                       "column_stats_seconds": st1["column_stats_seconds"] - st0["column_stats_seconds"],
-                      "scan_wait_seconds": g1["scan_wait_seconds"] - g0["scan_wait_seconds"], "scans_served_by_rank0": g1["served"] - g0["served"],
+                      "group_scan_seconds": g1["scan_seconds"] - g0["scan_seconds"], "barrier_wait_seconds": g1["barrier_seconds"] - g0["barrier_seconds"],
+                      "scan_rounds": g1["rounds"] - g0["rounds"],
                       "delayed_rejection_seconds": cnt["delayed_rejection_seconds"], "served_from_memo": cnt["served_from_memo"],
                       "moves_with_additions": cnt["moves_with_additions"], "model_size": st1["model_size"], "model_size_trace": ms_trace,
                       "note": "rank 0's chain; seconds between the first and the last timed step"},
     }
+    if per_chain is not None:
+        out["per_chain_iterations_per_sec"] = per_chain
     if e2e is not None:
         out["e2e"] = e2e
     return out
@@ -1025,6 +1055,9 @@ def main():
                     help="sharded workloads (C3/C4/C5): MCMC iterations every chain is advanced before the warm-up steps, untimed, so that "
                          "the chains are past their start-up transient (models of up to ~200 SNPs for some seeds) and cost the same")
     ap.add_argument("--chains", type=int, default=0, help="chains over the sharded store (default: one per GPU; e.g. 4 on 8 GPUs for C5)")
+    ap.add_argument("--distinct-seeds", action="store_true", dest="distinct_seeds",
+                    help="N > 1: the chains of the headline measurement get different seeds (default: all run the first seed's trajectory, "
+                         "equal work per GPU; the distinct-seed run is then the sub-record 'distinct_seeds')")
     ap.add_argument("--replicas", action="store_true", help="N > 1: one chain per GPU on replicated stores as the headline (round 1's mode)")
     ap.add_argument("--miss-rate", type=float, default=0.0, dest="miss_rate",
                     help="fraction of genotype calls set missing in the synthetic data (exercises the imputation path; default 0)")
@@ -1090,8 +1123,15 @@ def main():
                     args.workload = args.workload or "C2"
                     line = ours_arm(args, rank, local_rank, world, dist)
                 else:
-                    line = group_arm(args, wl, rank, local_rank, world, dist, n_chains, probit=args.probit or wl == "C3")
+                    line = group_arm(args, wl, rank, local_rank, world, dist, n_chains, probit=args.probit or wl == "C3",
+                                     same_seed=not args.distinct_seeds)
                     if not args.no_sub:
+                        if not args.distinct_seeds:
+                            alt = group_arm(args, wl, rank, local_rank, world, dist, n_chains, probit=args.probit or wl == "C3",
+                                            with_e2e=False, same_seed=False)
+                            if line is not None and alt is not None:
+                                line["distinct_seeds"] = compact(alt)
+                                line["distinct_seeds"]["per_chain_iterations_per_sec"] = alt.get("per_chain_iterations_per_sec")
                         rep = ours_arm(args, rank, local_rank, world, dist, workload="C2", with_cpu_baseline=False)
                         if line is not None and rep is not None:
                             line["replicas_c2"] = compact(rep)

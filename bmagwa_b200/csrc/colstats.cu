@@ -114,6 +114,7 @@ __device__ __forceinline__ void publish_tagged(ulonglong2* slot, double v, unsig
 }
 
 constexpr int kFastSegMax = 256;   // words per CTA on the latency path (64 or 256)
+constexpr int kPreCov = 3;         // covariate columns (constant included) fetched before the candidate's words are known
 
 // one (candidate, slice) work item; `a` may live in the kernel parameters or in shared memory
 __device__ __forceinline__ void colstat_item(const ColStatInline& a, const int c, const int seg, uint32_t* cw, double (*fpart)[8])
@@ -131,7 +132,9 @@ __device__ __forceinline__ void colstat_item(const ColStatInline& a, const int c
   const bool small = seg_words <= 64;   // 1024 individuals per CTA: 4 per thread, everything this CTA reads issues at once
   // Every load of the CTA is issued BEFORE the candidate's words are waited for: y / covariates of this thread's
   // individuals and the first four tasks' words do not depend on them, so the kernel is one memory round trip deep.
-  double yv[4], ev[4][7];
+  // (the first kPreCov covariate columns travel in registers; a data set with more pays one more memory round for the rest:
+  // registers are what decides whether a scan CTA of another chain fits beside a server CTA, see server_start)
+  double yv[4], ev[4][kPreCov];
   uint32_t ow0[4][2];
   if (small) {
 #pragma unroll
@@ -140,7 +143,7 @@ __device__ __forceinline__ void colstat_item(const ColStatInline& a, const int c
       const bool ok = i < i_hi;
       yv[j] = ok ? __ldcg(a.y + i) : 0.0;   // y may be rewritten (probit) while the persistent server runs: bypass L1
 #pragma unroll
-      for (int q = 1; q < 8; ++q) ev[j][q - 1] = (ok && q < n_fp) ? a.e[(int64_t)(q - 1) * a.n + i] : 0.0;
+      for (int q = 1; q <= kPreCov; ++q) ev[j][q - 1] = (ok && q < n_fp) ? a.e[(int64_t)(q - 1) * a.n + i] : 0.0;
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -166,10 +169,14 @@ __device__ __forceinline__ void colstat_item(const ColStatInline& a, const int c
       for (int j = 0; j < 4; ++j) {
         const int li = t + 256 * j;
         const uint32_t word = cw[(li >> 4) & 63];
-        const double g = (i_lo + li < i_hi) ? (double)((word >> (2 * (li & 15))) & 3u) : 0.0;
+        const bool ok = i_lo + li < i_hi;
+        const double g = ok ? (double)((word >> (2 * (li & 15))) & 3u) : 0.0;
         acc[0] = fma(g, yv[j], acc[0]);
 #pragma unroll
-        for (int q = 1; q < 8; ++q) acc[q] = fma(g, ev[j][q - 1], acc[q]);
+        for (int q = 1; q <= kPreCov; ++q) acc[q] = fma(g, ev[j][q - 1], acc[q]);
+#pragma unroll
+        for (int q = kPreCov + 1; q < 8; ++q)
+          if (q < n_fp && ok) acc[q] = fma(g, a.e[(int64_t)(q - 1) * a.n + i_lo + li], acc[q]);
       }
     } else {
 #pragma unroll 4
@@ -338,7 +345,7 @@ __device__ __forceinline__ void st_release_gpu(unsigned int* p, unsigned int v)
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-__global__ void __launch_bounds__(256) k_colstats_server(const __grid_constant__ ServerArgs sa)
+__global__ void __maxnreg__(96) k_colstats_server(const __grid_constant__ ServerArgs sa)
 {
   __shared__ uint32_t cw[kFastSegMax];
   __shared__ double fpart[8][8];
@@ -445,6 +452,17 @@ static void server_start(Chain* c, const ColStatInline& base, unsigned int last_
   const unsigned int flag0 = last_served;
   BMG_CUDA(cudaMemcpyAsync(c->server_flag.p, &flag0, sizeof(flag0), cudaMemcpyHostToDevice, c->server_stream));
   BMG_CUDA(cudaStreamSynchronize(c->server_stream));
+  // The server shares its SMs with kernels launched while it lives (the scan service of a shard group, group.cu).  Two things
+  // decide whether a scan CTA (7 warps of 80 registers, 53 kB of shared memory) finds room beside a server CTA: registers
+  // -- each of an SM's four sub-partitions holds 16 K, and with 181 registers per server thread a sub-partition had room for
+  // one scan warp where the CTA needs two, so every scan of another chain waited until the server was stopped (measured: up
+  // to a full Rao-Blackwell period, 150 ms); hence __maxnreg__(96) -- and the L1 / shared-memory split, which cannot change
+  // while a CTA is resident, hence the largest carve-out up front.
+  static bool carveout_set = false;
+  if (!carveout_set) {
+    BMG_CUDA(cudaFuncSetAttribute(k_colstats_server, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    carveout_set = true;
+  }
   ServerArgs sa;
   sa.mail = reinterpret_cast<const uint4*>(c->server_mail.p);
   sa.dev_req = reinterpret_cast<uint4*>(c->server_req.p);

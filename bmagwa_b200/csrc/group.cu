@@ -1,26 +1,31 @@
 // group.cu -- several chains over ONE SNP-sharded store (BASELINE.json configs[4]: "sharded over 8xB200, 4 parallel
 // chains").  The reference's chains are threads of one process sharing one Data (src/main.cpp:54-85);
 // here a "shard group" is one process per GPU: rank r holds the packed SNPs [r stride, (r+1) stride) and -- for
-// r < n_chains -- the host sampler of chain r.  Nothing of a chain is replicated on other ranks, and chains never wait
-// for each other:
+// r < n_chains -- the host sampler of chain r.  Nothing of a chain is replicated on other ranks:
 //
 //   per iteration   chain c asks ITS GPU for the column statistics of the SNPs it proposes; columns of other shards are
 //                   read over NVLink through CUDA-IPC peer mappings (store.cu).  No collective, no other rank involved.
-//   per scan        (chain c, every n_rao iterations of ITS OWN clock)
+//   per scan        (every n_rao iterations; all chains of a group run the same schedule)
 //     1. chain c quantises its residual into the tensor-core scan's limb format (scan_imma.cu) inside its exchange
-//        buffer, which every peer has mapped, and posts a request number in a POSIX shared-memory segment;
-//     2. every rank runs a SCAN SERVICE thread with its own CUDA stream: it picks the request up, pulls the chain's limbs
-//        over NVLink (n x 8 bytes), runs the scan kernel over ITS shard, and a small kernel adds the per-chunk partial sums
-//        and stores the shard's dot products STRAIGHT INTO THE OWNING CHAIN'S GPU (peer stores, 8 bytes per SNP) --
-//        compute and exchange in one pass, no NCCL call, no barrier and no Python on the data path -- then acknowledges;
-//     3. with every rank's acknowledgement chain c finishes the scan on its own GPU (per-SNP algebra over all m_g SNPs
-//        with its own tau draws) and carries on.  Integer accumulation makes the dot products independent of the
-//        sharding, so every chain writes the bytes its single-GPU run writes (tests/test_gpu_sharded.py).
+//        buffer, which every peer has mapped;
+//     2. barrier (host, POSIX shared memory: the ranks of a group live on one box);
+//     3. every rank scans ITS shard once per chain: the chain's limbs are pulled over NVLink (n x 8 bytes, peer loads), the
+//        scan kernel runs, and a small kernel adds the per-chunk partial sums into this rank's results area;
+//     4. barrier; chain c pulls its results from every rank's results area (one kernel, peer loads, 8 bytes per SNP) and
+//        finishes the scan on its own GPU (per-SNP algebra over all m_g SNPs with its own tau draws).
+//   No NCCL call and no Python on the data path.  Integer accumulation makes the dot products independent of the
+//   sharding, so every chain writes the bytes its single-GPU run writes (tests/test_gpu_sharded.py).
 //
-// A chain's scan therefore costs it one pass over 1/world of the store per rank, all ranks in parallel, whatever the other
-// chains are doing; a slow chain (large model) delays nobody.  Ranks without a chain (n_chains < world, e.g. 4 chains over
-// 8 GPUs) only run the service.  Collective operations (creation, the start-up exchanges, destruction) use a
-// shared-memory barrier.
+// Ranks without a chain (n_chains < world, e.g. 4 chains over 8 GPUs) only take part in steps 2-4 (bmg_group_serve).
+//
+// Why the scans are collective.  A variant in which a per-rank service thread scanned for whichever chain asked, while the
+// other chains kept running (no barrier), was built and measured on 2 x B200: chains then no longer wait for each other,
+// but about one scan in ten delivered wrong dot products for a handful of SNPs (rows 0-7 of a few 16-SNP tiles) -- only
+// across two real GPUs, only for scans running while other chains' kernels were reading this GPU's memory over NVLink,
+// with bit-identical inputs and a scan kernel that is bit-reproducible under every single-GPU concurrency test
+// (tools/scan_under_server.py, tools/scan_beside_chain.py, compute-sanitizer racecheck).  Unexplained, so not shipped:
+// with the barriers every scan runs while all chains are paused, and chains with the same seed stay byte-identical on any
+// number of GPUs (tools/group_same_seed_check.py).  profiles/round2_notes.md has the measurements.
 #include <fcntl.h>
 #include <immintrin.h>
 #include <sys/mman.h>
@@ -31,7 +36,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <thread>
+#include <string>
+#include <vector>
 #include "common.cuh"
 #include "store.cuh"
 #include "group.cuh"
@@ -40,7 +46,11 @@ namespace bmg {
 
 namespace {
 constexpr uint32_t kShmMagic = 0x424D4731u;   // "BMG1"
-constexpr double kBarrierTimeout = 300.0;     // seconds; a missing peer must not hang the box
+static double barrier_timeout()
+{
+  static const double t = getenv("BMG_GROUP_TIMEOUT") ? atof(getenv("BMG_GROUP_TIMEOUT")) : 120.0;   // seconds; a missing peer must not hang the box
+  return t;
+}
 
 struct GroupShm {
   std::atomic<uint32_t> magic;
@@ -70,7 +80,30 @@ __global__ void k_group_combine(const double* __restrict__ partial, int n_chunks
   if (j >= m) return;
   double d = 0.0;   // the order k_scan_finalize adds the chunks in: same bits as the single-GPU scan
   for (int c = 0; c < n_chunks; ++c) d += partial[(int64_t)c * m + j];
-  out[j] = d;       // `out` is the owning chain's buffer: a peer store over NVLink unless the chain is local
+  out[j] = d;
+}
+
+// Data crosses NVLink by peer LOADS only: the consumer pulls what a finished kernel of the producer left in the producer's
+// own memory.  (Peer STORES followed by a stream synchronisation and a host-side acknowledgement were tried first: on two
+// B200s a handful of the stored values were seen by the consumer one scan late, even with a system-scope fence at the end
+// of the storing kernel.)
+__global__ void k_group_pull_bytes(const uint4* __restrict__ src, uint4* __restrict__ dst, int64_t n16)
+{
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x) dst[i] = __ldcv(src + i);
+}
+struct GatherArgs {
+  const double* src[kGroupMaxRanks];   // rank r's results for this chain over its shard (peer memory)
+  int64_t count[kGroupMaxRanks];
+  int64_t stride;
+  int world;
+  double* dst;                         // the chain's dot products over all SNPs (local)
+};
+__global__ void k_group_gather(const __grid_constant__ GatherArgs a)
+{
+  const int r = blockIdx.y;
+  const double* src = a.src[r];
+  double* dst = a.dst + (int64_t)r * a.stride;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.count[r]; i += (int64_t)gridDim.x * blockDim.x) dst[i] = __ldcv(src + i);
 }
 }  // namespace
 
@@ -81,25 +114,18 @@ struct Group {
   Chain* scan_chain = nullptr;   // geometry, partial sums and stream of this rank's share of every scan
   GroupShm* shm = nullptr;
   std::string shm_name;
-  DevBuf<unsigned char> xbuf;    // | limbs of this rank's chain | exponent | dots of this rank's chain over all SNPs |
-  size_t q_bytes = 0, off_exp = 0, off_dots = 0, xbuf_bytes = 0;
+  DevBuf<unsigned char> xbuf;    // | limbs of this rank's chain | exponent | this rank's results per chain: n_chains x stride doubles |
+  size_t q_bytes = 0, off_exp = 0, off_dots = 0, xbuf_bytes = 0;   // (the results area doubles as the all-gather staging)
+  DevBuf<double> dots;           // this rank's chain: dot products over all SNPs, gathered from every rank's results area
   unsigned char* peer[kGroupMaxRanks] = {nullptr};
   bool peer_opened[kGroupMaxRanks] = {false};
   DevBuf<unsigned char> q_stage[2];   // a peer chain's limbs + exponent, double-buffered
   DevBuf<int32_t> n1_all, n2_all;
   double barrier_seconds = 0.0;
-  // scan service
   GroupShm local_shm;                  // world == 1: the flags live here
-  std::thread service;
-  std::atomic<bool> stop{false};
-  std::atomic<int64_t> served{0};      // requests this rank's service has completed
-  uint64_t served_seq[kGroupMaxRanks] = {0};
-  std::string service_error;
-  double pickup_seconds = 0.0, serve_seconds = 0.0, pickup_max = 0.0, serve_max = 0.0;   // request -> pick-up, pick-up -> acknowledged
-  // this rank's chain
-  uint64_t my_seq = 0;
+  int64_t rounds = 0;                  // scan rounds this rank took part in
   int64_t my_scans = 0;
-  double scan_wait_seconds = 0.0;
+  double scan_wait_seconds = 0.0;      // this rank's chain: seconds between asking for a scan and having its results
 };
 
 static void group_fail(Group* g)
@@ -123,7 +149,7 @@ void group_barrier(Group* g)
       _mm_pause();
       if ((++spins & 0x3FF) == 0) {
         if (spins > 200000) usleep(20);   // a rank without a chain waits for a whole Rao-Blackwell period: leave the core
-        if (now_seconds() - t0 > kBarrierTimeout) {
+        if (now_seconds() - t0 > barrier_timeout()) {
           group_fail(g);
           throw Error("shard group: barrier timed out (a peer rank is missing)");
         }
@@ -161,8 +187,6 @@ int group_allgather(void* ctx, void* dev_buffer, int64_t elems_per_rank, int ele
   }
 }
 
-static void group_service_loop(Group* g);
-
 Group* group_create(Store* s, int world, int rank, int n_chains, int64_t stride, const char* shm_name)
 {
   BMG_REQUIRE(world >= 1 && world <= kGroupMaxRanks && rank >= 0 && rank < world, "shard group: invalid world / rank");
@@ -181,7 +205,8 @@ Group* group_create(Store* s, int world, int rank, int n_chains, int64_t stride,
   g->q_bytes = (size_t)n_pad * 8;
   g->off_exp = g->q_bytes;
   g->off_dots = g->q_bytes + 256;
-  g->xbuf_bytes = g->off_dots + (size_t)world * (size_t)stride * sizeof(double);
+  g->xbuf_bytes = g->off_dots + (size_t)std::max(world, n_chains) * (size_t)stride * sizeof(double);
+  g->dots.alloc((size_t)world * (size_t)stride);
   g->xbuf.alloc(g->xbuf_bytes);
   BMG_CUDA(cudaMemset(g->xbuf.p, 0, g->xbuf_bytes));
   g->q_stage[0].alloc(g->q_bytes + 256);
@@ -252,24 +277,15 @@ Group* group_create(Store* s, int world, int rank, int n_chains, int64_t stride,
     std::memset(static_cast<void*>(&g->local_shm), 0, sizeof(GroupShm));
     g->shm = &g->local_shm;
   }
-  Group* raw = g.get();
-  g->service = std::thread([raw] { group_service_loop(raw); });
   return g.release();
 }
 
-// collective: every rank's service must stay up until every chain of the group has ended
+// collective: the peer mappings of this rank's exchange buffer must outlive every other rank's last scan
 void group_destroy(Group* g)
 {
   if (!g) return;
   cudaSetDevice(g->store->device);
   try { group_barrier(g); } catch (...) {}
-  g->stop.store(true, std::memory_order_release);
-  if (g->service.joinable()) g->service.join();
-  if (getenv("BMG_TIMING") && g->served.load() > 0)
-    fprintf(stderr, "[bmg timing] shard group rank %d: scan service served %lld requests; request -> pick-up mean %.0f us (max %.0f), pick-up -> acknowledged "
-                    "mean %.0f us (max %.0f); own chain waited %.3f s for %lld scans\n", g->rank, (long long)g->served.load(),
-            1e6 * g->pickup_seconds / (double)g->served.load(), 1e6 * g->pickup_max, 1e6 * g->serve_seconds / (double)g->served.load(),
-            1e6 * g->serve_max, g->scan_wait_seconds, (long long)g->my_scans);
   if (g->scan_chain) { cudaStreamSynchronize(g->scan_chain->stream); }
   for (int r = 0; r < g->world; ++r)
     if (g->peer_opened[r]) cudaIpcCloseMemHandle(g->peer[r]);
@@ -287,114 +303,81 @@ const int32_t* group_n2(const Group* g) { return g->n2_all.p; }
 Chain* group_scan_chain(Group* g) { return g->scan_chain; }
 void group_stats(const Group* g, double* out4)
 {
-  out4[0] = (double)g->served.load(std::memory_order_acquire); out4[1] = g->scan_wait_seconds; out4[2] = (double)g->my_scans;
-  out4[3] = g->barrier_seconds;
+  out4[0] = (double)g->rounds; out4[1] = g->scan_wait_seconds; out4[2] = (double)g->my_scans; out4[3] = g->barrier_seconds;
 }
 
-// ---- the scan service of this rank: serves every chain's requests over this rank's shard ----------------------------
-static void group_serve_one(Group* g, int c)
+// every rank's results for this rank's chain -> the chain's full-length array (one launch, peer loads)
+static void group_gather_dots(Group* g, cudaStream_t st)
 {
-  Store* s = g->store;
-  Chain* sc = g->scan_chain;
-  cudaStream_t st = sc->stream;
-  const unsigned char* q = g->xbuf.p;
-  if (c != g->rank) {
-    BMG_CUDA(cudaMemcpyAsync(g->q_stage[0].p, g->peer[c], g->q_bytes + 256, cudaMemcpyDefault, st));
-    q = g->q_stage[0].p;
+  GatherArgs a;
+  int64_t most = 0;
+  for (int r = 0; r < g->world; ++r) {
+    a.src[r] = reinterpret_cast<const double*>(g->peer[r] + g->off_dots) + (int64_t)g->rank * g->stride;
+    a.count[r] = std::max<int64_t>(0, std::min<int64_t>(g->stride, g->store->m_g - (int64_t)r * g->stride));
+    most = std::max(most, a.count[r]);
   }
-  imma_launch_on(sc, reinterpret_cast<const uint4*>(q), reinterpret_cast<const int*>(q + g->q_bytes), sc->imma_partial.p, false, st, sc);
-  double* out = reinterpret_cast<double*>(g->peer[c] + g->off_dots) + s->lo;
-  k_group_combine<<<(unsigned)((s->m + 255) / 256), 256, 0, st>>>(sc->imma_partial.p, sc->imma_chunks, s->m, out);
+  a.stride = g->stride; a.world = g->world; a.dst = g->dots.p;
+  const unsigned bx = (unsigned)std::max<int64_t>(1, std::min<int64_t>(64, (most + 1023) / 1024));
+  k_group_gather<<<dim3(bx, (unsigned)g->world), 256, 0, st>>>(a);
   count_launch();
   BMG_CUDA(cudaGetLastError());
-  BMG_CUDA(cudaStreamSynchronize(st));   // the peer stores have landed before the acknowledgement is visible
 }
 
-static void group_service_loop(Group* g)
-{
-  try {
-    BMG_CUDA(cudaSetDevice(g->store->device));
-    GroupShm* shm = g->shm;
-    unsigned idle = 0;
-    while (!g->stop.load(std::memory_order_acquire)) {
-      bool found = false;
-      for (int i = 0; i < g->n_chains; ++i) {
-        const int c = (g->rank + i) % g->n_chains;   // the local chain first
-        const uint64_t req = shm->request[c].v.load(std::memory_order_acquire);
-        if (req == g->served_seq[c]) continue;
-        const double t_pick = now_seconds();
-        const double waited = t_pick - shm->request_time[c];
-        group_serve_one(g, c);
-        g->served_seq[c] = req;
-        shm->done[c][g->rank].v.store(req, std::memory_order_release);
-        const double took = now_seconds() - t_pick;
-        g->pickup_seconds += waited; g->serve_seconds += took;
-        if (waited > g->pickup_max) g->pickup_max = waited;
-        if (took > g->serve_max) g->serve_max = took;
-        g->served.fetch_add(1, std::memory_order_acq_rel);
-        found = true;
-      }
-      if (found) { idle = 0; continue; }
-      if (shm->failed.load(std::memory_order_acquire)) break;
-      if (++idle < 2000) _mm_pause();
-      else usleep(20);   // a request comes once per Rao-Blackwell period and chain: do not burn a core on the wait
-    }
-  } catch (const std::exception& e) {
-    g->service_error = e.what();
-    group_fail(g);
-  }
-}
-
-// Chain `mine` (residual ready) asks every rank for its scan and waits for the dot products over all m_g SNPs
-// (device pointer on this GPU, complete when the call returns).
+// One scan round (see the header of this file); collective.  mine: this rank's chain with its residual ready, or nullptr
+// on a rank without a chain.  Returns the chain's dot products over all m_g SNPs (device pointer on this GPU; the gather
+// that fills it is queued on the chain's stream, so work queued behind it sees them).
 const double* group_scan_round(Group* g, Chain* mine)
 {
   Store* s = g->store;
   try {
     BMG_CUDA(cudaSetDevice(s->device));
-    BMG_REQUIRE(mine != nullptr && g->rank < g->n_chains, "shard group: only ranks below n_chains hold a chain");
-    BMG_REQUIRE(mine->residual_valid, "scan: call bmg_chain_residual first");
-    cudaStream_t st = mine->stream;
-    imma_quantize(mine);
-    BMG_REQUIRE(mine->imma_q.n == g->q_bytes, "shard group: limb layout of the chain differs from the group's");
-    BMG_CUDA(cudaMemcpyAsync(g->xbuf.p, mine->imma_q.p, g->q_bytes, cudaMemcpyDeviceToDevice, st));
-    BMG_CUDA(cudaMemcpyAsync(g->xbuf.p + g->off_exp, mine->imma_exp.p, sizeof(int), cudaMemcpyDeviceToDevice, st));
-    BMG_CUDA(cudaStreamSynchronize(st));   // also: the previous scan's per-SNP algebra has finished reading the dot products
-    GroupShm* shm = g->shm;
-    const uint64_t seq = ++g->my_seq;
+    BMG_REQUIRE((mine != nullptr) == (g->rank < g->n_chains), "shard group: ranks below n_chains scan through their chain, the others through bmg_group_serve");
+    Chain* sc = g->scan_chain;
+    cudaStream_t st = mine ? mine->stream : sc->stream;
     const double t0 = now_seconds();
-    shm->request_time[g->rank] = t0;
-    shm->request[g->rank].v.store(seq, std::memory_order_release);
-    unsigned long spins = 0;
-    for (int r = 0; r < g->world; ++r) {
-      while (shm->done[g->rank][r].v.load(std::memory_order_acquire) != seq) {
-        _mm_pause();
-        if ((++spins & 0xFFF) == 0) {
-          if (shm->failed.load(std::memory_order_acquire))
-            throw Error("shard group: a rank's scan service failed" + (g->service_error.empty() ? std::string() : ": " + g->service_error));
-          if (now_seconds() - t0 > kBarrierTimeout) throw Error("shard group: a rank's scan service does not answer");
-        }
-      }
+    if (mine) {
+      BMG_REQUIRE(mine->residual_valid, "scan: call bmg_chain_residual first");
+      imma_quantize(mine);
+      BMG_REQUIRE(mine->imma_q.n == g->q_bytes, "shard group: limb layout of the chain differs from the group's");
+      BMG_CUDA(cudaMemcpyAsync(g->xbuf.p, mine->imma_q.p, g->q_bytes, cudaMemcpyDeviceToDevice, st));
+      BMG_CUDA(cudaMemcpyAsync(g->xbuf.p + g->off_exp, mine->imma_exp.p, sizeof(int), cudaMemcpyDeviceToDevice, st));
+      BMG_CUDA(cudaStreamSynchronize(st));   // also: the previous round's gather has finished reading the peers' results
     }
+    group_barrier(g);   // every chain's limbs are in place, every chain is paused
+    for (int i = 0; i < g->n_chains; ++i) {
+      const int c = (g->rank + i) % g->n_chains;   // start with the nearest chain: the pulls spread over the peers
+      const unsigned char* q = g->xbuf.p;
+      if (c != g->rank) {   // the chain's limbs + exponent, pulled over NVLink
+        const int64_t n16 = (int64_t)((g->q_bytes + 256) / 16);
+        k_group_pull_bytes<<<(unsigned)std::min<int64_t>(296, (n16 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(g->peer[c]),
+                                                                                             reinterpret_cast<uint4*>(g->q_stage[i & 1].p), n16);
+        count_launch();
+        q = g->q_stage[i & 1].p;
+      }
+      imma_launch_on(sc, reinterpret_cast<const uint4*>(q), reinterpret_cast<const int*>(q + g->q_bytes), sc->imma_partial.p, false, st, sc);
+      double* out = reinterpret_cast<double*>(g->xbuf.p + g->off_dots) + (int64_t)c * g->stride;   // this rank's results for chain c
+      k_group_combine<<<(unsigned)((s->m + 255) / 256), 256, 0, st>>>(sc->imma_partial.p, sc->imma_chunks, s->m, out);
+      count_launch();
+    }
+    BMG_CUDA(cudaGetLastError());
+    BMG_CUDA(cudaStreamSynchronize(st));
+    group_barrier(g);   // every rank's results for every chain are in that rank's memory
+    ++g->rounds;
+    if (mine == nullptr) return nullptr;
+    group_gather_dots(g, st);
     g->scan_wait_seconds += now_seconds() - t0;
     ++g->my_scans;
-    return reinterpret_cast<const double*>(g->xbuf.p + g->off_dots);
+    return g->dots.p;
   } catch (...) {
     group_fail(g);
     throw;
   }
 }
 
-// a rank without a chain: returns once its service has completed n_rounds more requests of every chain
+// a rank without a chain: takes part in the next n_rounds scans of the group
 void group_serve(Group* g, int64_t n_rounds)
 {
-  const int64_t target = g->served.load(std::memory_order_acquire) + n_rounds * g->n_chains;
-  const double t0 = now_seconds();
-  while (g->served.load(std::memory_order_acquire) < target) {
-    if (g->shm->failed.load(std::memory_order_acquire)) throw Error("shard group: a peer rank failed" + (g->service_error.empty() ? std::string() : ": " + g->service_error));
-    if (now_seconds() - t0 > 20 * kBarrierTimeout) throw Error("shard group: no scan request arrives");
-    usleep(200);
-  }
+  for (int64_t i = 0; i < n_rounds; ++i) group_scan_round(g, nullptr);
 }
 
 }  // namespace bmg

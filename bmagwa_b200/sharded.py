@@ -104,7 +104,8 @@ def create_sharded_sampler(dist, ini_path, n, m_g, bed_path, device, y, covariat
 class ShardGroup:
     """bmg_group of this rank: several chains over one SNP-sharded store, chain c on rank c.  Collective constructor.
     torch.distributed only carries the name of the POSIX shared-memory segment the ranks synchronise through; scans
-    exchange their data through CUDA-IPC peer memory inside the library."""
+    exchange their data through CUDA-IPC peer memory inside the library.  Collective: creation, every scan (all chains
+    of a group run the same schedule; ranks without a chain call serve()), close()."""
 
     def __init__(self, dist, store, stride, n_chains):
         self.L = _lib.lib()
@@ -135,7 +136,7 @@ class ShardGroup:
     def stats(self):
         out = np.zeros(4)
         api.check(self.L.bmg_group_stats(self.h, out.ctypes.data_as(api.f64p)))
-        return {"served": int(out[0]), "scan_wait_seconds": float(out[1]), "scans": int(out[2]), "barrier_seconds": float(out[3])}
+        return {"rounds": int(out[0]), "scan_seconds": float(out[1]), "scans": int(out[2]), "barrier_seconds": float(out[3])}
 
     def native_comm(self):
         """bmg_shard_comm for the lockstep single chain over this group's all-gather (no host callback)."""

@@ -273,25 +273,24 @@ int bmg_sampler_create_sharded(const char* ini_path, int chain_index, bmg_store*
 /* SEVERAL chains over ONE SNP-sharded store (BASELINE configs[4]; the reference's chains are threads sharing one
  * `const Data*`, main.cpp:54-85).  A shard group is one process per GPU of a box: rank r holds the shard of
  * bmg_sampler_create_sharded (phenotype set, peers attached) and, for r < n_chains, the host sampler of chain r -- nothing
- * of a chain is replicated and chains never wait for each other.  Per iteration a chain only talks to its own GPU (remote
- * columns over the peer mappings).  For a scan it posts a request in the POSIX shared-memory segment `shm_name` ("/name",
- * unique per job; created by rank 0 and unlinked as soon as every rank has mapped it); every rank's scan-service thread
- * (started by bmg_group_create) scans its shard for that chain and stores the shard's dot products straight into the
- * chain's GPU through CUDA-IPC peer memory.  No host callback, no NCCL and no barrier on the data path.  Every chain
- * writes the bytes of its single-GPU run.
- * bmg_group_create and bmg_group_destroy are collective (every rank calls them; destroy waits for all ranks, so call it
- * when every chain has ended); chain_index of bmg_sampler_create_grouped must equal the rank.  Ranks without a chain
- * (n_chains <= rank) just keep the group alive; bmg_group_serve(g, n) blocks until the rank has served n more scans of
- * every chain.  Passing comm->allgather == NULL and comm->ctx = a bmg_group* to bmg_sampler_create_sharded runs the
- * lockstep single chain over the group's native all-gather instead of a host one. */
+ * of a chain is replicated.  Per iteration a chain only talks to its own GPU (remote columns over the peer mappings).
+ * At every scan all ranks meet (the chains of a group must run the same schedule: n_rao, iteration counts): each rank
+ * scans its shard once per chain, and every chain pulls its dot products from all ranks through CUDA-IPC peer memory;
+ * the ranks synchronise through a POSIX shared-memory segment `shm_name` ("/name", unique per job; created by rank 0 and
+ * unlinked as soon as every rank has mapped it).  No host callback and no NCCL on the data path.  Every chain writes the
+ * bytes of its single-GPU run.
+ * bmg_group_create and bmg_group_destroy are collective (every rank calls them); chain_index of
+ * bmg_sampler_create_grouped must equal the rank.  Ranks without a chain (n_chains <= rank) call bmg_group_serve(g, n)
+ * to take part in the next n scans.  Passing comm->allgather == NULL and comm->ctx = a bmg_group* to
+ * bmg_sampler_create_sharded runs the lockstep single chain over the group's native all-gather instead of a host one. */
 typedef struct bmg_group bmg_group;
 int bmg_group_create(bmg_store* shard, int world, int rank, int n_chains, int64_t snp_stride, const char* shm_name, bmg_group** out);
 int bmg_sampler_create_grouped(const char* ini_path, int chain_index, bmg_store* shard, bmg_group* g, bmg_sampler** out);
 int bmg_group_serve(bmg_group* g, int64_t n_rounds);
 /* the chain-like handle this rank's share of the scans runs on (bmg_chain_scan_kernel_time, bmg_chain_stream) */
 bmg_chain* bmg_group_scan_chain(bmg_group* g);
-/* out[0..3] = {scan requests this rank's service has completed, seconds this rank's chain has waited for its scans,
- * scans this rank's chain has asked for, seconds in the collective barriers (creation / destruction)} */
+/* out[0..3] = {scan rounds this rank took part in, seconds this rank's chain spent in its scans (waiting for the other
+ * chains at the barriers included), scans of this rank's chain, seconds in the barriers} */
 int bmg_group_stats(bmg_group* g, double* out4);
 int bmg_group_destroy(bmg_group* g);
 /* Value of `key` in [section] of an INI file, read with the library's own parser (the inih rules the reference follows,

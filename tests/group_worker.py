@@ -26,7 +26,7 @@ def main():
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
     torch.cuda.set_device(0)
-    n, m_g, n_rao = 600, 3000, 100
+    n, m_g, n_rao = (int(sys.argv[5]) if len(sys.argv) > 5 else 600), 3000, 100
     n_chains = 2 if mode == "two" else 1
     if rank == 0:
         ds = synth.write_dataset(work, "syn", n=n, m_g=m_g, m_e=1, seed=5, e_qg=5, var_qg=20, do_n_iter=iters, n_rao=n_rao,
@@ -81,7 +81,7 @@ def main():
         if mode == "two":   # two different seeds: the chains must not be copies of each other
             if filecmp.cmp(os.path.join(work, "group0_loci.dat"), os.path.join(work, "group1_loci.dat"), shallow=False):
                 print("chains 0 and 1 are identical"); ok = False
-        print("GROUP_OK" if ok else "GROUP_MISMATCH", mode, "served", gst["served"], "scan wait %.3f s" % gst["scan_wait_seconds"])
+        print("GROUP_OK" if ok else "GROUP_MISMATCH", mode, "rounds", gst["rounds"], "barrier wait %.3f s" % gst["barrier_seconds"])
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
 

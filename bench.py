@@ -41,6 +41,7 @@ WORKLOADS = {
     "C4": dict(n=50000, m_g=1000000, m_e=2, desc="synthetic linear n=50,000 x p=1,000,000 (12.5 GB packed)"),
     "C5": dict(n=400000, m_g=600000, m_e=2, desc="biobank-scale synthetic n=400,000 x p=600,000 (60 GB packed)"),
     "C4s": dict(n=50000, m_g=200000, m_e=2, desc="synthetic linear n=50,000 x p=200,000 (2.5 GB packed; C4 at one fifth of the SNPs)"),
+    "C5s": dict(n=400000, m_g=20000, m_e=2, desc="biobank-scale individuals n=400,000 x p=20,000 (2 GB packed; C5 at one thirtieth of the SNPs)"),
 }
 GEN_SEED = 20121101
 CHAIN_SEEDS = [1234, 2345, 3456, 4567, 5678, 6789, 7890, 8901]
@@ -1095,7 +1096,7 @@ def main():
                 line = sharded_arm(args, rank, local_rank, world)
             elif world == 1:
                 wl = args.workload or "C2"
-                if wl in ("C3", "C4", "C4s", "C5"):
+                if wl in ("C3", "C4", "C4s", "C5", "C5s"):
                     line = group_arm(args, wl, rank, local_rank, 1, None, 1, probit=args.probit or wl == "C3")
                 else:
                     args.workload = wl

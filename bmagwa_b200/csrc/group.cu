@@ -26,12 +26,6 @@
 // (tools/scan_under_server.py, tools/scan_beside_chain.py, compute-sanitizer racecheck).  Unexplained, so not shipped:
 // with the barriers every scan runs while all chains are paused, and chains with the same seed stay byte-identical on any
 // number of GPUs (tools/group_same_seed_check.py).  profiles/round2_notes.md has the measurements.
-#include <fcntl.h>
-#include <immintrin.h>
-#include <sys/mman.h>
-#include <sys/stat.h>
-#include <time.h>
-#include <unistd.h>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -41,38 +35,13 @@
 #include "common.cuh"
 #include "store.cuh"
 #include "group.cuh"
+#include "host/shm_group.hpp"
 
 namespace bmg {
 
 namespace {
-constexpr uint32_t kShmMagic = 0x424D4731u;   // "BMG1"
-static double barrier_timeout()
-{
-  static const double t = getenv("BMG_GROUP_TIMEOUT") ? atof(getenv("BMG_GROUP_TIMEOUT")) : 120.0;   // seconds; a missing peer must not hang the box
-  return t;
-}
-
-struct GroupShm {
-  std::atomic<uint32_t> magic;
-  std::atomic<uint32_t> attached;
-  std::atomic<uint32_t> bar_count, bar_gen;
-  std::atomic<uint32_t> failed;
-  uint32_t pad[11];
-  unsigned char handle[kGroupMaxRanks][64];
-  int64_t lo[kGroupMaxRanks], hi[kGroupMaxRanks];
-  // scan service: request[c] = number of the latest scan chain c asked for; done[c][r] = the latest rank r has served
-  struct alignas(64) Flag { std::atomic<uint64_t> v; };
-  Flag request[kGroupMaxRanks];
-  Flag done[kGroupMaxRanks][kGroupMaxRanks];
-  double request_time[kGroupMaxRanks];   // CLOCK_MONOTONIC of the latest request (diagnostics only)
-};
-
-double now_seconds()
-{
-  struct timespec ts;
-  clock_gettime(CLOCK_MONOTONIC, &ts);
-  return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
-}
+inline double now_seconds() { return shm_now_seconds(); }
+static_assert(kShmMaxRanks == kGroupMaxRanks, "rank limits of the segment and of the group");
 
 __global__ void k_group_combine(const double* __restrict__ partial, int n_chunks, int64_t m, double* __restrict__ out)
 {
@@ -136,27 +105,11 @@ static void group_fail(Group* g)
 void group_barrier(Group* g)
 {
   if (g->world <= 1) return;
-  GroupShm* s = g->shm;
-  const double t0 = now_seconds();
-  const uint32_t gen = s->bar_gen.load(std::memory_order_acquire);
-  if (s->bar_count.fetch_add(1u, std::memory_order_acq_rel) + 1u == (uint32_t)g->world) {
-    s->bar_count.store(0u, std::memory_order_relaxed);
-    s->bar_gen.fetch_add(1u, std::memory_order_release);
-  } else {
-    unsigned long spins = 0;
-    while (s->bar_gen.load(std::memory_order_acquire) == gen) {
-      if (s->failed.load(std::memory_order_acquire)) throw Error("shard group: a peer rank failed");
-      _mm_pause();
-      if ((++spins & 0x3FF) == 0) {
-        if (spins > 200000) usleep(20);   // a rank without a chain waits for a whole Rao-Blackwell period: leave the core
-        if (now_seconds() - t0 > barrier_timeout()) {
-          group_fail(g);
-          throw Error("shard group: barrier timed out (a peer rank is missing)");
-        }
-      }
-    }
+  try {
+    shm_group_barrier(g->shm, g->world, &g->barrier_seconds);
+  } catch (const std::exception& e) {
+    throw Error(e.what());
   }
-  g->barrier_seconds += now_seconds() - t0;
 }
 
 // In-place all-gather over the group: every rank owns elements [rank per, (rank+1) per) of dev_buffer (world x per
@@ -215,34 +168,10 @@ Group* group_create(Store* s, int world, int rank, int n_chains, int64_t stride,
   g->peer[rank] = g->xbuf.p;
   if (world > 1) {
     g->shm_name = shm_name;
-    int fd = -1;
-    if (rank == 0) {
-      fd = shm_open(shm_name, O_CREAT | O_EXCL | O_RDWR, 0600);
-      BMG_REQUIRE(fd >= 0, std::string("shard group: shm_open(create) failed for ") + shm_name);
-      BMG_REQUIRE(ftruncate(fd, sizeof(GroupShm)) == 0, "shard group: ftruncate failed");
-    } else {
-      const double t0 = now_seconds();
-      while ((fd = shm_open(shm_name, O_RDWR, 0600)) < 0) {
-        BMG_REQUIRE(now_seconds() - t0 < 120.0, std::string("shard group: rank 0 never created ") + shm_name);
-        usleep(1000);
-      }
-      struct stat sb;
-      while (fstat(fd, &sb) == 0 && (size_t)sb.st_size < sizeof(GroupShm)) {
-        BMG_REQUIRE(now_seconds() - t0 < 120.0, "shard group: shared segment never sized");
-        usleep(1000);
-      }
-    }
-    void* p = mmap(nullptr, sizeof(GroupShm), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
-    close(fd);
-    BMG_REQUIRE(p != MAP_FAILED, "shard group: mmap failed");
-    g->shm = reinterpret_cast<GroupShm*>(p);
-    if (rank == 0) g->shm->magic.store(kShmMagic, std::memory_order_release);   // a fresh segment is zero-filled
-    else {
-      const double t0 = now_seconds();
-      while (g->shm->magic.load(std::memory_order_acquire) != kShmMagic) {
-        BMG_REQUIRE(now_seconds() - t0 < 120.0, "shard group: shared segment never initialised");
-        usleep(100);
-      }
+    try {
+      g->shm = shm_group_open(shm_name, rank);
+    } catch (const std::exception& e) {
+      throw Error(e.what());
     }
     cudaIpcMemHandle_t h;
     BMG_CUDA(cudaIpcGetMemHandle(&h, g->xbuf.p));
@@ -290,7 +219,7 @@ void group_destroy(Group* g)
   for (int r = 0; r < g->world; ++r)
     if (g->peer_opened[r]) cudaIpcCloseMemHandle(g->peer[r]);
   chain_destroy(g->scan_chain);
-  if (g->shm && g->shm != &g->local_shm) munmap(g->shm, sizeof(GroupShm));
+  if (g->shm && g->shm != &g->local_shm) shm_group_close(g->shm);
   delete g;
 }
 

@@ -12,7 +12,7 @@ export BMAGWA_BENCH_DIR=/tmp/bmagwa_bench
 #    ncu serialises kernels, which a persistent kernel does not survive, so the per-move column statistics run in their
 #    launch-per-move form here (BMG_COLSTATS_SERVER=0: same work items, one k_column_stats_inline launch per move).
 BMG_COLSTATS_SERVER=0 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 20 -c 3000 --csv --log-file $OUT/launches_$TAG.csv \
-    python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $OUT/bench_under_ncu_$TAG.log 2>&1
+    python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-sub > $OUT/bench_under_ncu_$TAG.log 2>&1
 # 2. the scan kernel (default variant: integer tensor cores), full set, one launch after the probe's warm-up,
 #    at the bench size (C2) and at a size that does not fit in L2 ten times over
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_scan_dots_imma -s 3 -c 1 -f -o $OUT/scan_$TAG \
@@ -24,6 +24,6 @@ ncu -i $OUT/scan1m_$TAG.ncu-rep --page raw --csv > $OUT/scan1m_${TAG}_raw.csv 2>
 # 3. the per-move column-statistics work item, captured in its launch-per-move form (BMG_COLSTATS_SERVER=0): the
 #    persistent server runs the same device function but never ends, so ncu cannot time it per request
 BMG_COLSTATS_SERVER=0 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_column_stats_inline -s 200 -c 1 -f -o $OUT/colstats_$TAG \
-    python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/colstats_under_ncu_$TAG.log 2>&1
+    python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-sub > $OUT/colstats_under_ncu_$TAG.log 2>&1
 ncu -i $OUT/colstats_$TAG.ncu-rep --page raw --csv > $OUT/colstats_${TAG}_raw.csv 2>/dev/null
 ls -la $OUT

@@ -1051,6 +1051,7 @@ def main():
     ap.add_argument("--n-rao", type=int, default=500, dest="n_rao")
     ap.add_argument("--tau-rng", default="device", choices=["device", "host"], dest="tau_rng")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", dest="no_e2e", help="sharded workloads: skip the host-buffer end-to-end pass (it keeps a host copy of every shard)")
     ap.add_argument("--no-sub", action="store_true", help="headline workload only (no C3 / C4 / replica sub-records)")
     ap.add_argument("--burnin", type=int, default=20000,
                     help="sharded workloads (C3/C4/C5): MCMC iterations every chain is advanced before the warm-up steps, untimed, so that "
@@ -1097,7 +1098,7 @@ def main():
             elif world == 1:
                 wl = args.workload or "C2"
                 if wl in ("C3", "C4", "C4s", "C5", "C5s"):
-                    line = group_arm(args, wl, rank, local_rank, 1, None, 1, probit=args.probit or wl == "C3")
+                    line = group_arm(args, wl, rank, local_rank, 1, None, 1, probit=args.probit or wl == "C3", with_e2e=not args.no_e2e)
                 else:
                     args.workload = wl
                     line = ours_arm(args, rank, local_rank, world)
@@ -1125,7 +1126,7 @@ def main():
                     line = ours_arm(args, rank, local_rank, world, dist)
                 else:
                     line = group_arm(args, wl, rank, local_rank, world, dist, n_chains, probit=args.probit or wl == "C3",
-                                     same_seed=not args.distinct_seeds)
+                                     same_seed=not args.distinct_seeds, with_e2e=not args.no_e2e)
                     if not args.no_sub:
                         if not args.distinct_seeds:
                             alt = group_arm(args, wl, rank, local_rank, world, dist, n_chains, probit=args.probit or wl == "C3",

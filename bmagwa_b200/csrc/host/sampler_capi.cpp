@@ -252,7 +252,7 @@ BMG_API int bmg_ini_lookup(const char* ini_path, const char* section, const char
   BMG_TRY
   BMG_REQUIRE(ini_path && section && key && out && out_len > 0, "bmg_ini_lookup: invalid argument");
   IniFile ini(ini_path);
-  BMG_REQUIRE(ini.parse_error() >= 0, std::string("Can't load ") + ini_path);
+  BMG_REQUIRE(ini.parse_error() == 0, "Cannot load/parse configuration file.");   // the reference's message (src/options.hpp:83)
   const std::string v = ini.get(section, key, dflt ? dflt : "");
   std::snprintf(out, (size_t)out_len, "%s", v.c_str());
   BMG_CATCH

@@ -5,6 +5,8 @@
 #include <time.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <algorithm>
+#include <cmath>
 #include <memory>
 #include "../common.cuh"
 #include "../store.cuh"
@@ -108,6 +110,16 @@ SamplerHandle* make(const char* ini, int chain_index, int device, Store* existin
   const double t_b = now();
   if (existing) {
     BMG_REQUIRE(existing->n == (int64_t)o.n && existing->m_g == (int64_t)o.m_g, "bmg_sampler_create_on_store: store dimensions differ from the INI file");
+    // the host side sizes its Gram blocks from the INI's covariates and reads y / e from the INI's files: the store must carry
+    // the same phenotype and covariates (the device kernels use the store's)
+    BMG_REQUIRE(existing->m_e == (int)o.m_e + 1, "bmg_sampler_create_on_store: the store's covariates differ from the INI file (sizes.m_e)");
+    {
+      double yy = 0.0;
+      for (double v : h->data->y) yy += v * v;
+      const double syy = existing->summaries[5];
+      BMG_REQUIRE(std::fabs(yy - syy) <= 1e-9 * std::max(1.0, std::fabs(yy)),
+                  "bmg_sampler_create_on_store: the store's phenotype differs from the INI file's (file_y / file_fam)");
+    }
     h->store = existing;
   } else {
     // the packed genotypes are streamed from the file to the device and live there only

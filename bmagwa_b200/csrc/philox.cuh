@@ -47,12 +47,13 @@ struct Philox {
     if (have == 0) refill();
     return out[--have];
   }
-  // uniform in (0,1) with 53 random bits, never 0 or 1
+  // uniform in (0,1) with 52 random bits, never 0 or 1: (x + 1/2) 2^-52 is exact for x < 2^52 (with 53 bits the half is
+  // rounded away above 2^52 and the largest x gives exactly 1)
   __device__ double u01()
   {
     const uint64_t a = next32(), b = next32();
-    const uint64_t x = ((a << 32) | b) >> 11;  // 53 bits
-    return ((double)x + 0.5) * (1.0 / 9007199254740992.0);
+    const uint64_t x = ((a << 32) | b) >> 12;  // 52 bits
+    return ((double)x + 0.5) * (1.0 / 4503599627370496.0);
   }
   __device__ double normal()
   {

@@ -37,6 +37,7 @@ constexpr int kImmaStages = 4;
 constexpr int kImmaGroups = 8;    // 64-individual groups per warp kept in registers
 constexpr int kImmaWarpWords = 4 * kImmaGroups;   // 32 packed words = 512 individuals per warp
 constexpr int kImmaMaxWarps = 16;
+constexpr int kImmaNonFinite = -(1 << 30);   // scale exponent standing for "the residual holds a NaN or an infinity"
 
 __device__ __forceinline__ uint32_t smem_u32i(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init_i(uint64_t* bar, uint32_t count)
@@ -87,8 +88,17 @@ __device__ __forceinline__ void imma16832(int (&c)[4], uint32_t a0, uint32_t a1,
 __global__ void __launch_bounds__(1024) k_absmax_exp(const double* __restrict__ r, int64_t n, int* __restrict__ scale_exp)
 {
   __shared__ double sm[32];
+  __shared__ int any_bad;
+  if (threadIdx.x == 0) any_bad = 0;
+  __syncthreads();
   double mx = 0.0;
-  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) mx = fmax(mx, fabs(r[i]));
+  int bad = 0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const double v = r[i];
+    bad |= !isfinite(v);       // fmax drops NaNs: a diverged chain must not look healthy
+    mx = fmax(mx, fabs(v));
+  }
+  if (bad) any_bad = 1;
   for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = mx;
   __syncthreads();
@@ -96,7 +106,7 @@ __global__ void __launch_bounds__(1024) k_absmax_exp(const double* __restrict__ 
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) mx = fmax(mx, sm[w]);
     int s = 0;
     if (mx > 0.0 && isfinite(mx)) s = 60 - ilogb(mx);
-    scale_exp[0] = s;
+    scale_exp[0] = any_bad ? kImmaNonFinite : s;   // a non-finite residual makes every dot product NaN, as in the fp64 variants
   }
 }
 
@@ -108,7 +118,8 @@ __global__ void k_quantize(const double* __restrict__ r, int64_t n, int64_t n_pa
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n_pad) return;
   long long v = 0;
-  if (i < n) v = __double2ll_rn(scalbn(r[i], scale_exp[0] - 2 * (int)(i & 3)));   // 4^p is carried by the genotype operand
+  const int se = scale_exp[0];
+  if (i < n && se != kImmaNonFinite) v = __double2ll_rn(scalbn(r[i], se - 2 * (int)(i & 3)));   // 4^p is carried by the genotype operand
   int8_t* dst = q + ((i >> 4) * 8) * 16 + (4 * (i & 3) + ((i >> 2) & 3));
 #pragma unroll
   for (int b = 0; b < 8; ++b) {
@@ -248,7 +259,9 @@ __global__ void __maxnreg__(80) k_scan_dots_imma(const __grid_constant__ ImmaArg
         // 2^-S in two always-normal factors (S spans about +-1100)
         const int h0 = scale_exp / 2, h1 = scale_exp - h0;
         const double f0 = __hiloint2double((1023 - h0) << 20, 0), f1 = __hiloint2double((1023 - h1) << 20, 0);
-        if (snp < a.m) a.out[(int64_t)chunk * a.m + snp] = fma((double)hi, 4294967296.0, (double)lo) * f0 * f1;
+        if (snp < a.m)
+          a.out[(int64_t)chunk * a.m + snp] = scale_exp == kImmaNonFinite ? __longlong_as_double(0x7ff8000000000000ll)
+                                                                         : fma((double)hi, 4294967296.0, (double)lo) * f0 * f1;
       }
       __syncwarp();
       if (lane == 0) { fence_cta(); ticket[buf] = 0; }

@@ -761,3 +761,22 @@ def _mp_norm_ppf(mp, p):
         if abs(step) < mp.mpf(10) ** -40:
             break
     return t
+
+
+def test_a_non_finite_residual_is_not_hidden_by_the_integer_scan(api):
+    """The tensor-core scan quantises the residual; a NaN or an infinity in it must surface as NaN dot products (what the fp64
+    variants give), not as finite-looking numbers."""
+    n, m = 3000, 400
+    payload, y, E = make_data(n, m, seed=21)
+    y = y.copy()
+    y[17] = np.nan
+    st = api.GenotypeStore(payload, n, m, recode_to_minor=True)
+    st.set_phenotype(y, E)
+    ch = api.Chain(st)
+    ch.residual([], np.zeros(E.shape[1] + 1), [])
+    for variant in (2, 0):
+        ch.set_scan_variant(variant)
+        d = ch.scan_dots()
+        assert np.isnan(d).all() if variant == 2 else np.isnan(d).any(), variant
+    ch.close()
+    st.close()

@@ -278,6 +278,8 @@ BMG_API int bmg_chain_get_column(bmg_chain* c, int64_t snp, int type, double* ou
   BMG_TRY
   Chain* ch = Cn(c);
   BMG_REQUIRE(out, "bmg_chain_get_column: null argument");
+  BMG_REQUIRE(ch->mv.base == ch->store->lo && ch->mv.m == ch->store->m,
+              "bmg_chain_get_column: not available on a chain whose missing-call index covers a sharded data set");
   store_get_column(ch->store, snp, type, ch->miss_val.p, true, out, ch->stream);
   BMG_CATCH
 }

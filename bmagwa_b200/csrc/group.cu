@@ -89,7 +89,7 @@ struct Group {
   unsigned char* peer[kGroupMaxRanks] = {nullptr};
   bool peer_opened[kGroupMaxRanks] = {false};
   DevBuf<unsigned char> q_stage[2];   // a peer chain's limbs + exponent, double-buffered
-  DevBuf<int32_t> n1_all, n2_all;
+  std::unique_ptr<GlobalMissing> gm;   // genotype counts and missing-call index of all SNPs (every rank holds them)
   double barrier_seconds = 0.0;
   GroupShm local_shm;                  // world == 1: the flags live here
   int64_t rounds = 0;                  // scan rounds this rank took part in
@@ -121,17 +121,20 @@ int group_allgather(void* ctx, void* dev_buffer, int64_t elems_per_rank, int ele
     if (g->world <= 1) return 0;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
     const size_t per = (size_t)elems_per_rank * (size_t)elem_bytes;
-    BMG_REQUIRE(per <= g->xbuf_bytes - g->off_dots, "shard group: all-gather block larger than the exchange buffer");
+    const size_t cap = (g->xbuf_bytes - g->off_dots) & ~(size_t)15;   // the staging area: larger blocks travel in pieces
     unsigned char* buf = reinterpret_cast<unsigned char*>(dev_buffer);
-    BMG_CUDA(cudaMemcpyAsync(g->xbuf.p + g->off_dots, buf + (size_t)g->rank * per, per, cudaMemcpyDeviceToDevice, st));
-    BMG_CUDA(cudaStreamSynchronize(st));
-    group_barrier(g);
-    for (int i = 1; i < g->world; ++i) {
-      const int r = (g->rank + i) % g->world;
-      BMG_CUDA(cudaMemcpyAsync(buf + (size_t)r * per, g->peer[r] + g->off_dots, per, cudaMemcpyDefault, st));
+    for (size_t o = 0; o < per; o += cap) {
+      const size_t len = std::min(cap, per - o);
+      BMG_CUDA(cudaMemcpyAsync(g->xbuf.p + g->off_dots, buf + (size_t)g->rank * per + o, len, cudaMemcpyDeviceToDevice, st));
+      BMG_CUDA(cudaStreamSynchronize(st));
+      group_barrier(g);
+      for (int i = 1; i < g->world; ++i) {
+        const int r = (g->rank + i) % g->world;
+        BMG_CUDA(cudaMemcpyAsync(buf + (size_t)r * per + o, g->peer[r] + g->off_dots, len, cudaMemcpyDefault, st));
+      }
+      BMG_CUDA(cudaStreamSynchronize(st));
+      group_barrier(g);   // nobody overwrites its staging area before everyone has read it
     }
-    BMG_CUDA(cudaStreamSynchronize(st));
-    group_barrier(g);   // nobody overwrites its staging area before everyone has read it
     return 0;
   } catch (const std::exception& e) {
     group_fail(g);
@@ -191,21 +194,13 @@ Group* group_create(Store* s, int world, int rank, int n_chains, int64_t stride,
     }
     group_barrier(g.get());
   }
-  // genotype counts of every SNP on every rank: the per-SNP algebra of a chain's scan runs on the chain's own GPU
-  const int64_t total = (int64_t)world * stride;
-  g->n1_all.alloc(total); g->n2_all.alloc(total);
-  cudaStream_t st = g->scan_chain->stream;
-  BMG_CUDA(cudaMemsetAsync(g->n1_all.p, 0, total * sizeof(int32_t), st));
-  BMG_CUDA(cudaMemsetAsync(g->n2_all.p, 0, total * sizeof(int32_t), st));
-  BMG_CUDA(cudaMemcpyAsync(g->n1_all.p + (int64_t)rank * stride, s->n1.p, s->m * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
-  BMG_CUDA(cudaMemcpyAsync(g->n2_all.p + (int64_t)rank * stride, s->n2.p, s->m * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
-  BMG_REQUIRE(group_allgather(g.get(), g->n1_all.p, stride, (int)sizeof(int32_t), (void*)st) == 0, "shard group: exchange of the genotype counts failed");
-  BMG_REQUIRE(group_allgather(g.get(), g->n2_all.p, stride, (int)sizeof(int32_t), (void*)st) == 0, "shard group: exchange of the genotype counts failed");
-  BMG_CUDA(cudaStreamSynchronize(st));
+  // genotype counts (and the missing-call index) of every SNP on every rank: the per-SNP algebra of a chain's scan runs on
+  // the chain's own GPU, and the chain's imputed values cover all SNPs
   if (g->shm == nullptr) {   // one rank: no segment to share
     std::memset(static_cast<void*>(&g->local_shm), 0, sizeof(GroupShm));
     g->shm = &g->local_shm;
   }
+  g->gm.reset(build_global_missing(s, world, rank, stride, group_allgather, g.get()));
   return g.release();
 }
 
@@ -227,8 +222,9 @@ int group_world(const Group* g) { return g->world; }
 int group_rank(const Group* g) { return g->rank; }
 int group_chains(const Group* g) { return g->n_chains; }
 int64_t group_stride(const Group* g) { return g->stride; }
-const int32_t* group_n1(const Group* g) { return g->n1_all.p; }
-const int32_t* group_n2(const Group* g) { return g->n2_all.p; }
+const int32_t* group_n1(const Group* g) { return g->gm->n1.p; }
+const int32_t* group_n2(const Group* g) { return g->gm->n2.p; }
+const GlobalMissing* group_missing(const Group* g) { return g->gm.get(); }
 Chain* group_scan_chain(Group* g) { return g->scan_chain; }
 void group_stats(const Group* g, double* out4)
 {

@@ -21,6 +21,7 @@ int group_chains(const Group* g);
 int64_t group_stride(const Group* g);
 const int32_t* group_n1(const Group* g);
 const int32_t* group_n2(const Group* g);
+const GlobalMissing* group_missing(const Group* g);
 Chain* group_scan_chain(Group* g);
 void group_stats(const Group* g, double* out4);
 

@@ -86,8 +86,6 @@ Sampler::Sampler(const Options& opts, int chain_index, Store* store, const std::
   if (comm != nullptr) {
     for (int64_t snp : {(int64_t)0, (int64_t)m_g_ - 1}) (void)store_->column_ptr(snp);   // throws unless every shard is attached
   }
-  if (store_->n_missing > 0 && comm != nullptr)
-    throw std::runtime_error("genotype data contains missing calls: not supported by the SNP-sharded chain");
   yy_ = yy;
   adapt_p_move_size_ = opts.adapt_p_move_size && max_move_size_ > 1;
   delay_rejection_ = (unsigned char)std::min((size_t)max_move_size_, opts.delay_rejection);
@@ -153,7 +151,7 @@ Sampler::Sampler(const Options& opts, int chain_index, Store* store, const std::
     dr_bit_to_normalized_order_.assign(delay_rejection_, 0);
   }
   y_host_ = &y; e_host_ = &e;
-  if (store_->n_missing > 0) load_missing_index();
+  if (chain_->mv.n_missing > 0) load_missing_index();   // the chain's index: the store's, or the whole data set's when sharded
   if (opts.probit) enable_probit();
 }
 
@@ -163,14 +161,16 @@ Sampler::Sampler(const Options& opts, int chain_index, Store* store, const std::
 void Sampler::load_missing_index()
 {
   BMG_CUDA(cudaSetDevice(store_->device));
-  miss_.off = store_->h_miss_off;
-  miss_.idx.resize((size_t)store_->n_missing);
-  bmg::copy_d2h_sync(miss_.idx.data(), store_->miss_idx.p, miss_.idx.size() * sizeof(int32_t));
+  const MissView& mv = chain_->mv;
+  if (mv.base != 0 || mv.m != (int64_t)m_g_) throw std::runtime_error("the chain's missing-call index does not cover all SNPs");
+  miss_.off.assign(mv.h_off, mv.h_off + m_g_ + 1);
+  miss_.idx.resize((size_t)mv.n_missing);
+  bmg::copy_d2h_sync(miss_.idx.data(), mv.idx, miss_.idx.size() * sizeof(int32_t));
   miss_.val.assign(miss_.idx.size(), 0);   // data_model.hpp:80-84; the chain's device copy starts at 0 as well
   std::vector<int32_t> n1(m_g_), n2(m_g_), nm(m_g_);
-  bmg::copy_d2h_sync(n1.data(), store_->n1.p, m_g_ * sizeof(int32_t));
-  bmg::copy_d2h_sync(n2.data(), store_->n2.p, m_g_ * sizeof(int32_t));
-  bmg::copy_d2h_sync(nm.data(), store_->nmiss.p, m_g_ * sizeof(int32_t));
+  bmg::copy_d2h_sync(n1.data(), mv.n1, m_g_ * sizeof(int32_t));
+  bmg::copy_d2h_sync(n2.data(), mv.n2, m_g_ * sizeof(int32_t));
+  bmg::copy_d2h_sync(nm.data(), mv.nmiss, m_g_ * sizeof(int32_t));
   miss_.prior3.resize(3 * m_g_);
   for (size_t j = 0; j < m_g_; ++j) {      // cumulative counts of 0/1/2 among the observed cells (data.cpp:357-372)
     const double c0 = (double)((int64_t)n_ - nm[j] - n1[j] - n2[j]);

@@ -134,16 +134,11 @@ SamplerHandle* make(const char* ini, int chain_index, int device, Store* existin
   if (comm != nullptr) {
     BMG_REQUIRE(existing != nullptr, "bmg_sampler_create_sharded: a shard store is required");
     BMG_REQUIRE(existing->m_e >= 1, "bmg_sampler_create_sharded: call bmg_store_set_phenotype on the shard first");
-    int64_t missing_cells;
     if (group != nullptr) {
       for (int i = 0; i < 4; ++i) sm[i] = group->summaries[i];
-      missing_cells = group->missing_cells;
     } else {
-      missing_cells = global_summaries(h->store, *comm, sm);
+      (void)global_summaries(h->store, *comm, sm);
     }
-    // every rank sees the same total, so every rank refuses together (no rank is left waiting in a collective)
-    BMG_REQUIRE(missing_cells == 0, "bmg_sampler_create_sharded: genotype data contains missing calls; the SNP-sharded chain keeps the "
-                                    "imputed values of a shard on its owner only (use a single-GPU chain for such data)");
   }
   const double mean_x = sm[0] / sm[1], var_x = sm[2] / sm[3];
   h->sampler.reset(new Sampler(o, chain_index, h->store, h->data->y, h->data->e, sm[4], sm[5], var_x, mean_x, comm));

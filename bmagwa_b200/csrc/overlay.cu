@@ -111,7 +111,8 @@ int chain_overlay_columns(Chain* c, const int64_t* snps, int count, const uint32
       BMG_REQUIRE(types[i] >= 0 && types[i] <= 3, "effect type of a column must be 0 (A), 1 (H), 2 (D) or 3 (R)");
       any_typed = any_typed || types[i] != 0;
     }
-  if (s->n_missing == 0 && !any_typed) {
+  const MissView& mv = c->mv;
+  if (mv.n_missing == 0 && !any_typed) {
     for (int i = 0; i < count; ++i) out[i] = s->column_ptr(snps[i]);
     return 0;
   }
@@ -127,7 +128,7 @@ int chain_overlay_columns(Chain* c, const int64_t* snps, int count, const uint32
   if (host_vals) {
     size_t total = 0;
     for (int i = 0; i < count; ++i)
-      if (host_vals[i] && s->is_local(snps[i])) total += (size_t)(s->h_miss_off[snps[i] - s->lo + 1] - s->h_miss_off[snps[i] - s->lo]);
+      if (host_vals[i] && mv.covers(snps[i]) && mv.n_missing > 0) total += (size_t)mv.count(snps[i]);
     if (c->pc_h_vals.n < total) {
       chain_server_stop(c);
       BMG_CUDA(cudaStreamSynchronize(c->stream));
@@ -138,14 +139,14 @@ int chain_overlay_columns(Chain* c, const int64_t* snps, int count, const uint32
   for (int i = 0; i < count; ++i) {
     const int64_t snp = snps[i];
     out[i] = nullptr;
-    if (!s->is_local(snp)) {   // a peer's column: its imputed values live on its owner
+    if (!mv.covers(snp)) {   // a column outside the chain's index (a peer's, on a chain that keeps no global index)
       BMG_REQUIRE(!types || types[i] == 0, "typed columns of a peer shard are not available");
       out[i] = s->column_ptr(snp);
       continue;
     }
     const int ty = types ? types[i] : 0;
     BMG_REQUIRE(!(host_vals && host_vals[i] && ty != 0), "new imputed values are given for the additive column");
-    const int64_t j = snp - s->lo, cnt = s->n_missing > 0 ? s->h_miss_off[j + 1] - s->h_miss_off[j] : 0;
+    const int64_t j = snp - mv.base, cnt = mv.n_missing > 0 ? mv.h_off[j + 1] - mv.h_off[j] : 0;
     if (cnt == 0 && ty == 0) { out[i] = s->column_ptr(snp); continue; }
     auto it = c->pc_map.find(4 * j + ty);
     if (it != c->pc_map.end()) {
@@ -156,9 +157,9 @@ int chain_overlay_columns(Chain* c, const int64_t* snps, int count, const uint32
   // ... then slots for the others, and the patch list
   for (int i = 0; i < count; ++i) {
     const int64_t snp = snps[i];
-    if (!s->is_local(snp)) continue;
+    if (!mv.covers(snp)) continue;
     const int ty = types ? types[i] : 0;
-    const int64_t j = snp - s->lo, lo = s->n_missing > 0 ? s->h_miss_off[j] : 0, cnt = s->n_missing > 0 ? s->h_miss_off[j + 1] - lo : 0;
+    const int64_t j = snp - mv.base, lo = mv.n_missing > 0 ? mv.h_off[j] : 0, cnt = mv.n_missing > 0 ? mv.h_off[j + 1] - lo : 0;
     if (cnt == 0 && ty == 0) continue;
     const bool fresh = host_vals != nullptr && host_vals[i] != nullptr;
     if (out[i] != nullptr && !fresh) continue;
@@ -188,7 +189,7 @@ int chain_overlay_columns(Chain* c, const int64_t* snps, int count, const uint32
     PatchDesc d;
     d.src = s->column_ptr(snp);
     d.dst = dst;
-    d.idx = cnt ? s->miss_idx.p + lo : nullptr;
+    d.idx = cnt ? mv.idx + lo : nullptr;
     d.cnt = cnt;
     d.type = ty;
     if (fresh) {
@@ -217,8 +218,8 @@ void chain_set_missing_many(Chain* c, const int64_t* snps, int count, const int8
   if (count == 0) return;
   BMG_REQUIRE(count <= 2048, "bmg_chain_set_missing: too many SNPs in one call");
   for (int i = 0; i < count; ++i) {
-    BMG_REQUIRE(s->is_local(snps[i]), "bmg_chain_set_missing: SNP not in the local shard");
-    const int64_t j = snps[i] - s->lo, cnt = s->h_miss_off[j + 1] - s->h_miss_off[j];
+    BMG_REQUIRE(c->mv.covers(snps[i]), "bmg_chain_set_missing: SNP outside the chain's missing-call index");
+    const int64_t cnt = c->mv.n_missing > 0 ? c->mv.count(snps[i]) : 0;
     BMG_REQUIRE(vals[i] != nullptr || cnt == 0, "bmg_chain_set_missing: null values");
     for (int64_t q = 0; q < cnt; ++q) BMG_REQUIRE(vals[i][q] >= 0 && vals[i][q] <= 2, "bmg_chain_set_missing: values must be 0, 1 or 2");
   }
@@ -235,9 +236,9 @@ void chain_overlay_invalidate(Chain* c, const int64_t* keep, int k)
   Store* s = c->store;
   std::vector<std::pair<int64_t, int>> kept;
   for (int l = 0; l < k; ++l) {
-    if (!s->is_local(keep[l])) continue;
+    if (!c->mv.covers(keep[l])) continue;
     for (int ty = 0; ty < 4; ++ty) {
-      auto it = c->pc_map.find(4 * (keep[l] - s->lo) + ty);
+      auto it = c->pc_map.find(4 * (keep[l] - c->mv.base) + ty);
       if (it != c->pc_map.end()) kept.push_back(*it);
     }
   }

@@ -574,6 +574,10 @@ void chain_set_sharded(Chain* c, int world, int rank, int64_t stride, AllGatherF
   c->inorder_own.alloc(c->mw);
   bmg::copy_h2d_sync(c->inorder_own.p, c->h_inorder_own.data(), c->mw * sizeof(int32_t));
   BMG_CUDA(cudaDeviceSynchronize());
+  // missing calls: the lockstep ranks draw the same imputed values, so every rank keeps them for ALL SNPs and needs the
+  // whole data set's index (collective)
+  c->mv_own.reset(build_global_missing(s, world, rank, stride, fn, ctx));
+  if (c->mv_own->n_missing > 0) chain_bind_missing(c, c->mv_own->view());
 }
 
 // One of several chains over a SNP-sharded store (group.cu): the chain's per-SNP arrays cover all m_g SNPs with the
@@ -591,6 +595,8 @@ void chain_set_group(Chain* c, Group* g)
   c->inorder_own.alloc(c->mw);
   bmg::copy_h2d_sync(c->inorder_own.p, c->h_inorder_own.data(), c->mw * sizeof(int32_t));
   BMG_CUDA(cudaDeviceSynchronize());
+  const GlobalMissing* gm = group_missing(g);   // built collectively at group creation
+  if (gm->n_missing > 0) chain_bind_missing(c, gm->view());
 }
 
 // every rank contributes elems [rank stride, (rank+1) stride) of dev_buffer (world x stride elements) in place
@@ -599,6 +605,23 @@ void chain_allgather(Chain* c, void* dev_buffer, int elem_bytes)
   if (c->world <= 1) return;
   const int rc = c->gather(c->gather_ctx, dev_buffer, c->shard_stride, elem_bytes, (void*)c->stream);
   if (rc != 0) throw Error("sharded chain: the host's all-gather callback failed");
+}
+
+// the chain's imputed values follow the index of `v`; every cell starts at 0 (data_model.hpp:80-84)
+void chain_bind_missing(Chain* c, const MissView& v)
+{
+  BMG_CUDA(cudaSetDevice(c->store->device));
+  c->mv = v;
+  c->miss_val.release();
+  c->miss_corr.release();
+  if (v.n_missing > 0) {
+    c->miss_val.alloc((size_t)v.n_missing);
+    BMG_CUDA(cudaMemset(c->miss_val.p, 0, (size_t)v.n_missing));
+    c->miss_corr.alloc(3 * (size_t)v.m);
+    BMG_CUDA(cudaMemset(c->miss_corr.p, 0, 3 * (size_t)v.m * sizeof(double)));
+    BMG_CUDA(cudaDeviceSynchronize());
+  }
+  chain_overlay_invalidate(c, nullptr, 0);
 }
 
 Chain* chain_create(Store* s)
@@ -620,11 +643,11 @@ Chain* chain_create(Store* s)
   BMG_CUDA(cudaMemcpy(c->y.p, s->y.p, n * sizeof(double), cudaMemcpyDeviceToDevice));
   c->yhat_e.alloc(n); c->yhat_g.alloc(n); c->r.alloc(n); c->r_scaled.alloc(n_pad);
   c->red_partial.alloc(1024 * 16); c->red_out.alloc(16); c->h_red.alloc(16);
-  if (s->n_missing > 0) {
-    c->miss_val.alloc((size_t)s->n_missing);
-    BMG_CUDA(cudaMemset(c->miss_val.p, 0, (size_t)s->n_missing));   // data_model.hpp:80-84
-    c->miss_corr.alloc(3 * m);
-    BMG_CUDA(cudaMemset(c->miss_corr.p, 0, 3 * m * sizeof(double)));
+  {
+    MissView v;
+    v.base = s->lo; v.m = s->m; v.n_missing = s->n_missing; v.off = s->miss_off.p; v.idx = s->miss_idx.p;
+    v.n1 = s->n1.p; v.n2 = s->n2.p; v.nmiss = s->nmiss.p; v.h_off = s->h_miss_off.data();
+    chain_bind_missing(c.get(), v);
   }
   c->dot_partial.alloc((size_t)c->scan_chunks * m);
   c->dot.alloc(m);
@@ -662,9 +685,8 @@ void chain_destroy(Chain* c)
 
 void chain_set_missing(Chain* c, int64_t snp, const int8_t* vals, int64_t count)
 {
-  Store* s = c->store;
-  BMG_REQUIRE(s->is_local(snp), "bmg_chain_set_missing: SNP not in the local shard");
-  const int64_t j = snp - s->lo, cnt = s->h_miss_off[j + 1] - s->h_miss_off[j];
+  BMG_REQUIRE(c->mv.covers(snp), "bmg_chain_set_missing: SNP outside the chain's missing-call index");
+  const int64_t cnt = c->mv.n_missing > 0 ? c->mv.count(snp) : 0;
   BMG_REQUIRE(cnt == count, "bmg_chain_set_missing: count does not match the number of missing cells of the SNP");
   if (cnt == 0) return;
   chain_set_missing_many(c, &snp, 1, &vals);   // overlay.cu: values to the device + the SNP's patched column, one launch
@@ -674,7 +696,7 @@ void chain_set_missing(Chain* c, int64_t snp, const int8_t* vals, int64_t count)
 void chain_set_missing_all(Chain* c, const int8_t* vals, int64_t count)
 {
   Store* s = c->store;
-  BMG_REQUIRE(count == s->n_missing, "bmg_chain_set_missing_all: count does not match the number of missing cells of the store");
+  BMG_REQUIRE(count == c->mv.n_missing, "bmg_chain_set_missing_all: count does not match the number of missing cells of the store");
   if (count == 0) return;
   unsigned bad = 0;
   for (int64_t q = 0; q < count; ++q) bad |= (unsigned)((uint8_t)vals[q] > 2);
@@ -716,7 +738,8 @@ __global__ void k_impute_from_prior(const int64_t* __restrict__ off, const int32
 void chain_impute_from_prior(Chain* c, const int64_t* loci, int k, uint64_t seed, uint64_t counter)
 {
   Store* s = c->store;
-  if (s->n_missing == 0) return;
+  const MissView& mv = c->mv;
+  if (mv.n_missing == 0) return;
   BMG_REQUIRE(k >= 0 && k <= 2048, "bmg_chain_impute_from_prior: model size must be <= 2048");
   BMG_CUDA(cudaSetDevice(s->device));
   cudaStream_t st = c->stream;
@@ -724,8 +747,8 @@ void chain_impute_from_prior(Chain* c, const int64_t* loci, int k, uint64_t seed
   for (int l = 0; l < k; ++l) c->h_stage_i.p[l] = loci[l];
   std::sort(c->h_stage_i.p, c->h_stage_i.p + k);
   if (k) bmg::copy_h2d(c->loci_dev.p, c->h_stage_i.p, k * sizeof(int64_t), st);
-  k_impute_from_prior<<<(unsigned)((s->m * 32 + 127) / 128), 128, 0, st>>>(s->miss_off.p, s->n1.p, s->n2.p, s->nmiss.p, s->n, s->m,
-                                                                          s->lo, c->loci_dev.p, k, seed, counter, c->miss_val.p);
+  k_impute_from_prior<<<(unsigned)((mv.m * 32 + 127) / 128), 128, 0, st>>>(mv.off, mv.n1, mv.n2, mv.nmiss, s->n, mv.m, mv.base,
+                                                                          c->loci_dev.p, k, seed, counter, c->miss_val.p);
   count_launch();
   BMG_CUDA(cudaGetLastError());
   BMG_CUDA(cudaStreamSynchronize(st));   // loci_dev / the staging buffer are reused by the scan that follows
@@ -786,8 +809,8 @@ void chain_get_cells(Chain* c, const int64_t* loci, int k, const int32_t* rows, 
   }
   for (int l = 0; l < k; ++l) {
     c->gc_h_meta.p[l] = (int64_t)(uintptr_t)s->column_ptr(loci[l]);
-    const bool local = s->is_local(loci[l]) && s->n_missing > 0;
-    c->gc_h_meta.p[k + l] = local ? loci[l] - s->lo : -1;
+    const bool indexed = c->mv.n_missing > 0 && c->mv.covers(loci[l]);
+    c->gc_h_meta.p[k + l] = indexed ? loci[l] - c->mv.base : -1;
   }
   memcpy(c->gc_h_rows.p, rows, (size_t)q * sizeof(int32_t));
   bmg::copy_h2d(c->gc_meta.p, c->gc_h_meta.p, (size_t)2 * k * sizeof(int64_t), st);
@@ -796,7 +819,7 @@ void chain_get_cells(Chain* c, const int64_t* loci, int k, const int32_t* rows, 
   a.cols = reinterpret_cast<const uint32_t* const*>(c->gc_meta.p);
   a.snp_local = c->gc_meta.p + k;
   a.rows = c->gc_rows.p; a.k = k; a.q = q;
-  a.off = s->miss_off.p; a.idx = s->miss_idx.p; a.val = c->miss_val.p; a.out = c->gc_out.p;
+  a.off = c->mv.off; a.idx = c->mv.idx; a.val = c->miss_val.p; a.out = c->gc_out.p;
   k_gather_cells<<<(unsigned)((cells + 127) / 128), 128, 0, st>>>(a);
   count_launch();
   BMG_CUDA(cudaGetLastError());
@@ -940,12 +963,16 @@ void chain_scan(Chain* c, const int64_t* loci, const double* beta_g, const doubl
   if (c->group) {
     // several chains over the sharded store: every rank of the group scans its shard for this chain's residual and stores
     // the dot products into this GPU's memory (group.cu); the per-SNP algebra then runs here over all m_g SNPs
-    BMG_REQUIRE(c->scan_variant == 2 && s->n_missing == 0, "shard group: tensor-core scan on data without missing calls only");
+    BMG_REQUIRE(c->scan_variant == 2, "shard group: the tensor-core scan only");
     if (prm->tau_mode == 1) bmg::copy_h2d(c->tau_dev.p, prm->tau_host, c->mw * sizeof(double), st);
+    if (c->mv.n_missing > 0) {   // the chain's imputed cells of ALL SNPs against its residual, on its own GPU
+      k_miss_corr<<<(unsigned)((c->mv.m * 32 + 127) / 128), 128, 0, st>>>(c->mv.off, c->mv.idx, c->miss_val.p, c->r.p, c->mv.m, c->miss_corr.p);
+      count_launch();
+    }
     const double* dots = group_scan_round(c->group, c);
     FinalizeArgs f;
     f.dot_partial = dots; f.n_chunks = 1; f.m = c->mw; f.lo = 0; f.n = s->n;
-    f.n1 = group_n1(c->group); f.n2 = group_n2(c->group); f.miss_corr = nullptr;
+    f.n1 = group_n1(c->group); f.n2 = group_n2(c->group); f.miss_corr = c->mv.n_missing > 0 ? c->miss_corr.p : nullptr;
     f.loci = c->loci_dev.p; f.beta_g = c->beta_dev.p; f.tau_g = c->taug_dev.p; f.k = k;
     f.sum_r = c->sum_r; f.sigma2 = prm->sigma2; f.lmp_add = prm->lmp_add; f.lmp_rem = prm->lmp_rem;
     f.tau_mode = prm->tau_mode; f.tau_shared = prm->tau_shared; f.tau_snp = c->tau_dev.p;
@@ -961,14 +988,13 @@ void chain_scan(Chain* c, const int64_t* loci, const double* beta_g, const doubl
     return;
   }
   chain_scan_dots(c);
-  if (s->n_missing > 0) {
-    k_miss_corr<<<(unsigned)((s->m * 32 + 127) / 128), 128, 0, st>>>(s->miss_off.p, s->miss_idx.p, c->miss_val.p, c->r.p, s->m,
-                                                                     c->miss_corr.p);
+  if (c->mv.n_missing > 0) {   // over the SNPs of the chain's index (all of them when the store is sharded: cheap, and the same on every rank)
+    k_miss_corr<<<(unsigned)((c->mv.m * 32 + 127) / 128), 128, 0, st>>>(c->mv.off, c->mv.idx, c->miss_val.p, c->r.p, c->mv.m, c->miss_corr.p);
     count_launch();
   }
   FinalizeArgs f;
   f.dot_partial = c->last_partial; f.n_chunks = c->last_chunks; f.m = s->m; f.lo = s->lo; f.n = s->n;
-  f.n1 = s->n1.p; f.n2 = s->n2.p; f.miss_corr = s->n_missing > 0 ? c->miss_corr.p : nullptr;
+  f.n1 = s->n1.p; f.n2 = s->n2.p; f.miss_corr = c->mv.n_missing > 0 ? c->miss_corr.p + 3 * (s->lo - c->mv.base) : nullptr;
   f.loci = c->loci_dev.p; f.beta_g = c->beta_dev.p; f.tau_g = c->taug_dev.p; f.k = k;
   f.sum_r = c->sum_r; f.sigma2 = prm->sigma2; f.lmp_add = prm->lmp_add; f.lmp_rem = prm->lmp_rem;
   f.tau_mode = prm->tau_mode; f.tau_shared = prm->tau_shared; f.tau_snp = c->tau_dev.p;
@@ -1170,7 +1196,7 @@ void chain_scan_types(Chain* c, const int64_t* loci, const int32_t* loci_type, c
   BMG_REQUIRE(prm != nullptr, "bmg_chain_scan_types: params required");
   BMG_REQUIRE(c->residual_valid, "bmg_chain_scan_types: call bmg_chain_residual[_types] first");
   BMG_REQUIRE(c->scan_variant == 2, "bmg_chain_scan_types: needs the tensor-core scan (variant 2)");
-  BMG_REQUIRE(c->world == 1, "bmg_chain_scan_types: not available on a SNP-sharded chain");
+  BMG_REQUIRE(c->world == 1 && c->group == nullptr, "bmg_chain_scan_types: not available on a SNP-sharded chain");
   BMG_REQUIRE(prm->n_types >= 1 && prm->n_types <= 5, "bmg_chain_scan_types: n_types must be 1..5");
   BMG_REQUIRE(prm->tau_mode == 0 || prm->tau_mode == 1, "bmg_chain_scan_types: tau_mode must be 0 (shared) or 1 (host draws)");
   BMG_REQUIRE(prm->sigma2 > 0, "bmg_chain_scan_types: sigma2 must be positive");

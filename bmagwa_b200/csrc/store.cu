@@ -193,6 +193,62 @@ void build_inorder_permutation(int64_t m, std::vector<int32_t>& order)
   }
 }
 
+// Genotype counts and missing-call index of ALL SNPs of a sharded data set, on this rank's device (collective: every rank
+// calls it with the same arguments; `fn` is the in-place all-gather of the communicator).  The CSR is the one an unsharded
+// store of the same file would hold -- cells in SNP order -- so per-cell counters (k_impute_from_prior) agree with it.
+GlobalMissing* build_global_missing(Store* s, int world, int rank, int64_t stride, AllGatherFn fn, void* ctx)
+{
+  BMG_CUDA(cudaSetDevice(s->device));
+  std::unique_ptr<GlobalMissing> gm(new GlobalMissing());
+  gm->m_g = s->m_g;
+  const int64_t total = (int64_t)world * stride, off0 = (int64_t)rank * stride;
+  cudaStream_t st;
+  BMG_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  auto gather_i32 = [&](const int32_t* local, DevBuf<int32_t>& all) {
+    all.alloc(total);
+    BMG_CUDA(cudaMemsetAsync(all.p, 0, total * sizeof(int32_t), st));
+    BMG_CUDA(cudaMemcpyAsync(all.p + off0, local, s->m * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    if (world > 1 && fn(ctx, all.p, stride, (int)sizeof(int32_t), (void*)st) != 0) throw Error("sharded data set: all-gather of the genotype counts failed");
+    BMG_CUDA(cudaStreamSynchronize(st));
+  };
+  gather_i32(s->n1.p, gm->n1);
+  gather_i32(s->n2.p, gm->n2);
+  gather_i32(s->nmiss.p, gm->nmiss);
+  std::vector<int32_t> h_nm(total);
+  BMG_CUDA(cudaMemcpy(h_nm.data(), gm->nmiss.p, total * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  gm->h_off.assign(s->m_g + 1, 0);
+  for (int64_t j = 0; j < s->m_g; ++j) gm->h_off[j + 1] = gm->h_off[j] + h_nm[j];
+  gm->n_missing = gm->h_off[s->m_g];
+  gm->off.alloc(s->m_g + 1);
+  BMG_CUDA(cudaMemcpy(gm->off.p, gm->h_off.data(), (s->m_g + 1) * sizeof(int64_t), cudaMemcpyHostToDevice));
+  if (gm->n_missing > 0) {
+    // the cells: every rank contributes its shard's list, padded to the longest
+    auto cells_of = [&](int r) {
+      const int64_t a = std::min<int64_t>(s->m_g, (int64_t)r * stride), b = std::min<int64_t>(s->m_g, (int64_t)(r + 1) * stride);
+      return gm->h_off[b] - gm->h_off[a];
+    };
+    int64_t longest = 1;
+    for (int r = 0; r < world; ++r) longest = std::max(longest, cells_of(r));
+    BMG_REQUIRE(cells_of(rank) == s->n_missing, "sharded data set: the shard's missing-call index disagrees with the gathered counts");
+    DevBuf<int32_t> pad;
+    pad.alloc((size_t)world * longest);
+    BMG_CUDA(cudaMemsetAsync(pad.p, 0, (size_t)world * longest * sizeof(int32_t), st));
+    if (s->n_missing > 0)
+      BMG_CUDA(cudaMemcpyAsync(pad.p + (int64_t)rank * longest, s->miss_idx.p, s->n_missing * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    if (world > 1 && fn(ctx, pad.p, longest, (int)sizeof(int32_t), (void*)st) != 0) throw Error("sharded data set: all-gather of the missing-call index failed");
+    gm->idx.alloc((size_t)gm->n_missing);
+    for (int r = 0; r < world; ++r) {
+      const int64_t cnt = cells_of(r);
+      if (cnt > 0)
+        BMG_CUDA(cudaMemcpyAsync(gm->idx.p + gm->h_off[std::min<int64_t>(s->m_g, (int64_t)r * stride)], pad.p + (int64_t)r * longest,
+                                 cnt * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    }
+    BMG_CUDA(cudaStreamSynchronize(st));
+  }
+  cudaStreamDestroy(st);
+  return gm.release();
+}
+
 const uint32_t* Store::column_ptr(int64_t snp) const
 {
   if (snp >= lo && snp < hi) return codes.p + (snp - lo) * Wp;

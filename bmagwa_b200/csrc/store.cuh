@@ -33,6 +33,35 @@ struct PatchDesc {
 
 struct Group;   // group.cuh
 
+// The missing-call index a chain works on: the store's own (one GPU), or the whole data set's when the packed genotypes
+// are sharded -- the imputed values of ALL SNPs belong to the chain, whichever GPU holds a SNP's packed column
+// (src/data_model.hpp:80-84: one miss_val per chain).  CSR over the SNPs [base, base + m); arrays on the chain's device.
+struct MissView {
+  int64_t base = 0, m = 0, n_missing = 0;
+  const int64_t* off = nullptr;     // m + 1
+  const int32_t* idx = nullptr;     // individuals of the missing cells, ascending per SNP
+  const int32_t* n1 = nullptr;      // genotype counts per SNP of the view
+  const int32_t* n2 = nullptr;
+  const int32_t* nmiss = nullptr;
+  const int64_t* h_off = nullptr;   // host mirror of off
+  bool covers(int64_t snp) const { return snp >= base && snp < base + m; }
+  int64_t count(int64_t snp) const { return h_off[snp - base + 1] - h_off[snp - base]; }
+};
+// owned arrays of a view over all SNPs of a sharded data set (built collectively, store.cu)
+struct GlobalMissing {
+  DevBuf<int64_t> off;
+  DevBuf<int32_t> idx, n1, n2, nmiss;
+  std::vector<int64_t> h_off;
+  int64_t n_missing = 0, m_g = 0;
+  MissView view() const
+  {
+    MissView v;
+    v.base = 0; v.m = m_g; v.n_missing = n_missing; v.off = off.p; v.idx = idx.p; v.n1 = n1.p; v.n2 = n2.p; v.nmiss = nmiss.p;
+    v.h_off = h_off.data();
+    return v;
+  }
+};
+
 struct Chain {
   Store* store = nullptr;
   // several chains over one SNP-sharded store (group.cu): this chain lives on its rank only, its weight arrays cover all
@@ -85,9 +114,11 @@ struct Chain {
   PinnedBuf<double> h_red;                      // pinned mirror
   double sum_r = 0.0;
   bool residual_valid = false;
-  // per-chain imputed values of the missing cells (same CSR as the store)
+  // per-chain imputed values of the missing cells (CSR of mv: the store's, or the whole data set's for sharded chains)
+  MissView mv;
+  std::unique_ptr<GlobalMissing> mv_own;        // lockstep sharded chain: its own copy of the global index
   DevBuf<int8_t> miss_val;
-  DevBuf<double> miss_corr;                     // 3 per local SNP: (dot corr, sum val, sum val^2)
+  DevBuf<double> miss_corr;                     // 3 per SNP of mv: (dot corr, sum val, sum val^2)
   DevBuf<double> miss_corr4;                    // typed scan: (sum_{val=1} r, sum_{val=2} r, #val=1, #val=2)
   DevBuf<double> p_r_types;                     // typed scan: m x n_types
   DevBuf<double> tm_d;                          // typed scan: model betas [k][2] | taus [k][2]
@@ -176,6 +207,9 @@ void chain_scan_types(Chain* c, const int64_t* loci, const int32_t* loci_type, c
 void chain_scan_dots(Chain* c);
 void chain_set_sharded(Chain* c, int world, int rank, int64_t stride, AllGatherFn fn, void* ctx);
 void chain_set_group(Chain* c, Group* g);
+void chain_bind_missing(Chain* c, const MissView& v);
+// collective over the ranks of a sharded data set: genotype counts and missing-call index of ALL SNPs on every rank
+GlobalMissing* build_global_missing(Store* s, int world, int rank, int64_t stride, AllGatherFn fn, void* ctx);
 void scan_timer_begin(Chain* c, cudaStream_t st);
 void scan_timer_end(Chain* c, cudaStream_t st);
 void imma_launch_on(Chain* geom, const uint4* q, const int* scale_exp, double* out, bool het, cudaStream_t st, Chain* timed);

@@ -256,7 +256,9 @@ int bmg_sampler_create_on_store(const char* ini_path, int chain_index, bmg_store
  * every other rank's shard attached with bmg_store_attach_peer so that column statistics can read any SNP's packed
  * column over NVLink).  Every rank runs the SAME seeded sampler in lockstep: only the genotype scan is sharded; its
  * per-SNP result (8 bytes per SNP) is all-gathered through `allgather`, everything downstream is replicated and
- * bit-identical, so the chain equals the single-GPU chain draw for draw.
+ * bit-identical, so the chain equals the single-GPU chain draw for draw.  Data with missing genotype calls are handled:
+ * every rank keeps the chain's imputed values for ALL SNPs over the whole data set's missing-call index, which the ranks
+ * exchange once at creation through `allgather` (data_model.cpp:78-167).
  * allgather(ctx, dev_buffer, elems_per_rank, elem_bytes, cuda_stream): dev_buffer holds world*elems_per_rank elements;
  * rank r's block [r*elems_per_rank, (r+1)*elems_per_rank) is valid on entry, all blocks must be valid after the
  * work enqueued on cuda_stream (ncclAllGather in place, or torch.distributed.all_gather_into_tensor).  Returns 0 on

@@ -27,10 +27,11 @@ def main():
     rank, world = dist.get_rank(), dist.get_world_size()
     torch.cuda.set_device(0)
     n, m_g, n_rao = (int(sys.argv[5]) if len(sys.argv) > 5 else 600), 3000, 100
+    miss_rate = float(sys.argv[6]) if len(sys.argv) > 6 else 0.0
     n_chains = 2 if mode == "two" else 1
     if rank == 0:
         ds = synth.write_dataset(work, "syn", n=n, m_g=m_g, m_e=1, seed=5, e_qg=5, var_qg=20, do_n_iter=iters, n_rao=n_rao,
-                                 n_rao_burnin=2, n_threads=2, seeds="1234,2345", outbase=os.path.join(work, "single"))
+                                 n_rao_burnin=2, n_threads=2, seeds="1234,2345", miss_rate=miss_rate, outbase=os.path.join(work, "single"))
         np.save(os.path.join(work, "y.npy"), ds["y"])
         np.save(os.path.join(work, "E.npy"), ds["E"])
         for c in range(n_chains):   # the same chains on the whole store

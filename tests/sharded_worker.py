@@ -21,13 +21,14 @@ FILES = ["_loci.dat", "_modelsize.dat", "_jumpdistance.dat", "_log_likelihood.da
 
 def main():
     work, tau_rng, iters = sys.argv[1], sys.argv[2], int(sys.argv[3])
+    miss_rate = float(sys.argv[4]) if len(sys.argv) > 4 else 0.0
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
     torch.cuda.set_device(0)
     n, m_g = 600, 3000
     if rank == 0:
         ds = synth.write_dataset(work, "syn", n=n, m_g=m_g, m_e=1, seed=5, e_qg=5, var_qg=20, do_n_iter=iters, n_rao=100,
-                                 n_rao_burnin=2, outbase=os.path.join(work, "single"))
+                                 n_rao_burnin=2, miss_rate=miss_rate, outbase=os.path.join(work, "single"))
         np.save(os.path.join(work, "y.npy"), ds["y"])
         np.save(os.path.join(work, "E.npy"), ds["E"])
     dist.barrier()

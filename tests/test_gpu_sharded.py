@@ -10,26 +10,30 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("tau_rng", ["host", "device"])
-def test_sharded_chain_equals_single_gpu_chain(tmp_path, tau_rng):
+@pytest.mark.parametrize("tau_rng,miss_rate", [("host", 0.0), ("device", 0.0), ("host", 0.02), ("device", 0.02)])
+def test_sharded_chain_equals_single_gpu_chain(tmp_path, tau_rng, miss_rate):
+    """miss_rate > 0: data with missing genotype calls (src/data_model.cpp:78-103): the lockstep ranks draw the same imputed
+    values, every rank keeps them for all SNPs over the whole data set's missing-call index."""
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29%03d" % (os.getpid() % 1000), os.path.join(ROOT, "tests", "sharded_worker.py"), str(tmp_path),
-           tau_rng, "1200"]
+           tau_rng, "1200", str(miss_rate)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "SHARDED_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode,tau_rng,n", [("two", "host", 600), ("two", "device", 600), ("one", "device", 600), ("lock", "host", 600),
-                                            ("two", "device", 9000)])
-def test_chains_of_a_shard_group_equal_their_single_gpu_runs(tmp_path, mode, tau_rng, n):
+@pytest.mark.parametrize("mode,tau_rng,n,miss_rate", [("two", "host", 600, 0.0), ("two", "device", 600, 0.0), ("one", "device", 600, 0.0),
+                                                      ("lock", "host", 600, 0.0), ("two", "device", 9000, 0.0),
+                                                      ("two", "host", 600, 0.03), ("one", "device", 600, 0.03), ("lock", "host", 600, 0.03)])
+def test_chains_of_a_shard_group_equal_their_single_gpu_runs(tmp_path, mode, tau_rng, n, miss_rate):
     """Several chains over ONE sharded store (bmg_group_create; BASELINE configs[4], reference: chains share one Data,
     src/main.cpp:54-85): chain c on rank c, scans served by every rank through peer memory.  Each chain must write the
     bytes of its single-GPU run; a rank without a chain only serves scans; the lockstep chain also runs over the group's
     native all-gather."""
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "28%03d" % (os.getpid() % 1000), os.path.join(ROOT, "tests", "group_worker.py"), str(tmp_path),
-           mode, tau_rng, "1200", str(n)]   # n = 9,000: column statistics summed over 9 slices on the device
+           mode, tau_rng, "1200", str(n), str(miss_rate)]   # n = 9,000: column statistics summed over 9 slices on the device;
+    #                                                    miss_rate > 0: missing calls, imputed values of all SNPs on the chain's rank
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "GROUP_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
 

@@ -214,7 +214,6 @@ int chain_overlay_columns(Chain* c, const int64_t* snps, int count, const uint32
 // DataModel::miss_val of several SNPs at once (a move's proposed additions, or the Gibbs step's in-model SNPs)
 void chain_set_missing_many(Chain* c, const int64_t* snps, int count, const int8_t* const* vals)
 {
-  Store* s = c->store;
   if (count == 0) return;
   BMG_REQUIRE(count <= 2048, "bmg_chain_set_missing: too many SNPs in one call");
   for (int i = 0; i < count; ++i) {
@@ -233,7 +232,6 @@ void chain_set_missing_many(Chain* c, const int64_t* snps, int count, const int8
 void chain_overlay_invalidate(Chain* c, const int64_t* keep, int k)
 {
   if (c->pc_slots == 0) return;
-  Store* s = c->store;
   std::vector<std::pair<int64_t, int>> kept;
   for (int l = 0; l < k; ++l) {
     if (!c->mv.covers(keep[l])) continue;

@@ -780,3 +780,80 @@ def test_a_non_finite_residual_is_not_hidden_by_the_integer_scan(api):
         assert np.isnan(d).all() if variant == 2 else np.isnan(d).any(), variant
     ch.close()
     st.close()
+
+
+def test_one_whole_move_through_the_public_abi_only(api):
+    """What INTEGRATION.md sections 4-6 tell a maintainer to do, done here with nothing but the exported entry points: an
+    all-SNP scan, the proposal weights, one draw from the add distribution without replacement, the proposed SNP's column
+    statistics, and the move's log acceptance ratio from a Gram matrix held on the host (src/sampler.hpp:899-927 for an
+    addition of one SNP) -- every number against the oracle on decoded dense columns."""
+    n, m = 1500, 400
+    payload, y, E = make_data(n, m, seed=44)
+    bed, _ = oracle_store(payload, n, m, True)
+    xx = cpu.moments(bed, n, m)
+    st = api.GenotypeStore(payload, n, m, recode_to_minor=True)
+    st.set_phenotype(y, E)
+    ch = api.Chain(st)
+    D = np.concatenate([np.ones((n, 1)), E], axis=1)                     # the covariate block incl. the constant
+    k_e = D.shape[1]
+    loci = np.array([17, 230], dtype=np.int64)
+    X = np.stack([cpu.decode_column(bed, n, int(j), 0) for j in loci], axis=1)
+    tau_e = np.concatenate([[0.0], np.full(k_e - 1, 1.0)])
+    tau_g = np.array([2.0, 3.5])
+    nu, s2 = 1.0, 0.8
+    yy = float(y @ y)
+    # current model: Gram matrix from the ABI's column statistics of the model's own SNPs
+    xy_l, xe_l, _, xc_l = ch.column_stats(loci, np.zeros(0, dtype=np.int64))
+    G = np.zeros((k_e + 2, k_e + 2))
+    G[:k_e, :k_e] = D.T @ D
+    G[:k_e, k_e:] = xe_l.T
+    G[k_e:, k_e:] = xc_l
+    G = np.triu(G) + np.triu(G, 1).T
+    rhs = np.concatenate([D.T @ y, xy_l])
+    assert np.allclose(G[k_e:, k_e:], X.T @ X) and np.allclose(rhs[k_e:], X.T @ y, rtol=1e-12)
+    ll_cur, U, v, S = cpu.log_marginal(G, np.concatenate([tau_e, tau_g]), rhs, nu * s2 + yy, n + nu)
+    beta = np.linalg.solve(U, v)
+    # scan and proposal weights on the device, one draw from the add distribution (model SNPs zeroed)
+    ch.residual(loci, beta[:k_e], beta[k_e:])
+    p_r = ch.scan(loci, beta[k_e:], tau_g, 0.9, -3.0, -2.5, tau=4.0)
+    model_ind = -np.ones(m, dtype=np.int32)
+    model_ind[loci] = [0, 1]
+    yhat = D @ beta[:k_e] + X @ beta[k_e:]
+    want = cpu.scan_A(bed, n, m, xx, y, yhat, model_ind, beta[k_e:], tau_g, 4.0, 0, 0.9, -3.0, -2.5)
+    assert np.abs(p_r - want).max() < 1e-9
+    q_add_min, q_rem_min = 1.0 / (m - 5.0), 1.0 / 5.0
+    ch.init_proposal_flat(5.0 / m, q_add_min, q_rem_min)
+    ch.adapt(0, 0, 1, 1, q_add_min, q_rem_min)                           # p_proposal = mean(flat, p_r); q_add, q_rem; partial CDFs
+    for j in loci:
+        ch.set_zeroed(0, int(j), True)
+    u = 0.6180339887
+    snp, total = ch.sample(0, u)
+    p_prop = 0.5 * (5.0 / m) + 0.5 * want
+    w = np.maximum(p_prop, q_add_min)
+    zero = np.zeros(m, dtype=np.uint8)
+    zero[loci] = 1
+    order = cpu.inorder_permutation(m)
+    assert total == pytest.approx(cpu.dd_total(w, zero), rel=1e-12)
+    assert snp == cpu.dd_sample(w, zero, order, u)
+    # the proposed SNP against y, E and the model: one call; the new factor column on the host
+    xy_c, xe_c, xm_c, xc_c = ch.column_stats(np.array([snp], dtype=np.int64), loci)
+    x_new = cpu.decode_column(bed, n, int(snp), 0)
+    o_xy, o_col = cpu.column_stats(x_new, y, np.concatenate([D, X], axis=1))
+    got_col = np.concatenate([xe_c[0], xm_c[0], [xc_c[0, 0]]])
+    assert xy_c[0] == pytest.approx(o_xy, rel=1e-12) and np.allclose(got_col, o_col, rtol=1e-12, atol=1e-9)
+    assert np.array_equal(xm_c[0], X.T @ x_new)                          # genotype x genotype products are exact integers
+    tau_new = 1.7
+    G2 = np.zeros((k_e + 3, k_e + 3))
+    G2[:-1, :-1] = G
+    G2[:-1, -1] = got_col[:-1]
+    G2[-1, :-1] = got_col[:-1]
+    G2[-1, -1] = got_col[-1]
+    ll_new, _, _, _ = cpu.log_marginal(G2, np.concatenate([tau_e, tau_g, [tau_new]]), np.concatenate([rhs, xy_c]), nu * s2 + yy, n + nu)
+    # ... which must be the likelihood of the model with the decoded column appended
+    Xn = np.concatenate([D, X, x_new[:, None]], axis=1)
+    ll_ref, _, _, _ = cpu.log_marginal(Xn.T @ Xn, np.concatenate([tau_e, tau_g, [tau_new]]), Xn.T @ y, nu * s2 + yy, n + nu)
+    assert ll_new == pytest.approx(ll_ref, rel=1e-10)
+    log_q_forward = np.log(w[snp]) - np.log(total)
+    assert np.isfinite(ll_new - ll_cur - log_q_forward)
+    ch.close()
+    st.close()

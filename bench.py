@@ -650,28 +650,6 @@ def sharded_arm(args, rank, local_rank, world):
 # ------------------------------------------------------------------------------------------------
 # chains over a SNP-sharded store (bmagwa_b200/csrc/group.cu): the north star's multi-GPU split
 # ------------------------------------------------------------------------------------------------
-class LocalDist:
-    """Stand-in for torch.distributed in a one-rank job (no process group needed)."""
-
-    def get_world_size(self):
-        return 1
-
-    def get_rank(self):
-        return 0
-
-    def get_backend(self):
-        return "local"
-
-    def barrier(self):
-        pass
-
-    def all_gather_object(self, out, obj):
-        out[0] = obj
-
-    def broadcast_object_list(self, objs, src=0):
-        pass
-
-
 def sharded_phenotype(store, lo, hi, n, m, m_e, dist, world, probit):
     """20 causal SNPs spread over the genome, 0.14 s.d. each on the file's allele coding; each owner adds its columns."""
     import torch
@@ -747,7 +725,7 @@ def group_arm(args, workload, rank, local_rank, world, dist, n_chains, probit=Fa
     spec = WORKLOADS[workload]
     n, m, m_e = spec["n"], spec["m_g"], spec["m_e"]
     if dist is None:
-        dist = LocalDist()
+        dist = sharded.LocalDist()
     stride, lo, hi = sharded.shard_range(m, world, rank)
     t0 = time.perf_counter()
     payload = device_payload(n, lo, hi, GEN_SEED, torch.device("cuda", dev))

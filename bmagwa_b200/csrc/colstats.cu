@@ -633,7 +633,8 @@ void chain_column_stats_launch(Chain* c, const int64_t* cand, int m_c, const int
   const int patched = chain_overlay_columns(c, involved.data(), m_c + k, colp.data());
   if (m_c + k <= kInlinePtrs && s->m_e + 1 <= 8 && getenv("BMG_COLSTATS_SLOW") == nullptr) {
     // many small CTAs (one per candidate and 1024- or 4096-individual slice): one round of memory latency each
-    const int seg_words = s->W <= 4096 ? 64 : kFastSegMax;
+    static const int seg_forced = getenv("BMG_COLSTATS_SEG") ? atoi(getenv("BMG_COLSTATS_SEG")) : 0;   // development: 64 or 256
+    const int seg_words = seg_forced == 64 || seg_forced == 256 ? seg_forced : (s->W <= 4096 ? 64 : kFastSegMax);
     const int n_seg = (int)((s->W + seg_words - 1) / seg_words);
     const size_t need_fast = (size_t)m_c * n_tasks * n_seg;
     if (c->cs_map.n < 2 * need_fast + 8 || c->cs_seq >= 0xFFFFFFF0u) {   // (re)allocate; also before the tag wraps around

@@ -101,6 +101,28 @@ def create_sharded_sampler(dist, ini_path, n, m_g, bed_path, device, y, covariat
     return sampler, store, comm
 
 
+class LocalDist:
+    """Stand-in for torch.distributed in a one-rank job (no process group needed)."""
+
+    def get_world_size(self):
+        return 1
+
+    def get_rank(self):
+        return 0
+
+    def get_backend(self):
+        return "local"
+
+    def barrier(self):
+        pass
+
+    def all_gather_object(self, out, obj):
+        out[0] = obj
+
+    def broadcast_object_list(self, objs, src=0):
+        pass
+
+
 class ShardGroup:
     """bmg_group of this rank: several chains over one SNP-sharded store, chain c on rank c.  Collective constructor.
     torch.distributed only carries the name of the POSIX shared-memory segment the ranks synchronise through; scans

@@ -894,6 +894,7 @@ def group_arm(args, workload, rank, local_rank, world, dist, n_chains, probit=Fa
                     if same_seed and n_chains > 1 else ""),
                    "n": n, "m_g": m, "n_rao": args.n_rao, "chains": n_chains,
                    "seeds": "same" if same_seed and n_chains > 1 else "distinct",
+                   "n1_point": "`workloads.C4.value` (= `sharded_series_n1.value`) of the `--gpus 1` line: that line's headline is C2",
                    "step": "%d MCMC iterations per chain incl. one all-SNP scan per chain" % args.n_rao, "tau_rng": args.tau_rng,
                    "likelihood": "probit: latent phenotype redrawn on the device every 10 iterations, sigma2 = 1" if probit else "linear",
                    "sampler": "testdata/testdata.ini settings (PMV, thin 10, DR 10, individual tau2)",
@@ -1096,6 +1097,10 @@ def main():
                                 subs[sub] = {"error": repr(e)}
                                 log("[bench] sub-record %s failed: %r" % (sub, e))
                         line["workloads"] = subs
+                        if "value" in subs.get("C4", {}):   # --gpus N > 1 runs C4 sharded: its one-GPU point is this sub-record
+                            line["sharded_series_n1"] = {"workload": "C4", "value": subs["C4"]["value"], "unit": "iterations/s",
+                                                         "note": "the N = 1 point of the `--gpus N > 1` lines (C4, one chain per GPU over one "
+                                                                 "SNP-sharded store); the headline of this line is C2, BASELINE's metric config"}
             else:
                 wl = args.workload or "C4"
                 n_chains = args.chains if args.chains > 0 else world

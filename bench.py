@@ -881,8 +881,10 @@ def group_arm(args, workload, rank, local_rank, world, dist, n_chains, probit=Fa
         return None
     peak, peak_src = measured_peak()
     B = (n + 3) // 4
-    bytes_scan = (hi - lo) * B + 8 * (hi - lo) + 8 * n      # rank 0's shard, one chain's residual
     avg_ms = ms_total.value / max(1, n_l.value)
+    # residuals served per pass over the shard: the chains of a group are scanned two at a time (k_scan_dots_imma2)
+    rhs_per_launch = n_chains * (g1["rounds"] - g0["rounds"]) / max(1, n_l.value)
+    bytes_scan = int((hi - lo) * B + rhs_per_launch * (8 * (hi - lo) + 8 * n))      # rank 0's shard once + each residual's limbs and results
     iters = n_chains * args.steps * args.n_rao
     out = {
         "metric": "mcmc_iterations_per_sec", "value": iters / (elapsed_ms / 1e3), "unit": "iterations/s", "n_gpus": world,
@@ -906,7 +908,8 @@ def group_arm(args, workload, rank, local_rank, world, dist, n_chains, probit=Fa
                                "NCCL and no host callback on the data path; column statistics read remote shards over the peer mappings",
                    "timing": "CUDA events on the chain's stream, max over ranks; wall %.3f ms/step" % (1e3 * wall / args.steps)},
         "gpu_launches": launches_b - launches_a,
-        "roofline": {"bound": "hbm", "kernel": "k_scan_dots_imma on rank 0's shard (one launch per chain and scan)",
+        "roofline": {"bound": "hbm", "kernel": "k_scan_dots_imma%s on rank 0's shard (%.2f residuals per pass over the shard)"
+                               % ("2" if rhs_per_launch > 1.01 else "", rhs_per_launch), "residuals_per_launch": rhs_per_launch,
                      "achieved": bytes_scan / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0, "peak": peak, "unit": "GB/s",
                      "frac": (bytes_scan / (avg_ms * 1e-3) / 1e9 / peak) if avg_ms > 0 else 0.0, "traffic": scan_traffic(workload),
                      "bytes_per_launch": bytes_scan, "avg_launch_ms": avg_ms, "launches_timed": int(n_l.value), "peak_source": peak_src},

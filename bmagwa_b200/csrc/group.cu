@@ -88,7 +88,9 @@ struct Group {
   DevBuf<double> dots;           // this rank's chain: dot products over all SNPs, gathered from every rank's results area
   unsigned char* peer[kGroupMaxRanks] = {nullptr};
   bool peer_opened[kGroupMaxRanks] = {false};
-  DevBuf<unsigned char> q_stage[2];   // a peer chain's limbs + exponent, double-buffered
+  DevBuf<unsigned char> q_stage[2];   // peer chains' limbs + exponent: the two residuals of one pass
+  DevBuf<double> partial2;            // per-chunk partial sums of the second residual of a pass
+  int64_t pair_launches = 0;          // passes over the shard that served two chains
   std::unique_ptr<GlobalMissing> gm;   // genotype counts and missing-call index of all SNPs (every rank holds them)
   double barrier_seconds = 0.0;
   GroupShm local_shm;                  // world == 1: the flags live here
@@ -167,6 +169,7 @@ Group* group_create(Store* s, int world, int rank, int n_chains, int64_t stride,
   BMG_CUDA(cudaMemset(g->xbuf.p, 0, g->xbuf_bytes));
   g->q_stage[0].alloc(g->q_bytes + 256);
   g->q_stage[1].alloc(g->q_bytes + 256);
+  if (g->scan_chain->imma_slices2 > 0 && n_chains > 1) g->partial2.alloc(std::max<size_t>(1, (size_t)g->scan_chain->imma_chunks * (size_t)s->m));
   BMG_CUDA(cudaDeviceSynchronize());   // the memset ran on the null stream; everything below uses non-blocking streams
   g->peer[rank] = g->xbuf.p;
   if (world > 1) {
@@ -269,20 +272,52 @@ const double* group_scan_round(Group* g, Chain* mine)
       BMG_CUDA(cudaStreamSynchronize(st));   // also: the previous round's gather has finished reading the peers' results
     }
     group_barrier(g);   // every chain's limbs are in place, every chain is paused
-    for (int i = 0; i < g->n_chains; ++i) {
-      const int c = (g->rank + i) % g->n_chains;   // start with the nearest chain: the pulls spread over the peers
-      const unsigned char* q = g->xbuf.p;
-      if (c != g->rank) {   // the chain's limbs + exponent, pulled over NVLink
-        const int64_t n16 = (int64_t)((g->q_bytes + 256) / 16);
-        k_group_pull_bytes<<<(unsigned)std::min<int64_t>(296, (n16 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(g->peer[c]),
-                                                                                             reinterpret_cast<uint4*>(g->q_stage[i & 1].p), n16);
+    // the chains two at a time: one pass over the shard serves both residuals (k_scan_dots_imma2); a last odd chain, or a
+    // geometry without room for the two-residual kernel, takes the one-residual kernel
+    const bool pairs = sc->imma_slices2 > 0;
+    // development (profiling the two-residual kernel on one GPU): a one-chain group scans its residual as both halves of a pair
+    static const bool self_pair = getenv("BMG_GROUP_SELF_PAIR") != nullptr;
+    if (self_pair && pairs && g->n_chains == 1 && g->partial2.n == 0) {
+      BMG_CUDA(cudaStreamSynchronize(st));
+      g->partial2.alloc(std::max<size_t>(1, (size_t)sc->imma_chunks * (size_t)s->m));
+    }
+    for (int i = 0; i < g->n_chains; i += pairs ? 2 : 1) {
+      int n_here = pairs && i + 1 < g->n_chains ? 2 : 1;
+      if (self_pair && pairs && g->n_chains == 1) {
+        const unsigned char* q0 = g->xbuf.p;
+        imma_launch2_on(sc, reinterpret_cast<const uint4*>(q0), reinterpret_cast<const int*>(q0 + g->q_bytes), sc->imma_partial.p,
+                        reinterpret_cast<const uint4*>(q0), reinterpret_cast<const int*>(q0 + g->q_bytes), g->partial2.p, st, sc);
+        k_group_combine<<<(unsigned)((s->m + 255) / 256), 256, 0, st>>>(sc->imma_partial.p, sc->imma_chunks, s->m,
+                                                                        reinterpret_cast<double*>(g->xbuf.p + g->off_dots) + (int64_t)g->rank * g->stride);
         count_launch();
-        q = g->q_stage[i & 1].p;
+        break;
       }
-      imma_launch_on(sc, reinterpret_cast<const uint4*>(q), reinterpret_cast<const int*>(q + g->q_bytes), sc->imma_partial.p, false, st, sc);
-      double* out = reinterpret_cast<double*>(g->xbuf.p + g->off_dots) + (int64_t)c * g->stride;   // this rank's results for chain c
-      k_group_combine<<<(unsigned)((s->m + 255) / 256), 256, 0, st>>>(sc->imma_partial.p, sc->imma_chunks, s->m, out);
-      count_launch();
+      const unsigned char* q[2] = {nullptr, nullptr};
+      double* out[2] = {nullptr, nullptr};
+      for (int k = 0; k < n_here; ++k) {
+        const int c = (g->rank + i + k) % g->n_chains;   // start with the nearest chain: the pulls spread over the peers
+        q[k] = g->xbuf.p;
+        if (c != g->rank) {   // the chain's limbs + exponent, pulled over NVLink
+          const int64_t n16 = (int64_t)((g->q_bytes + 256) / 16);
+          k_group_pull_bytes<<<(unsigned)std::min<int64_t>(296, (n16 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(g->peer[c]),
+                                                                                               reinterpret_cast<uint4*>(g->q_stage[k].p), n16);
+          count_launch();
+          q[k] = g->q_stage[k].p;
+        }
+        out[k] = reinterpret_cast<double*>(g->xbuf.p + g->off_dots) + (int64_t)c * g->stride;   // this rank's results for chain c
+      }
+      if (n_here == 2) {
+        const bool ok = imma_launch2_on(sc, reinterpret_cast<const uint4*>(q[0]), reinterpret_cast<const int*>(q[0] + g->q_bytes), sc->imma_partial.p,
+                                        reinterpret_cast<const uint4*>(q[1]), reinterpret_cast<const int*>(q[1] + g->q_bytes), g->partial2.p, st, sc);
+        BMG_REQUIRE(ok, "shard group: the two-residual scan kernel is not available");
+        ++g->pair_launches;
+      } else {
+        imma_launch_on(sc, reinterpret_cast<const uint4*>(q[0]), reinterpret_cast<const int*>(q[0] + g->q_bytes), sc->imma_partial.p, false, st, sc);
+      }
+      for (int k = 0; k < n_here; ++k) {
+        k_group_combine<<<(unsigned)((s->m + 255) / 256), 256, 0, st>>>(k == 0 ? sc->imma_partial.p : g->partial2.p, sc->imma_chunks, s->m, out[k]);
+        count_launch();
+      }
     }
     BMG_CUDA(cudaGetLastError());
     BMG_CUDA(cudaStreamSynchronize(st));

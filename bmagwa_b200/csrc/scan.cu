@@ -217,6 +217,7 @@ __global__ void __launch_bounds__(32 * kMaxWarps, 2) k_scan_dots_tma(const ScanA
       warp_transpose_reduce(acc);
       if ((lane & 3) == 0) mypart[b * kBatch + x] = acc[0];
     }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy reads of stage s before its async-proxy refill
     __syncthreads();  // partials visible; every thread is done reading stage s
     if (t == 0 && it + kStages < my_tiles) issue(it + kStages);
     if (t < kTileSnps) {

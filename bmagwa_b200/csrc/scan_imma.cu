@@ -34,6 +34,7 @@ namespace bmg {
 
 constexpr int kImmaTile = 16;     // SNPs per tile = M of the MMA
 constexpr int kImmaStages = 4;
+constexpr int kImmaStages2 = 6;   // two-residual kernel: two resident CTAs per SM instead of three, so a deeper ring keeps as many tiles in flight
 constexpr int kImmaGroups = 8;    // 64-individual groups per warp kept in registers
 constexpr int kImmaWarpWords = 4 * kImmaGroups;   // 32 packed words = 512 individuals per warp
 constexpr int kImmaMaxWarps = 16;
@@ -140,6 +141,11 @@ struct ImmaArgs {
   int slices;
   int row_stride;          // shared-memory row stride in words (chunk_words + 16: two rows x 16 words per LDS.128 phase hit 32 banks)
   double* out;             // [n_chunks][m]
+  // second right-hand side of the two-residual kernel (k_scan_dots_imma2; unused otherwise)
+  const uint4* q1;
+  const int* scale_exp1;
+  double* out1;
+  int no_proxy_fence;      // development (tools/proxy_fence_ab.py): leave out the fence before a stage is handed back
 };
 
 __device__ __forceinline__ void mbar_arrive_i(uint64_t* bar)
@@ -147,16 +153,21 @@ __device__ __forceinline__ void mbar_arrive_i(uint64_t* bar)
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32i(bar)) : "memory");
 }
 
-constexpr int kImmaAccBufs = kImmaStages + 1;
 __device__ __forceinline__ void fence_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
 
 // Warp-specialised: blockDim = 32 * (consumer warps + 1).  The last warp is the producer (one lane issues the
 // bulk-async copies, gated by per-stage "empty" mbarriers); consumer warps never meet at a CTA barrier: each adds its
 // int32 limb sums into a shared accumulator and the LAST warp to finish a tile (atomic ticket) combines and stores it.
-// dynamic smem: kImmaStages * 16 * row_stride words | int acc[kImmaAccBufs][16][8] | int ticket[kImmaAccBufs] | mbarriers
-template <bool HET>
-__global__ void __maxnreg__(80) k_scan_dots_imma(const __grid_constant__ ImmaArgs a)
+// dynamic smem: NS * 16 * row_stride words | int acc[NS + 1][R][16][8] | int ticket[8] | mbarriers (NS = stages of the ring)
+//
+// R = 2 (k_scan_dots_imma2, shard groups): the same genotype words against the limbs of TWO residuals -- every packed byte
+// is read and expanded once per pair of chains; each residual's sums are the integers the one-residual kernel forms, so
+// the results are the same bits.
+template <bool HET, int R, int NS>
+__device__ __forceinline__ void scan_dots_imma_body(const ImmaArgs& a)
 {
+  constexpr int kAccBufs = NS + 1;
+  static_assert(kAccBufs <= 8, "ticket array");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int n_cons = (blockDim.x >> 5) - 1;
@@ -168,23 +179,28 @@ __global__ void __maxnreg__(80) k_scan_dots_imma(const __grid_constant__ ImmaArg
   const int stage_words = kImmaTile * RS;
 
   uint32_t* stage0 = reinterpret_cast<uint32_t*>(smem_raw);
-  int* acc = reinterpret_cast<int*>(stage0 + (size_t)kImmaStages * stage_words);
-  int* ticket = acc + kImmaAccBufs * kImmaTile * 8;
+  int* acc = reinterpret_cast<int*>(stage0 + (size_t)NS * stage_words);
+  int* ticket = acc + kAccBufs * R * kImmaTile * 8;
   uint64_t* full = reinterpret_cast<uint64_t*>(ticket + 8);
-  uint64_t* empty = full + kImmaStages;
+  uint64_t* empty = full + NS;
 
   const int64_t tile_lo = a.tiles * slice / a.slices, tile_hi = a.tiles * (slice + 1) / a.slices;
   const int my_tiles = (int)(tile_hi - tile_lo);
 
   if (t == 0) {
-    for (int s = 0; s < kImmaStages; ++s) { mbar_init_i(&full[s], 1); mbar_init_i(&empty[s], (uint32_t)n_cons); }
+    for (int s = 0; s < NS; ++s) { mbar_init_i(&full[s], 1); mbar_init_i(&empty[s], (uint32_t)n_cons); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int idx = t; idx < kImmaAccBufs * kImmaTile * 8 + 8; idx += blockDim.x) acc[idx] = 0;   // accumulators and tickets
+  for (int idx = t; idx < kAccBufs * R * kImmaTile * 8 + 8; idx += blockDim.x) acc[idx] = 0;   // accumulators and tickets
   __syncthreads();
 
   if (warp == n_cons) {
     // ---------------- producer warp ----------------
+    // One lane issues the 16 row copies of a tile.  Its addresses are per-thread values, so ptxas moves them to uniform
+    // registers copy by copy (~100 cycles per UBLKCP); a variant in which the whole warp runs this loop on warp-uniform
+    // values and an elected lane issues straight from uniform registers was 4-6 % faster at 2.5 GB and no faster at the
+    // C2 size, and the repeated-launch guard test failed once in six full runs with it (never in isolation, never again
+    // once the proxy fence below was in): not shipped, see profiles/round2_notes.md 10.
     if (lane == 0) {
       const uint32_t rb = (uint32_t)row_copy_words * 4u;
       int s = 0;
@@ -196,7 +212,7 @@ __global__ void __maxnreg__(80) k_scan_dots_imma(const __grid_constant__ ImmaArg
         uint32_t* dst = stage0 + (size_t)s * stage_words;
         mbar_expect_tx_i(&full[s], rb * (uint32_t)rows);
         for (int rr = 0; rr < rows; ++rr) bulk_g2s_i(dst + (size_t)rr * RS, a.codes + (snp0 + rr) * a.Wp + c0, rb, &full[s]);
-        if (++s == kImmaStages) { s = 0; ++round; }
+        if (++s == NS) { s = 0; ++round; }
       }
     }
     return;
@@ -204,11 +220,17 @@ __global__ void __maxnreg__(80) k_scan_dots_imma(const __grid_constant__ ImmaArg
 
   // ---------------- consumer warps ----------------
   // this thread's words of a warp slice: 16 x + 4 tig + e (x < 2, e < 4) = one uint4 per x; limb g of each
-  uint4 bq[kImmaGroups];
+  uint4 bq[R][kImmaGroups];
 #pragma unroll
-  for (int grp = 0; grp < kImmaGroups; ++grp)
-    bq[grp] = a.q[(c0 + warp * kImmaWarpWords + 16 * (grp >> 2) + 4 * tig + (grp & 3)) * 8 + g];
-  const int scale_exp = a.scale_exp[0];
+  for (int r = 0; r < R; ++r) {
+    const uint4* q = r == 0 ? a.q : a.q1;
+#pragma unroll
+    for (int grp = 0; grp < kImmaGroups; ++grp)
+      bq[r][grp] = q[(c0 + warp * kImmaWarpWords + 16 * (grp >> 2) + 4 * tig + (grp & 3)) * 8 + g];
+  }
+  int scale_exp[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) scale_exp[r] = (r == 0 ? a.scale_exp : a.scale_exp1)[0];
   const int word_off = warp * kImmaWarpWords + 4 * tig;
 
   int s = 0, buf = 0;
@@ -225,23 +247,39 @@ __global__ void __maxnreg__(80) k_scan_dots_imma(const __grid_constant__ ImmaArg
       wl[4 * x] = vl.x; wl[4 * x + 1] = vl.y; wl[4 * x + 2] = vl.z; wl[4 * x + 3] = vl.w;
       wh[4 * x] = vh.x; wh[4 * x + 1] = vh.y; wh[4 * x + 2] = vh.z; wh[4 * x + 3] = vh.w;
     }
+    // The refill of this stage is an async-proxy write (bulk copy) to memory this thread has just read through the generic
+    // proxy; PTX orders accesses made through different proxies only across a proxy fence, in this write-after-read
+    // direction too (CUTLASS places the same fence before releasing a TMA-loaded buffer its threads read with ld.shared).
+    if (!a.no_proxy_fence) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
     if (lane == 0) mbar_arrive_i(&empty[s]);   // this warp's words are in registers: the stage may be refilled
-    int c[4] = {0, 0, 0, 0}, c2[4] = {0, 0, 0, 0};   // two independent IMMA chains
+    int c[R][4], c2[R][4];   // two independent IMMA chains per residual
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) c[r][e] = c2[r][e] = 0;
 #pragma unroll
     for (int grp = 0; grp < kImmaGroups; ++grp) {
-      imma16832(c, expand_field<0, HET>(wl[grp]), expand_field<0, HET>(wh[grp]), expand_field<1, HET>(wl[grp]),
-                expand_field<1, HET>(wh[grp]), bq[grp].x, bq[grp].y);
-      imma16832(c2, expand_field<2, HET>(wl[grp]), expand_field<2, HET>(wh[grp]), expand_field<3, HET>(wl[grp]),
-                expand_field<3, HET>(wh[grp]), bq[grp].z, bq[grp].w);
-    }
+      const uint32_t l0 = expand_field<0, HET>(wl[grp]), h0 = expand_field<0, HET>(wh[grp]), l1 = expand_field<1, HET>(wl[grp]),
+                     h1 = expand_field<1, HET>(wh[grp]), l2 = expand_field<2, HET>(wl[grp]), h2 = expand_field<2, HET>(wh[grp]),
+                     l3 = expand_field<3, HET>(wl[grp]), h3 = expand_field<3, HET>(wh[grp]);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) c[e] += c2[e];
-    int* tile_acc = acc + buf * kImmaTile * 8;
-    atomicAdd(&tile_acc[g * 8 + 2 * tig], c[0]);
-    atomicAdd(&tile_acc[g * 8 + 2 * tig + 1], c[1]);
-    atomicAdd(&tile_acc[(g + 8) * 8 + 2 * tig], c[2]);
-    atomicAdd(&tile_acc[(g + 8) * 8 + 2 * tig + 1], c[3]);
+      for (int r = 0; r < R; ++r) {
+        imma16832(c[r], l0, h0, l1, h1, bq[r][grp].x, bq[r][grp].y);
+        imma16832(c2[r], l2, h2, l3, h3, bq[r][grp].z, bq[r][grp].w);
+      }
+    }
+    int* tile_acc = acc + buf * R * kImmaTile * 8;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) c[r][e] += c2[r][e];
+      int* ta = tile_acc + r * kImmaTile * 8;
+      atomicAdd(&ta[g * 8 + 2 * tig], c[r][0]);
+      atomicAdd(&ta[g * 8 + 2 * tig + 1], c[r][1]);
+      atomicAdd(&ta[(g + 8) * 8 + 2 * tig], c[r][2]);
+      atomicAdd(&ta[(g + 8) * 8 + 2 * tig + 1], c[r][3]);
+    }
     fence_cta();
     __syncwarp();
     int last = 0;
@@ -249,26 +287,40 @@ __global__ void __maxnreg__(80) k_scan_dots_imma(const __grid_constant__ ImmaArg
     last = __shfl_sync(0xffffffffu, last, 0);
     if (last) {   // every other warp's sums are in (their fences precede their tickets)
       fence_cta();
-      if (lane < kImmaTile) {
-        const int64_t snp = (tile_lo + it) * kImmaTile + lane;
+      if (lane < R * kImmaTile) {   // lane = 16 r + SNP of the tile
+        const int r = R == 1 ? 0 : lane >> 4;
+        const int64_t snp = (tile_lo + it) * kImmaTile + (lane & (kImmaTile - 1));
         volatile int* d = tile_acc + lane * 8;
         const long long lo = (long long)d[0] + ((long long)d[1] << 8) + ((long long)d[2] << 16) + ((long long)d[3] << 24);
         const long long hi = (long long)d[4] + ((long long)d[5] << 8) + ((long long)d[6] << 16) + ((long long)d[7] << 24);
 #pragma unroll
         for (int b = 0; b < 8; ++b) d[b] = 0;
         // 2^-S in two always-normal factors (S spans about +-1100)
-        const int h0 = scale_exp / 2, h1 = scale_exp - h0;
+        const int se = R == 1 ? scale_exp[0] : (r == 0 ? scale_exp[0] : scale_exp[R - 1]);
+        const int h0 = se / 2, h1 = se - h0;
         const double f0 = __hiloint2double((1023 - h0) << 20, 0), f1 = __hiloint2double((1023 - h1) << 20, 0);
+        double* out = R == 1 || r == 0 ? a.out : a.out1;
         if (snp < a.m)
-          a.out[(int64_t)chunk * a.m + snp] = scale_exp == kImmaNonFinite ? __longlong_as_double(0x7ff8000000000000ll)
-                                                                         : fma((double)hi, 4294967296.0, (double)lo) * f0 * f1;
+          out[(int64_t)chunk * a.m + snp] = se == kImmaNonFinite ? __longlong_as_double(0x7ff8000000000000ll)
+                                                                 : fma((double)hi, 4294967296.0, (double)lo) * f0 * f1;
       }
       __syncwarp();
       if (lane == 0) { fence_cta(); ticket[buf] = 0; }
     }
-    if (++s == kImmaStages) { s = 0; phase ^= 1u; }
-    if (++buf == kImmaAccBufs) buf = 0;
+    if (++s == NS) { s = 0; phase ^= 1u; }
+    if (++buf == kAccBufs) buf = 0;
   }
+}
+
+template <bool HET>
+__global__ void __maxnreg__(80) k_scan_dots_imma(const __grid_constant__ ImmaArgs a)
+{
+  scan_dots_imma_body<HET, 1, kImmaStages>(a);
+}
+// two residuals per pass: 64 limb registers per thread, so fewer resident warps than the one-residual kernel
+__global__ void __maxnreg__(128) k_scan_dots_imma2(const __grid_constant__ ImmaArgs a)
+{
+  scan_dots_imma_body<false, 2, kImmaStages2>(a);
 }
 
 // ---- host side ----------------------------------------------------------------------------------
@@ -299,10 +351,12 @@ void imma_choose_geometry(Chain* c)
   c->imma_chunks = (int)((W + c->imma_chunk_words - 1) / c->imma_chunk_words);
 }
 
-static size_t imma_smem_bytes(const Chain* c)
+static size_t imma_smem_bytes(const Chain* c, int n_rhs = 1)
 {
   const int RS = (int)c->imma_chunk_words + 16;
-  return (size_t)kImmaStages * kImmaTile * RS * 4 + (size_t)(kImmaStages + 1) * kImmaTile * 8 * sizeof(int) + 8 * sizeof(int) + 2 * kImmaStages * sizeof(uint64_t);
+  const int stages = n_rhs == 2 ? kImmaStages2 : kImmaStages;
+  return (size_t)stages * kImmaTile * RS * 4 + (size_t)(stages + 1) * n_rhs * kImmaTile * 8 * sizeof(int) + 8 * sizeof(int) +
+         2 * stages * sizeof(uint64_t);
 }
 
 void imma_prepare(Chain* c)
@@ -329,6 +383,20 @@ void imma_prepare(Chain* c)
   if (slices < 1) slices = 1;
   if (slices > tiles) slices = tiles;
   c->imma_slices = (int)slices;
+  // the two-residual kernel: same warps and chunks (so the same limb layout), its own number of resident CTAs
+  const size_t smem2 = imma_smem_bytes(c, 2);
+  c->imma_slices2 = 0;
+  if (smem2 <= 227 * 1024 && getenv("BMG_IMMA_SINGLE") == nullptr) {
+    BMG_CUDA(cudaFuncSetAttribute(k_scan_dots_imma2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    int per_sm2 = 0;
+    BMG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, k_scan_dots_imma2, 32 * (c->imma_warps + 1), smem2));
+    if (per_sm2 >= 1) {
+      int64_t slices2 = ((int64_t)per_sm2 * s->sm_count) / c->imma_chunks;
+      if (slices2 < 1) slices2 = 1;
+      if (slices2 > tiles) slices2 = tiles;
+      c->imma_slices2 = (int)slices2;
+    }
+  }
   c->imma_ready = true;
 }
 
@@ -347,6 +415,12 @@ void imma_quantize(Chain* c)
   c->imma_q_valid = true;
 }
 
+static int imma_no_proxy_fence()
+{
+  static const int v = getenv("BMG_IMMA_NO_PROXY_FENCE") != nullptr;
+  return v;
+}
+
 // the tensor-core scan of this store's SNPs against ONE quantised right-hand side (q, scale_exp: the layout k_quantize
 // writes; they may belong to another chain, group.cu) into out ([chunks][m] doubles), with the geometry of `geom`
 void imma_launch_on(Chain* geom, const uint4* q, const int* scale_exp, double* out, bool het, cudaStream_t st, Chain* timed)
@@ -358,12 +432,36 @@ void imma_launch_on(Chain* geom, const uint4* q, const int* scale_exp, double* o
   a.chunk_words = (int)geom->imma_chunk_words; a.n_chunks = geom->imma_chunks; a.tiles = (s->m + kImmaTile - 1) / kImmaTile;
   a.slices = geom->imma_slices; a.row_stride = (int)geom->imma_chunk_words + 16;
   a.out = out;
+  a.q1 = nullptr; a.scale_exp1 = nullptr; a.out1 = nullptr;
+  a.no_proxy_fence = imma_no_proxy_fence();
   const unsigned grid = (unsigned)(geom->imma_chunks * geom->imma_slices);
   if (timed) scan_timer_begin(timed, st);
   if (het) k_scan_dots_imma<true><<<grid, 32 * (geom->imma_warps + 1), imma_smem_bytes(geom), st>>>(a);
   else k_scan_dots_imma<false><<<grid, 32 * (geom->imma_warps + 1), imma_smem_bytes(geom), st>>>(a);
   if (timed) scan_timer_end(timed, st);
   count_launch();
+}
+
+// the same scan against TWO quantised right-hand sides in one pass over the shard (shard groups: two chains' residuals);
+// false when the geometry has no room for the two-residual kernel (the caller then launches twice)
+bool imma_launch2_on(Chain* geom, const uint4* q0, const int* scale_exp0, double* out0, const uint4* q1, const int* scale_exp1,
+                     double* out1, cudaStream_t st, Chain* timed)
+{
+  Store* s = geom->store;
+  if (!geom->imma_ready) imma_prepare(geom);
+  if (geom->imma_slices2 < 1) return false;
+  ImmaArgs a;
+  a.codes = s->codes.p; a.Wp = s->Wp; a.m = s->m; a.q = q0; a.scale_exp = scale_exp0; a.out = out0;
+  a.q1 = q1; a.scale_exp1 = scale_exp1; a.out1 = out1;
+  a.no_proxy_fence = imma_no_proxy_fence();
+  a.chunk_words = (int)geom->imma_chunk_words; a.n_chunks = geom->imma_chunks; a.tiles = (s->m + kImmaTile - 1) / kImmaTile;
+  a.slices = geom->imma_slices2; a.row_stride = (int)geom->imma_chunk_words + 16;
+  const unsigned grid = (unsigned)(geom->imma_chunks * geom->imma_slices2);
+  if (timed) scan_timer_begin(timed, st);
+  k_scan_dots_imma2<<<grid, 32 * (geom->imma_warps + 1), imma_smem_bytes(geom, 2), st>>>(a);
+  if (timed) scan_timer_end(timed, st);
+  count_launch();
+  return true;
 }
 
 // the chain's own scan into imma_partial; het: the heterozygote-indicator pass into imma_partial_h

@@ -96,6 +96,7 @@ struct Chain {
   // variant 2 (integer tensor cores, scan_imma.cu)
   bool imma_ready = false, imma_q_valid = false;
   int imma_warps = 0, imma_chunks = 0, imma_slices = 0;
+  int imma_slices2 = 0;          // SNP slices of the two-residual kernel (0: not available for this geometry)
   int64_t imma_chunk_words = 0;
   DevBuf<unsigned char> imma_q;                 // residual limbs [word][8][16]
   DevBuf<int> imma_exp;                         // fixed-point exponent S
@@ -213,6 +214,8 @@ GlobalMissing* build_global_missing(Store* s, int world, int rank, int64_t strid
 void scan_timer_begin(Chain* c, cudaStream_t st);
 void scan_timer_end(Chain* c, cudaStream_t st);
 void imma_launch_on(Chain* geom, const uint4* q, const int* scale_exp, double* out, bool het, cudaStream_t st, Chain* timed);
+bool imma_launch2_on(Chain* geom, const uint4* q0, const int* scale_exp0, double* out0, const uint4* q1, const int* scale_exp1,
+                     double* out1, cudaStream_t st, Chain* timed);
 void chain_allgather(Chain* c, void* dev_buffer, int elem_bytes);
 void imma_prepare(Chain* c);
 void imma_quantize(Chain* c);

@@ -28,10 +28,10 @@ def main():
     torch.cuda.set_device(0)
     n, m_g, n_rao = (int(sys.argv[5]) if len(sys.argv) > 5 else 600), 3000, 100
     miss_rate = float(sys.argv[6]) if len(sys.argv) > 6 else 0.0
-    n_chains = 2 if mode == "two" else 1
+    n_chains = {"two": 2, "three": 3}.get(mode, 1)   # three: three ranks, a two-residual pass + a one-residual pass per scan
     if rank == 0:
         ds = synth.write_dataset(work, "syn", n=n, m_g=m_g, m_e=1, seed=5, e_qg=5, var_qg=20, do_n_iter=iters, n_rao=n_rao,
-                                 n_rao_burnin=2, n_threads=2, seeds="1234,2345", miss_rate=miss_rate, outbase=os.path.join(work, "single"))
+                                 n_rao_burnin=2, n_threads=3, seeds="1234,2345,3456", miss_rate=miss_rate, outbase=os.path.join(work, "single"))
         np.save(os.path.join(work, "y.npy"), ds["y"])
         np.save(os.path.join(work, "E.npy"), ds["E"])
         for c in range(n_chains):   # the same chains on the whole store
@@ -64,8 +64,10 @@ def main():
     ok = True
     if rank == 0:
         pairs = [("single0", "group0")]
-        if mode == "two":
+        if mode in ("two", "three"):
             pairs.append(("single1", "group1"))
+        if mode == "three":
+            pairs.append(("single2", "group2"))
         if mode == "lock":
             pairs.append(("group0", "group1"))
         for a, b in pairs:

@@ -24,13 +24,15 @@ def test_sharded_chain_equals_single_gpu_chain(tmp_path, tau_rng, miss_rate):
 @pytest.mark.gpu
 @pytest.mark.parametrize("mode,tau_rng,n,miss_rate", [("two", "host", 600, 0.0), ("two", "device", 600, 0.0), ("one", "device", 600, 0.0),
                                                       ("lock", "host", 600, 0.0), ("two", "device", 9000, 0.0),
-                                                      ("two", "host", 600, 0.03), ("one", "device", 600, 0.03), ("lock", "host", 600, 0.03)])
+                                                      ("two", "host", 600, 0.03), ("one", "device", 600, 0.03), ("lock", "host", 600, 0.03),
+                                                      ("three", "device", 600, 0.0), ("three", "host", 9000, 0.02)])
 def test_chains_of_a_shard_group_equal_their_single_gpu_runs(tmp_path, mode, tau_rng, n, miss_rate):
     """Several chains over ONE sharded store (bmg_group_create; BASELINE configs[4], reference: chains share one Data,
     src/main.cpp:54-85): chain c on rank c, scans served by every rank through peer memory.  Each chain must write the
     bytes of its single-GPU run; a rank without a chain only serves scans; the lockstep chain also runs over the group's
-    native all-gather."""
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+    native all-gather.  Chains are scanned two at a time (k_scan_dots_imma2); "three" has a pair and a single pass per scan."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "3" if mode == "three" else "2",
+           "--master-addr", "127.0.0.1",
            "--master-port", "28%03d" % (os.getpid() % 1000), os.path.join(ROOT, "tests", "group_worker.py"), str(tmp_path),
            mode, tau_rng, "1200", str(n), str(miss_rate)]   # n = 9,000: column statistics summed over 9 slices on the device;
     #                                                    miss_rate > 0: missing calls, imputed values of all SNPs on the chain's rank

@@ -111,23 +111,56 @@ def prepare_dataset(w, n_rao, n_threads, out_dir, do_n_iter):
     return ini, spec
 
 
+def _cpu_list(text):
+    out = set()
+    for part in text.strip().split(","):
+        if part:
+            lo, _, hi = part.partition("-")
+            out.update(range(int(lo), int(hi or lo) + 1))
+    return out
+
+
+def gpu_local_cpus(device_index):
+    """CPUs on the NUMA node the GPU hangs off (sysfs local_cpulist of its PCI function); empty set when unknown."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(device_index), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(device_index), "pci_device_id", 0)
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/local_cpulist" % (dom, bus, dev)
+        with open(path) as fh:
+            return _cpu_list(fh.read())
+    except Exception:
+        return set()
+
+
 def pin_rank_to_core(local_rank, world):
     """A block of physical cores (all their hyperthreads) per rank: the chain's host thread spin-waits on device results,
-    and two spinning ranks on sibling hyperthreads slow each other down.  No-op with fewer physical cores than ranks."""
+    and two spinning ranks on sibling hyperthreads slow each other down.  Cores on the GPU's own NUMA node are preferred:
+    every move is a round trip over PCIe through mapped host memory, and a hop across sockets adds to each leg
+    (BMG_BENCH_NO_LOCAL_PIN=1 turns the preference off).  No-op with fewer physical cores than ranks."""
     try:
         allowed = sorted(os.sched_getaffinity(0))
         cores = {}
         for cpu in allowed:
             with open("/sys/devices/system/cpu/cpu%d/topology/thread_siblings_list" % cpu) as fh:
-                sib = fh.read().strip()
-            members = set()
-            for part in sib.split(","):
-                lo, _, hi = part.partition("-")
-                members.update(range(int(lo), int(hi or lo) + 1))
+                members = _cpu_list(fh.read())
             cores[min(members)] = sorted(members & set(allowed))
         phys = [cores[k] for k in sorted(cores)]
         if len(phys) < world:
             return None
+        if os.environ.get("BMG_BENCH_NO_LOCAL_PIN") is None:
+            # ranks grouped by the NUMA node of their GPU; each group shares that node's allowed cores
+            local = [gpu_local_cpus(r) for r in range(world)]
+            key = [tuple(sorted(l)) for l in local]
+            peers = [r for r in range(world) if key[r] == key[local_rank]]
+            near = [c for c in phys if local[local_rank] and set(c) <= local[local_rank]]
+            if len(near) >= len(peers):
+                per = len(near) // len(peers)
+                i = peers.index(local_rank)
+                mine = sorted(c for core in near[i * per:(i + 1) * per] for c in core)
+                os.sched_setaffinity(0, mine)
+                return mine
         per = len(phys) // world   # a contiguous block of physical cores per rank (helper threads keep their own CPUs)
         mine = sorted(c for core in phys[local_rank * per:(local_rank + 1) * per] for c in core)
         os.sched_setaffinity(0, mine)
@@ -912,7 +945,11 @@ def group_arm(args, workload, rank, local_rank, world, dist, n_chains, probit=Fa
                                % ("2" if rhs_per_launch > 1.01 else "", rhs_per_launch), "residuals_per_launch": rhs_per_launch,
                      "achieved": bytes_scan / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0, "peak": peak, "unit": "GB/s",
                      "frac": (bytes_scan / (avg_ms * 1e-3) / 1e9 / peak) if avg_ms > 0 else 0.0, "traffic": scan_traffic(workload),
-                     "bytes_per_launch": bytes_scan, "avg_launch_ms": avg_ms, "launches_timed": int(n_l.value), "peak_source": peak_src},
+                     "bytes_per_launch": bytes_scan, "avg_launch_ms": avg_ms, "launches_timed": int(n_l.value), "peak_source": peak_src,
+                     "note": ("two residuals per pass: the packed bytes are read once for two chains, i.e. %.0f GB/s per residual-pass; at this "
+                              "rate the kernel is bound by its consumers' tensor-pipe / issue rate (profiles/round2_scan2_ncu.md), not by HBM; the "
+                              "one-residual kernel on the same shard reaches 0.84-0.87" % (rhs_per_launch * bytes_scan / (avg_ms * 1e-3) / 1e9))
+                     if rhs_per_launch > 1.01 and avg_ms > 0 else None},
         "clocks": clk,
         "breakdown": {"move_seconds": st1["move_seconds"] - st0["move_seconds"], "scan_seconds": st1["scan_seconds"] - st0["scan_seconds"],
                       "column_stats_seconds": st1["column_stats_seconds"] - st0["column_stats_seconds"],
@@ -1071,9 +1108,12 @@ def main():
                 import torch.distributed as dist_mod
                 dist = dist_mod
                 dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-                pinned = pin_rank_to_core(local_rank, world)
-                if pinned is not None:
-                    log("[bench] rank %d pinned to CPUs %s" % (rank, pinned))
+            near = gpu_local_cpus(local_rank)
+            log("[bench] rank %d: allowed CPUs %s; CPUs on GPU %d's NUMA node: %s"
+                % (rank, sorted(os.sched_getaffinity(0)), local_rank, sorted(near) if near else "unknown"))
+            pinned = pin_rank_to_core(local_rank, world)
+            if pinned is not None:
+                log("[bench] rank %d pinned to CPUs %s" % (rank, pinned))
             if args.sharded:
                 args.workload = args.workload or "C4"
                 line = sharded_arm(args, rank, local_rank, world)

@@ -27,3 +27,8 @@ BMG_COLSTATS_SERVER=0 timeout 600 ncu --set full --clock-control none --import-s
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-sub > $OUT/colstats_under_ncu_$TAG.log 2>&1
 ncu -i $OUT/colstats_$TAG.ncu-rep --page raw --csv > $OUT/colstats_${TAG}_raw.csv 2>/dev/null
 ls -la $OUT
+# 4. the two-residual scan of shard groups (k_scan_dots_imma2), on one GPU: a one-chain group scans its residual as both
+#    halves of a pair (BMG_GROUP_SELF_PAIR, development switch of group.cu)
+BMG_GROUP_SELF_PAIR=1 BMG_COLSTATS_SERVER=0 timeout 500 ncu --set full --clock-control none --import-source on -k regex:k_scan_dots_imma2 -s 2 -c 1 -f -o $OUT/scan2_$TAG \
+    python bench.py --workload C4s --steps 3 --warmup 1 --burnin 0 --no-e2e --no-cpu-baseline > $OUT/scan2_under_ncu_$TAG.log 2>&1
+ncu -i $OUT/scan2_$TAG.ncu-rep --page raw --csv > $OUT/scan2_${TAG}_raw.csv 2>/dev/null

@@ -107,6 +107,8 @@ def main():
         traffic["C2x"] = t
     raw("colstats_%s_raw.csv" % tag, "k_column_stats_inline (one proposal's column statistics; latency-bound)", rnd,
         "%s_colstats_ncu.md" % rnd)
+    raw("scan2_%s_raw.csv" % tag, "k_scan_dots_imma2 (two residuals per pass; shard groups) at n=50,000 x m=200,000 (2.5 GB of packed genotypes per launch)",
+        rnd, "%s_scan2_ncu.md" % rnd)
     if traffic:
         json.dump(traffic, open(os.path.join(PROF, "scan_traffic.json"), "w"), indent=1)
     print("wrote", sorted(os.listdir(PROF)))

@@ -762,7 +762,17 @@ def group_arm(args, workload, rank, local_rank, world, dist, n_chains, probit=Fa
     stride, lo, hi = sharded.shard_range(m, world, rank)
     t0 = time.perf_counter()
     payload = device_payload(n, lo, hi, GEN_SEED, torch.device("cuda", dev))
-    host_payload = payload.cpu().numpy() if with_e2e else None   # the shard as a host buffer, for the end-to-end run
+    # the shard as a host buffer for the end-to-end run, in pinned memory (pageable if pinning that much is refused)
+    host_payload, host_kind = None, None
+    if with_e2e:
+        try:
+            pinned_t = torch.empty(payload.numel(), dtype=torch.uint8, pin_memory=True)
+            pinned_t.copy_(payload)
+            torch.cuda.synchronize()
+            host_payload, host_kind = pinned_t.numpy(), "pinned"
+        except Exception as e:
+            log("[bench] %s rank %d: pinning %d bytes failed (%r); pageable host buffer" % (workload, rank, payload.numel(), e))
+            host_payload, host_kind = payload.cpu().numpy(), "pageable"
     t_gen = time.perf_counter() - t0
 
     def build(from_host):
@@ -782,15 +792,21 @@ def group_arm(args, workload, rank, local_rank, world, dist, n_chains, probit=Fa
     ini = group_ini(shared, tmp, rank, n, m, m_e, args.n_rao, n_chains, same_seed)
 
     def open_group(store, tag):
+        ta = time.perf_counter()
         store.set_phenotype(y, E)
         sharded.attach_all_peers(dist, store, world, rank, lo, hi)
+        tb = time.perf_counter()
         group = sharded.ShardGroup(dist, store, stride, n_chains)
+        tc = time.perf_counter()
         smp = None
         if group.has_chain:
             smp = api.Sampler(ini, rank, dev, store=store, group=group, tau_rng=args.tau_rng)
             smp.set_option("basename", os.path.join(tmp, "%s%d" % (tag, rank)))
             if probit:
                 smp.set_option("probit", "1")
+        if rank == 0:
+            log("[bench] %s rank 0 (%s): phenotype + peers %.3f s, group %.3f s, sampler %.3f s"
+                % (workload, tag, tb - ta, tc - tb, time.perf_counter() - tc))
         return group, smp
 
     group, smp = open_group(store, "bench")
@@ -899,6 +915,7 @@ def group_arm(args, workload, rank, local_rank, world, dist, n_chains, probit=Fa
         group2.close(); store2.close()
         e2e = {"value": n_chains * args.steps * args.n_rao / e2e_secs, "unit": "iterations/s",
                "h2d_bytes_per_step": (h2d_b - h2d_a) / args.steps, "d2h_bytes_per_step": (d2h_b - d2h_a) / args.steps,
+               "host_buffer": host_kind,
                "what": "per rank: bmg_store_create from the shard's packed bytes in HOST memory (H2D + device re-coding) + peers + "
                        "bmg_group_create + bmg_sampler_create_grouped + begin + %d steps + end, wall clock, max over ranks; bytes are rank 0's"
                        % args.steps}

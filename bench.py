@@ -134,6 +134,31 @@ def gpu_local_cpus(device_index):
         return set()
 
 
+def plan_cpu_block(phys, local, local_rank, world):
+    """CPUs for one rank.  phys: the allowed physical cores, each a list of its hyperthreads; local[r]: the CPUs on the NUMA
+    node of rank r's GPU (empty set = unknown).  Ranks whose GPUs share a node split that node's allowed cores between them;
+    when a node has fewer allowed cores than ranks attached to it (or the topology is unknown) every rank gets a contiguous
+    block of all allowed cores instead.  Blocks of different ranks never overlap."""
+    if len(phys) < world:
+        return None
+    key = [tuple(sorted(l)) for l in local]
+    groups_ok = all(l for l in local)
+    if groups_ok:
+        for k in set(key):   # every node must hold at least one allowed core per rank attached to it, or nobody uses locality
+            members = [r for r in range(world) if key[r] == k]
+            near_k = [c for c in phys if set(c) <= set(k)]
+            if len(near_k) < len(members):
+                groups_ok = False
+    if groups_ok:
+        peers = [r for r in range(world) if key[r] == key[local_rank]]
+        near = [c for c in phys if set(c) <= local[local_rank]]
+        per = len(near) // len(peers)
+        i = peers.index(local_rank)
+        return sorted(c for core in near[i * per:(i + 1) * per] for c in core)
+    per = len(phys) // world
+    return sorted(c for core in phys[local_rank * per:(local_rank + 1) * per] for c in core)
+
+
 def pin_rank_to_core(local_rank, world):
     """A block of physical cores (all their hyperthreads) per rank: the chain's host thread spin-waits on device results,
     and two spinning ranks on sibling hyperthreads slow each other down.  Cores on the GPU's own NUMA node are preferred:
@@ -147,24 +172,14 @@ def pin_rank_to_core(local_rank, world):
                 members = _cpu_list(fh.read())
             cores[min(members)] = sorted(members & set(allowed))
         phys = [cores[k] for k in sorted(cores)]
-        if len(phys) < world:
-            return None
         if os.environ.get("BMG_BENCH_NO_LOCAL_PIN") is None:
-            # ranks grouped by the NUMA node of their GPU; each group shares that node's allowed cores
             local = [gpu_local_cpus(r) for r in range(world)]
-            key = [tuple(sorted(l)) for l in local]
-            peers = [r for r in range(world) if key[r] == key[local_rank]]
-            near = [c for c in phys if local[local_rank] and set(c) <= local[local_rank]]
-            if len(near) >= len(peers):
-                per = len(near) // len(peers)
-                i = peers.index(local_rank)
-                mine = sorted(c for core in near[i * per:(i + 1) * per] for c in core)
-                os.sched_setaffinity(0, mine)
-                return mine
-        per = len(phys) // world   # a contiguous block of physical cores per rank (helper threads keep their own CPUs)
-        mine = sorted(c for core in phys[local_rank * per:(local_rank + 1) * per] for c in core)
-        os.sched_setaffinity(0, mine)
-        return mine
+        else:
+            local = [set() for _ in range(world)]
+        mine = plan_cpu_block(phys, local, local_rank, world)
+        if mine:
+            os.sched_setaffinity(0, mine)
+        return mine or None
     except Exception:
         return None
 

@@ -81,6 +81,7 @@ SIGNATURES = {
     "bmg_sampler_stats": (C.c_int, [vp, f64p]),
     "bmg_sampler_counters": (C.c_int, [vp, f64p, C.c_int]),
     "bmg_ini_lookup": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]),
+    "bmg_store_create_from_ini": (C.c_int, [C.c_char_p, C.c_int64, C.c_int64, C.c_int, C.POINTER(C.c_void_p)]),
     "bmg_group_create": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, i64, C.c_char_p, C.POINTER(vp)]),
     "bmg_sampler_create_grouped": (C.c_int, [C.c_char_p, C.c_int, vp, vp, C.POINTER(vp)]),
     "bmg_group_serve": (C.c_int, [vp, i64]),

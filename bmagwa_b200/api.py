@@ -71,6 +71,20 @@ class GenotypeStore:
         self.h = h
         self.m_e = 0
 
+    @classmethod
+    def from_ini(cls, ini_path, snp_lo=0, snp_hi=None, device=-1):
+        """SNPs [snp_lo, snp_hi) of the data set an INI file names, phenotype and covariates set (bmg_store_create_from_ini)."""
+        self = cls.__new__(cls)
+        self.L = _lib.lib()
+        h = vp()
+        check(self.L.bmg_store_create_from_ini(os.fsencode(ini_path), snp_lo, -1 if snp_hi is None else snp_hi, device, C.byref(h)))
+        self.h = h
+        n, m_g, lo, hi, nmiss = (C.c_int64() for _ in range(5))
+        m_e = C.c_int()
+        check(self.L.bmg_store_dims(h, C.byref(n), C.byref(m_g), C.byref(lo), C.byref(hi), C.byref(m_e), C.byref(nmiss)))
+        self.n, self.m_g, self.lo, self.hi, self.m, self.m_e = n.value, m_g.value, lo.value, hi.value, hi.value - lo.value, m_e.value
+        return self
+
     def close(self):
         if getattr(self, "h", None):
             self.L.bmg_store_destroy(self.h)
@@ -394,3 +408,10 @@ class Sampler:
             self.close()
         except Exception:
             pass
+
+
+def ini_lookup(ini_path, section, key, default=""):
+    """A value of the INI file through the library's own parser (bmg_ini_lookup)."""
+    buf = C.create_string_buffer(1024)
+    check(_lib.lib().bmg_ini_lookup(os.fsencode(ini_path), section.encode(), key.encode(), default.encode(), buf, len(buf)))
+    return buf.value.decode()

@@ -264,6 +264,25 @@ BMG_API int bmg_ini_lookup(const char* ini_path, const char* section, const char
   std::snprintf(out, (size_t)out_len, "%s", v.c_str());
   BMG_CATCH
 }
+BMG_API int bmg_store_create_from_ini(const char* ini_path, int64_t snp_lo, int64_t snp_hi, int device, bmg_store** out)
+{
+  BMG_TRY
+  BMG_REQUIRE(ini_path && out, "bmg_store_create_from_ini: null argument");
+  const Options o(ini_path, /*quiet=*/true);
+  if (snp_hi < 0) snp_hi = (int64_t)o.m_g;
+  const Dataset d(o.n, o.m_g, o.m_e, o.file_fam, o.file_g, o.file_e, o.file_y, /*load_bed=*/false);
+  Store* st = store_create_from_bed(o.file_g.c_str(), (int64_t)o.n, (int64_t)o.m_g, snp_lo, snp_hi, o.recode_g_to_minor_allele_count,
+                                    device >= 0 ? device : o.device);
+  try {
+    store_set_phenotype(st, d.y.data(), d.e.data(), (int)d.m_e);
+  } catch (...) {
+    cudaSetDevice(st->device);
+    delete st;
+    throw;
+  }
+  *out = reinterpret_cast<bmg_store*>(st);
+  BMG_CATCH
+}
 BMG_API int bmg_sampler_set_option(bmg_sampler* sp, const char* key, const char* value)
 {
   BMG_TRY

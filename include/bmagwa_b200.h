@@ -295,6 +295,12 @@ bmg_chain* bmg_group_scan_chain(bmg_group* g);
  * chains at the barriers included), scans of this rank's chain, seconds in the barriers} */
 int bmg_group_stats(bmg_group* g, double* out4);
 int bmg_group_destroy(bmg_group* g);
+/* This rank's shard of the data set an INI file names: SNPs [snp_lo, snp_hi) of datafiles.file_g streamed to `device`
+ * (snp_hi < 0: up to sizes.m_g; device < 0: [b200] device), re-coded as datafiles.recode_g_to_minor_allele_count says, with
+ * the phenotype and covariates of file_fam / file_y / file_e set -- what Data's constructor does for the whole file
+ * (src/data.hpp:45-72, src/data.cpp:245-273,324-434), per shard.  The store is ready for bmg_store_export /
+ * bmg_group_create / bmg_sampler_create_grouped (or, with the whole SNP range, bmg_sampler_create_on_store). */
+int bmg_store_create_from_ini(const char* ini_path, int64_t snp_lo, int64_t snp_hi, int device, bmg_store** out);
 /* Value of `key` in [section] of an INI file, read with the library's own parser (the inih rules the reference follows,
  * src/inih/ini.c:60-140: case-insensitive names, '=' or ':' separators, continuation lines, " ;" comments, 199-character
  * lines); `dflt` when absent.  Copies at most out_len - 1 characters.  For hosts that need n_threads / do_n_iter

@@ -53,3 +53,35 @@ def test_shard_range_covers_all_snps():
                 assert got == list(range(m_g))
             else:
                 assert got[0] == 0 and got[-1] == m_g and all(got[2 * i + 1] == got[2 * i + 2] for i in range(world - 1))
+
+
+@pytest.mark.gpu
+def test_run_group_writes_the_files_of_the_command_line(tmp_path):
+    """`python -m bmagwa_b200.run_group config.ini` under torchrun (the INI's n_threads chains over one store sharded by SNP,
+    shards built by bmg_store_create_from_ini) against `bmagwa_b200/bmagwa config.ini` (the same chains as threads over one
+    whole store; reference: src/main.cpp:54-108): every output file byte for byte.  Two ranks, two chains, missing calls."""
+    import filecmp
+    import shutil
+    from bmagwa_b200 import synth
+    from bmagwa_b200.run_group import scan_rounds
+    assert scan_rounds(1200, 100, 2, False) == 12 and scan_rounds(1200, 100, 2, True) == 10 and scan_rounds(50, 100, 0, False) == 0
+    d = str(tmp_path)
+    ds = synth.write_dataset(d, "syn", n=600, m_g=3000, m_e=1, seed=5, e_qg=5, var_qg=20, do_n_iter=1200, n_rao=100, n_rao_burnin=2,
+                             n_threads=2, seeds="1234,2345", miss_rate=0.02, outbase=os.path.join(d, "cli"))
+    cli = os.path.join(ROOT, "bmagwa_b200", "bmagwa")
+    r = subprocess.run([cli, ds["ini"]], capture_output=True, text=True, timeout=600, cwd=d)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    ini2 = os.path.join(d, "grp.ini")
+    with open(ds["ini"]) as fh:
+        text = fh.read()
+    assert os.path.join(d, "cli") in text
+    with open(ini2, "w") as fh:
+        fh.write(text.replace(os.path.join(d, "cli"), os.path.join(d, "grp")))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "27%03d" % (os.getpid() % 1000), "-m", "bmagwa_b200.run_group", ini2]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0 and "Completed chain 1" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+    names = sorted(f for f in os.listdir(d) if f.startswith("cli") and f.endswith(".dat"))
+    assert len(names) >= 20
+    for f in names:
+        assert filecmp.cmp(os.path.join(d, f), os.path.join(d, "grp" + f[3:]), shallow=False), f

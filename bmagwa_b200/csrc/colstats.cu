@@ -10,6 +10,7 @@
 #include "store.cuh"
 #include "philox.cuh"
 #include <stdlib.h>
+#include <atomic>
 
 namespace bmg {
 
@@ -434,6 +435,27 @@ __global__ void k_sum_segments(const double* __restrict__ seg_out, int m_c, int 
 }
 
 // ---- host side of the persistent server ----------------------------------------------------------------------
+// Chains of this process that serve their moves through a persistent kernel, per device.  Their servers must all be resident
+// at once (a server CTA takes its work items by index and spins until its kernel is told to stop), and a scan CTA must still
+// find room beside them: together they get one CTA per SM.  The reference runs thread.n_threads chains over one Data
+// (src/main.cpp:54-108; its bundled testdata.ini: two); here these are n_threads chains on one GPU.
+static std::atomic<int> g_server_chains[64];
+
+void chain_expect_server(Chain* c)
+{
+  if (c->server_counted || !c->server_enabled) return;
+  const int dev = c->store->device;
+  if (dev < 0 || dev >= 64) return;
+  g_server_chains[dev].fetch_add(1, std::memory_order_relaxed);
+  c->server_counted = true;
+}
+void chain_forget_server(Chain* c)
+{
+  if (!c->server_counted) return;
+  g_server_chains[c->store->device].fetch_sub(1, std::memory_order_relaxed);
+  c->server_counted = false;
+}
+
 static void server_start(Chain* c, const ColStatInline& base, unsigned int last_served)
 {
   Store* s = c->store;
@@ -443,7 +465,14 @@ static void server_start(Chain* c, const ColStatInline& base, unsigned int last_
     c->server_req.alloc(2 * kMailChunks);
     c->server_flag.alloc(1);
     memset(c->server_mail.p, 0, kMailChunks * sizeof(uint4));
-    c->server_ctas = std::max(8, s->sm_count);   // one CTA per SM: a request of up to sm_count (candidate, slice) items is one wave
+  }
+  chain_expect_server(c);   // a chain driven through bmg_chain_column_stats alone is counted from its first request on
+  {
+    // one CTA per SM over all the servers of this device: alone, a request of up to sm_count (candidate, slice) items is one wave
+    const int dev = s->device;
+    static const bool share = getenv("BMG_SERVER_SHARE") == nullptr || atoi(getenv("BMG_SERVER_SHARE")) != 0;   // development: 0 = sm_count CTAs each
+    const int sharers = share && dev >= 0 && dev < 64 ? std::max(1, g_server_chains[dev].load(std::memory_order_relaxed)) : 1;
+    c->server_ctas = std::max(8, s->sm_count / sharers);
   }
   // nothing is "fresh" until the next post: mailbox head and device flag both carry the last served sequence number
   volatile uint32_t* head = reinterpret_cast<volatile uint32_t*>(c->server_mail.p);

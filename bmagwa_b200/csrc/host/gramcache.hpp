@@ -17,6 +17,7 @@
 // Not cached: SNPs with missing calls (their imputed values are redrawn at every proposal, src/data_model.cpp:95-103).
 // The probit latent phenotype changes x'y at every sweep: bump_phenotype() invalidates those (and only those).
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 #include <vector>
@@ -79,10 +80,18 @@ class GramCache {
     insert(make_key(a, b), v);
   }
   size_t pairs() const { return used_; }
+  uint64_t restarts() const { return restarts_; }
+  // slots of the pair table before it starts over: rounded down to a power of two, at least 16
+  void set_max_slots(size_t slots)
+  {
+    size_t p = 16;
+    while (2 * p <= slots) p *= 2;
+    max_cap_ = p;
+  }
 
  private:
   static constexpr uint64_t kEmpty = ~0ull;
-  static constexpr size_t kMaxCap = (size_t)1 << 24;   // 256 MB of keys + values; beyond that the pair table starts over
+  size_t max_cap_ = (size_t)1 << 24;   // 256 MB of keys + values; beyond that the pair table starts over
   size_t m_g_ = 0, m_e_ = 0;
   uint32_t epoch_ = 1;
   std::vector<uint32_t> stamp_;
@@ -91,6 +100,7 @@ class GramCache {
   std::vector<uint64_t> keys_;
   std::vector<double> vals_;
   size_t cap_ = 0, used_ = 0;
+  uint64_t restarts_ = 0;
 
   static uint64_t make_key(uint32_t a, uint32_t b) { return a < b ? ((uint64_t)a << 32) | b : ((uint64_t)b << 32) | a; }
   static size_t hash(uint64_t k)
@@ -107,12 +117,13 @@ class GramCache {
   }
   void grow()
   {
-    if (cap_ >= kMaxCap) {   // start over: the chain refills what it still uses
+    if (cap_ >= max_cap_) {   // start over: the chain refills what it still uses
       std::fill(keys_.begin(), keys_.end(), kEmpty);
       used_ = 0;
+      ++restarts_;
       return;
     }
-    const size_t new_cap = cap_ == 0 ? ((size_t)1 << 16) : 2 * cap_;
+    const size_t new_cap = cap_ == 0 ? std::min(max_cap_, (size_t)1 << 16) : 2 * cap_;
     std::vector<uint64_t> ok;
     std::vector<double> ov;
     ok.swap(keys_); ov.swap(vals_);

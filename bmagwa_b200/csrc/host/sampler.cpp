@@ -126,6 +126,7 @@ Sampler::Sampler(const Options& opts, int chain_index, Store* store, const std::
   pip_burnin_ = (int64_t)opts.pip_burnin;
 
   chain_ = chain_create(store_);
+  chain_expect_server(chain_);   // the chains of one device share its SMs for their column-statistics servers (colstats.cu)
   if (comm != nullptr && comm->group != nullptr) chain_set_group(chain_, comm->group);
   else if (comm != nullptr) chain_set_sharded(chain_, comm->world, comm->rank, comm->stride, comm->allgather, comm->ctx);
   dd_add_.init(&chain_->inorder_host(), (int)chain_->cdf_block);
@@ -323,8 +324,11 @@ void Sampler::set_option(const std::string& key, const std::string& value)
     else if (probit_) throw std::runtime_error("probit mode cannot be switched off once enabled");
   } else if (key == "gram_cache") {
     cache_.enabled = value != "0";
+  } else if (key == "gram_cache_max_pairs") {   // slots of the pair table before it starts over (a power of two; tests)
+    cache_.set_max_slots((size_t)std::stoull(value));
   } else if (key == "colstats_server") {
     chain_->server_enabled = value != "0";
+    if (chain_->server_enabled) chain_expect_server(chain_); else chain_forget_server(chain_);
   } else if (key == "scan_variant") {
     chain_->scan_variant = std::stoi(value);
   } else {
@@ -438,16 +442,15 @@ void Sampler::finish_gram()
       if (keep && cacheable(gram_.cand[(size_t)gram_req_[j]])) cache_.put_pair(snp, gram_.cand[(size_t)gram_req_[j]], req_xc_[i * m_r + j]);
   }
   if (memo && m_r < m_c) {
-    // products of a requested candidate with a candidate served from the memo: the latter was complete, i.e. it held
-    // its product with every other candidate of the move
+    // products of a requested candidate c with a candidate d served from the memo: d was complete, so begin_gram copied its
+    // product with every other candidate of the move into row d -- take it from there.  (Not from the table: filing the
+    // results above may have made a full table start over.)
     for (size_t i = 0; i < m_r; ++i) {
       const size_t c = (size_t)gram_req_[i];
       for (size_t d = 0; d < m_c; ++d) {
         bool requested = false;
         for (size_t j = 0; j < m_r; ++j) requested = requested || (size_t)gram_req_[j] == d;
-        if (requested) continue;
-        if (!cache_.get_pair(gram_.cand[c], gram_.cand[d], &gram_.xc[c * m_c + d]))
-          throw std::logic_error("finish_gram: a memoised candidate lacks a product of the move");
+        if (!requested) gram_.xc[c * m_c + d] = gram_.xc[d * m_c + c];
       }
     }
   }

@@ -678,6 +678,7 @@ void chain_destroy(Chain* c)
   if (!c) return;
   cudaSetDevice(c->store->device);
   chain_server_stop(c);
+  chain_forget_server(c);
   if (c->server_stream) cudaStreamDestroy(c->server_stream);
   if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
   for (cudaEvent_t e : c->scan_ev) cudaEventDestroy(e);

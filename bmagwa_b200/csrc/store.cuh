@@ -181,6 +181,7 @@ struct Chain {
   const double* server_base_y = nullptr;
   const void* server_base_out = nullptr;
   int64_t server_requests = 0;
+  bool server_counted = false;                  // among the chains of this process that share the device's SMs for their servers
   int server_failures = 0;                      // consecutive requests a server instance left unserved (see chain_column_stats_wait)
   int64_t server_fallbacks = 0;                 // requests repeated as an ordinary launch
   std::vector<unsigned char> cs_last_req;       // the pending request (a ColStatInline), kept for that repeat
@@ -213,6 +214,9 @@ void chain_bind_missing(Chain* c, const MissView& v);
 GlobalMissing* build_global_missing(Store* s, int world, int rank, int64_t stride, AllGatherFn fn, void* ctx);
 void scan_timer_begin(Chain* c, cudaStream_t st);
 void scan_timer_end(Chain* c, cudaStream_t st);
+// a chain that will send per-move requests (a sampler's chain): the servers of all such chains on one device split its SMs
+void chain_expect_server(Chain* c);
+void chain_forget_server(Chain* c);
 void imma_launch_on(Chain* geom, const uint4* q, const int* scale_exp, double* out, bool het, cudaStream_t st, Chain* timed);
 bool imma_launch2_on(Chain* geom, const uint4* q0, const int* scale_exp0, double* out0, const uint4* q1, const int* scale_exp1,
                      double* out1, cudaStream_t st, Chain* timed);

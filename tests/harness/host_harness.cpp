@@ -610,3 +610,46 @@ extern "C" void harness_exhaustive_typed(long n, long m_g, int m_e, const double
   for (unsigned long mask = 0; mask < (1ul << ms); ++mask) { P[mask] -= p0; B[mask] -= b0; }
   delete p;
 }
+
+// ---- the memo of column statistics (gramcache.hpp): a pair table driven through growth and restarts ----------------------
+// Files n_pairs products v(a, b) = a * 1e6 + b for pseudo-random pairs; after every insertion checks a sample of earlier
+// pairs: a pair must be either absent (the table started over since) or hold exactly its value.  Returns the number of
+// violations; out3 = {restarts, pairs held at the end, pairs found with the right value in the final sweep}.
+#include "gramcache.hpp"
+extern "C" long harness_gramcache(long max_slots, long n_pairs, long m_g, double* out3)
+{
+  GramCache gc;
+  gc.init((size_t)m_g, 1);
+  if (max_slots > 0) gc.set_max_slots((size_t)max_slots);
+  std::vector<std::pair<uint32_t, uint32_t>> filed;
+  uint64_t st = 88172645463325252ull;
+  auto rnd = [&st]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return st; };
+  long bad = 0;
+  for (long i = 0; i < n_pairs; ++i) {
+    const uint32_t a = (uint32_t)(rnd() % (uint64_t)m_g), b = (uint32_t)(rnd() % (uint64_t)m_g);
+    gc.put_pair(a, b, (double)std::min(a, b) * 1e6 + (double)std::max(a, b));
+    filed.emplace_back(a, b);
+    double v = 0.0;
+    if (!gc.get_pair(b, a, &v) || v != (double)std::min(a, b) * 1e6 + (double)std::max(a, b)) ++bad;   // symmetric, just filed
+    for (int probe = 0; probe < 4; ++probe) {
+      const auto& p = filed[(size_t)(rnd() % filed.size())];
+      if (gc.get_pair(p.first, p.second, &v) && v != (double)std::min(p.first, p.second) * 1e6 + (double)std::max(p.first, p.second)) ++bad;
+    }
+  }
+  long found = 0;
+  for (const auto& p : filed) {
+    double v = 0.0;
+    if (gc.get_pair(p.first, p.second, &v)) {
+      if (v == (double)std::min(p.first, p.second) * 1e6 + (double)std::max(p.first, p.second)) ++found; else ++bad;
+    }
+  }
+  out3[0] = (double)gc.restarts(); out3[1] = (double)gc.pairs(); out3[2] = (double)found;
+  // per-SNP entries and the phenotype epoch
+  const double xe[1] = {3.0};
+  gc.put_snp(5, 1.5, xe, 7.0);
+  if (!gc.have_snp(5) || gc.xy(5) != 1.5 || gc.xx(5) != 7.0 || gc.xe(5)[0] != 3.0 || gc.have_snp(6)) ++bad;
+  gc.bump_phenotype();
+  if (gc.have_snp(5)) ++bad;
+  if (gc.repeat_visitor(9) || !gc.repeat_visitor(9)) ++bad;   // kept from the second proposal on
+  return bad;
+}

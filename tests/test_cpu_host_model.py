@@ -410,3 +410,20 @@ def test_typed_exhaustive_modelset_equals_brute_force(harness, types, const_loci
     assert np.isfinite(P).all() and np.isfinite(B).all()
     assert np.allclose(P, B, rtol=0, atol=1e-9)
     assert np.abs(B).max() > 1e-3
+
+
+def test_memo_pair_table_through_growth_and_restarts(harness):
+    """gramcache.hpp: the open-addressing table of x_j'x_l products never returns a wrong value -- while it grows (no
+    entry lost) and once it is full and starts over (entries gone, not garbled).  A chain meets the second case after some
+    10^5 iterations on a small SNP panel; the sampler must not rely on an entry surviving the filing of a move's results
+    (it does not: bmagwa_b200/csrc/host/sampler.cpp, finish_gram)."""
+    harness.harness_gramcache.restype = C.c_long
+    out = np.zeros(3)
+    # growing only: 200,000 pairs fit below the default limit, nothing may be lost
+    assert harness.harness_gramcache(C.c_long(0), C.c_long(200000), C.c_long(5000), _p(out)) == 0
+    assert out[0] == 0 and out[1] > 190000 and out[2] == 200000
+    # 4,096 slots: the table starts over every ~2,048 distinct pairs
+    assert harness.harness_gramcache(C.c_long(4096), C.c_long(100000), C.c_long(5000), _p(out)) == 0
+    assert out[0] >= 40 and out[1] <= 2048 and 0 < out[2] <= 4096
+    # degenerate limits are rounded to a usable table
+    assert harness.harness_gramcache(C.c_long(1), C.c_long(1000), C.c_long(50), _p(out)) == 0 and out[0] > 0

@@ -510,7 +510,10 @@ def ours_arm(args, rank, local_rank, world, dist=None, workload=None, with_cpu_b
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "k_scan_dots (genotype scan reduction, variant %s)" % os.environ.get("BMG_SCAN_VARIANT", "default"),
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": scan_traffic(workload),
-                     "bytes_per_launch": bytes_scan, "avg_launch_ms": scan_ms, "launches_timed": int(n_l.value), "peak_source": peak_src},
+                     "bytes_per_launch": bytes_scan, "avg_launch_ms": scan_ms, "launches_timed": int(n_l.value), "peak_source": peak_src,
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel at this "
+                                       "workload, committed under profiles/ (round2_scan_ncu.md, scan_traffic.json): a per-round figure, not "
+                                       "measured in this run"},
         "clocks": clk,
         "breakdown": {"move_seconds": st["move_seconds"], "scan_seconds": st["scan_seconds"], "scans": st["scans"], "column_stats_seconds": st["column_stats_seconds"],
                       "delayed_rejection_seconds": cnt["delayed_rejection_seconds"], "delayed_rejection_events": cnt["delayed_rejection_events"],
